@@ -1,0 +1,901 @@
+"""CPU ORACLE (test infrastructure, NOT product code) -- numpy restatement of the Bijectors.jl hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` leg may
+import this module.  The product path (``bijectors.jl_b200``) never imports it and never falls back to it.
+
+Every function follows the reference source line by line (citations are ``path:line`` relative to the
+reference checkout, Bijectors.jl v0.16.2).  The reference is pure Julia and no Julia toolchain exists in
+the build container, so the reference itself cannot be executed here: this restatement is pinned by
+
+  * the deterministic golden vectors the reference's own tests hold (``tests/golden/reference_vectors.json``,
+    transcribed from test/bijectors/{coupling,permute,stacked,rational_quadratic_spline}.jl,
+    test/normalising_flows.jl and the doctest at src/interface.jl:21-31), checked in
+    ``tests/test_oracle_golden.py``;
+  * the reference's property tests restated in ``tests/test_oracle_properties.py`` (logjac vs. the
+    log|det| of a numerical Jacobian, inverse∘forward = id, ``ires == (x, -logjac)``, the find_alpha
+    residual grid of test/normalising_flows.jl:47-71).
+
+Values in the reference tests that depend on Julia RNG streams (``randn`` after ``seed!``, ``StableRNG``)
+are NOT reproducible without Julia: for those inputs parity is "pinned by property, not by value".
+
+Arithmetic that lives in third-party Julia packages (not under /root/reference; no Manifest is vendored,
+only compat ranges in Project.toml) is restated from its published maths:
+  LogExpFunctions (compat 0.3.3, 1.0)  log1pexp, softmax
+  Roots (compat 1.3.15, 2, 3)          find_zero(..., A42()) -> any bracketing solver converging to
+                                        adjacent floats is admissible (results are pinned by the residual)
+  ChangesOfVariables 0.1                with_logabsdet_jacobian of ComposedFunction / Fix1{broadcast}
+  InverseFunctions 0.1                  inverse(f∘g) = inverse(g)∘inverse(f)
+  Distributions 0.25.33 + PDMats        logpdf(MvNormal(mu, Diagonal), x)
+
+Layout convention: a Julia ``D×N`` column-major matrix is a numpy array of shape ``(D, N)`` here
+(numpy keeps Julia's index semantics; memory order is irrelevant for the oracle).
+All functions compute in the dtype of their inputs (float32 in -> float32 arithmetic, like Julia).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------------------
+# third-party scalar functions
+# --------------------------------------------------------------------------------------------------
+
+
+def log1pexp(x):
+    """LogExpFunctions.log1pexp: numerically stable log(1 + exp(x)) (softplus).
+
+    Restated from the documented maths: log1p(exp(x)) for x <= 0 and x + log1p(exp(-x)) for x > 0,
+    which agrees with the package's 4-branch form to < 1 ulp.  Call sites: src/bijectors/planar_layer.jl:67-68,
+    src/bijectors/radial_layer.jl:44-45,77-78,91-92, src/bijectors/rational_quadratic_spline.jl:105,116.
+    """
+    x = np.asarray(x)
+    dt = x.dtype if x.dtype.kind == "f" else np.float64
+    x = x.astype(dt, copy=False)
+    with np.errstate(over="ignore"):
+        out = np.where(x > 0, x + np.log1p(np.exp(-np.abs(x))), np.log1p(np.exp(-np.abs(x))))
+    return out.astype(dt)[()]
+
+
+def softmax_rows(v):
+    """LogExpFunctions.softmax(v; dims=2): exp(v - max) / sum(exp(v - max)) along each row.
+
+    Call site: src/bijectors/rational_quadratic_spline.jl:103-104,112-113.
+    """
+    v = np.asarray(v)
+    m = v.max(axis=-1, keepdims=True)
+    e = np.exp(v - m)
+    return e / e.sum(axis=-1, keepdims=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# PlanarLayer  (src/bijectors/planar_layer.jl)
+# --------------------------------------------------------------------------------------------------
+
+
+def get_u_hat(u, w):
+    """src/bijectors/planar_layer.jl:65-70 -> (u_hat, wT_u_hat)."""
+    dt = w.dtype
+    wT_u = dt.type(np.dot(w, u))
+    u_hat = u + ((log1pexp(-wT_u) - dt.type(1)) / dt.type(np.sum(w * w))) * w
+    wT_u_hat = log1pexp(wT_u) - dt.type(1)
+    return u_hat.astype(dt), dt.type(wT_u_hat)
+
+
+def planar_forward(w, u, b, z):
+    """with_logabsdet_jacobian(::PlanarLayer, z) -- src/bijectors/planar_layer.jl:73-80,102-110.
+
+    ``z`` is (D,) or (D, N); returns (y, logjac) with logjac scalar or (N,).
+    """
+    dt = z.dtype
+    b = dt.type(np.asarray(b).reshape(-1)[0])  # first(flow.b), :75
+    u_hat, wT_u_hat = get_u_hat(u.astype(dt), w.astype(dt))
+    wT_z = w.astype(dt) @ z  # aT_b, src/utils.jl:2-4
+    a = wT_z + b
+    if z.ndim == 1:
+        y = z + u_hat * np.tanh(a)
+    else:
+        y = z + u_hat[:, None] * np.tanh(a)[None, :]  # :78
+    with np.errstate(over="ignore"):
+        sech2 = (dt.type(1) / np.cosh(a)) ** 2  # abs2(sech(.)), :107
+    logjac = np.log1p(wT_u_hat * sech2)
+    return y.astype(dt), np.asarray(logjac, dtype=dt)[()]
+
+
+def find_alpha(wt_y, wt_u_hat, b):
+    """src/bijectors/planar_layer.jl:160-185, vectorised over ``wt_y``.
+
+    Roots.A42 narrows the bracket to adjacent floats; here: Newton steps safeguarded by bisection on the
+    monotone f(a) = a + c*tanh(a+b) - t until the bracket is adjacent floats or f == 0.
+    """
+    t = np.asarray(wt_y)
+    dt = np.result_type(t.dtype, np.asarray(wt_u_hat).dtype, np.asarray(b).dtype)  # promote(...), :162
+    if dt.kind != "f":
+        dt = np.dtype(np.float64)
+    t = np.atleast_1d(t.astype(dt))
+    c = dt.type(wt_u_hat)
+    bb = dt.type(b)
+    delta = dt.type(2) * abs(c)  # :166
+    lo = t - delta
+    hi = t + delta
+    alpha = t.copy()
+    active = lo != hi  # empty bracket -> return lower, :171-173
+    alpha[~active] = lo[~active]
+
+    def f(a):
+        return a + c * np.tanh(a + bb) - t
+
+    flo = f(lo)
+    fhi = f(hi)
+    # exact roots at the ends
+    hit_lo = active & (flo == 0)
+    alpha[hit_lo] = lo[hit_lo]
+    active &= ~hit_lo
+    hit_hi = active & (fhi == 0)
+    alpha[hit_hi] = hi[hit_hi]
+    active &= ~hit_hi
+    x = np.where(active, (lo + hi) / dt.type(2), alpha)
+    for _ in range(200):
+        if not active.any():
+            break
+        fx = f(x)
+        root = active & (fx == 0)
+        alpha[root] = x[root]
+        active &= ~root
+        neg = fx < 0
+        lo = np.where(active & neg, x, lo)
+        hi = np.where(active & ~neg, x, hi)
+        # converged when lo and hi are adjacent floats
+        adj = active & (np.nextafter(lo, hi) >= hi)
+        if adj.any():
+            # pick the end with the smaller residual
+            fl = np.abs(f(lo))
+            fh = np.abs(f(hi))
+            alpha[adj] = np.where(fl <= fh, lo, hi)[adj]
+            active &= ~adj
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            sech2 = (dt.type(1) / np.cosh(x + bb)) ** 2
+            newton = x - fx / (dt.type(1) + c * sech2)
+        mid = lo + (hi - lo) / dt.type(2)
+        ok = np.isfinite(newton) & (newton > lo) & (newton < hi)
+        x = np.where(active, np.where(ok, newton, mid), x)
+        # guard against Newton stalling on one side: force bisection every few steps
+        if _ % 3 == 2:
+            x = np.where(active, mid, x)
+    alpha[active] = x[active]
+    return alpha if np.ndim(wt_y) else alpha[0]
+
+
+def planar_inverse(w, u, b, y):
+    """with_logabsdet_jacobian(Inverse(PlanarLayer), y):
+    transform src/bijectors/planar_layer.jl:112-127 + default inverse logjac src/interface.jl:276-281
+    (the forward pass is recomputed on the recovered z, as the reference does)."""
+    dt = y.dtype
+    w = w.astype(dt)
+    bb = dt.type(np.asarray(b).reshape(-1)[0])
+    u_hat, wT_u_hat = get_u_hat(u.astype(dt), w)
+    wT_y = w @ y
+    alpha = find_alpha(wT_y, wT_u_hat, bb)
+    th = np.tanh(alpha + bb)
+    if y.ndim == 1:
+        z = y - u_hat * th
+    else:
+        z = y - u_hat[:, None] * np.asarray(th)[None, :]
+    z = z.astype(dt)
+    _, lj = planar_forward(w, u, b, z)
+    return z, -lj
+
+
+# --------------------------------------------------------------------------------------------------
+# RadialLayer  (src/bijectors/radial_layer.jl)
+# --------------------------------------------------------------------------------------------------
+
+
+def radial_forward(alpha_raw, beta, z0, z):
+    """with_logabsdet_jacobian(::RadialLayer, z) -- src/bijectors/radial_layer.jl:43-53,58-72."""
+    dt = z.dtype
+    a_ = dt.type(np.asarray(alpha_raw).reshape(-1)[0])  # first(.), :41
+    be = dt.type(np.asarray(beta).reshape(-1)[0])
+    z0 = z0.astype(dt)
+    alpha = dt.type(log1pexp(a_))  # :44
+    beta_hat = dt.type(-alpha + log1pexp(be))  # :45
+    if z.ndim == 1:
+        diff = z - z0
+        # LinearAlgebra.norm, :47 (scaled 2-norm; equals sqrt(sum(abs2)) up to rounding)
+        r = dt.type(np.sqrt(np.sum(diff * diff)))
+        y = z + beta_hat / (alpha + r) * diff  # :51
+    else:
+        diff = z - z0[:, None]
+        r = np.sqrt(np.sum(diff * diff, axis=0)).astype(dt)  # :49
+        y = z + (beta_hat / (alpha + r))[None, :] * diff
+    d = z0.shape[0]
+    h_ = dt.type(1) / (alpha + r)  # h(α, r), :36
+    logjac = dt.type(d - 1) * np.log(dt.type(1) + beta_hat * h_) + np.log(
+        dt.type(1) + beta_hat * h_ + beta_hat * (-(h_ ** 2)) * r
+    )  # :68-70
+    return y.astype(dt), np.asarray(logjac, dtype=dt)[()]
+
+
+def compute_r(y_minus_z0, alpha, alpha_plus_beta_hat):
+    """src/bijectors/radial_layer.jl:124-129 (vector or per-column for a matrix)."""
+    dt = y_minus_z0.dtype
+    gamma = np.sqrt(np.sum(y_minus_z0 * y_minus_z0, axis=0)).astype(dt)  # norm, :125
+    a = alpha_plus_beta_hat - gamma
+    r = (np.sqrt(a * a + dt.type(4) * alpha * gamma) - a) / dt.type(2)
+    return r.astype(dt) if np.ndim(r) else dt.type(r)
+
+
+def radial_inverse(alpha_raw, beta, z0, y):
+    """with_logabsdet_jacobian(Inverse(RadialLayer), y):
+    src/bijectors/radial_layer.jl:74-86 (vector), :88-102 (matrix) + src/interface.jl:276-281."""
+    dt = y.dtype
+    a_ = dt.type(np.asarray(alpha_raw).reshape(-1)[0])
+    be = dt.type(np.asarray(beta).reshape(-1)[0])
+    z0 = z0.astype(dt)
+    alpha = dt.type(log1pexp(a_))
+    apb = dt.type(log1pexp(be))
+    ymz = y - (z0 if y.ndim == 1 else z0[:, None])
+    r = compute_r(ymz, alpha, apb)
+    gamma = (alpha + r) / (apb + r)
+    if y.ndim == 1:
+        z = z0 + gamma * ymz
+    else:
+        z = z0[:, None] + np.asarray(gamma)[None, :] * ymz
+    z = z.astype(dt)
+    _, lj = radial_forward(alpha_raw, beta, z0, z)
+    return z, -lj
+
+
+# --------------------------------------------------------------------------------------------------
+# RationalQuadraticSpline  (src/bijectors/rational_quadratic_spline.jl)
+# --------------------------------------------------------------------------------------------------
+
+
+def rqs_params(raw_widths, raw_heights, raw_derivs, B):
+    """Parameter-normalising constructors, src/bijectors/rational_quadratic_spline.jl:99-107 (vector)
+    and :109-123 (matrix).  Returns processed (widths, heights, derivatives) with K+1 knots per row."""
+    rw = np.asarray(raw_widths)
+    dt = rw.dtype
+    rh = np.asarray(raw_heights).astype(dt)
+    rd = np.asarray(raw_derivs).astype(dt)
+    vec = rw.ndim == 1
+    if vec:
+        rw, rh, rd = rw[None, :], rh[None, :], rd[None, :]
+    d = rw.shape[0]
+    ws = np.concatenate([np.zeros((d, 1), dt), softmax_rows(rw).astype(dt)], axis=1)
+    hs = np.concatenate([np.zeros((d, 1), dt), softmax_rows(rh).astype(dt)], axis=1)
+    ds = np.concatenate([np.ones((d, 1), dt), log1pexp(rd).astype(dt), np.ones((d, 1), dt)], axis=1)
+    twoB = dt.type(2 * B)
+    Bt = dt.type(B)
+    W = (twoB * np.cumsum(ws, axis=1, dtype=dt) - Bt).astype(dt)
+    H = (twoB * np.cumsum(hs, axis=1, dtype=dt) - Bt).astype(dt)
+    if vec:
+        return W[0], H[0], ds[0]
+    return W, H, ds
+
+
+def rqs_validate(widths, heights, derivs):
+    """Struct asserts, src/bijectors/rational_quadratic_spline.jl:84-85,93-94."""
+    if widths.ndim == 1:
+        assert len(widths) == len(heights) == len(derivs)
+    else:
+        assert widths.shape[1] == heights.shape[1] == derivs.shape[1]
+    assert np.all(derivs > 0), "derivatives need to be positive"
+
+
+def _searchsortedfirst(knots, x):
+    """Julia searchsortedfirst(knots, x): 1-based index of the first knot >= x (len+1 if none)."""
+    return int(np.searchsorted(knots, x, side="left")) + 1
+
+
+def rqs_forward_scalar(widths, heights, derivs, x):
+    """rqs_forward, src/bijectors/rational_quadratic_spline.jl:317-357 (1-based indexing kept)."""
+    dt = np.result_type(widths.dtype, np.asarray(x).dtype)
+    one = dt.type(1)
+    x = dt.type(x)
+    W = lambda k: widths[k - 1]  # noqa: E731  (1-based access)
+    H = lambda k: heights[k - 1]  # noqa: E731
+    Dv = lambda k: derivs[k - 1]  # noqa: E731
+    Kn = len(widths)
+    if (x <= -W(Kn)) or (x >= W(Kn)):  # :322-324
+        return x, dt.type(0) * x
+    k = _searchsortedfirst(widths, x) - 1  # :328
+    w_k = -W(Kn) if k == 0 else W(k)  # :331
+    w = W(k + 1) - w_k
+    h_k = -H(Kn) if k == 0 else H(k)  # :335
+    dy = H(k + 1) - h_k
+    s = dy / w  # :339
+    xi = (x - w_k) / w
+    d_k = one if k == 0 else Dv(k)  # :342
+    d_k1 = one if k == Kn - 1 else Dv(k + 1)
+    den = s + (d_k1 + d_k - 2 * s) * xi * (one - xi)  # :346
+    num_jl = s ** 2 * (d_k1 * xi ** 2 + 2 * s * xi * (one - xi) + d_k * (one - xi) ** 2)  # :349
+    logjac = np.log(num_jl) - 2 * np.log(den)
+    num_y = dy * (s * xi ** 2 + d_k * xi * (one - xi))  # :353
+    y = h_k + num_y / den
+    return dt.type(y), dt.type(logjac)
+
+
+def rqs_inverse_scalar(widths, heights, derivs, y):
+    """rqs_univariate_inverse, src/bijectors/rational_quadratic_spline.jl:183-220."""
+    dt = np.result_type(widths.dtype, np.asarray(y).dtype)
+    one = dt.type(1)
+    y = dt.type(y)
+    W = lambda k: widths[k - 1]  # noqa: E731
+    H = lambda k: heights[k - 1]  # noqa: E731
+    Dv = lambda k: derivs[k - 1]  # noqa: E731
+    Kn = len(widths)
+    if (y <= -H(Kn)) or (y >= H(Kn)):  # :186-188
+        return y
+    k = _searchsortedfirst(heights, y) - 1  # :191
+    w_k = -W(Kn) if k == 0 else W(k)
+    w = W(k + 1) - w_k
+    h_k = -H(Kn) if k == 0 else H(k)
+    dy = H(k + 1) - h_k
+    s = dy / w
+    d_k = one if k == 0 else Dv(k)
+    d_k1 = one if k == Kn - 1 else Dv(k + 1)
+    ds = d_k1 + d_k - 2 * s  # :205
+    a1 = dy * (s - d_k) + (y - h_k) * ds  # :208
+    a2 = dy * d_k - (y - h_k) * ds  # :210
+    a3 = -s * (y - h_k)  # :212
+    num = -2 * a3
+    den = a2 + np.sqrt(a2 ** 2 - 4 * a1 * a3)  # :216
+    xi = num / den
+    return dt.type(xi * w + w_k)
+
+
+def _rqs_bins(knots, v):
+    """Vectorised bin lookup: knots (D, Kn), v (D, N) -> 1-based k = searchsortedfirst - 1, shape (D, N)."""
+    # number of knots strictly below v  == searchsortedfirst(knots, v) - 1
+    return (knots[:, :, None] < v[:, None, :]).sum(axis=1)
+
+
+def rqs_forward(widths, heights, derivs, x):
+    """Batched map-over-columns of the multivariate RQS (reference defines vectors only:
+    transform :173-178, logabsdetjac :304-309, with_logabsdet_jacobian :363-367).
+    widths/heights/derivs: (D, Kn); x: (D,) or (D, N) -> (y, logjac[N])."""
+    vec = x.ndim == 1
+    X = x[:, None] if vec else x
+    dt = X.dtype
+    W = widths.astype(dt)
+    Hh = heights.astype(dt)
+    Dv = derivs.astype(dt)
+    D, Kn = W.shape
+    one = dt.type(1)
+    Bw = W[:, -1][:, None]
+    outside = (X <= -Bw) | (X >= Bw)
+    k = _rqs_bins(W, X)  # 1-based k (0..Kn)
+    kc = np.clip(k, 0, Kn - 1)
+    rows = np.arange(D)[:, None]
+
+    def g1(A, kk):  # A[k] with 1-based k (k>=1)
+        return A[rows, np.clip(kk - 1, 0, Kn - 1)]
+
+    w_k = np.where(kc == 0, -Bw, g1(W, kc))
+    w = g1(W, kc + 1) - w_k
+    h_k = np.where(kc == 0, -Hh[:, -1][:, None], g1(Hh, kc))
+    dy = g1(Hh, kc + 1) - h_k
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = dy / w
+        xi = (X - w_k) / w
+        d_k = np.where(kc == 0, one, g1(Dv, kc))
+        d_k1 = np.where(kc == Kn - 1, one, g1(Dv, kc + 1))
+        den = s + (d_k1 + d_k - 2 * s) * xi * (one - xi)
+        num_jl = s ** 2 * (d_k1 * xi ** 2 + 2 * s * xi * (one - xi) + d_k * (one - xi) ** 2)
+        lj = np.log(num_jl) - 2 * np.log(den)
+        y = h_k + dy * (s * xi ** 2 + d_k * xi * (one - xi)) / den
+    y = np.where(outside, X, y).astype(dt)
+    lj = np.where(outside, dt.type(0), lj).astype(dt)
+    logjac = lj.sum(axis=0, dtype=dt)
+    if vec:
+        return y[:, 0], logjac[0]
+    return y, logjac
+
+
+def rqs_inverse(widths, heights, derivs, y):
+    """with_logabsdet_jacobian(Inverse(RQS), y): transform :227-233 + src/interface.jl:276-281."""
+    vec = y.ndim == 1
+    Y = y[:, None] if vec else y
+    dt = Y.dtype
+    W = widths.astype(dt)
+    Hh = heights.astype(dt)
+    Dv = derivs.astype(dt)
+    D, Kn = W.shape
+    one = dt.type(1)
+    Bh = Hh[:, -1][:, None]
+    outside = (Y <= -Bh) | (Y >= Bh)
+    k = _rqs_bins(Hh, Y)
+    kc = np.clip(k, 0, Kn - 1)
+    rows = np.arange(D)[:, None]
+
+    def g1(A, kk):
+        return A[rows, np.clip(kk - 1, 0, Kn - 1)]
+
+    w_k = np.where(kc == 0, -W[:, -1][:, None], g1(W, kc))
+    w = g1(W, kc + 1) - w_k
+    h_k = np.where(kc == 0, -Bh, g1(Hh, kc))
+    dy = g1(Hh, kc + 1) - h_k
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = dy / w
+        d_k = np.where(kc == 0, one, g1(Dv, kc))
+        d_k1 = np.where(kc == Kn - 1, one, g1(Dv, kc + 1))
+        ds = d_k1 + d_k - 2 * s
+        a1 = dy * (s - d_k) + (Y - h_k) * ds
+        a2 = dy * d_k - (Y - h_k) * ds
+        a3 = -s * (Y - h_k)
+        xi = (-2 * a3) / (a2 + np.sqrt(a2 ** 2 - 4 * a1 * a3))
+        x = xi * w + w_k
+    x = np.where(outside, Y, x).astype(dt)
+    _, lj = rqs_forward(W, Hh, Dv, x)
+    if vec:
+        return x[:, 0], -lj
+    return x, -lj
+
+
+# --------------------------------------------------------------------------------------------------
+# PartitionMask / Coupling  (src/bijectors/coupling.jl), Shift / Scale
+# --------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class PartitionMask:
+    """src/bijectors/coupling.jl:51-118.  Indices are 1-based like the reference; the sparse 0/1
+    selector matrices are represented by their index lists (A_i[idx_i[j], j] = 1)."""
+
+    n: int
+    indices_1: np.ndarray
+    indices_2: np.ndarray
+    indices_3: np.ndarray
+
+    @staticmethod
+    def make(n, indices_1, indices_2=None, indices_3=None):
+        i1 = np.asarray(list(indices_1), dtype=np.int64)
+        if indices_2 is None and indices_3 is None:
+            # PartitionMask(n, indices): split, :107-115
+            i2 = np.asarray([i for i in range(1, n + 1) if i not in set(i1.tolist())], dtype=np.int64)
+            i3 = np.zeros((0,), dtype=np.int64)
+        elif indices_3 is None:
+            i2 = np.asarray(list(indices_2), dtype=np.int64)
+            used = set(i1.tolist()) | set(i2.tolist())
+            i3 = np.asarray([i for i in range(1, n + 1) if i not in used], dtype=np.int64)  # :85-92
+        elif indices_2 is None:
+            i3 = np.asarray(list(indices_3), dtype=np.int64)
+            used = set(i1.tolist()) | set(i3.tolist())
+            i2 = np.asarray([i for i in range(1, n + 1) if i not in used], dtype=np.int64)  # :94-101
+        else:
+            i2 = np.asarray(list(indices_2), dtype=np.int64)
+            i3 = np.asarray(list(indices_3), dtype=np.int64)
+        return PartitionMask(n, i1, i2, i3)
+
+
+def partition(m: PartitionMask, x):
+    """src/bijectors/coupling.jl:132-134: (A_1' x, A_2' x, A_3' x)."""
+    return x[m.indices_1 - 1], x[m.indices_2 - 1], x[m.indices_3 - 1]
+
+
+def combine(m: PartitionMask, x_1, x_2, x_3):
+    """src/bijectors/coupling.jl:125: A_1 x_1 + A_2 x_2 + A_3 x_3."""
+    shape = (m.n,) + tuple(np.shape(x_1)[1:])
+    dt = np.result_type(x_1, x_2, x_3) if np.size(x_3) else np.result_type(x_1, x_2)
+    out = np.zeros(shape, dtype=dt)
+    out[m.indices_1 - 1] += x_1
+    out[m.indices_2 - 1] += x_2
+    if len(m.indices_3):
+        out[m.indices_3 - 1] += x_3
+    return out
+
+
+@dataclass
+class Shift:
+    """src/bijectors/shift.jl:4-24."""
+
+    a: object
+
+    def wladj(self, x):
+        x = np.asarray(x)
+        return self.a + x, x.dtype.type(0)  # zero(eltype(x)), :21
+
+    def inv_wladj(self, y):
+        y = np.asarray(y)
+        return (-np.asarray(self.a)) + y, y.dtype.type(0)  # inverse(b) = Shift(-a), :12
+
+
+@dataclass
+class Scale:
+    """src/bijectors/scale.jl:1-39 (scalar / vector ``a``)."""
+
+    a: object
+
+    def _logjac(self, x):
+        a = np.asarray(self.a)
+        x = np.asarray(x)
+        if a.ndim == 0:
+            return np.log(np.abs(a)) * (x.size if x.ndim else 1)  # :26-28
+        return np.sum(np.log(np.abs(a)))  # :31-32
+
+    def wladj(self, x):
+        return np.asarray(self.a) * np.asarray(x), self._logjac(x)
+
+    def inv_wladj(self, y):
+        ia = 1.0 / np.asarray(self.a)  # inv.(a), :15-16
+        return ia * np.asarray(y), Scale(ia)._logjac(y)
+
+
+@dataclass
+class ComposedLaw:
+    """outer ∘ inner for coupling laws (ChangesOfVariables ComposedFunction rule)."""
+
+    outer: object
+    inner: object
+
+    def wladj(self, x):
+        y1, l1 = self.inner.wladj(x)
+        y, l2 = self.outer.wladj(y1)
+        return y, l1 + l2
+
+    def inv_wladj(self, y):
+        x1, l1 = self.outer.inv_wladj(y)
+        x, l2 = self.inner.inv_wladj(x1)
+        return x, l1 + l2
+
+
+def coupling_forward(theta: Callable, mask: PartitionMask, x):
+    """with_logabsdet_jacobian(::Coupling, x::vector) -- src/bijectors/coupling.jl:206-215."""
+    x_1, x_2, x_3 = partition(mask, x)
+    b = theta(x_2)
+    y_1, logjac = b.wladj(x_1)
+    return combine(mask, y_1, x_2, x_3), logjac
+
+
+def coupling_inverse(theta: Callable, mask: PartitionMask, y):
+    """with_logabsdet_jacobian(::Inverse{<:Coupling}, y) -- src/bijectors/coupling.jl:217-228."""
+    y_1, y_2, y_3 = partition(mask, y)
+    b = theta(y_2)
+    x_1, logjac = b.inv_wladj(y_1)
+    return combine(mask, x_1, y_2, y_3), logjac
+
+
+def affine_law(Wm, c):
+    """The affine coupling law θ(x₂) = Shift(t) ∘ Scale(exp.(s)), [s;t] = W·x₂ + c:
+    Scale src/bijectors/scale.jl:13,31, Shift src/bijectors/shift.jl:14,21."""
+
+    def theta(x_2):
+        st = Wm @ x_2 + c
+        n1 = st.shape[0] // 2
+        return ComposedLaw(Shift(st[n1:]), Scale(np.exp(st[:n1])))
+
+    return theta
+
+
+def coupling_affine_forward(idx1, idx2, Wm, c, x):
+    """Batched (map over columns) affine coupling, SURVEY Appendix A.6.
+    idx1/idx2 are 1-based row lists; Wm is (2*n1, n2); x is (D,) or (D, N)."""
+    vec = x.ndim == 1
+    X = x[:, None] if vec else x
+    dt = X.dtype
+    i1 = np.asarray(idx1) - 1
+    i2 = np.asarray(idx2) - 1
+    n1 = len(i1)
+    st = Wm.astype(dt) @ X[i2] + c.astype(dt)[:, None]
+    s, t = st[:n1], st[n1:]
+    Y = X.copy()
+    Y[i1] = np.exp(s) * X[i1] + t
+    # logjac = Σ log|exp(s_j)|  (scale.jl:31) -- evaluated as Σ s_j (identical unless exp overflows)
+    logjac = s.sum(axis=0, dtype=dt)
+    if vec:
+        return Y[:, 0], logjac[0]
+    return Y, logjac
+
+
+def coupling_affine_inverse(idx1, idx2, Wm, c, y):
+    """Inverse affine coupling: x₁ = inv.(exp(s)) .* (y₁ + (-t)) (shift.jl:12, scale.jl:15-16)."""
+    vec = y.ndim == 1
+    Y = y[:, None] if vec else y
+    dt = Y.dtype
+    i1 = np.asarray(idx1) - 1
+    i2 = np.asarray(idx2) - 1
+    n1 = len(i1)
+    st = Wm.astype(dt) @ Y[i2] + c.astype(dt)[:, None]
+    s, t = st[:n1], st[n1:]
+    X = Y.copy()
+    X[i1] = (dt.type(1) / np.exp(s)) * (Y[i1] + (-t))
+    logjac = -s.sum(axis=0, dtype=dt)
+    if vec:
+        return X[:, 0], logjac[0]
+    return X, logjac
+
+
+# --------------------------------------------------------------------------------------------------
+# InvertibleBatchNorm  (src/bijectors/normalise.jl)
+# --------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class BatchNormParams:
+    """InvertibleBatchNorm(chs; eps=1f-5, mtm=1f-1) defaults, src/bijectors/normalise.jl:26-37."""
+
+    b: np.ndarray
+    logs: np.ndarray
+    m: np.ndarray
+    v: np.ndarray
+    eps: float = np.float32(1e-5)
+    mtm: float = np.float32(1e-1)
+
+    @staticmethod
+    def default(chs, dtype=np.float32):
+        dt = np.dtype(dtype)
+        return BatchNormParams(
+            np.zeros(chs, dt), np.zeros(chs, dt), np.zeros(chs, dt), np.ones(chs, dt), dt.type(1e-5), dt.type(1e-1)
+        )
+
+
+def batchnorm_forward(bn: BatchNormParams, x, training=False):
+    """src/bijectors/normalise.jl:41-69.  x is (C, N) (channels = ndims-1 axis).  ``training=True``
+    follows :51-60 and returns the updated moving stats as a third value."""
+    if x.ndim < 2 or x.shape[-2] != len(bn.b):
+        raise ValueError(f"InvertibleBatchNorm expected {len(bn.b)} channels, got {x.shape[-2] if x.ndim >= 2 else x.shape}")
+    dt = x.dtype
+    logs = bn.logs.astype(dt)[:, None]
+    s = np.exp(logs)
+    b = bn.b.astype(dt)[:, None]
+    new_stats = None
+    if training:
+        n = x.shape[-1]
+        m = x.mean(axis=-1, keepdims=True)
+        v = ((x - m) ** 2).sum(axis=-1, keepdims=True) / dt.type(n)
+        mtm = dt.type(bn.mtm)
+        new_m = (1 - mtm) * bn.m + mtm * m[:, 0]
+        new_v = (1 - mtm) * bn.v + (mtm * n / (n - 1)) * v[:, 0]
+        new_stats = (new_m.astype(bn.m.dtype), new_v.astype(bn.v.dtype))
+    else:
+        m = bn.m.astype(dt)[:, None]
+        v = bn.v.astype(dt)[:, None]
+    eps = dt.type(bn.eps)
+    result = s * (x - m) / np.sqrt(v + eps) + b  # :66
+    lj = np.sum(logs - np.log(v + eps) / dt.type(2), dtype=dt)
+    logabsdetjac = np.full(x.shape[-1], lj, dtype=dt)  # fill(...), :67
+    if training:
+        return result.astype(dt), logabsdetjac, new_stats
+    return result.astype(dt), logabsdetjac
+
+
+def batchnorm_inverse(bn: BatchNormParams, y):
+    """src/bijectors/normalise.jl:74-86 (eval mode only, asserted at :75)."""
+    dt = y.dtype
+    s = np.exp(bn.logs.astype(dt))[:, None]
+    b = bn.b.astype(dt)[:, None]
+    m = bn.m.astype(dt)[:, None]
+    v = bn.v.astype(dt)[:, None]
+    x = (y - b) / s * np.sqrt(v + dt.type(bn.eps)) + m  # :84
+    x = x.astype(dt)
+    _, lj = batchnorm_forward(bn, x)
+    return x, -lj
+
+
+# --------------------------------------------------------------------------------------------------
+# Permute  (src/bijectors/permute.jl)
+# --------------------------------------------------------------------------------------------------
+
+
+def permute_matrix_from_indices(indices):
+    """Permute(indices::Vector{Int}), src/bijectors/permute.jl:90-100: A[idx, i] = 1."""
+    n = len(indices)
+    A = np.zeros((n, n))
+    for i, idx in enumerate(indices, start=1):
+        A[idx - 1, i - 1] = 1.0
+    return A
+
+
+def permute_matrix_from_pairs(n, *pairs):
+    """Permute(n, src=>dst...) and Permute(n, [srcs]=>[dsts]...), src/bijectors/permute.jl:102-150.
+    Raises ValueError where the reference raises ArgumentError (@argcheck)."""
+    A = np.eye(n)
+    dests, sources = set(), set()
+    for src, dst in pairs:
+        srcs = list(src) if np.ndim(src) else [src]
+        dsts = list(dst) if np.ndim(dst) else [dst]
+        if len(srcs) != len(dsts):
+            raise ValueError(f"{srcs} => {dsts} is not bijective")  # :132
+        for s_, d_ in zip(srcs, dsts):
+            if d_ in dests:
+                raise ValueError(f"{d_} used more than once")
+            if s_ in sources:
+                raise ValueError(f"{s_} used more than once")
+            dests.add(d_)
+            sources.add(s_)
+            A[d_ - 1, s_ - 1] = 1.0
+            A[s_ - 1, s_ - 1] = 0.0
+    if (sources & dests) != (sources | dests):  # :119, :145
+        raise ValueError(f"{sources} ∩ {dests} ≠ {sources} ∪ {dests}")
+    return A
+
+
+def permute_dst_of_src(A):
+    """Index form of a permutation matrix: y = A x  <=>  y[dst[i]] = x[i] (0-based dst)."""
+    A = np.asarray(A)
+    if not (np.all((A == 0) | (A == 1)) and np.all(A.sum(0) == 1) and np.all(A.sum(1) == 1)):
+        raise ValueError("not a permutation matrix")
+    return np.argmax(A, axis=0).astype(np.int64)
+
+
+def permute_forward(A, x):
+    """transform(b::Permute, x) = A * x (src/bijectors/permute.jl:152); logjac zero (:155).
+    Implemented as index movement so every payload (NaN, -0.0) is preserved bit-for-bit."""
+    dst = permute_dst_of_src(A)
+    y = np.empty_like(x)
+    y[dst] = x
+    lj = np.zeros(x.shape[1], x.dtype) if x.ndim == 2 else x.dtype.type(0)
+    return y, lj
+
+
+def permute_inverse(A, y):
+    """inverse(b::Permute) = Permute(transpose(A)), src/bijectors/permute.jl:153."""
+    return permute_forward(np.asarray(A).T, y)
+
+
+# --------------------------------------------------------------------------------------------------
+# elementwise exp/log, Stacked  (src/bijectors/exp_log.jl, src/bijectors/stacked.jl)
+# --------------------------------------------------------------------------------------------------
+
+
+def elementwise_exp(x):
+    """with_logabsdet_jacobian(elementwise(exp), x) = (exp.(x), sum(x)):
+    src/interface.jl:33, src/bijectors/exp_log.jl:6 (+ ChangesOfVariables Fix1{broadcast} rule)."""
+    return np.exp(x), np.sum(x, dtype=x.dtype)
+
+
+def elementwise_log(x):
+    """(log.(x), -sum(log, x)) -- src/bijectors/exp_log.jl:9."""
+    return np.log(x), -np.sum(np.log(x), dtype=x.dtype)
+
+
+class EW:
+    """Elementwise law codes shared with the device ABI (include/b2b.h, B2B_EW_*)."""
+
+    IDENTITY, EXP, LOG, SHIFT, SCALE = 0, 1, 2, 3, 4
+
+
+def stacked_forward(ops: Sequence[Tuple[int, float]], ranges: Sequence[Tuple[int, int]], x):
+    """Stacked(bs, ranges) with elementwise blocks -- src/bijectors/stacked.jl:157-166 (transform),
+    :168-193 (logabsdetjac), :242-252 (with_logabsdet_jacobian).  ``ranges`` are 1-based inclusive
+    (lo, hi) like Julia UnitRanges; ``ops[i] = (code, a)``.  x is (D,) or (D, N)."""
+    length_in = sum(hi - lo + 1 for lo, hi in ranges)
+    if length_in != x.shape[0]:
+        raise ValueError(f"input length mismatch ({length_in} != {x.shape[0]})")  # :158-160
+    dt = x.dtype
+    y = np.empty_like(x)
+    lj = np.zeros(x.shape[1:], dt)
+    for (code, a), (lo, hi) in zip(ops, ranges):
+        blk = x[lo - 1 : hi]
+        nrow = hi - lo + 1
+        if code == EW.IDENTITY:
+            yb, l = blk, 0
+        elif code == EW.EXP:
+            yb, l = np.exp(blk), blk.sum(axis=0, dtype=dt)
+        elif code == EW.LOG:
+            yb, l = np.log(blk), -np.log(blk).sum(axis=0, dtype=dt)
+        elif code == EW.SHIFT:
+            yb, l = dt.type(a) + blk, 0
+        elif code == EW.SCALE:
+            yb, l = dt.type(a) * blk, dt.type(np.log(abs(a)) * nrow)
+        else:
+            raise ValueError(code)
+        y[lo - 1 : hi] = yb
+        lj = lj + l
+    return y, np.asarray(lj, dtype=dt)[()]
+
+
+def stacked_inverse(ops, ranges, y):
+    inv = []
+    for code, a in ops:
+        if code == EW.EXP:
+            inv.append((EW.LOG, a))
+        elif code == EW.LOG:
+            inv.append((EW.EXP, a))
+        elif code == EW.SHIFT:
+            inv.append((EW.SHIFT, -a))
+        elif code == EW.SCALE:
+            inv.append((EW.SCALE, 1.0 / a))
+        else:
+            inv.append((code, a))
+    return stacked_forward(inv, ranges, y)
+
+
+# --------------------------------------------------------------------------------------------------
+# MvNormal (Distributions/PDMats), chains, TransformedDistribution
+# --------------------------------------------------------------------------------------------------
+
+
+def mvnormal_diag_logpdf(mu, sigma, x):
+    """logpdf(MvNormal(mu, Diagonal(sigma.^2)), x) for x (D,) or (D, N) (Distributions + PDMats):
+    -(D*log(2π) + Σ log σ²)/2 - Σ ((x-μ)/σ)² / 2."""
+    dt = x.dtype
+    D = x.shape[0]
+    mu = np.zeros(D, dt) if mu is None else np.asarray(mu, dt)
+    sigma = np.ones(D, dt) if sigma is None else np.asarray(sigma, dt)
+    zc = (x - (mu if x.ndim == 1 else mu[:, None])) / (sigma if x.ndim == 1 else sigma[:, None])
+    const = -(dt.type(D) * dt.type(math.log(2 * math.pi)) + np.sum(np.log(sigma * sigma), dtype=dt)) / dt.type(2)
+    return (const - np.sum(zc * zc, axis=0, dtype=dt) / dt.type(2)).astype(dt)[()]
+
+
+@dataclass
+class Layer:
+    """One chain element: kind in {planar, radial, rqs, coupling_affine, batchnorm, permute, stacked}."""
+
+    kind: str
+    params: dict = field(default_factory=dict)
+
+    def forward(self, x):
+        p = self.params
+        k = self.kind
+        if k == "planar":
+            return planar_forward(p["w"], p["u"], p["b"], x)
+        if k == "radial":
+            return radial_forward(p["alpha_raw"], p["beta"], p["z0"], x)
+        if k == "rqs":
+            return rqs_forward(p["widths"], p["heights"], p["derivs"], x)
+        if k == "coupling_affine":
+            return coupling_affine_forward(p["idx1"], p["idx2"], p["W"], p["c"], x)
+        if k == "batchnorm":
+            if x.ndim == 1:  # the reference needs >= 2 dims; a vector is treated as one column
+                y, lj = batchnorm_forward(p["bn"], x[:, None])
+                return y[:, 0], lj[0]
+            return batchnorm_forward(p["bn"], x)
+        if k == "permute":
+            return permute_forward(p["A"], x)
+        if k == "stacked":
+            return stacked_forward(p["ops"], p["ranges"], x)
+        raise ValueError(k)
+
+    def inverse(self, y):
+        p = self.params
+        k = self.kind
+        if k == "planar":
+            return planar_inverse(p["w"], p["u"], p["b"], y)
+        if k == "radial":
+            return radial_inverse(p["alpha_raw"], p["beta"], p["z0"], y)
+        if k == "rqs":
+            return rqs_inverse(p["widths"], p["heights"], p["derivs"], y)
+        if k == "coupling_affine":
+            return coupling_affine_inverse(p["idx1"], p["idx2"], p["W"], p["c"], y)
+        if k == "batchnorm":
+            if y.ndim == 1:
+                x, lj = batchnorm_inverse(p["bn"], y[:, None])
+                return x[:, 0], lj[0]
+            return batchnorm_inverse(p["bn"], y)
+        if k == "permute":
+            return permute_inverse(p["A"], y)
+        if k == "stacked":
+            return stacked_inverse(p["ops"], p["ranges"], y)
+        raise ValueError(k)
+
+
+def chain_forward(layers: List[Layer], x):
+    """with_logabsdet_jacobian(L_n ∘ … ∘ L_1, x): inner-most (layers[0]) first, logjacs added
+    (ChangesOfVariables ComposedFunction rule; src/bijectors/composed.jl:4,11-14)."""
+    lj = None
+    y = x
+    for L in layers:
+        y, l = L.forward(y)
+        lj = l if lj is None else lj + l
+    return y, lj
+
+
+def chain_inverse(layers: List[Layer], y):
+    """with_logabsdet_jacobian(inverse(L_n ∘ … ∘ L_1), y): inverse(f∘g) = inverse(g)∘inverse(f)
+    (InverseFunctions) -> the last-applied layer is inverted first."""
+    lj = None
+    x = y
+    for L in reversed(layers):
+        x, l = L.inverse(x)
+        lj = l if lj is None else lj + l
+    return x, lj
+
+
+def transformed_logpdf(layers: List[Layer], mu, sigma, y):
+    """logpdf(td::MvTransformed, y::Matrix) -- src/transformed_distribution.jl:165-169."""
+    x, lj = chain_inverse(layers, y)
+    return mvnormal_diag_logpdf(mu, sigma, x) + lj

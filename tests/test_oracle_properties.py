@@ -1,0 +1,132 @@
+"""Property tests the reference uses to pin its own behaviour (test/bijectors/utils.jl:43-62,
+test/normalising_flows.jl), restated for the numpy oracle.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import oracle_np as O
+
+
+def num_logabsdet(f, x, h=1e-6):
+    """log|det J| of f at vector x by central differences (stands in for ForwardDiff.jacobian)."""
+    n = x.size
+    J = np.zeros((n, n))
+    for j in range(n):
+        e = np.zeros(n)
+        e[j] = h
+        J[:, j] = (f(x + e) - f(x - e)) / (2 * h)
+    return np.linalg.slogdet(J)[1]
+
+
+def make_layers(rng, D):
+    K, B = 6, 3.0
+    W, H, Dv = O.rqs_params(rng.standard_normal((D, K)), rng.standard_normal((D, K)), rng.standard_normal((D, K - 1)), B)
+    n1 = D // 2
+    idx1 = np.arange(1, n1 + 1)
+    idx2 = np.arange(n1 + 1, D + 1)
+    bn = O.BatchNormParams(
+        rng.standard_normal(D) * 0.1, rng.standard_normal(D) * 0.1, rng.standard_normal(D) * 0.1,
+        rng.uniform(0.5, 1.5, D), np.float64(1e-5), np.float64(0.1))
+    perm = rng.permutation(D) + 1
+    return {
+        "planar": O.Layer("planar", dict(w=rng.standard_normal(D), u=rng.standard_normal(D), b=rng.standard_normal(1))),
+        "radial": O.Layer("radial", dict(alpha_raw=rng.standard_normal(1), beta=rng.standard_normal(1), z0=rng.standard_normal(D))),
+        "rqs": O.Layer("rqs", dict(widths=W, heights=H, derivs=Dv)),
+        "coupling_affine": O.Layer("coupling_affine", dict(idx1=idx1, idx2=idx2, W=rng.standard_normal((2 * n1, D - n1)) * 0.3, c=rng.standard_normal(2 * n1) * 0.1)),
+        "batchnorm": O.Layer("batchnorm", dict(bn=bn)),
+        "permute": O.Layer("permute", dict(A=O.permute_matrix_from_indices(perm.tolist()))),
+        "stacked": O.Layer("stacked", dict(ops=[(O.EW.EXP, 0.0), (O.EW.SCALE, -1.7), (O.EW.SHIFT, 0.3)], ranges=[(1, 2), (3, D - 1), (D, D)])),
+    }
+
+
+KINDS = ["planar", "radial", "rqs", "coupling_affine", "batchnorm", "permute", "stacked"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_logjac_matches_numerical_jacobian(kind, seed):
+    # test/normalising_flows.jl:17-20,29-32,78-81; test/bijectors/utils.jl:43-50
+    rng = np.random.default_rng(seed)
+    D = 6
+    L = make_layers(rng, D)[kind]
+    x = rng.standard_normal(D)
+    y, lj = L.forward(x)
+    ref = num_logabsdet(lambda v: L.forward(v)[0], x)
+    assert float(lj) == pytest.approx(ref, rel=2e-6, abs=2e-7)
+    # batch: per-column logjac equals the single-column result (column independence)
+    X = rng.standard_normal((D, 9))
+    Y, LJ = L.forward(X)
+    for n in range(X.shape[1]):
+        yn, ljn = L.forward(X[:, n].copy())
+        np.testing.assert_allclose(Y[:, n], yn, rtol=1e-12, atol=1e-14)
+        assert float(LJ[n]) == pytest.approx(float(ljn), rel=1e-11, abs=1e-13)
+    # permuting columns permutes outputs
+    p = rng.permutation(9)
+    Yp, LJp = L.forward(X[:, p])
+    np.testing.assert_allclose(Yp, Y[:, p], rtol=1e-13, atol=1e-15)  # BLAS may reassociate
+    np.testing.assert_allclose(LJp, LJ[p], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_inverse_roundtrip_and_ires(kind, seed):
+    # test/bijectors/utils.jl:53-62: inverse∘forward ≈ id and ires == (x, -logjac)
+    rng = np.random.default_rng(100 + seed)
+    D = 8
+    L = make_layers(rng, D)[kind]
+    X = rng.standard_normal((D, 33))
+    Y, LJ = L.forward(X)
+    Xi, LJi = L.inverse(Y)
+    np.testing.assert_allclose(Xi, X, rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(LJi, -LJ, rtol=1e-7, atol=1e-9)
+
+
+def test_chain_and_logpdf():
+    rng = np.random.default_rng(5)
+    D = 6
+    Ls = make_layers(rng, D)
+    chain = [Ls[k] for k in ["planar", "batchnorm", "coupling_affine", "permute", "radial", "rqs"]]
+    X = rng.standard_normal((D, 17))
+    Y, LJ = O.chain_forward(chain, X)
+    ref = [num_logabsdet(lambda v: O.chain_forward(chain, v)[0], X[:, n].copy()) for n in range(3)]
+    np.testing.assert_allclose(LJ[:3], ref, rtol=5e-6, atol=5e-7)
+    Xi, LJi = O.chain_inverse(chain, Y)
+    np.testing.assert_allclose(Xi, X, rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(LJi, -LJ, rtol=1e-6, atol=1e-8)
+    # logpdf(td, y) = logpdf(d, x) - logjac_fwd(x)   (test/normalising_flows.jl:97-111)
+    mu, sigma = rng.standard_normal(D) * 0.1, rng.uniform(0.5, 2.0, D)
+    lp = O.transformed_logpdf(chain, mu, sigma, Y)
+    np.testing.assert_allclose(lp, O.mvnormal_diag_logpdf(mu, sigma, X) - LJ, rtol=1e-6, atol=1e-8)
+    # MvNormal closed form vs scipy
+    from scipy.stats import multivariate_normal
+    ref_lp = multivariate_normal(mean=mu, cov=np.diag(sigma ** 2)).logpdf(X.T)
+    np.testing.assert_allclose(O.mvnormal_diag_logpdf(mu, sigma, X), ref_lp, rtol=1e-12)
+
+
+def test_float32_oracle_close_to_float64():
+    rng = np.random.default_rng(9)
+    D = 16
+    Ls = make_layers(rng, D)
+    X = rng.standard_normal((D, 64))
+    for k in KINDS:
+        L64 = Ls[k]
+        p32 = {}
+        for key, v in L64.params.items():
+            if isinstance(v, np.ndarray) and v.dtype == np.float64 and key != "A":
+                p32[key] = v.astype(np.float32)
+            elif isinstance(v, O.BatchNormParams):
+                p32[key] = O.BatchNormParams(*(a.astype(np.float32) for a in (v.b, v.logs, v.m, v.v)), np.float32(v.eps), np.float32(v.mtm))
+            else:
+                p32[key] = v
+        L32 = O.Layer(k, p32)
+        Y64, LJ64 = L64.forward(X)
+        Y32, LJ32 = L32.forward(X.astype(np.float32))
+        assert Y32.dtype == np.float32 and np.asarray(LJ32).dtype == np.float32
+        assert np.linalg.norm(Y32 - Y64) <= 2e-6 * np.linalg.norm(Y64), k
+        assert np.linalg.norm(LJ32 - LJ64) <= 2e-5 * max(np.linalg.norm(LJ64), 1e-3), k
+
+
+def test_log1pexp_tails():
+    import mpmath as mp
+    for x in [-100.0, -37.0, -10.0, -1.0, 0.0, 1.0, 10.0, 18.0, 33.3, 50.0, 700.0]:
+        ref = float(mp.log1p(mp.e ** mp.mpf(x)))
+        assert float(O.log1pexp(np.float64(x))) == pytest.approx(ref, rel=1e-14, abs=1e-300)
