@@ -1,0 +1,21 @@
+"""bijectors.jl_b200 -- B200-native batched bijector evaluation path behind Bijectors.jl's Transform API.
+
+Import name: ``bijectors_jl_b200`` (the directory name contains a dot; ``bijectors_jl_b200.py`` at the
+repository root registers this package under that name).
+"""
+from ._lib import B2BError, LIB_PATH, exported_symbols, lib  # noqa: F401
+from .interface import (  # noqa: F401
+    Bijector, Composed, ComposedFunction, Inverse, Transform, colmajor_empty, compose, flatten, from_numpy,
+    inverse, isclosedform, isinvertible, logabsdetjac, logabsdetjac_, run_chain, to_numpy, transform, transform_,
+    with_logabsdet_jacobian, with_logabsdet_jacobian_,
+)
+from .layers import (  # noqa: F401
+    AffineConditioner, Coupling, Elementwise, InvertibleBatchNorm, PartitionMask, Permute, PlanarLayer, RadialLayer,
+    RationalQuadraticSpline, Scale, Shift, Stacked, coupling, elementwise,
+)
+from .transformed_distribution import (  # noqa: F401
+    MvNormal, TransformedDistribution, logpdf, logpdf_sum, rand, transformed,
+)
+from . import distributed  # noqa: F401
+
+lib()  # fail loudly at import time when libb2b.so has not been built

@@ -1,0 +1,339 @@
+// C ABI of libb2b.so (include/b2b.h): argument validation, chain segmentation, launch bookkeeping.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "b2b_internal.h"
+
+int b2b_chain_grid_size_v0(const B2BChainParams& p);
+int b2b_chain_grid_size_v1(const B2BChainParams& p);
+
+static thread_local int g_last_launches = 0;
+static int g_variant = 0;  // 0 auto, 1 v0, 2 v1
+
+extern "C" int b2b_version(void) { return B2B_VERSION; }
+
+extern "C" const char* b2b_status_string(int status) {
+  switch (status) {
+    case B2B_OK: return "ok";
+    case B2B_EINVAL: return "b2b: invalid argument (null pointer, shape, range or alignment)";
+    case B2B_EUNSUPPORTED: return "b2b: not implemented on the device path (no CPU fallback exists)";
+    case B2B_EWORKSPACE: return "b2b: workspace too small (see b2b_chain_workspace_bytes)";
+    case B2B_ENONCCL: return "b2b: libnccl.so.2 could not be loaded";
+    default: break;
+  }
+  if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+  return "b2b: unknown status";
+}
+
+extern "C" int b2b_last_launch_count(void) { return g_last_launches; }
+
+extern "C" int b2b_set_kernel_variant(int variant) {
+  if (variant < 0 || variant > 2) return B2B_EINVAL;
+  g_variant = variant;
+  return B2B_OK;
+}
+
+static bool fusable(int kind) {
+  return kind == B2B_PLANAR || kind == B2B_RADIAL || kind == B2B_RQS || kind == B2B_BATCHNORM ||
+         kind == B2B_PERMUTE || kind == B2B_STACKED_EW || kind == B2B_MVNORMAL_DIAG;
+}
+
+static int validate_layer(const b2b_layer_desc& d, int D, bool last) {
+  switch (d.kind) {
+    case B2B_PLANAR:
+      if (!d.p0 || !d.p1 || !d.p2) return B2B_EINVAL;
+      break;
+    case B2B_RADIAL:
+      if (!d.p0 || !d.p1 || !d.p2) return B2B_EINVAL;
+      break;
+    case B2B_RQS:
+      if (!d.p0 || !d.p1 || !d.p2 || d.n0 < 2) return B2B_EINVAL;
+      if (d.n0 > 64) return B2B_EUNSUPPORTED;
+      break;
+    case B2B_COUPLING_AFFINE:
+      if (!d.p0 || !d.i0 || !d.i1 || d.n0 < 1 || d.n1 < 1 || d.n0 + d.n1 > D) return B2B_EINVAL;
+      break;
+    case B2B_BATCHNORM:
+      if (!d.p0 || !d.p1 || !d.p2 || !d.p3) return B2B_EINVAL;
+      break;
+    case B2B_PERMUTE:
+      if (!d.i0) return B2B_EINVAL;
+      break;
+    case B2B_STACKED_EW:
+      if (!d.i0) return B2B_EINVAL;
+      break;
+    case B2B_MVNORMAL_DIAG:
+      if (!last || d.inverse) return B2B_EINVAL;
+      break;
+    default:
+      return B2B_EINVAL;
+  }
+  return B2B_OK;
+}
+
+static int launch_fused(B2BChainParams& p, cudaStream_t stream) {
+  int rc = B2B_EUNSUPPORTED;
+  if (g_variant != 1) {
+    rc = b2b_launch_chain_v1(p, stream);
+    if (rc == B2B_OK) return rc;
+    if (g_variant == 2 || rc != B2B_EUNSUPPORTED) return rc;
+  }
+  return b2b_launch_chain_v0(p, stream);
+}
+
+static int fused_grid(const B2BChainParams& p) {
+  if (g_variant != 1) {
+    const int g = b2b_chain_grid_size_v1(p);
+    if (g > 0) return g;
+  }
+  return b2b_chain_grid_size_v0(p);
+}
+
+extern "C" size_t b2b_chain_workspace_bytes(const b2b_layer_desc* layers, int32_t L, int32_t D, int64_t N,
+                                            int want_y, int want_sum) {
+  size_t bytes = 0;
+  bool has_coupling = false;
+  for (int l = 0; l < L; ++l) has_coupling |= layers[l].kind == B2B_COUPLING_AFFINE;
+  // a D x N scratch matrix is needed only when y == NULL but the chain has more than one segment
+  if (!want_y && has_coupling && L > 1) bytes += (size_t)D * (size_t)N * sizeof(float);
+  if (want_sum) bytes += 4096 * sizeof(double);
+  return bytes;
+}
+
+extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const float* x, float* y,
+                                 float* logjac, double* sum_out, int32_t D, int64_t N, int64_t ldx,
+                                 int64_t ldy, int accumulate_logjac, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  g_last_launches = 0;
+  if (!layers || L < 1 || L > B2B_MAX_CHAIN || !x || D < 1 || N < 0 || ldx < D) return B2B_EINVAL;
+  if (y && ldy < D) return B2B_EINVAL;
+  if (!y && !logjac && !sum_out) return B2B_EINVAL;
+  for (int l = 0; l < L; ++l) {
+    const int rc = validate_layer(layers[l], D, l == L - 1);
+    if (rc != B2B_OK) return rc;
+  }
+  if (N == 0) {
+    if (sum_out) return (int)cudaMemsetAsync(sum_out, 0, sizeof(double), stream);
+    return B2B_OK;
+  }
+  const bool terminal = layers[L - 1].kind == B2B_MVNORMAL_DIAG;
+  if (sum_out && !logjac && !terminal) return B2B_EINVAL;
+
+  // segments: maximal runs of fusable layers, and single coupling layers
+  struct Seg {
+    int begin, end;
+    bool coupling;
+  };
+  std::vector<Seg> segs;
+  for (int l = 0; l < L;) {
+    if (layers[l].kind == B2B_COUPLING_AFFINE) {
+      segs.push_back({l, l + 1, true});
+      ++l;
+    } else {
+      int e = l;
+      while (e < L && fusable(layers[e].kind)) ++e;
+      segs.push_back({l, e, false});
+      l = e;
+    }
+  }
+  // workspace carve-up
+  char* ws = static_cast<char*>(workspace);
+  size_t ws_left = workspace ? workspace_bytes : 0;
+  float* scratch = nullptr;
+  if (!y && segs.size() > 1) {
+    const size_t need = (size_t)D * (size_t)N * sizeof(float);
+    if (ws_left < need) return B2B_EWORKSPACE;
+    scratch = reinterpret_cast<float*>(ws);
+    ws += need;
+    ws_left -= need;
+  }
+  double* partials = nullptr;
+  if (sum_out) {
+    if (ws_left < 4096 * sizeof(double)) return B2B_EWORKSPACE;
+    partials = reinterpret_cast<double*>(ws);
+  }
+
+  const float* cur = x;
+  long long cur_ld = ldx;
+  bool lj_started = accumulate_logjac != 0;
+  for (size_t s = 0; s < segs.size(); ++s) {
+    const bool last_seg = s + 1 == segs.size();
+    // destination of this segment: y when given, else scratch for intermediates, nothing for the last
+    float* dst = y ? y : (last_seg ? nullptr : scratch);
+    const long long dst_ld = y ? ldy : D;
+    int rc;
+    if (segs[s].coupling) {
+      float* cdst = dst;
+      // logjac-only call with a trailing coupling layer still needs no store
+      rc = b2b_launch_coupling_affine(layers[segs[s].begin], cur, cdst, logjac, D, N, cur_ld, dst_ld,
+                                      lj_started ? 1 : 0, stream);
+      if (rc != B2B_OK) return rc;
+      ++g_last_launches;
+    } else {
+      B2BChainParams p;
+      memset(&p, 0, sizeof(p));
+      p.x = cur;
+      p.y = dst;
+      p.logjac = logjac;
+      p.N = N;
+      p.ldx = cur_ld;
+      p.ldy = dst_ld;
+      p.D = D;
+      p.L = segs[s].end - segs[s].begin;
+      p.accumulate = lj_started ? 1 : 0;
+      for (int l = 0; l < p.L; ++l) p.layers[l] = layers[segs[s].begin + l];
+      int grid = 0;
+      if (sum_out && last_seg) {
+        grid = fused_grid(p);
+        if (grid <= 0 || grid > 4096) return B2B_EUNSUPPORTED;
+        p.partials = partials;
+      }
+      rc = launch_fused(p, stream);
+      if (rc != B2B_OK) return rc;
+      ++g_last_launches;
+      if (sum_out && last_seg) {
+        rc = b2b_launch_sum_partials(partials, grid, sum_out, stream);
+        if (rc != B2B_OK) return rc;
+        ++g_last_launches;
+      }
+    }
+    if (dst) {
+      cur = dst;
+      cur_ld = dst_ld;
+    }
+    lj_started = true;
+  }
+  if (sum_out && segs.back().coupling) {
+    // batch sum over a chain that ends in a coupling layer: one extra pass over logjac
+    return B2B_EUNSUPPORTED;
+  }
+  return B2B_OK;
+}
+
+// ---- single-layer wrappers -------------------------------------------------------------------------
+static int run1(const b2b_layer_desc& d, const float* x, float* y, float* logjac, int32_t D, int64_t N,
+                int64_t ldx, int64_t ldy, int acc, void* stream) {
+  return b2b_chain_run_f32(&d, 1, x, y, logjac, nullptr, D, N, ldx, ldy, acc, nullptr, 0, stream);
+}
+
+static b2b_layer_desc mk(int kind, int inverse) {
+  b2b_layer_desc d;
+  memset(&d, 0, sizeof(d));
+  d.kind = kind;
+  d.inverse = inverse;
+  return d;
+}
+
+#define B2B_PLANAR_IMPL(NAME, INV)                                                                       \
+  extern "C" int NAME(const float* x, float* y, float* logjac, const float* w, const float* u,           \
+                      const float* b, int32_t D, int64_t N, int64_t ldx, int64_t ldy, int acc,           \
+                      void* stream) {                                                                    \
+    b2b_layer_desc d = mk(B2B_PLANAR, INV);                                                              \
+    d.p0 = w;                                                                                            \
+    d.p1 = u;                                                                                            \
+    d.p2 = b;                                                                                            \
+    return run1(d, x, y, logjac, D, N, ldx, ldy, acc, stream);                                           \
+  }
+B2B_PLANAR_IMPL(b2b_planar_fwd_f32, 0)
+B2B_PLANAR_IMPL(b2b_planar_inv_f32, 1)
+
+#define B2B_RADIAL_IMPL(NAME, INV)                                                                       \
+  extern "C" int NAME(const float* x, float* y, float* logjac, const float* alpha_raw,                   \
+                      const float* beta, const float* z0, int32_t D, int64_t N, int64_t ldx,             \
+                      int64_t ldy, int acc, void* stream) {                                              \
+    b2b_layer_desc d = mk(B2B_RADIAL, INV);                                                              \
+    d.p0 = alpha_raw;                                                                                    \
+    d.p1 = beta;                                                                                         \
+    d.p2 = z0;                                                                                           \
+    return run1(d, x, y, logjac, D, N, ldx, ldy, acc, stream);                                           \
+  }
+B2B_RADIAL_IMPL(b2b_radial_fwd_f32, 0)
+B2B_RADIAL_IMPL(b2b_radial_inv_f32, 1)
+
+#define B2B_RQS_IMPL(NAME, INV)                                                                          \
+  extern "C" int NAME(const float* x, float* y, float* logjac, const float* widths,                      \
+                      const float* heights, const float* derivs, int32_t K1, int32_t D, int64_t N,       \
+                      int64_t ldx, int64_t ldy, int acc, void* stream) {                                 \
+    b2b_layer_desc d = mk(B2B_RQS, INV);                                                                 \
+    d.p0 = widths;                                                                                       \
+    d.p1 = heights;                                                                                      \
+    d.p2 = derivs;                                                                                       \
+    d.n0 = K1;                                                                                           \
+    return run1(d, x, y, logjac, D, N, ldx, ldy, acc, stream);                                           \
+  }
+B2B_RQS_IMPL(b2b_rqs_fwd_f32, 0)
+B2B_RQS_IMPL(b2b_rqs_inv_f32, 1)
+
+#define B2B_COUPLING_IMPL(NAME, INV)                                                                     \
+  extern "C" int NAME(const float* x, float* y, float* logjac, const int32_t* idx1, int32_t n1,          \
+                      const int32_t* idx2, int32_t n2, const float* W, const float* c, int32_t D,        \
+                      int64_t N, int64_t ldx, int64_t ldy, int acc, void* stream) {                      \
+    b2b_layer_desc d = mk(B2B_COUPLING_AFFINE, INV);                                                     \
+    d.p0 = W;                                                                                            \
+    d.p1 = c;                                                                                            \
+    d.i0 = idx1;                                                                                         \
+    d.i1 = idx2;                                                                                         \
+    d.n0 = n1;                                                                                           \
+    d.n1 = n2;                                                                                           \
+    return run1(d, x, y, logjac, D, N, ldx, ldy, acc, stream);                                           \
+  }
+B2B_COUPLING_IMPL(b2b_coupling_affine_fwd_f32, 0)
+B2B_COUPLING_IMPL(b2b_coupling_affine_inv_f32, 1)
+
+#define B2B_BN_IMPL(NAME, INV)                                                                           \
+  extern "C" int NAME(const float* x, float* y, float* logjac, const float* b, const float* logs,        \
+                      const float* m, const float* v, float eps, int32_t D, int64_t N, int64_t ldx,      \
+                      int64_t ldy, int acc, void* stream) {                                              \
+    b2b_layer_desc d = mk(B2B_BATCHNORM, INV);                                                           \
+    d.p0 = b;                                                                                            \
+    d.p1 = logs;                                                                                         \
+    d.p2 = m;                                                                                            \
+    d.p3 = v;                                                                                            \
+    d.f0 = eps;                                                                                          \
+    return run1(d, x, y, logjac, D, N, ldx, ldy, acc, stream);                                           \
+  }
+B2B_BN_IMPL(b2b_batchnorm_eval_fwd_f32, 0)
+B2B_BN_IMPL(b2b_batchnorm_eval_inv_f32, 1)
+
+extern "C" int b2b_permute_rows_f32(const float* x, float* y, float* logjac, const int32_t* dst_of_src,
+                                    int inverse, int32_t D, int64_t N, int64_t ldx, int64_t ldy, int acc,
+                                    void* stream) {
+  b2b_layer_desc d = mk(B2B_PERMUTE, inverse ? 1 : 0);
+  d.i0 = dst_of_src;
+  return run1(d, x, y, logjac, D, N, ldx, ldy, acc, stream);
+}
+
+extern "C" int b2b_stacked_elementwise_f32(const float* x, float* y, float* logjac, const int32_t* code,
+                                           const float* a, int inverse, int32_t D, int64_t N, int64_t ldx,
+                                           int64_t ldy, int acc, void* stream) {
+  b2b_layer_desc d = mk(B2B_STACKED_EW, inverse ? 1 : 0);
+  d.i0 = code;
+  d.p0 = a;
+  return run1(d, x, y, logjac, D, N, ldx, ldy, acc, stream);
+}
+
+extern "C" int b2b_mvnormal_diag_logpdf_f32(const float* x, const float* mu, const float* sigma,
+                                            const float* logjac_in, float* logpdf_out, double* sum_out,
+                                            int32_t D, int64_t N, int64_t ldx, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  if (!logpdf_out && !sum_out) return B2B_EINVAL;
+  b2b_layer_desc d = mk(B2B_MVNORMAL_DIAG, 0);
+  d.p0 = mu;
+  d.p1 = sigma;
+  int acc = 0;
+  if (logjac_in) {
+    if (!logpdf_out) return B2B_EINVAL;
+    if (logjac_in != logpdf_out) {
+      cudaError_t e = cudaMemcpyAsync(logpdf_out, logjac_in, (size_t)N * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+      if (e != cudaSuccess) return (int)e;
+    }
+    acc = 1;
+  }
+  return b2b_chain_run_f32(&d, 1, x, nullptr, logpdf_out, sum_out, D, N, ldx, D, acc, workspace,
+                           workspace_bytes, stream);
+}

@@ -1,0 +1,223 @@
+// Device-side math and parameter staging shared by the chain kernels.
+// Every function cites the reference lines (Bijectors.jl v0.16.2) whose arithmetic it restates.
+#pragma once
+#include "b2b_internal.h"
+
+namespace b2b {
+
+// ---- scalar math ---------------------------------------------------------------------------------
+
+// LogExpFunctions.log1pexp (softplus), used only on per-layer scalars / small tables
+// (planar_layer.jl:67-68, radial_layer.jl:44-45,91-92).
+__device__ __forceinline__ float softplus(float x) {
+  return x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x));
+}
+
+// tanh(a) and sech(a)^2 from ONE exponential: e = exp(-2|a|), tanh = (1-e)/(1+e), sech^2 = 4e/(1+e)^2.
+// sech^2 has no cancellation for large |a| (the reference evaluates abs2(sech(a)), planar_layer.jl:107);
+// for |a| < 0.25 an odd polynomial keeps tanh accurate to ~1 ulp where (1-e) would cancel.
+__device__ __forceinline__ void tanh_sech2(float a, float& t, float& s2) {
+  const float ax = fabsf(a);
+  const float e = __expf(-2.0f * ax);
+  const float r = __frcp_rn(1.0f + e);
+  float tb = (1.0f - e) * r;
+  const float a2 = a * a;
+  float p = fmaf(a2, 0.021869488f, -0.053968254f);  // 62/2835, -17/315
+  p = fmaf(a2, p, 0.13333334f);                      // 2/15
+  p = fmaf(a2, p, -0.33333334f);                     // -1/3
+  const float ts = fmaf(ax * a2, p, ax);
+  tb = ax < 0.25f ? ts : tb;
+  t = copysignf(tb, a);
+  s2 = 4.0f * e * r * r;
+}
+
+// find_alpha (planar_layer.jl:160-185): root of f(α) = α + c·tanh(α+b) − t in [t−2|c|, t+2|c|].
+// The reference narrows a bracket with Roots.A42; results are pinned by the equation residual
+// (test/normalising_flows.jl:47-71), so a bisection-safeguarded Newton on the monotone f is admissible.
+__device__ __forceinline__ float find_alpha(float t, float c, float b) {
+  const float delta = 2.0f * fabsf(c);
+  float lo = t - delta, hi = t + delta;
+  if (lo == hi) return lo;  // empty bracket, planar_layer.jl:171-173
+  float x = t;
+#pragma unroll 1
+  for (int it = 0; it < 64; ++it) {
+    float th, s2;
+    tanh_sech2(x + b, th, s2);
+    const float f = fmaf(c, th, x) - t;
+    if (f == 0.0f) break;
+    if (f < 0.0f) lo = x; else hi = x;
+    float xn = x - f / fmaf(c, s2, 1.0f);
+    if (!(xn > lo && xn < hi)) {
+      xn = 0.5f * (lo + hi);
+      if (!(xn > lo && xn < hi)) break;  // bracket is adjacent floats
+    }
+    const bool done = fabsf(xn - x) <= 6e-8f * fabsf(xn);
+    x = xn;
+    if (done) break;
+  }
+  return x;
+}
+
+// One RQS element (rational_quadratic_spline.jl:317-357 forward, :183-220 inverse + the forward
+// log-Jacobian at the recovered point, interface.jl:276-281).  Tables are knot-major [k][Dp].
+// `k` below is the reference's 1-based bin index (searchsortedfirst − 1).
+template <bool INV>
+__device__ __forceinline__ void rqs_element(const float* __restrict__ W, const float* __restrict__ H,
+                                            const float* __restrict__ Dv, int K1, int Dp, int row,
+                                            float v, float& out, float& lj) {
+  const float* S = INV ? H : W;  // table searched: heights for the inverse (:191), widths otherwise (:328)
+  const float Bs = S[(K1 - 1) * Dp + row];
+  if ((v <= -Bs) || (v >= Bs)) {  // identity outside the box, :322-324 / :186-188
+    out = v;
+    lj = 0.0f;
+    return;
+  }
+  int k = 0;
+  for (int q = 0; q < K1; ++q) k += (S[q * Dp + row] < v) ? 1 : 0;
+  const int km = (k > 0 ? k : 1) - 1;
+  const float w_k = (k == 0) ? -W[(K1 - 1) * Dp + row] : W[km * Dp + row];  // :331
+  const float w = W[k * Dp + row] - w_k;
+  const float h_k = (k == 0) ? -H[(K1 - 1) * Dp + row] : H[km * Dp + row];  // :335
+  const float dy = H[k * Dp + row] - h_k;
+  const float s = dy / w;  // :339
+  const float d_k = (k == 0) ? 1.0f : Dv[km * Dp + row];        // :342
+  const float d_k1 = (k == K1 - 1) ? 1.0f : Dv[k * Dp + row];   // :343
+  float xi;
+  if (INV) {
+    const float ds = d_k1 + d_k - 2.0f * s;            // :205
+    const float yh = v - h_k;
+    const float a1 = dy * (s - d_k) + yh * ds;         // :208
+    const float a2 = dy * d_k - yh * ds;               // :210
+    const float a3 = -s * yh;                          // :212
+    xi = (-2.0f * a3) / (a2 + sqrtf(a2 * a2 - 4.0f * a1 * a3));  // :215-217
+    out = xi * w + w_k;                                // :219
+  } else {
+    xi = (v - w_k) / w;  // :340
+  }
+  const float omx = 1.0f - xi;
+  const float den = s + (d_k1 + d_k - 2.0f * s) * xi * omx;  // :346
+  const float rden = 1.0f / den;
+  const float num = s * s * (d_k1 * xi * xi + 2.0f * s * xi * omx + d_k * omx * omx);  // :349
+  const float l = logf(num * rden * rden);  // = log(num) − 2·log(den), :350
+  if (INV) {
+    lj = -l;
+  } else {
+    lj = l;
+    out = h_k + dy * (s * xi * xi + d_k * xi * omx) * rden;  // :353-354
+  }
+}
+
+// ---- parameter staging (once per CTA) --------------------------------------------------------------
+// Layout of the staged block of one layer (floats, Dp = padded depth, rows >= D are zero):
+//   PLANAR    : w[Dp] | û[Dp] | {c = wᵀû, b, -, -}                      (get_u_hat, planar_layer.jl:65-70)
+//   RADIAL    : z0[Dp] | {α, β̂, α+β̂, -}                                 (radial_layer.jl:44-45,91-92)
+//   BATCHNORM : m[Dp] | A[Dp] | b[Dp] | 1/A[Dp] | {Σ(logs − log(v+eps)/2)}  (normalise.jl:61-67)
+//   RQS       : W[K1][Dp] | H[K1][Dp] | Dv[K1][Dp]
+//   PERMUTE   : src_of_dst[Dp] (int)
+//   STACKED_EW: code[Dp] (int) | a[Dp]
+//   MVNORMAL  : mu[Dp] | 1/sigma[Dp] | {−(D·log2π + Σ log σ²)/2}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Executed by ONE warp per layer (different warps stage different layers concurrently).
+__device__ inline void stage_layer(const b2b_layer_desc& d, float* sm, int D, int Dp, int lane) {
+  switch (d.kind) {
+    case B2B_PLANAR: {
+      float s = 0.f, q = 0.f;
+      for (int i = lane; i < D; i += 32) {
+        const float w = d.p0[i], u = d.p1[i];
+        s = fmaf(w, u, s);
+        q = fmaf(w, w, q);
+      }
+      s = warp_sum(s);
+      q = warp_sum(q);
+      const float k = (softplus(-s) - 1.0f) / q;  // planar_layer.jl:67
+      for (int i = lane; i < Dp; i += 32) {
+        const bool in = i < D;
+        const float w = in ? d.p0[i] : 0.f;
+        sm[i] = w;
+        sm[Dp + i] = in ? fmaf(k, w, d.p1[i]) : 0.f;
+      }
+      if (lane == 0) {
+        sm[2 * Dp + 0] = softplus(s) - 1.0f;  // wᵀû, planar_layer.jl:68
+        sm[2 * Dp + 1] = d.p2[0];             // first(flow.b), :75
+      }
+    } break;
+    case B2B_RADIAL: {
+      for (int i = lane; i < Dp; i += 32) sm[i] = i < D ? d.p2[i] : 0.f;
+      if (lane == 0) {
+        const float alpha = softplus(d.p0[0]);  // radial_layer.jl:44
+        const float apb = softplus(d.p1[0]);    // α + β̂, :45,:92
+        sm[Dp + 0] = alpha;
+        sm[Dp + 1] = apb - alpha;
+        sm[Dp + 2] = apb;
+      }
+    } break;
+    case B2B_BATCHNORM: {
+      float lj = 0.f;
+      for (int i = lane; i < Dp; i += 32) {
+        const bool in = i < D;
+        float A = 0.f, iA = 0.f, m = 0.f, b = 0.f;
+        if (in) {
+          const float ve = d.p3[i] + d.f0;
+          const float sd = sqrtf(ve);
+          const float sc = expf(d.p1[i]);
+          A = sc / sd;
+          iA = sd / sc;
+          m = d.p2[i];
+          b = d.p0[i];
+          lj += d.p1[i] - logf(ve) * 0.5f;  // normalise.jl:67
+        }
+        sm[i] = m;
+        sm[Dp + i] = A;
+        sm[2 * Dp + i] = b;
+        sm[3 * Dp + i] = iA;
+      }
+      lj = warp_sum(lj);
+      if (lane == 0) sm[4 * Dp] = lj;
+    } break;
+    case B2B_RQS: {
+      const int K1 = d.n0;
+      for (int t = 0; t < 3; ++t) {
+        const float* src = t == 0 ? d.p0 : (t == 1 ? d.p1 : d.p2);
+        float* dst = sm + t * K1 * Dp;
+        for (int k = 0; k < K1; ++k)
+          for (int i = lane; i < Dp; i += 32) dst[k * Dp + i] = i < D ? src[(size_t)k * D + i] : 0.f;
+      }
+    } break;
+    case B2B_PERMUTE: {
+      int* sp = reinterpret_cast<int*>(sm);
+      for (int i = lane; i < Dp; i += 32) {
+        if (i >= D) sp[i] = i;
+        else if (d.inverse) sp[i] = d.i0[i];  // inverse: y[i] = x[dst[i]]  (Permute(transpose(A)), permute.jl:153)
+      }
+      if (!d.inverse)
+        for (int i = lane; i < D; i += 32) sp[d.i0[i]] = i;  // y[dst[i]] = x[i], permute.jl:95-97,152
+    } break;
+    case B2B_STACKED_EW: {
+      int* sc = reinterpret_cast<int*>(sm);
+      for (int i = lane; i < Dp; i += 32) {
+        sc[i] = i < D ? d.i0[i] : B2B_EW_IDENTITY;
+        sm[Dp + i] = (i < D && d.p0) ? d.p0[i] : 0.f;
+      }
+    } break;
+    case B2B_MVNORMAL_DIAG: {
+      float ls = 0.f;
+      for (int i = lane; i < Dp; i += 32) {
+        const bool in = i < D;
+        const float sg = (in && d.p1) ? d.p1[i] : 1.0f;
+        sm[i] = (in && d.p0) ? d.p0[i] : 0.f;
+        sm[Dp + i] = in ? 1.0f / sg : 0.f;
+        if (in) ls += logf(sg * sg);
+      }
+      ls = warp_sum(ls);
+      if (lane == 0) sm[2 * Dp] = -0.5f * (D * 1.8378770664093453f + ls);
+    } break;
+    default: break;
+  }
+}
+
+}  // namespace b2b

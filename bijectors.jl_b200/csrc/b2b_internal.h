@@ -1,0 +1,47 @@
+// Internal declarations shared by the translation units of libb2b.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2b.h"
+
+// Kernel argument block of the fused column-local chain kernels (passed by value, < 4 KB).
+struct B2BChainParams {
+  const float* x;
+  float* y;          // may be NULL (no D x N store)
+  float* logjac;     // N (or logpdf when the chain ends in MVNORMAL_DIAG); may be NULL
+  double* partials;  // per-CTA partial sums of the last op's output (NULL unless a batch sum is wanted)
+  long long N, ldx, ldy;
+  int D, L, accumulate;
+  int scratch_off;  // float offset of the per-warp permute scratch in dynamic smem, -1 if unused
+  int soff[B2B_MAX_CHAIN];  // float offset of layer l's staged parameters in dynamic smem
+  b2b_layer_desc layers[B2B_MAX_CHAIN];
+};
+
+// number of floats of staged (derived) parameters a layer needs for padded depth Dp
+static inline int b2b_layer_smem_floats(const b2b_layer_desc& d, int Dp) {
+  switch (d.kind) {
+    case B2B_PLANAR: return 2 * Dp + 4;
+    case B2B_RADIAL: return Dp + 4;
+    case B2B_BATCHNORM: return 4 * Dp + 4;
+    case B2B_RQS: return 3 * d.n0 * Dp;
+    case B2B_PERMUTE: return Dp;
+    case B2B_STACKED_EW: return 2 * Dp;
+    case B2B_MVNORMAL_DIAG: return 2 * Dp + 4;
+    default: return 0;
+  }
+}
+
+// ---- launchers (each returns a cudaError_t as int, or a negative B2B_E* code) ---------------------
+// v0: lane-group direct-global fused interpreter (any D <= 1024)
+int b2b_launch_chain_v0(const B2BChainParams& p, cudaStream_t stream);
+// v1: TMA-staged thread-per-column fused interpreter (D in {32,64,128}); returns B2B_EUNSUPPORTED otherwise
+int b2b_launch_chain_v1(const B2BChainParams& p, cudaStream_t stream);
+// number of CTAs the v0/v1 launch of `p` will use (size of the partials array)
+int b2b_chain_grid_size(const B2BChainParams& p);
+// deterministic final sum of per-CTA partials into *sum_out
+int b2b_launch_sum_partials(const double* partials, int n, double* sum_out, cudaStream_t stream);
+// affine coupling (own kernel)
+int b2b_launch_coupling_affine(const b2b_layer_desc& d, const float* x, float* y, float* logjac,
+                               int D, long long N, long long ldx, long long ldy, int accumulate,
+                               cudaStream_t stream);

@@ -1,0 +1,69 @@
+"""Multi-GPU: columns are i.i.d. samples, so the batch shards by column with NO data-path collective;
+the only exchange is one sum of the scalar batch log-density.  One process per GPU
+(torchrun); torch.distributed is used for rendezvous only, the all-reduce itself is libb2b's NCCL call
+site (b2b_allreduce_sum_f64).  On a CPU/gloo world (unit tests) the scalar is reduced with gloo."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ._lib import check, lib
+
+
+def shard_columns(N: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous column block [lo, hi) of rank `rank`; blocks differ by at most one column."""
+    base, rem = divmod(N, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class Communicator:
+    """b2b_comm wrapper: the NCCL unique id is created on rank 0 and broadcast through torch.distributed."""
+
+    def __init__(self):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.handle = None
+        if dist.get_backend() == "nccl" and torch.cuda.is_available():
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                buf = ctypes.create_string_buffer(128)
+                check(lib().b2b_comm_unique_id(buf), "b2b_comm_unique_id")
+                uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+            uid = uid.cuda()
+            dist.broadcast(uid, src=0)
+            raw = bytes(uid.cpu().tolist())
+            h = ctypes.c_void_p()
+            check(lib().b2b_comm_init_rank(ctypes.byref(h), self.world, self.rank, raw), "b2b_comm_init_rank")
+            self.handle = h
+
+    def allreduce_sum_(self, value: torch.Tensor) -> torch.Tensor:
+        """In-place sum over ranks of a float64 tensor (device scalar on NCCL worlds)."""
+        if value.dtype != torch.float64:
+            raise TypeError("allreduce_sum_ expects float64")
+        if self.handle is not None and value.is_cuda:
+            check(lib().b2b_allreduce_sum_f64(self.handle, value.data_ptr(), value.numel(),
+                                              torch.cuda.current_stream().cuda_stream), "b2b_allreduce_sum_f64")
+        else:
+            dist.all_reduce(value, op=dist.ReduceOp.SUM)
+        return value
+
+    def close(self):
+        if self.handle is not None:
+            lib().b2b_comm_destroy(self.handle)
+            self.handle = None
+
+
+def sharded_logpdf_sum(td, y_local: torch.Tensor, comm: Optional[Communicator]) -> torch.Tensor:
+    """Σ over ALL ranks of logpdf(td, y) given this rank's column shard: local fused inverse-chain +
+    MvNormal + reduction, then one all-reduce of 8 bytes."""
+    from .transformed_distribution import logpdf_sum
+
+    total, _ = logpdf_sum(td, y_local)
+    if comm is not None and comm.world > 1:
+        comm.allreduce_sum_(total.reshape(1))
+    return total

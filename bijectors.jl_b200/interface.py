@@ -1,0 +1,354 @@
+"""Host-side mirror of Bijectors.jl's Transform interface (src/interface.jl) for the batched device path.
+
+Same names, argument meaning and error behaviour as the reference:
+  Transform / Bijector / Inverse            src/interface.jl:133,246-271
+  transform, logabsdetjac,
+  with_logabsdet_jacobian (+ in-place "!")  src/interface.jl:144,156-166,183-192,212-218
+  inverse                                   src/interface.jl:265-266
+  ∘ (here `@` or compose(...)), Composed    Base.ComposedFunction + src/bijectors/composed.jl
+  default inverse log-Jacobian              src/interface.jl:276-281 (fused on the device)
+
+Batches are Julia-layout column-major ``D×N`` Float32 matrices: a torch tensor of shape ``(D, N)`` with
+strides ``(1, D)`` (see :func:`colmajor_empty` / :func:`from_numpy`).  A 1-D tensor of length D is a single
+column.  Device tensors take the device entry points; host (CPU) tensors take the chunked
+host-buffer entry point ``b2b_chain_run_host_f32`` and return host tensors.  All arithmetic happens in
+libb2b.so -- this module only builds layer descriptors and launches.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B2BError, LayerDesc, check, lib
+
+# --------------------------------------------------------------------------------------------------
+# layout helpers
+# --------------------------------------------------------------------------------------------------
+
+
+def colmajor_empty(D: int, N: int, device="cuda", dtype=torch.float32, pin_memory=False) -> torch.Tensor:
+    """Uninitialised Julia-layout (column-major) D×N matrix: shape (D, N), strides (1, D)."""
+    if pin_memory:
+        base = torch.empty((N, D), dtype=dtype, pin_memory=True)
+    else:
+        base = torch.empty((N, D), dtype=dtype, device=device)
+    return base.t()
+
+
+def from_numpy(a: np.ndarray, device="cuda", pin_memory=False) -> torch.Tensor:
+    """numpy (D, N) or (D,) array -> Julia-layout float32 tensor on ``device``."""
+    a = np.asarray(a, dtype=np.float32)
+    if a.ndim == 1:
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.pin_memory() if (pin_memory and device == "cpu") else t.to(device)
+    base = torch.from_numpy(np.ascontiguousarray(a.T))  # (N, D) row-major == (D, N) column-major
+    if device == "cpu":
+        return (base.pin_memory() if pin_memory else base).t()
+    return base.to(device).t()
+
+
+def to_numpy(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+def _batch_view(x: torch.Tensor) -> Tuple[int, int, int]:
+    """(D, N, ld) of a column batch; raises like a Julia MethodError for anything else."""
+    if x.dtype != torch.float32:
+        raise TypeError(f"device path is Float32 only (got {x.dtype}); Float64 is handled by the reference on the CPU")
+    if x.dim() == 1:
+        if x.stride(0) != 1:
+            raise ValueError("vector input must be contiguous")
+        return x.shape[0], 1, x.shape[0]
+    if x.dim() != 2:
+        raise ValueError(f"expected a D×N matrix or a length-D vector, got {tuple(x.shape)}")
+    D, N = x.shape
+    if N == 1:
+        return D, 1, D
+    if x.stride(0) != 1 or x.stride(1) < D:
+        raise ValueError(
+            "batch must be Julia-layout column-major (shape (D, N), strides (1, ld>=D)); "
+            "use colmajor_empty / from_numpy, or `x.t().contiguous().t()`"
+        )
+    return D, N, x.stride(1)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# --------------------------------------------------------------------------------------------------
+# Transform hierarchy
+# --------------------------------------------------------------------------------------------------
+
+
+class Transform:
+    """abstract type Transform (src/interface.jl:133); callable: (t::Transform)(x) = transform(t, x) (:135)."""
+
+    def __call__(self, x):
+        return transform(self, x)
+
+    # `outer @ inner` plays the role of `outer ∘ inner`
+    def __matmul__(self, inner):
+        return ComposedFunction(self, inner)
+
+    def _descs(self, inverse: bool, D: int) -> List[LayerDesc]:
+        raise NotImplementedError(
+            f"`transform` not implemented for {type(self).__name__}; implement `transform` and/or "
+            "`with_logabsdet_jacobian`."  # src/interface.jl:159-163
+        )
+
+    def _keepalive(self):
+        return ()
+
+
+class Bijector(Transform):
+    """abstract type Bijector <: Transform (src/interface.jl:271)."""
+
+
+class Inverse(Transform):
+    """Inverse(orig) (src/interface.jl:246-266); with_logabsdet_jacobian(Inverse(b), y) =
+    (x, -logabsdetjac(b, x)) (:278-281) is evaluated by ONE fused kernel per layer."""
+
+    def __init__(self, orig: Transform):
+        if not isinstance(orig, Transform):
+            raise TypeError(f"{orig} is not invertible")
+        self.orig = orig
+
+    def _descs(self, inverse, D):
+        return self.orig._descs(not inverse, D)
+
+    def _keepalive(self):
+        return self.orig._keepalive()
+
+    def __eq__(self, other):
+        return isinstance(other, Inverse) and self.orig == other.orig
+
+
+def inverse(t):
+    """inverse(t::Transform) = Inverse(t); inverse(ib::Inverse) = ib.orig (src/interface.jl:265-266);
+    inverse(f∘g) = inverse(g) ∘ inverse(f) (InverseFunctions)."""
+    if isinstance(t, Inverse):
+        return t.orig
+    if isinstance(t, ComposedFunction):
+        return ComposedFunction(inverse(t.inner), inverse(t.outer))
+    if isinstance(t, Composed):
+        return Composed(*[inverse(b) for b in reversed(t.layers)])
+    if hasattr(t, "_inverse"):
+        return t._inverse()
+    return Inverse(t)
+
+
+class ComposedFunction(Transform):
+    """outer ∘ inner (Base.ComposedFunction; methods in src/bijectors/composed.jl)."""
+
+    def __init__(self, outer, inner):
+        self.outer, self.inner = outer, inner
+
+    def _descs(self, inverse_, D):
+        if inverse_:
+            return inverse(self)._descs(False, D)
+        return self.inner._descs(False, D) + self.outer._descs(False, D)
+
+    def _keepalive(self):
+        return tuple(self.inner._keepalive()) + tuple(self.outer._keepalive())
+
+
+class Composed(Transform):
+    """Flat chain: Composed(L1, L2, ..., Ln) applies L1 first (== Ln ∘ … ∘ L1).  Accepts `∘` trees and
+    flattens them."""
+
+    def __init__(self, *layers):
+        flat = []
+        for b in layers:
+            flat.extend(flatten(b))
+        self.layers = flat
+
+    def _descs(self, inverse_, D):
+        if inverse_:
+            return inverse(self)._descs(False, D)
+        out = []
+        for b in self.layers:
+            out.extend(b._descs(False, D))
+        return out
+
+    def _keepalive(self):
+        return tuple(k for b in self.layers for k in b._keepalive())
+
+
+def compose(*fs):
+    """compose(fn, ..., f2, f1) == fn ∘ … ∘ f2 ∘ f1."""
+    out = fs[-1]
+    for f in reversed(fs[:-1]):
+        out = ComposedFunction(f, out)
+    return out
+
+
+def flatten(t) -> list:
+    """Leaves of a `∘` tree in application order (inner-most first)."""
+    if isinstance(t, ComposedFunction):
+        return flatten(t.inner) + flatten(t.outer)
+    if isinstance(t, Composed):
+        return list(t.layers)
+    return [t]
+
+
+# --------------------------------------------------------------------------------------------------
+# chain execution
+# --------------------------------------------------------------------------------------------------
+
+_HOST_CTX = {}
+
+
+def _host_ctx(D: int, chunk_cols: int, n_streams: int):
+    key = (torch.cuda.current_device(), chunk_cols, n_streams)
+    ent = _HOST_CTX.get(key)
+    if ent is None or ent[1] < D:
+        if ent is not None:
+            lib().b2b_host_ctx_destroy(ent[0])
+        h = ctypes.c_void_p()
+        check(lib().b2b_host_ctx_create(ctypes.byref(h), max(D, 1), chunk_cols, n_streams), "b2b_host_ctx_create")
+        ent = (h, D)
+        _HOST_CTX[key] = ent
+    return ent[0]
+
+
+HOST_CHUNK_COLS = 1 << 16
+HOST_STREAMS = 3
+
+
+def _desc_array(descs: Sequence[LayerDesc]):
+    if len(descs) > _lib.MAX_CHAIN:
+        raise B2BError(_lib.B2B_EUNSUPPORTED, f"chain of {len(descs)} layers (max {_lib.MAX_CHAIN})")
+    return (LayerDesc * len(descs))(*descs)
+
+
+def run_chain(t, x: torch.Tensor, *, want_y=True, want_logjac=True, y: Optional[torch.Tensor] = None,
+              logjac: Optional[torch.Tensor] = None, accumulate=False, sum_out: Optional[torch.Tensor] = None,
+              extra_descs: Sequence[LayerDesc] = (), keepalive=()):
+    """Evaluate transform ``t`` (any Transform / chain) on batch ``x``.  Returns (y, logjac)."""
+    D, N, ldx = _batch_view(x)
+    descs = list(t._descs(False, D)) + list(extra_descs)
+    if not descs:
+        raise ValueError("empty chain")
+    arr = _desc_array(descs)
+    L = len(descs)
+    if not x.is_cuda:
+        return _run_chain_host(arr, L, x, D, N, want_y, want_logjac, sum_out)
+    L_ = lib()
+    if want_y:
+        if y is None:
+            y = torch.empty_like(x) if x.dim() == 1 else colmajor_empty(D, N, x.device)
+        Dy, Ny, ldy = _batch_view(y)
+        if (Dy, Ny) != (D, N) or not y.is_cuda:
+            raise ValueError("output shape mismatch")
+    else:
+        y, ldy = None, D
+    if want_logjac or sum_out is not None:
+        if logjac is None:
+            logjac = torch.empty((N,), dtype=torch.float32, device=x.device)
+        elif logjac.numel() != N or logjac.dtype != torch.float32 or not logjac.is_contiguous():
+            raise ValueError("logjac must be a contiguous float32 vector of length N")
+    else:
+        logjac = None
+    ws_bytes = L_.b2b_chain_workspace_bytes(arr, L, D, N, 1 if want_y else 0, 1 if sum_out is not None else 0)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device) if ws_bytes else None
+    rc = L_.b2b_chain_run_f32(
+        arr, L, x.data_ptr(), y.data_ptr() if y is not None else None,
+        logjac.data_ptr() if logjac is not None else None,
+        sum_out.data_ptr() if sum_out is not None else None,
+        D, N, ldx, ldy, 1 if accumulate else 0,
+        ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+    check(rc, "b2b_chain_run_f32")
+    del keepalive
+    lj_out = logjac
+    if lj_out is not None and x.dim() == 1:
+        lj_out = lj_out.reshape(())
+    return y, lj_out
+
+
+def _run_chain_host(arr, L, x, D, N, want_y, want_logjac, sum_out):
+    """Host tensors: b2b_chain_run_host_f32 (chunked H2D/compute/D2H pipeline)."""
+    if not torch.cuda.is_available():
+        raise B2BError(_lib.B2B_EUNSUPPORTED, "no CUDA device: bijectors.jl_b200 has no CPU fallback")
+    if x.dim() == 2 and N > 1 and x.stride(1) != D:
+        raise ValueError("host batches must be dense column-major (ld == D)")
+    ctx = _host_ctx(D, HOST_CHUNK_COLS, HOST_STREAMS)
+    pin = x.is_pinned()
+    y = None
+    if want_y:
+        y = torch.empty_like(x) if x.dim() == 1 else colmajor_empty(D, N, "cpu", pin_memory=pin)
+    lj = None
+    if want_logjac:
+        lj = torch.empty((N,), dtype=torch.float32, pin_memory=pin)
+    hs = ctypes.c_double(0.0)
+    rc = lib().b2b_chain_run_host_f32(
+        ctx, arr, L, x.data_ptr(), y.data_ptr() if y is not None else None,
+        lj.data_ptr() if lj is not None else None,
+        ctypes.byref(hs) if sum_out is not None else None, D, N)
+    check(rc, "b2b_chain_run_host_f32")
+    if sum_out is not None:
+        sum_out.fill_(hs.value)
+    if lj is not None and x.dim() == 1:
+        lj = lj.reshape(())
+    return y, lj
+
+
+# --------------------------------------------------------------------------------------------------
+# generic functions (src/interface.jl)
+# --------------------------------------------------------------------------------------------------
+
+
+def with_logabsdet_jacobian(t, x):
+    """(transform(t, x), logabsdetjac(t, x)) in one fused pass (src/interface.jl:144)."""
+    if hasattr(t, "_host_wladj") and not (isinstance(x, torch.Tensor) and x.is_cuda):
+        return t._host_wladj(x)
+    return run_chain(t, x)
+
+
+def transform(t, x):
+    """transform(b, x) (src/interface.jl:156-166)."""
+    if hasattr(t, "_host_wladj") and not (isinstance(x, torch.Tensor) and x.is_cuda):
+        return t._host_wladj(x)[0]
+    return run_chain(t, x, want_logjac=False)[0]
+
+
+def logabsdetjac(t, x):
+    """logabsdetjac(b, x) (src/interface.jl:183-192): no D×N store is issued."""
+    if hasattr(t, "_host_wladj") and not (isinstance(x, torch.Tensor) and x.is_cuda):
+        return t._host_wladj(x)[1]
+    return run_chain(t, x, want_y=False)[1]
+
+
+def transform_(t, x, y=None):
+    """transform!(b, x[, y]) (src/interface.jl:175-176): y defaults to x (in place)."""
+    return run_chain(t, x, want_logjac=False, y=x if y is None else y)[0]
+
+
+def with_logabsdet_jacobian_(t, x, y=None, logjac=None):
+    """with_logabsdet_jacobian!(b, x[, y, logjac]) (src/interface.jl:212-218): returns
+    (y, logjac + logjac_) with y defaulting to x."""
+    return run_chain(t, x, y=x if y is None else y, logjac=logjac, accumulate=logjac is not None)
+
+
+def logabsdetjac_(t, x, logjac=None):
+    """logabsdetjac!(b, x[, logjac]) (src/interface.jl:199-200)."""
+    return run_chain(t, x, want_y=False, logjac=logjac, accumulate=logjac is not None)[1]
+
+
+def isinvertible(t) -> bool:
+    return isinstance(t, Transform)
+
+
+def isclosedform(t) -> bool:
+    """isclosedform (src/interface.jl:233; planar_layer.jl:188: Inverse{PlanarLayer} is not)."""
+    from .layers import PlanarLayer
+
+    if isinstance(t, Inverse) and isinstance(t.orig, PlanarLayer):
+        return False
+    if isinstance(t, (ComposedFunction, Composed)):
+        return all(isclosedform(b) for b in flatten(t))
+    return True

@@ -1,0 +1,217 @@
+/*
+ * b2b.h -- C ABI of libb2b.so: the B200-native batched bijector evaluation path.
+ *
+ * This is the drop-in boundary for the hot path of TuringLang/Bijectors.jl (v0.16.2): batched
+ * `with_logabsdet_jacobian` / `transform` / `logabsdetjac` / `logpdf` of normalising-flow layers over a
+ * (D x N) Float32 column-batch.  The reference has no FFI for this path -- "plugging in" means adding
+ * more specific Julia methods of its generic functions (src/interface.jl:144,156,183,265) that `ccall`
+ * the entry points below; INTEGRATION.md shows that binding (julia/B200Bijectors.jl).
+ *
+ * Conventions
+ *   - Batches are Julia column-major D x N Float32 matrices: column n (one sample) is D contiguous
+ *     floats at  x + n*ldx  (ldx >= D, in elements).  Outputs: y (D x N, column stride ldy) and a
+ *     length-N vector `logjac` with logjac[n] = log|det J| of the map at column n -- exactly what the
+ *     reference's matrix methods return (planar_layer.jl:102-110, radial_layer.jl:58-72,
+ *     normalise.jl:41-69); for layers the reference only defines on vectors it equals mapping over
+ *     eachcol.
+ *   - ALL pointers are DEVICE pointers unless the name says `host`.  The caller owns every buffer;
+ *     the library never allocates or frees device memory on the hot path (b2b_host_ctx_create is the
+ *     one explicit allocation site, for the host-buffer entry point).
+ *   - `y` may alias `x` (in place; mirrors transform!/with_logabsdet_jacobian!, interface.jl:175-176,
+ *     212-218).  `accumulate_logjac != 0` adds into `logjac` (mirrors `logjac + logjac_`,
+ *     interface.jl:217); otherwise `logjac` is overwritten.  `y == NULL` skips the D x N store
+ *     (logabsdetjac / logpdf only).
+ *   - Layer parameters are passed as device pointers to the RAW reference struct fields (e.g.
+ *     PlanarLayer.w/u/b, planar_layer.jl:13-18); derived quantities (û, wᵀû, softplus terms) are
+ *     computed on the device so no host synchronisation is needed when parameters change every step.
+ *   - Index arguments are 0-based.
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*.  All work is enqueued on it; no entry
+ *     point synchronises the host except b2b_chain_run_host_f32 and b2b_host_ctx_* .
+ *   - Return value: 0 = success; negative = argument error (B2B_E*); positive = cudaError_t /
+ *     ncclResult_t passed through.  Never aborts, never throws.  The Julia shim turns non-zero into
+ *     `error(b2b_status_string(rc))`, matching the reference's error sites (interface.jl:160,186;
+ *     normalise.jl:43; stacked.jl:158; permute.jl:109-119; rational_quadratic_spline.jl:84-85).
+ *   - There is NO CPU fallback anywhere in this library.
+ */
+#ifndef B2B_H_
+#define B2B_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2B_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define B2B_OK 0
+#define B2B_EINVAL (-1)       /* NULL / shape / alignment / range error                         */
+#define B2B_EUNSUPPORTED (-2) /* valid request the device path does not implement (e.g. D > 1024) */
+#define B2B_EWORKSPACE (-3)   /* workspace too small: see b2b_chain_workspace_bytes              */
+#define B2B_ENONCCL (-4)      /* libnccl.so.2 could not be loaded                                */
+
+/* layer kinds (b2b_layer_desc.kind) */
+#define B2B_PLANAR 1          /* PlanarLayer                src/bijectors/planar_layer.jl            */
+#define B2B_RADIAL 2          /* RadialLayer                src/bijectors/radial_layer.jl            */
+#define B2B_RQS 3             /* RationalQuadraticSpline    src/bijectors/rational_quadratic_spline.jl */
+#define B2B_COUPLING_AFFINE 4 /* Coupling, θ = Shift(t)∘Scale(exp.(s)), [s;t]=W·x₂+c  coupling.jl    */
+#define B2B_BATCHNORM 5       /* InvertibleBatchNorm (eval) src/bijectors/normalise.jl               */
+#define B2B_PERMUTE 6         /* Permute                    src/bijectors/permute.jl                 */
+#define B2B_STACKED_EW 7      /* Stacked of elementwise laws on row ranges  src/bijectors/stacked.jl */
+#define B2B_MVNORMAL_DIAG 8   /* terminal op: logpdf of MvNormal(mu, Diagonal(sigma.^2)) + logjac    */
+
+/* elementwise law codes for B2B_STACKED_EW (one code per row) */
+#define B2B_EW_IDENTITY 0
+#define B2B_EW_EXP 1   /* elementwise(exp): y=exp(x), logjac += x          exp_log.jl:5-6  */
+#define B2B_EW_LOG 2   /* elementwise(log): y=log(x), logjac -= log(x)     exp_log.jl:8-9  */
+#define B2B_EW_SHIFT 3 /* Shift(a): y = a + x                              shift.jl:14,21  */
+#define B2B_EW_SCALE 4 /* Scale(a): y = a * x, logjac += log|a|            scale.jl:13,26  */
+
+/*
+ * One element of a chain.  `inverse != 0` evaluates Inverse(layer) and its log-Jacobian
+ * (interface.jl:276-281) in one fused pass.
+ *
+ * kind               p0          p1          p2          p3       i0              i1            n0    n1   f0
+ * PLANAR             w[D]        u[D]        b[1]        -        -               -             -     -    -
+ * RADIAL             α_[1]       β[1]        z_0[D]      -        -               -             -     -    -
+ * RQS                widths      heights     derivatives -        -               -             K1    -    -
+ *                    (each D x K1 column-major = the struct fields of rational_quadratic_spline.jl:75-79)
+ * COUPLING_AFFINE    W[2n1 x n2] c[2n1]      -           -        idx1[n1]        idx2[n2]      n1    n2   -
+ *                    (W column-major; rows 0..n1-1 give s, rows n1..2n1-1 give t; idx = PartitionMask rows)
+ * BATCHNORM          b[D]        logs[D]     m[D]        v[D]     -               -             -     -    eps
+ * PERMUTE            -           -           -           -        dst_of_src[D]   -             -     -    -
+ *                    (y[dst_of_src[i]] = x[i], i.e. Permute(indices) of permute.jl:90-100, 0-based)
+ * STACKED_EW         a[D]        -           -           -        code[D]         -             -     -    -
+ * MVNORMAL_DIAG      mu[D]|NULL  sigma[D]|NULL -         -        -               -             -     -    -
+ */
+typedef struct b2b_layer_desc {
+  int32_t kind;
+  int32_t inverse;
+  int32_t n0, n1, n2, n3;
+  float f0, f1;
+  const float* p0;
+  const float* p1;
+  const float* p2;
+  const float* p3;
+  const int32_t* i0;
+  const int32_t* i1;
+} b2b_layer_desc;
+
+#define B2B_MAX_CHAIN 24
+
+int b2b_version(void);
+const char* b2b_status_string(int status);
+
+/* ---- chain evaluation: Composed / ComposedFunction (src/bijectors/composed.jl:4,11-14 and the
+ * ChangesOfVariables rule for ComposedFunction) ----------------------------------------------------
+ * Applies layers[0], layers[1], ... in order (inner-most first), accumulating per-column log-Jacobians.
+ * Consecutive column-local layers are fused into ONE kernel launch (each column is read once and
+ * written once for the whole fused run); COUPLING_AFFINE layers run in their own GEMM kernel.
+ * If the last element is B2B_MVNORMAL_DIAG, `logjac` receives logpdf[n] = logpdf(MvNormal)(x_n) +
+ * accumulated logjac (transformed_distribution.jl:165-169 when the preceding layers are the inverse
+ * chain) and, when sum_out != NULL, *sum_out (device double) receives Σ_n logpdf[n] (fixed summation
+ * order, deterministic).
+ * workspace: device scratch of at least b2b_chain_workspace_bytes(...) bytes (may be NULL when 0).
+ */
+int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const float* x, float* y, float* logjac,
+                      double* sum_out, int32_t D, int64_t N, int64_t ldx, int64_t ldy,
+                      int accumulate_logjac, void* workspace, size_t workspace_bytes, void* stream);
+
+size_t b2b_chain_workspace_bytes(const b2b_layer_desc* layers, int32_t L, int32_t D, int64_t N,
+                                 int want_y, int want_sum);
+
+/* Number of kernel launches the previous b2b_chain_run_f32 call on this thread enqueued. */
+int b2b_last_launch_count(void);
+
+/* Select the implementation of the fused column-local kernel: 0 = auto (default), 1 = lane-group
+ * direct-global kernel (v0), 2 = TMA-staged thread-per-column kernel where available. */
+int b2b_set_kernel_variant(int variant);
+
+/* ---- single layers (thin wrappers over a 1-element chain) --------------------------------------- */
+/* PlanarLayer: planar_layer.jl:102-110 (fwd), :112-127 + find_alpha :160-185 (inverse) */
+int b2b_planar_fwd_f32(const float* x, float* y, float* logjac, const float* w, const float* u,
+                       const float* b, int32_t D, int64_t N, int64_t ldx, int64_t ldy,
+                       int accumulate_logjac, void* stream);
+int b2b_planar_inv_f32(const float* x, float* y, float* logjac, const float* w, const float* u,
+                       const float* b, int32_t D, int64_t N, int64_t ldx, int64_t ldy,
+                       int accumulate_logjac, void* stream);
+/* RadialLayer: radial_layer.jl:58-72 (fwd), :88-102,124-129 (inverse) */
+int b2b_radial_fwd_f32(const float* x, float* y, float* logjac, const float* alpha_raw,
+                       const float* beta, const float* z0, int32_t D, int64_t N, int64_t ldx,
+                       int64_t ldy, int accumulate_logjac, void* stream);
+int b2b_radial_inv_f32(const float* x, float* y, float* logjac, const float* alpha_raw,
+                       const float* beta, const float* z0, int32_t D, int64_t N, int64_t ldx,
+                       int64_t ldy, int accumulate_logjac, void* stream);
+/* RationalQuadraticSpline: rational_quadratic_spline.jl:317-357 (fwd), :183-220 (inverse) */
+int b2b_rqs_fwd_f32(const float* x, float* y, float* logjac, const float* widths,
+                    const float* heights, const float* derivs, int32_t K1, int32_t D, int64_t N,
+                    int64_t ldx, int64_t ldy, int accumulate_logjac, void* stream);
+int b2b_rqs_inv_f32(const float* x, float* y, float* logjac, const float* widths,
+                    const float* heights, const float* derivs, int32_t K1, int32_t D, int64_t N,
+                    int64_t ldx, int64_t ldy, int accumulate_logjac, void* stream);
+/* Coupling with the affine law: coupling.jl:206-215 (fwd), :217-228 (inverse) */
+int b2b_coupling_affine_fwd_f32(const float* x, float* y, float* logjac, const int32_t* idx1,
+                                int32_t n1, const int32_t* idx2, int32_t n2, const float* W,
+                                const float* c, int32_t D, int64_t N, int64_t ldx, int64_t ldy,
+                                int accumulate_logjac, void* stream);
+int b2b_coupling_affine_inv_f32(const float* x, float* y, float* logjac, const int32_t* idx1,
+                                int32_t n1, const int32_t* idx2, int32_t n2, const float* W,
+                                const float* c, int32_t D, int64_t N, int64_t ldx, int64_t ldy,
+                                int accumulate_logjac, void* stream);
+/* InvertibleBatchNorm, eval mode: normalise.jl:61-67 (fwd), :74-86 (inverse) */
+int b2b_batchnorm_eval_fwd_f32(const float* x, float* y, float* logjac, const float* b,
+                               const float* logs, const float* m, const float* v, float eps,
+                               int32_t D, int64_t N, int64_t ldx, int64_t ldy, int accumulate_logjac,
+                               void* stream);
+int b2b_batchnorm_eval_inv_f32(const float* x, float* y, float* logjac, const float* b,
+                               const float* logs, const float* m, const float* v, float eps,
+                               int32_t D, int64_t N, int64_t ldx, int64_t ldy, int accumulate_logjac,
+                               void* stream);
+/* Permute rows (also serves PartitionMask / Stacked range movement): permute.jl:152-155. Bit-exact. */
+int b2b_permute_rows_f32(const float* x, float* y, float* logjac, const int32_t* dst_of_src,
+                         int inverse, int32_t D, int64_t N, int64_t ldx, int64_t ldy,
+                         int accumulate_logjac, void* stream);
+/* Stacked of elementwise laws on rows: stacked.jl:157-166,242-252 */
+int b2b_stacked_elementwise_f32(const float* x, float* y, float* logjac, const int32_t* code,
+                                const float* a, int inverse, int32_t D, int64_t N, int64_t ldx,
+                                int64_t ldy, int accumulate_logjac, void* stream);
+/* logpdf(MvNormal(mu, Diagonal(sigma.^2)), x) + logjac_in  (Distributions/PDMats);
+ * logpdf_out may alias logjac_in; sum_out (device double) optional; workspace as for chains. */
+int b2b_mvnormal_diag_logpdf_f32(const float* x, const float* mu, const float* sigma,
+                                 const float* logjac_in, float* logpdf_out, double* sum_out,
+                                 int32_t D, int64_t N, int64_t ldx, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
+/* ---- host-buffer entry point (what a caller holding plain host Arrays uses; the bench's `e2e`) ----
+ * Streams the batch through the device in column chunks: H2D copy, chain kernels and D2H copy of
+ * successive chunks overlap on `n_streams` streams.  x_host / y_host / logjac_host are HOST pointers
+ * (pinned memory gives full PCIe bandwidth; pageable memory works but is slower); layer parameter
+ * pointers inside `layers` stay DEVICE pointers.  Synchronises before returning.
+ */
+typedef struct b2b_host_ctx b2b_host_ctx;
+int b2b_host_ctx_create(b2b_host_ctx** ctx, int32_t D_max, int64_t chunk_cols, int32_t n_streams);
+int b2b_host_ctx_destroy(b2b_host_ctx* ctx);
+int b2b_chain_run_host_f32(b2b_host_ctx* ctx, const b2b_layer_desc* layers, int32_t L,
+                           const float* x_host, float* y_host, float* logjac_host, double* sum_host,
+                           int32_t D, int64_t N);
+/* cudaHostRegister / cudaHostUnregister passthroughs so a host runtime can pin its own arrays */
+int b2b_host_register(void* ptr, size_t bytes);
+int b2b_host_unregister(void* ptr);
+
+/* ---- multi-GPU: the ONE collective of the path -----------------------------------
+ * Columns shard across ranks with no data-path collective; the batch log-density Σ_n logpdf[n] is
+ * summed across ranks with a single ncclAllReduce(sum) of one double.  NCCL is loaded with
+ * dlopen("libnccl.so.2") so the library has no link-time NCCL dependency.
+ */
+typedef struct b2b_comm b2b_comm;
+int b2b_comm_unique_id(char id_out[128]);
+int b2b_comm_init_rank(b2b_comm** comm, int nranks, int rank, const char id[128]);
+int b2b_allreduce_sum_f64(b2b_comm* comm, double* dev_values, int32_t count, void* stream);
+int b2b_comm_destroy(b2b_comm* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2B_H_ */

@@ -1,0 +1,419 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle on identical seeded inputs.
+
+Tolerance (north_star): Float32 layers within 1e-5 RELATIVE of the reference CPU path, measured norm-wise
+(`‖a−b‖ ≤ rtol·max(‖a‖,‖b‖)` -- the semantics of Julia's `≈` on arrays that the reference's own tests use);
+index movement (Permute / PartitionMask / Stacked ranges) bit-exact.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(a), np.linalg.norm(b), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def B():
+    import torch
+
+    assert torch.cuda.is_available()
+    import bijectors_jl_b200 as B
+
+    return B
+
+
+f32 = np.float32
+
+
+def make_case(kind, D, rng):
+    """(device layer, oracle layer) with float32 parameters."""
+    import bijectors_jl_b200 as B
+
+    if kind == "planar":
+        w, u, b = (rng.standard_normal(D) / np.sqrt(D)).astype(f32), (rng.standard_normal(D) / np.sqrt(D)).astype(f32), rng.standard_normal(1).astype(f32)
+        return B.PlanarLayer(w, u, b), O.Layer("planar", dict(w=w, u=u, b=b))
+    if kind == "planar_randn":  # reference default init randn(dims): saturates tanh at large D (stress variant)
+        w, u, b = rng.standard_normal(D).astype(f32), rng.standard_normal(D).astype(f32), rng.standard_normal(1).astype(f32)
+        return B.PlanarLayer(w, u, b), O.Layer("planar", dict(w=w, u=u, b=b))
+    if kind == "radial":
+        a, be, z0 = rng.standard_normal(1).astype(f32), rng.standard_normal(1).astype(f32), rng.standard_normal(D).astype(f32)
+        return B.RadialLayer(a, be, z0), O.Layer("radial", dict(alpha_raw=a, beta=be, z0=z0))
+    if kind == "rqs":
+        K, Bx = 8, 3.0
+        rw, rh, rd = rng.standard_normal((D, K)).astype(f32), rng.standard_normal((D, K)).astype(f32), rng.standard_normal((D, K - 1)).astype(f32)
+        lay = B.RationalQuadraticSpline(rw, rh, rd, Bx)
+        W, H, Dv = lay.knots()
+        return lay, O.Layer("rqs", dict(widths=W, heights=H, derivs=Dv))
+    if kind == "batchnorm":
+        b, logs, m = (rng.standard_normal(D) * 0.1).astype(f32), (rng.standard_normal(D) * 0.1).astype(f32), (rng.standard_normal(D) * 0.1).astype(f32)
+        v = rng.uniform(0.5, 1.5, D).astype(f32)
+        return (B.InvertibleBatchNorm(b=b, logs=logs, m=m, v=v),
+                O.Layer("batchnorm", dict(bn=O.BatchNormParams(b, logs, m, v, f32(1e-5), f32(0.1)))))
+    if kind == "permute":
+        perm = (rng.permutation(D) + 1).tolist()
+        return B.Permute(perm), O.Layer("permute", dict(A=O.permute_matrix_from_indices(perm)))
+    if kind == "coupling":
+        n1 = D // 2
+        mask_first = rng.integers(0, 2) == 0
+        idx1 = list(range(1, n1 + 1)) if mask_first else list(range(D - n1 + 1, D + 1))
+        idx2 = [i for i in range(1, D + 1) if i not in set(idx1)]
+        W = (rng.standard_normal((2 * n1, len(idx2))) * 0.5 / np.sqrt(len(idx2))).astype(f32)
+        c = (rng.standard_normal(2 * n1) * 0.1).astype(f32)
+        return (B.Coupling(B.AffineConditioner(W, c), B.PartitionMask(D, idx1, idx2)),
+                O.Layer("coupling_affine", dict(idx1=np.asarray(idx1), idx2=np.asarray(idx2), W=W, c=c)))
+    if kind == "stacked":
+        r1, r2 = max(1, D // 4), max(2, D // 2)
+        ranges = [(1, r1), (r1 + 1, r2), (r2 + 1, D)]
+        return (B.Stacked([B.elementwise("exp"), B.Scale(-1.7), B.Shift(0.3)], ranges),
+                O.Layer("stacked", dict(ops=[(O.EW.EXP, 0.0), (O.EW.SCALE, f32(-1.7)), (O.EW.SHIFT, f32(0.3))], ranges=ranges)))
+    raise ValueError(kind)
+
+
+KINDS = ["planar", "planar_randn", "radial", "rqs", "batchnorm", "permute", "coupling", "stacked"]
+
+
+@pytest.mark.parametrize("D,N", [(128, 1000), (64, 517), (32, 2049), (256, 300), (10, 100), (3, 7), (36, 65), (200, 33)])
+@pytest.mark.parametrize("kind", KINDS)
+def test_layer_forward_inverse_parity(B, kind, D, N):
+    if kind in ("coupling", "stacked") and D < 3:
+        pytest.skip("needs D >= 3")
+    import zlib
+
+    rng = np.random.default_rng(zlib.crc32(f"{kind}-{D}-{N}".encode()))
+    lay, olay = make_case(kind, D, rng)
+    scale = 1.5 if kind == "rqs" else 1.0  # ~5% of RQS inputs outside the box (identity branch)
+    x = (rng.standard_normal((D, N)) * scale).astype(f32)
+    xd = B.from_numpy(x)
+    y, lj = B.with_logabsdet_jacobian(lay, xd)
+    yo, ljo = olay.forward(x)  # float32 oracle
+    yo64, ljo64 = olay.forward(x.astype(np.float64)) if kind not in ("permute",) else (yo, ljo)
+    yh, ljh = B.to_numpy(y), B.to_numpy(lj)
+    if kind == "permute":
+        assert np.array_equal(yh.view(np.uint32), yo.view(np.uint32))  # bit-exact
+        assert np.all(ljh == 0)
+    else:
+        assert rel(yh, yo) <= RTOL, ("y vs f32 oracle", rel(yh, yo))
+        assert rel(yh, yo64) <= RTOL, ("y vs f64 oracle", rel(yh, yo64))
+        # logjac: norm-wise with an absolute floor for vectors that are ~0 (e.g. saturated tanh)
+        assert np.linalg.norm(ljh - ljo64) <= RTOL * max(np.linalg.norm(ljo64), math.sqrt(N) * 1e-2), rel(ljh, ljo64)
+    # transform / logabsdetjac alone agree with the fused call
+    assert np.array_equal(B.to_numpy(B.transform(lay, xd)), yh)
+    assert np.array_equal(B.to_numpy(B.logabsdetjac(lay, xd)), ljh)
+    # inverse: ires == (x, -logjac)  (test/bijectors/utils.jl:53-62)
+    xi, lji = B.with_logabsdet_jacobian(B.inverse(lay), y)
+    xih, ljih = B.to_numpy(xi), B.to_numpy(lji)
+    xo, ljio = olay.inverse(yh.astype(np.float64) if kind != "permute" else yh)
+    if kind == "permute":
+        assert np.array_equal(xih.view(np.uint32), x.view(np.uint32))
+    else:
+        tol = 2e-4 if kind == "planar_randn" else RTOL  # flat regions of a saturated planar layer are ill-conditioned
+        assert rel(xih, xo) <= tol, ("inverse vs f64 oracle", rel(xih, xo))
+        assert np.linalg.norm(ljih - ljio) <= 10 * tol * max(np.linalg.norm(ljio), math.sqrt(N) * 1e-2)
+        assert rel(xih, x) <= 10 * tol  # inverse∘forward ≈ id
+
+
+@pytest.mark.parametrize("D", [128, 64, 32, 256, 10])
+def test_fused_chain_matches_layerwise_and_oracle(B, D):
+    rng = np.random.default_rng(D)
+    N = 1537
+    kinds = ["planar", "batchnorm", "radial", "permute", "rqs", "planar", "stacked", "coupling", "radial", "planar"]
+    pairs = [make_case(k, D, rng) for k in kinds]
+    flow = B.Composed(*[p[0] for p in pairs])
+    x = rng.standard_normal((D, N)).astype(f32)
+    xd = B.from_numpy(x)
+    y, lj = B.with_logabsdet_jacobian(flow, xd)
+    yo, ljo = O.chain_forward([p[1] for p in pairs], x.astype(np.float64))
+    assert rel(B.to_numpy(y), yo) <= RTOL
+    assert rel(B.to_numpy(lj), ljo) <= RTOL
+    # the `∘` spelling (outer @ inner) builds the same chain
+    comp = pairs[0][0]
+    for p in pairs[1:]:
+        comp = p[0] @ comp
+    y2, lj2 = B.with_logabsdet_jacobian(comp, xd)
+    assert np.array_equal(B.to_numpy(y2), B.to_numpy(y)) and np.array_equal(B.to_numpy(lj2), B.to_numpy(lj))
+    # layer by layer with the in-place, accumulating variants (with_logabsdet_jacobian!)
+    import torch
+
+    buf = xd.t().contiguous().t().clone() if False else B.from_numpy(x)
+    acc = torch.zeros(N, dtype=torch.float32, device="cuda")
+    for p in pairs:
+        buf, acc = B.with_logabsdet_jacobian_(p[0], buf, None, acc)
+    assert rel(B.to_numpy(buf), B.to_numpy(y)) <= 2e-6
+    assert rel(B.to_numpy(acc), B.to_numpy(lj)) <= 2e-6
+    # inverse chain
+    xi, lji = B.with_logabsdet_jacobian(B.inverse(flow), y)
+    assert rel(B.to_numpy(xi), x) <= 1e-4
+    assert rel(B.to_numpy(lji), -ljo) <= 1e-4
+    # TransformedDistribution logpdf (transformed_distribution.jl:165-169)
+    mu, sigma = (rng.standard_normal(D) * 0.1).astype(f32), rng.uniform(0.5, 2.0, D).astype(f32)
+    td = B.transformed(B.MvNormal(D, mu, sigma), flow)
+    lp = B.to_numpy(B.logpdf(td, y))
+    lpo = O.mvnormal_diag_logpdf(mu.astype(np.float64), sigma.astype(np.float64), x.astype(np.float64)) - ljo
+    assert rel(lp, lpo) <= 1e-4
+    tot, lp2 = B.logpdf_sum(td, y)
+    assert np.array_equal(B.to_numpy(lp2), lp)
+    assert abs(float(tot) - float(lp.astype(np.float64).sum())) <= 1e-9 * abs(float(tot)) + 1e-6
+
+
+def test_c_abi_single_layer_entry_points(B):
+    """Every per-layer symbol of include/b2b.h called directly (plain pointers, no Python layer objects)."""
+    import torch
+
+    L = B.lib()
+    rng = np.random.default_rng(42)
+    D, N = 64, 777
+    x = rng.standard_normal((D, N)).astype(f32)
+    xd = B.from_numpy(x)
+    yd = B.colmajor_empty(D, N)
+    ljd = torch.empty(N, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a)).cuda()  # noqa: E731
+
+    def check_pair(fwd, inv, args_dev, olayer, tol=RTOL):
+        rc = fwd(xd.data_ptr(), yd.data_ptr(), ljd.data_ptr(), *args_dev, D, N, D, D, 0, s)
+        assert rc == 0, L.b2b_status_string(rc)
+        yo, ljo = olayer.forward(x.astype(np.float64))
+        assert rel(B.to_numpy(yd), yo) <= tol and rel(B.to_numpy(ljd), ljo) <= tol
+        # in place inverse: y aliases x
+        rc = inv(yd.data_ptr(), yd.data_ptr(), ljd.data_ptr(), *args_dev, D, N, D, D, 1, s)
+        assert rc == 0, L.b2b_status_string(rc)
+        assert rel(B.to_numpy(yd), x) <= 10 * tol
+        assert np.linalg.norm(B.to_numpy(ljd)) <= 1e-4 * math.sqrt(N)  # fwd + inverse logjac cancel
+
+    w, u, b = (rng.standard_normal(D) / 8).astype(f32), (rng.standard_normal(D) / 8).astype(f32), f32([0.2])
+    t = [dev(w), dev(u), dev(b)]
+    check_pair(L.b2b_planar_fwd_f32, L.b2b_planar_inv_f32, [a.data_ptr() for a in t], O.Layer("planar", dict(w=w, u=u, b=b)))
+    a_, be, z0 = f32([0.3]), f32([-0.4]), rng.standard_normal(D).astype(f32)
+    t = [dev(a_), dev(be), dev(z0)]
+    check_pair(L.b2b_radial_fwd_f32, L.b2b_radial_inv_f32, [a.data_ptr() for a in t], O.Layer("radial", dict(alpha_raw=a_, beta=be, z0=z0)))
+    K = 8
+    W, H, Dv = O.rqs_params(rng.standard_normal((D, K)).astype(f32), rng.standard_normal((D, K)).astype(f32), rng.standard_normal((D, K - 1)).astype(f32), 3.0)
+    t = [dev(W.T), dev(H.T), dev(Dv.T)]  # Julia column-major (D x K1) == row-major (K1 x D)
+    check_pair(L.b2b_rqs_fwd_f32, L.b2b_rqs_inv_f32, [a.data_ptr() for a in t] + [K + 1], O.Layer("rqs", dict(widths=W, heights=H, derivs=Dv)))
+    bb, logs, m, v = (rng.standard_normal(D) * 0.1).astype(f32), (rng.standard_normal(D) * 0.1).astype(f32), (rng.standard_normal(D) * 0.1).astype(f32), rng.uniform(0.5, 1.5, D).astype(f32)
+    t = [dev(bb), dev(logs), dev(m), dev(v)]
+    check_pair(L.b2b_batchnorm_eval_fwd_f32, L.b2b_batchnorm_eval_inv_f32, [a.data_ptr() for a in t] + [1e-5],
+               O.Layer("batchnorm", dict(bn=O.BatchNormParams(bb, logs, m, v, f32(1e-5), f32(0.1)))))
+    n1 = D // 2
+    idx1, idx2 = np.arange(n1, dtype=np.int32), np.arange(n1, D, dtype=np.int32)
+    Wc, c = (rng.standard_normal((2 * n1, D - n1)) * 0.05).astype(f32), (rng.standard_normal(2 * n1) * 0.1).astype(f32)
+    t = [dev(idx1), dev(idx2), dev(Wc.T), dev(c)]
+    args = [t[0].data_ptr(), n1, t[1].data_ptr(), D - n1, t[2].data_ptr(), t[3].data_ptr()]
+    check_pair(L.b2b_coupling_affine_fwd_f32, L.b2b_coupling_affine_inv_f32, args,
+               O.Layer("coupling_affine", dict(idx1=idx1 + 1, idx2=idx2 + 1, W=Wc, c=c)))
+    # permute + stacked + mvnormal
+    perm = rng.permutation(D).astype(np.int32)
+    pd = dev(perm)
+    assert L.b2b_permute_rows_f32(xd.data_ptr(), yd.data_ptr(), ljd.data_ptr(), pd.data_ptr(), 0, D, N, D, D, 0, s) == 0
+    ye = np.empty_like(x)
+    ye[perm] = x
+    assert np.array_equal(B.to_numpy(yd), ye) and np.all(B.to_numpy(ljd) == 0)
+    assert L.b2b_permute_rows_f32(yd.data_ptr(), yd.data_ptr(), None, pd.data_ptr(), 1, D, N, D, D, 0, s) == 0
+    assert np.array_equal(B.to_numpy(yd), x)
+    code = np.zeros(D, np.int32)
+    code[:4] = 1
+    code[4:8] = 2
+    av = np.zeros(D, f32)
+    xp = np.abs(x) + f32(0.1)
+    xpd = B.from_numpy(xp)
+    cd, ad = dev(code), dev(av)
+    assert L.b2b_stacked_elementwise_f32(xpd.data_ptr(), yd.data_ptr(), ljd.data_ptr(), cd.data_ptr(), ad.data_ptr(), 0, D, N, D, D, 0, s) == 0
+    ye = xp.copy()
+    ye[:4] = np.exp(xp[:4])
+    ye[4:8] = np.log(xp[4:8])
+    assert rel(B.to_numpy(yd), ye) <= 1e-6
+    assert rel(B.to_numpy(ljd), xp[:4].sum(0) - np.log(xp[4:8]).sum(0)) <= 1e-5
+    mu, sg = rng.standard_normal(D).astype(f32), rng.uniform(0.5, 2, D).astype(f32)
+    mud, sgd = dev(mu), dev(sg)
+    lj_in = rng.standard_normal(N).astype(f32)
+    ljin_d = dev(lj_in)
+    out = torch.empty(N, device="cuda")
+    sm = torch.zeros((), dtype=torch.float64, device="cuda")
+    ws = torch.empty(4096 * 8, dtype=torch.uint8, device="cuda")
+    rc = L.b2b_mvnormal_diag_logpdf_f32(xd.data_ptr(), mud.data_ptr(), sgd.data_ptr(), ljin_d.data_ptr(), out.data_ptr(),
+                                        sm.data_ptr(), D, N, D, ws.data_ptr(), ws.numel(), s)
+    assert rc == 0, L.b2b_status_string(rc)
+    ref = O.mvnormal_diag_logpdf(mu.astype(np.float64), sg.astype(np.float64), x.astype(np.float64)) + lj_in
+    assert rel(B.to_numpy(out), ref) <= RTOL
+    assert abs(float(sm) - ref.sum()) <= 1e-5 * abs(ref.sum())
+    # error convention: negative status, never a crash
+    assert L.b2b_planar_fwd_f32(None, yd.data_ptr(), ljd.data_ptr(), None, None, None, D, N, D, D, 0, s) == -1
+    assert L.b2b_rqs_fwd_f32(xd.data_ptr(), yd.data_ptr(), ljd.data_ptr(), t[0].data_ptr(), t[0].data_ptr(), t[0].data_ptr(), 1, D, N, D, D, 0, s) == -1
+    assert b"invalid" in L.b2b_status_string(-1)
+
+
+def test_reference_golden_vectors_on_device(B, golden):
+    import torch
+
+    # Permute (test/bijectors/permute.jl:30-64) incl. the 4 constructor spellings; bit-exact payloads
+    g = golden["permute_3"]
+    bs = [B.Permute(np.array(g["matrix"])), B.Permute(g["indices"]), B.Permute(3, *[tuple(p) for p in g["pairs"]]),
+          B.Permute(3, *[(p[0], p[1]) for p in g["vector_pairs"]])]
+    assert all(b == bs[0] for b in bs)
+    x = B.from_numpy(np.array(g["x"], f32))
+    for b in bs:
+        y, lj = B.with_logabsdet_jacobian(b, x)
+        assert B.to_numpy(y).tolist() == g["y"] and float(lj) == 0.0
+        assert B.to_numpy(B.inverse(b)(b(x))).tolist() == g["x"]
+    for case in golden["permute_invalid"]["cases"]:
+        with pytest.raises(ValueError):
+            if "pairs" in case:
+                B.Permute(case["n"], *[tuple(p) for p in case["pairs"]])
+            else:
+                B.Permute(case["n"], *[(p[0], p[1]) for p in case["vector_pairs"]])
+    payload = np.array([np.nan, -0.0, 1.5, np.inf], dtype=f32)
+    payload.view(np.uint32)[0] = 0x7FC12345  # NaN with a payload
+    yb = B.to_numpy(B.Permute([3, 1, 4, 2])(B.from_numpy(payload)))
+    assert yb.view(np.uint32).tolist() == payload.view(np.uint32)[[1, 3, 0, 2]].tolist()
+    # Coupling with the Shift law x₁ + x₂ (test/bijectors/coupling.jl:18-42) as s = 0, t = x₂
+    g = golden["coupling_shift"]
+    cl = B.Coupling(B.AffineConditioner(np.array([[0.0], [1.0]], f32)), B.PartitionMask(3, [1], [2]))
+    x = B.from_numpy(np.array(g["x"], f32))
+    y, lj = B.with_logabsdet_jacobian(cl, x)
+    assert B.to_numpy(y).tolist() == g["y"] and float(lj) == 0.0
+    xi, lji = B.with_logabsdet_jacobian(B.inverse(cl), y)
+    assert B.to_numpy(xi).tolist() == g["x"] and float(lji) == 0.0
+    m = B.PartitionMask(3, [1], [2])
+    assert m == B.PartitionMask(3, [1], [2], [3]) and m.indices_3 == [3]
+    # Planar deterministic case (test/normalising_flows.jl:37-42)
+    flow = B.PlanarLayer(np.ones(10, f32), np.zeros(10, f32), f32(1.0))
+    z = B.from_numpy(np.ones((10, 100), f32))
+    y, lj = B.with_logabsdet_jacobian(flow, z)
+    uh = (math.log(2) - 1) / 10
+    assert rel(B.to_numpy(y), np.full((10, 100), 1 + uh * math.tanh(11.0))) <= 1e-6
+    assert np.allclose(B.to_numpy(lj), math.log1p((math.log(2) - 1) / math.cosh(11.0) ** 2), rtol=1e-4, atol=1e-12)
+    assert rel(B.to_numpy(B.inverse(flow)(flow(z))), np.ones((10, 100))) <= 1e-6
+    # Radial deterministic case (test/normalising_flows.jl:86-91): β̂ = 0 ⇒ identity
+    rflow = B.RadialLayer(f32(1.0), f32(1.0), np.zeros(10, f32))
+    y, lj = B.with_logabsdet_jacobian(rflow, z)
+    assert rel(B.to_numpy(y), np.ones((10, 100))) <= 1e-6 and np.abs(B.to_numpy(lj)).max() <= 1e-5
+    assert rel(B.to_numpy(B.inverse(rflow)(rflow(z))), np.ones((10, 100))) <= 1e-6
+    # InvertibleBatchNorm defaults (test/normalising_flows.jl:7-23)
+    bn = B.InvertibleBatchNorm(2)
+    xr = np.random.default_rng(1).standard_normal((2, 20)).astype(f32)
+    xd = B.from_numpy(xr)
+    y, lj = B.with_logabsdet_jacobian(bn, xd)
+    assert rel(B.to_numpy(y), xr / np.sqrt(f32(1) + f32(1e-5))) <= 1e-6
+    assert np.allclose(B.to_numpy(lj), -math.log(1 + 1e-5), rtol=1e-2)
+    assert rel(B.to_numpy(B.inverse(bn)(bn(xd))), xr) <= 1e-6
+    assert B.inverse(B.inverse(bn)) == bn
+    with pytest.raises(RuntimeError, match="expected 2 channels"):
+        B.with_logabsdet_jacobian(bn, B.from_numpy(np.zeros((10, 2), f32)))
+    # RQS outside the box is the identity with zero logjac (test/bijectors/rational_quadratic_spline.jl:47-61)
+    rng = np.random.default_rng(5)
+    b_mv = B.RationalQuadraticSpline(rng.standard_normal((2, 3)), rng.standard_normal((2, 3)), rng.standard_normal((2, 2)), 2)
+    xo = B.from_numpy(np.array([-5.0, 5.0], f32))
+    y, lj = B.with_logabsdet_jacobian(b_mv, xo)
+    assert B.to_numpy(y).tolist() == [-5.0, 5.0] and float(lj) == 0.0
+    W, H, Dv = b_mv.knots()
+    assert np.allclose(W[:, 0], -2) and np.allclose(W[:, -1], 2, rtol=1e-6) and np.all(Dv[:, 0] == 1) and np.all(Dv[:, -1] == 1)
+    with pytest.raises(AssertionError):
+        B.RationalQuadraticSpline(W, H, -Dv)
+    # Stacked value test (test/bijectors/stacked.jl:100-108)
+    sb = B.Stacked([B.elementwise("exp"), B.elementwise("log"), B.Shift(5.0)])
+    y, lj = B.with_logabsdet_jacobian(sb, B.from_numpy(np.ones(3, f32)))
+    assert np.allclose(B.to_numpy(y), [math.e, 0.0, 6.0], rtol=1e-6) and float(lj) == pytest.approx(1.0, rel=1e-6)
+    with pytest.raises(RuntimeError, match="input length mismatch"):
+        sb(B.from_numpy(np.ones(4, f32)))
+    # elementwise(exp) doctest (src/interface.jl:21-31) -- host plumbing, Float64
+    ye, le = B.with_logabsdet_jacobian(B.elementwise("exp"), torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64))
+    assert ye.tolist() == golden["elementwise_exp_doctest"]["y"] and float(le) == 6.0
+
+
+def test_find_alpha_residual_on_device(B, golden):
+    """test/normalising_flows.jl:47-71 restated for the fp32 device solver through a D=1 PlanarLayer
+    (w = 1 ⇒ û = wᵀû = softplus(u) − 1, and inverse(y) IS α)."""
+    g = golden["find_alpha_grid"]
+    for c in g["wt_u_hat"]:
+        if c <= -1.0:
+            continue  # c = −1 needs u = −∞
+        u = math.log(math.expm1(c + 1.0)) if c + 1.0 < 30 else c + 1.0
+        for b in g["b"]:
+            flow = B.PlanarLayer(np.ones(1, f32), f32([u]), f32([b]))
+            ys = np.array(g["wt_y"], f32)[None, :]
+            alpha = B.to_numpy(B.inverse(flow)(B.from_numpy(ys))).astype(np.float64)[0]
+            c32 = float(np.log1p(np.exp(np.float64(f32(u)))) - 1.0)
+            resid = alpha + c32 * np.tanh(alpha + float(f32(b))) - ys[0].astype(np.float64)
+            assert np.all(np.abs(resid) <= 2e-5 * np.maximum(np.abs(ys[0]), 1.0)), (c, b, resid)
+    # issue 204 (b = −1e8): α ≈ wt_y + wt_u_hat
+    gi = golden["find_alpha_issue_204"]
+    u = math.log(math.expm1(gi["wt_u_hat"] + 1.0))
+    flow = B.PlanarLayer(np.ones(1, f32), f32([u]), f32([gi["b"]]))
+    a = float(B.to_numpy(B.inverse(flow)(B.from_numpy(np.array([gi["wt_y"]], f32))))[0])
+    assert a == pytest.approx(gi["wt_y"] + gi["wt_u_hat"], rel=1e-5)
+
+
+def test_host_buffer_entry_point_matches_device_path(B):
+    import torch
+
+    rng = np.random.default_rng(8)
+    D, N = 128, 200_000  # > 3 chunks of 2^16 columns: exercises the multi-stream pipeline and the tail
+    pairs = [make_case("planar", D, rng) for _ in range(4)]
+    flow = B.Composed(*[p[0] for p in pairs])
+    xh = B.from_numpy(rng.standard_normal((D, N)).astype(f32), device="cpu", pin_memory=True)
+    yh, ljh = B.with_logabsdet_jacobian(flow, xh)
+    assert not yh.is_cuda and yh.is_pinned()
+    yd, ljd = B.with_logabsdet_jacobian(flow, xh.cuda())
+    assert np.array_equal(B.to_numpy(yh), B.to_numpy(yd)) and np.array_equal(B.to_numpy(ljh), B.to_numpy(ljd))
+    td = B.transformed(B.MvNormal(D), flow)
+    tot_h, lp_h = B.logpdf_sum(td, yh)
+    tot_d, lp_d = B.logpdf_sum(td, yd)
+    assert np.array_equal(B.to_numpy(lp_h), B.to_numpy(lp_d))
+    assert abs(float(tot_h) - float(tot_d)) <= 1e-9 * abs(float(tot_d))
+
+
+def test_full_size_properties_config2(B):
+    """BASELINE config 2 at FULL size (8×Planar, D=128, N=2^20): size-independent properties + a
+    4096-column sample against the oracle."""
+    import torch
+
+    rng = np.random.default_rng(100)
+    D, N, Lc = 128, 1 << 20, 8
+    pairs = [make_case("planar", D, np.random.default_rng(100 + l)) for l in range(Lc)]
+    flow = B.Composed(*[p[0] for p in pairs])
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn((N, D), device="cuda", generator=gen).t()
+    y, lj = B.with_logabsdet_jacobian(flow, x)
+    assert y.shape == (D, N) and lj.shape == (N,) and bool(torch.isfinite(y).all()) and bool(torch.isfinite(lj).all())
+    cols = np.sort(rng.choice(N, 4096, replace=False))
+    ct = torch.as_tensor(cols, device="cuda")
+    xs = x[:, ct].cpu().numpy()
+    yo, ljo = O.chain_forward([p[1] for p in pairs], xs.astype(np.float64))
+    assert rel(y[:, ct].cpu().numpy(), yo) <= RTOL and rel(lj[ct].cpu().numpy(), ljo) <= RTOL
+    xi, lji = B.with_logabsdet_jacobian(B.inverse(flow), y)
+    assert float((xi - x).norm() / x.norm()) <= 1e-4  # inverse∘forward ≈ id
+    assert float((lji + lj).norm()) <= 1e-4 * max(float(lj.norm()), 1.0)  # ires == (x, −logjac)
+    # column independence: a permuted batch gives permuted outputs (bit-identical)
+    perm = torch.randperm(N, device="cuda")[: 1 << 16]
+    y2, lj2 = B.with_logabsdet_jacobian(flow, x[:, perm].t().contiguous().t())
+    assert torch.equal(y2, y[:, perm]) and torch.equal(lj2, lj[perm])
+    # variant cross-check: every kernel variant gives the same answer as the v0 kernel
+    B.lib().b2b_set_kernel_variant(1)
+    try:
+        y0, lj0 = B.with_logabsdet_jacobian(flow, x)
+    finally:
+        B.lib().b2b_set_kernel_variant(0)
+    assert float((y0 - y).norm() / y.norm()) <= 2e-6 and float((lj0 - lj).norm() / lj.norm()) <= 2e-6
+
+
+def test_rand_and_shapes(B):
+    import torch
+
+    rng = np.random.default_rng(3)
+    D = 64
+    flow = B.Composed(*[make_case("radial", D, rng)[0] for _ in range(3)])
+    td = B.transformed(B.MvNormal(D), flow)
+    s = B.rand(td, 1000, generator=torch.Generator(device="cuda").manual_seed(0))
+    assert s.shape == (D, 1000) and s.stride(0) == 1 and bool(torch.isfinite(s).all())
+    lp = B.logpdf(td, s)
+    assert lp.shape == (1000,) and bool(torch.isfinite(lp).all())
+    assert not B.isclosedform(B.inverse(B.PlanarLayer(4))) and B.isclosedform(flow)

@@ -1,0 +1,220 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every symbol include/b2b.h declares
+(no compute calls without a GPU), chain flattening / inversion order, constructors and error behaviour
+mirror the reference, and the world_size-2 gloo path of the sharded log-density sum."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import bijectors_jl_b200 as B
+from bijectors_jl_b200 import _lib
+from oracle import oracle_np as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+f32 = np.float32
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b2b.h")).read()
+    declared = set(re.findall(r"\b(b2b_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(B.exported_symbols()), declared ^ set(B.exported_symbols())
+    handle = ctypes.CDLL(B.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert B.lib().b2b_version() == 100
+    assert ctypes.sizeof(_lib.LayerDesc) == 80  # layout of b2b_layer_desc
+    for code in (0, -1, -2, -3, -4):
+        assert B.lib().b2b_status_string(code)
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    flow = B.PlanarLayer(np.ones(4, f32), np.zeros(4, f32), f32(0.0), device="cpu")
+    with pytest.raises(B.B2BError, match="no CPU fallback"):
+        B.with_logabsdet_jacobian(flow, torch.zeros(4))
+
+
+def kinds(descs):
+    return [(d.kind, d.inverse) for d in descs]
+
+
+def test_chain_flattening_and_inverse_order():
+    D = 4
+    p1 = B.PlanarLayer(np.ones(D, f32), np.zeros(D, f32), f32(0.0), device="cpu")
+    r1 = B.RadialLayer(f32(0.1), f32(0.2), np.zeros(D, f32), device="cpu")
+    bn = B.InvertibleBatchNorm(D, device="cpu")
+    pm = B.Permute([2, 1, 4, 3], device="cpu")
+    flow = pm @ bn @ r1 @ p1  # pm ∘ bn ∘ r1 ∘ p1: p1 applied first
+    assert kinds(flow._descs(False, D)) == [(_lib.PLANAR, 0), (_lib.RADIAL, 0), (_lib.BATCHNORM, 0), (_lib.PERMUTE, 0)]
+    assert [type(b) for b in B.flatten(flow)] == [B.PlanarLayer, B.RadialLayer, B.InvertibleBatchNorm, B.Permute]
+    # inverse(f∘g) = inverse(g)∘inverse(f): last-applied layer inverted first (InverseFunctions)
+    inv = B.inverse(flow)
+    assert kinds(inv._descs(False, D)) == [(_lib.PERMUTE, 1), (_lib.BATCHNORM, 1), (_lib.RADIAL, 1), (_lib.PLANAR, 1)]
+    assert kinds(B.inverse(inv)._descs(False, D)) == kinds(flow._descs(False, D))
+    flat = B.Composed(p1, r1, B.Composed(bn, pm))
+    assert kinds(flat._descs(False, D)) == kinds(flow._descs(False, D))
+    assert kinds(B.inverse(flat)._descs(False, D)) == kinds(inv._descs(False, D))
+    assert kinds(B.compose(pm, bn, r1, p1)._descs(False, D)) == kinds(flow._descs(False, D))
+    assert B.inverse(B.inverse(p1)) is p1 and B.inverse(p1) == B.Inverse(p1)
+    assert not B.isclosedform(inv) and B.isclosedform(B.inverse(r1))
+    with pytest.raises(ValueError, match="DimensionMismatch"):
+        flow._descs(False, D + 1)
+    too_long = B.Composed(*([p1] * 25))
+    with pytest.raises(B.B2BError):
+        from bijectors_jl_b200.interface import _desc_array
+
+        _desc_array(too_long._descs(False, D))
+
+
+def test_layout_helpers():
+    a = np.arange(12, dtype=f32).reshape(3, 4)
+    t = B.from_numpy(a, device="cpu")
+    assert t.shape == (3, 4) and t.stride() == (1, 3)
+    assert np.array_equal(B.to_numpy(t), a)
+    from bijectors_jl_b200.interface import _batch_view
+
+    assert _batch_view(t) == (3, 4, 3)
+    assert _batch_view(torch.zeros(5)) == (5, 1, 5)
+    with pytest.raises(ValueError, match="column-major"):
+        _batch_view(torch.zeros(3, 4))
+    with pytest.raises(TypeError):
+        _batch_view(torch.zeros(3, dtype=torch.float64))
+    e = B.colmajor_empty(7, 5, device="cpu")
+    assert e.shape == (7, 5) and e.stride() == (1, 7)
+
+
+def test_constructors_and_error_behaviour(golden):
+    # PartitionMask (test/bijectors/coupling.jl:4-16) and default split (coupling.jl:183-186)
+    m = B.PartitionMask(3, [1], [2])
+    assert m == B.PartitionMask(3, [1], [2], [3])
+    m6 = B.PartitionMask(6, range(1, 4))
+    assert (m6.indices_1, m6.indices_2, m6.indices_3) == ([1, 2, 3], [4, 5, 6], [])
+    with pytest.raises(ValueError):
+        B.PartitionMask(3, [1], [1])
+    # Coupling: arbitrary θ cannot run on the device path (no CPU fallback)
+    with pytest.raises(B.B2BError):
+        B.Coupling(lambda x2: None, m)
+    cond = B.AffineConditioner(np.zeros((2, 1), f32), device="cpu")
+    cl = B.Coupling(cond, m, device="cpu")
+    d = cl._descs(False, 3)[0]
+    assert (d.kind, d.n0, d.n1) == (_lib.COUPLING_AFFINE, 1, 1) and B.coupling(cl) is cond
+    with pytest.raises(ValueError):
+        B.Coupling(B.AffineConditioner(np.zeros((4, 1), f32), device="cpu"), m)
+    # Permute spellings agree; invalid ones raise (test/bijectors/permute.jl:9-21)
+    g = golden["permute_2"]
+    bs = [B.Permute(np.array(g["matrix"]), device="cpu"), B.Permute(g["indices"], device="cpu"),
+          B.Permute(2, *[tuple(p) for p in g["pairs"]], device="cpu"),
+          B.Permute(2, *[(p[0], p[1]) for p in g["vector_pairs"]], device="cpu")]
+    assert all(b == bs[0] for b in bs) and np.array_equal(bs[0].A, np.array(g["matrix"]))
+    assert np.array_equal(B.Permute([2, 3, 1], device="cpu").A, O.permute_matrix_from_indices([2, 3, 1]))
+    for case in golden["permute_invalid"]["cases"]:
+        with pytest.raises(ValueError, match="ArgumentError"):
+            if "pairs" in case:
+                B.Permute(case["n"], *[tuple(p) for p in case["pairs"]], device="cpu")
+            else:
+                B.Permute(case["n"], *[(p[0], p[1]) for p in case["vector_pairs"]], device="cpu")
+    # InvertibleBatchNorm channel mismatch: reference error text (normalise.jl:43-45); training mode unsupported
+    bn = B.InvertibleBatchNorm(2, device="cpu")
+    assert bn.eps == pytest.approx(1e-5) and bn.mtm == pytest.approx(0.1)
+    assert set(bn.params()) == {"b", "logs", "m", "v"}
+    with pytest.raises(RuntimeError, match="InvertibleBatchNorm expected 2 channels, got 10"):
+        bn._descs(False, 10)
+    with pytest.raises(B.B2BError):
+        B.InvertibleBatchNorm(2, device="cpu", training=True)._descs(False, 2)
+    # Stacked: ranges bookkeeping + length mismatch error text (stacked.jl:158-160)
+    sb = B.Stacked([B.elementwise("exp"), B.elementwise("log"), B.Shift(5.0)], device="cpu")
+    assert sb.ranges_in == [(1, 1), (2, 2), (3, 3)] and sb.length_in == 3
+    with pytest.raises(RuntimeError, match=r"input length mismatch \(3 != 4\)"):
+        sb._descs(False, 4)
+    with pytest.raises(B.B2BError):
+        B.Stacked([B.PlanarLayer(2, device="cpu")], [(1, 2)], device="cpu")
+    assert B.inverse(B.elementwise("exp")) == B.elementwise("log") and B.inverse(B.Shift(2.0)) == B.Shift(-2.0)
+    # RQS: the normalising constructor agrees with the oracle restatement; asserts fire
+    rng = np.random.default_rng(0)
+    rw, rh, rd = rng.standard_normal((5, 8)).astype(f32), rng.standard_normal((5, 8)).astype(f32), rng.standard_normal((5, 7)).astype(f32)
+    lay = B.RationalQuadraticSpline(rw, rh, rd, 3.0, device="cpu")
+    W, H, Dv = lay.knots()
+    Wo, Ho, Do = O.rqs_params(rw.astype(np.float64), rh.astype(np.float64), rd.astype(np.float64), 3.0)
+    assert np.allclose(W, Wo, atol=2e-6) and np.allclose(H, Ho, atol=2e-6) and np.allclose(Dv, Do, rtol=1e-6)
+    assert lay.K1 == 9 and lay.widths.shape == (9, 5)  # device table is knot-major
+    with pytest.raises(AssertionError, match="positive"):
+        B.RationalQuadraticSpline(W, H, -Dv, device="cpu")
+    uv = B.RationalQuadraticSpline(rw[0], rh[0], rd[0], 2, device="cpu")
+    assert uv.D == 1 and uv.K1 == 9
+
+
+def test_config1_elementwise_exp_plumbing(golden):
+    """BASELINE configs[0]: Exp bijector with_logabsdet_jacobian on a Float64 vector of length 1024 --
+    CPU plumbing, runs without a GPU (src/interface.jl:21-31, exp_log.jl:6)."""
+    g = golden["elementwise_exp_doctest"]
+    y, lj = B.with_logabsdet_jacobian(B.elementwise("exp"), torch.tensor(g["x"], dtype=torch.float64))
+    assert y.tolist() == g["y"] and float(lj) == g["logjac"]
+    x = np.random.default_rng(1).standard_normal(1024)
+    y, lj = B.with_logabsdet_jacobian(B.elementwise(math.exp), torch.from_numpy(x))
+    yo, ljo = O.elementwise_exp(x)
+    assert y.dtype == torch.float64 and np.allclose(y.numpy(), yo, rtol=1e-15) and float(lj) == pytest.approx(ljo, rel=1e-12)
+    xb, ljb = B.with_logabsdet_jacobian(B.inverse(B.elementwise("exp")), y)
+    assert np.allclose(xb.numpy(), x, rtol=1e-12, atol=1e-14) and float(ljb) == pytest.approx(-ljo, rel=1e-10)
+    assert float(B.logabsdetjac(B.elementwise("exp"), torch.from_numpy(x))) == pytest.approx(x.sum(), rel=1e-12)
+
+
+def test_shard_columns():
+    from bijectors_jl_b200.distributed import shard_columns
+
+    for N, W in [(1 << 20, 8), (1000, 3), (7, 8), (0, 2)]:
+        blocks = [shard_columns(N, r, W) for r in range(W)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == N
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(W - 1))
+        sizes = [hi - lo for lo, hi in blocks]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    from bijectors_jl_b200.distributed import Communicator, shard_columns
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)
+        D, N = 6, 1001
+        w, u, b = rng.standard_normal(D), rng.standard_normal(D), rng.standard_normal(1)
+        y = rng.standard_normal((D, N))
+        layers = [O.Layer("planar", dict(w=w, u=u, b=b))]
+        lo, hi = shard_columns(N, rank, world)
+        # each rank evaluates ITS column shard (with the oracle here: there is no GPU in this test) ...
+        local = torch.tensor(O.transformed_logpdf(layers, None, None, y[:, lo:hi]).sum(), dtype=torch.float64)
+        comm = Communicator()
+        assert comm.handle is None and comm.world == world
+        total = comm.allreduce_sum_(local.reshape(1))  # ... and ONE scalar is summed across ranks
+        full = O.transformed_logpdf(layers, None, None, y).sum()
+        assert abs(float(total) - full) <= 1e-9 * abs(full)
+        if rank == 0:
+            out.put(float(total))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_logdensity_sum_gloo_world2():
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert math.isfinite(out.get(timeout=5))
