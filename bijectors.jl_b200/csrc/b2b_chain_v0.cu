@@ -217,33 +217,19 @@ __global__ void __launch_bounds__(256) chain_v0_kernel(const __grid_constant__ B
           }
         } break;
         case B2B_BATCHNORM: {
-          // normalise.jl:61-67 (fwd), :76-85 (inverse); eval mode
-          const float4* m4 = reinterpret_cast<const float4*>(sp);
-          const float4* A4 = reinterpret_cast<const float4*>(sp + Dp);
-          const float4* b4 = reinterpret_cast<const float4*>(sp + 2 * Dp);
-          const float4* iA4 = reinterpret_cast<const float4*>(sp + 3 * Dp);
+          // normalise.jl:61-67 (fwd), :76-85 (inverse); eval mode, constants folded at staging time
+          const float4* A4 = reinterpret_cast<const float4*>(sp + (d.inverse ? 2 * Dp : 0));
+          const float4* C4 = reinterpret_cast<const float4*>(sp + (d.inverse ? 3 * Dp : Dp));
           const float ljc = sp[4 * Dp];
 #pragma unroll
           for (int v = 0; v < V; ++v) {
-            const float4 m = m4[v * G + j], b = b4[v * G + j];
-            if (!d.inverse) {
-              const float4 A = A4[v * G + j];
+            const float4 A = A4[v * G + j], K = C4[v * G + j];
 #pragma unroll
-              for (int c = 0; c < C; ++c) {
-                xr[c][v].x = fmaf(xr[c][v].x - m.x, A.x, b.x);
-                xr[c][v].y = fmaf(xr[c][v].y - m.y, A.y, b.y);
-                xr[c][v].z = fmaf(xr[c][v].z - m.z, A.z, b.z);
-                xr[c][v].w = fmaf(xr[c][v].w - m.w, A.w, b.w);
-              }
-            } else {
-              const float4 iA = iA4[v * G + j];
-#pragma unroll
-              for (int c = 0; c < C; ++c) {
-                xr[c][v].x = fmaf(xr[c][v].x - b.x, iA.x, m.x);
-                xr[c][v].y = fmaf(xr[c][v].y - b.y, iA.y, m.y);
-                xr[c][v].z = fmaf(xr[c][v].z - b.z, iA.z, m.z);
-                xr[c][v].w = fmaf(xr[c][v].w - b.w, iA.w, m.w);
-              }
+            for (int c = 0; c < C; ++c) {
+              xr[c][v].x = fmaf(xr[c][v].x, A.x, K.x);
+              xr[c][v].y = fmaf(xr[c][v].y, A.y, K.y);
+              xr[c][v].z = fmaf(xr[c][v].z, A.z, K.z);
+              xr[c][v].w = fmaf(xr[c][v].w, A.w, K.w);
             }
           }
           lj += d.inverse ? -ljc : ljc;

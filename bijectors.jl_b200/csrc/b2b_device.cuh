@@ -47,13 +47,15 @@ __device__ __forceinline__ float find_alpha(float t, float c, float b) {
     if (f == 0.0f) break;
     if (f < 0.0f) lo = x; else hi = x;
     float xn = x - f / fmaf(c, s2, 1.0f);
+    if (fabsf(xn - x) <= 1.2e-7f * fabsf(x) + 1e-30f) {  // Newton step below one ulp: converged
+      if (xn >= lo && xn <= hi) x = xn;
+      break;
+    }
     if (!(xn > lo && xn < hi)) {
       xn = 0.5f * (lo + hi);
       if (!(xn > lo && xn < hi)) break;  // bracket is adjacent floats
     }
-    const bool done = fabsf(xn - x) <= 6e-8f * fabsf(xn);
     x = xn;
-    if (done) break;
   }
   return x;
 }
@@ -111,7 +113,7 @@ __device__ __forceinline__ void rqs_element(const float* __restrict__ W, const f
 // Layout of the staged block of one layer (floats, Dp = padded depth, rows >= D are zero):
 //   PLANAR    : w[Dp] | û[Dp] | {c = wᵀû, b, -, -}                      (get_u_hat, planar_layer.jl:65-70)
 //   RADIAL    : z0[Dp] | {α, β̂, α+β̂, -}                                 (radial_layer.jl:44-45,91-92)
-//   BATCHNORM : m[Dp] | A[Dp] | b[Dp] | 1/A[Dp] | {Σ(logs − log(v+eps)/2)}  (normalise.jl:61-67)
+//   BATCHNORM : A[Dp] | C[Dp] | iA[Dp] | iC[Dp] | {Σ(logs − log(v+eps)/2)}   y = A·x + C, x = iA·y + iC
 //   RQS       : W[K1][Dp] | H[K1][Dp] | Dv[K1][Dp]
 //   PERMUTE   : src_of_dst[Dp] (int)
 //   STACKED_EW: code[Dp] (int) | a[Dp]
@@ -157,24 +159,25 @@ __device__ inline void stage_layer(const b2b_layer_desc& d, float* sm, int D, in
       }
     } break;
     case B2B_BATCHNORM: {
+      // y = s·(x − m)/sqrt(v+eps) + b = A·x + C  (normalise.jl:66);  x = (y − b)/s·sqrt(v+eps) + m = iA·y + iC (:84)
       float lj = 0.f;
       for (int i = lane; i < Dp; i += 32) {
         const bool in = i < D;
-        float A = 0.f, iA = 0.f, m = 0.f, b = 0.f;
+        float A = 0.f, iA = 0.f, Cc = 0.f, iC = 0.f;
         if (in) {
           const float ve = d.p3[i] + d.f0;
           const float sd = sqrtf(ve);
           const float sc = expf(d.p1[i]);
           A = sc / sd;
           iA = sd / sc;
-          m = d.p2[i];
-          b = d.p0[i];
+          Cc = fmaf(-d.p2[i], A, d.p0[i]);
+          iC = fmaf(-d.p0[i], iA, d.p2[i]);
           lj += d.p1[i] - logf(ve) * 0.5f;  // normalise.jl:67
         }
-        sm[i] = m;
-        sm[Dp + i] = A;
-        sm[2 * Dp + i] = b;
-        sm[3 * Dp + i] = iA;
+        sm[i] = A;
+        sm[Dp + i] = Cc;
+        sm[2 * Dp + i] = iA;
+        sm[3 * Dp + i] = iC;
       }
       lj = warp_sum(lj);
       if (lane == 0) sm[4 * Dp] = lj;

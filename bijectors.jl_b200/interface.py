@@ -68,7 +68,7 @@ def _batch_view(x: torch.Tensor) -> Tuple[int, int, int]:
     D, N = x.shape
     if N == 1:
         return D, 1, D
-    if x.stride(0) != 1 or x.stride(1) < D:
+    if (D > 1 and x.stride(0) != 1) or x.stride(1) < D:  # the stride of a size-1 dimension is arbitrary
         raise ValueError(
             "batch must be Julia-layout column-major (shape (D, N), strides (1, ld>=D)); "
             "use colmajor_empty / from_numpy, or `x.t().contiguous().t()`"
