@@ -62,10 +62,13 @@ _SIGS = {
     "b2b_radial_inv_f32": (c_int, [_F32P] * 6 + [c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b2b_rqs_fwd_f32": (c_int, [_F32P] * 6 + [c_int32, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b2b_rqs_inv_f32": (c_int, [_F32P] * 6 + [c_int32, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
-    "b2b_coupling_affine_fwd_f32": (c_int, [_F32P] * 3 + [c_void_p, c_int32, c_void_p, c_int32, _F32P, _F32P,
-                                            c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
-    "b2b_coupling_affine_inv_f32": (c_int, [_F32P] * 3 + [c_void_p, c_int32, c_void_p, c_int32, _F32P, _F32P,
-                                            c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "b2b_coupling_affine_fwd_f32": (c_int, [_F32P] * 3 + [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, _F32P,
+                                            _F32P, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t,
+                                            c_void_p]),
+    "b2b_coupling_affine_inv_f32": (c_int, [_F32P] * 3 + [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, _F32P,
+                                            _F32P, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t,
+                                            c_void_p]),
+    "b2b_coupling_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "b2b_batchnorm_eval_fwd_f32": (c_int, [_F32P] * 7 + [c_float, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b2b_batchnorm_eval_inv_f32": (c_int, [_F32P] * 7 + [c_float, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b2b_permute_rows_f32": (c_int, [_F32P] * 3 + [c_void_p, c_int, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),

@@ -11,7 +11,8 @@ int b2b_chain_grid_size_v0(const B2BChainParams& p);
 int b2b_chain_grid_size_v1(const B2BChainParams& p);
 
 static thread_local int g_last_launches = 0;
-static int g_variant = 0;  // 0 auto, 1 v0, 2 v1
+static int g_variant = 0;           // fused chain kernel: 0 auto, 1 v0, 2 v1
+static int g_coupling_variant = 0;  // coupling: 0 auto (tensor cores when possible), 1 force the fp32 CUDA-core kernel
 
 extern "C" int b2b_version(void) { return B2B_VERSION; }
 
@@ -24,6 +25,10 @@ extern "C" const char* b2b_status_string(int status) {
     case B2B_ENONCCL: return "b2b: libnccl.so.2 could not be loaded";
     default: break;
   }
+  if (status >= 100000) return "b2b: NCCL error (status - 100000 is the ncclResult_t)";
+  switch (status) {
+    default: break;
+  }
   if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
   return "b2b: unknown status";
 }
@@ -31,8 +36,11 @@ extern "C" const char* b2b_status_string(int status) {
 extern "C" int b2b_last_launch_count(void) { return g_last_launches; }
 
 extern "C" int b2b_set_kernel_variant(int variant) {
-  if (variant < 0 || variant > 2) return B2B_EINVAL;
-  g_variant = variant;
+  // low decimal digit: fused chain kernel variant; tens digit: coupling variant (10 = force fp32 CUDA cores)
+  const int chain = variant % 10, cpl = variant / 10;
+  if (variant < 0 || chain > 2 || cpl > 1) return B2B_EINVAL;
+  g_variant = chain;
+  g_coupling_variant = cpl;
   return B2B_OK;
 }
 
@@ -54,7 +62,8 @@ static int validate_layer(const b2b_layer_desc& d, int D, bool last) {
       if (d.n0 > 64) return B2B_EUNSUPPORTED;
       break;
     case B2B_COUPLING_AFFINE:
-      if (!d.p0 || !d.i0 || !d.i1 || d.n0 < 1 || d.n1 < 1 || d.n0 + d.n1 > D) return B2B_EINVAL;
+      if (!d.p0 || d.n0 < 1 || d.n1 < 1 || d.n0 + d.n1 > D) return B2B_EINVAL;
+      if ((!d.i0 && d.n2 < 0) || (!d.i1 && d.n3 < 0)) return B2B_EINVAL;
       break;
     case B2B_BATCHNORM:
       if (!d.p0 || !d.p1 || !d.p2 || !d.p3) return B2B_EINVAL;
@@ -92,13 +101,32 @@ static int fused_grid(const B2BChainParams& p) {
   return b2b_chain_grid_size_v0(p);
 }
 
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// workspace layout: [tensor-core W image (shared by all coupling layers; they run one after another)]
+//                   [D x N scratch when y == NULL and the chain has several segments] [batch-sum partials]
+static size_t chain_tc_bytes(const b2b_layer_desc* layers, int32_t L) {
+  size_t tc = 0;
+  for (int l = 0; l < L; ++l)
+    if (layers[l].kind == B2B_COUPLING_AFFINE && layers[l].n2 >= 0 && layers[l].n3 >= 0) {
+      const size_t b = b2b_coupling_tc_workspace_bytes(layers[l].n0, layers[l].n1);
+      if (b > tc) tc = b;
+    }
+  return tc ? align_up(tc, 1024) + 1024 : 0;
+}
+
+extern "C" size_t b2b_coupling_workspace_bytes(int32_t n1, int32_t n2) {
+  const size_t b = b2b_coupling_tc_workspace_bytes(n1, n2);
+  return b ? align_up(b, 1024) + 1024 : 0;
+}
+
 extern "C" size_t b2b_chain_workspace_bytes(const b2b_layer_desc* layers, int32_t L, int32_t D, int64_t N,
                                             int want_y, int want_sum) {
-  size_t bytes = 0;
+  size_t bytes = chain_tc_bytes(layers, L);
   bool has_coupling = false;
   for (int l = 0; l < L; ++l) has_coupling |= layers[l].kind == B2B_COUPLING_AFFINE;
   // a D x N scratch matrix is needed only when y == NULL but the chain has more than one segment
-  if (!want_y && has_coupling && L > 1) bytes += (size_t)D * (size_t)N * sizeof(float);
+  if (!want_y && has_coupling && L > 1) bytes += align_up((size_t)D * (size_t)N * sizeof(float), 1024);
   if (want_sum) bytes += 4096 * sizeof(double);
   return bytes;
 }
@@ -143,9 +171,21 @@ extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const 
   // workspace carve-up
   char* ws = static_cast<char*>(workspace);
   size_t ws_left = workspace ? workspace_bytes : 0;
+  void* tc_ws = nullptr;
+  size_t tc_bytes = 0;
+  {
+    const size_t want = chain_tc_bytes(layers, L);
+    if (want && ws_left >= want) {
+      const size_t pad = (1024 - (reinterpret_cast<uintptr_t>(ws) & 1023)) & 1023;
+      tc_ws = ws + pad;
+      tc_bytes = want - pad;
+      ws += want;
+      ws_left -= want;
+    }
+  }
   float* scratch = nullptr;
   if (!y && segs.size() > 1) {
-    const size_t need = (size_t)D * (size_t)N * sizeof(float);
+    const size_t need = align_up((size_t)D * (size_t)N * sizeof(float), 1024);
     if (ws_left < need) return B2B_EWORKSPACE;
     scratch = reinterpret_cast<float*>(ws);
     ws += need;
@@ -153,6 +193,7 @@ extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const 
   }
   double* partials = nullptr;
   if (sum_out) {
+    if (segs.back().coupling) return B2B_EUNSUPPORTED;  // batch sum needs a fusable last segment
     if (ws_left < 4096 * sizeof(double)) return B2B_EWORKSPACE;
     partials = reinterpret_cast<double*>(ws);
   }
@@ -169,10 +210,18 @@ extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const 
     if (segs[s].coupling) {
       float* cdst = dst;
       // logjac-only call with a trailing coupling layer still needs no store
-      rc = b2b_launch_coupling_affine(layers[segs[s].begin], cur, cdst, logjac, D, N, cur_ld, dst_ld,
-                                      lj_started ? 1 : 0, stream);
+      rc = B2B_EUNSUPPORTED;
+      if (tc_ws && g_coupling_variant != 1) {
+        rc = b2b_launch_coupling_affine_tc(layers[segs[s].begin], cur, cdst, logjac, D, N, cur_ld, dst_ld,
+                                           lj_started ? 1 : 0, tc_ws, tc_bytes, stream);
+        if (rc == B2B_OK) g_last_launches += 2;  // W preparation + main kernel
+      }
+      if (rc == B2B_EUNSUPPORTED) {
+        rc = b2b_launch_coupling_affine(layers[segs[s].begin], cur, cdst, logjac, D, N, cur_ld, dst_ld,
+                                        lj_started ? 1 : 0, stream);
+        if (rc == B2B_OK) ++g_last_launches;
+      }
       if (rc != B2B_OK) return rc;
-      ++g_last_launches;
     } else {
       B2BChainParams p;
       memset(&p, 0, sizeof(p));
@@ -206,10 +255,6 @@ extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const 
       cur_ld = dst_ld;
     }
     lj_started = true;
-  }
-  if (sum_out && segs.back().coupling) {
-    // batch sum over a chain that ends in a coupling layer: one extra pass over logjac
-    return B2B_EUNSUPPORTED;
   }
   return B2B_OK;
 }
@@ -269,9 +314,10 @@ B2B_RQS_IMPL(b2b_rqs_fwd_f32, 0)
 B2B_RQS_IMPL(b2b_rqs_inv_f32, 1)
 
 #define B2B_COUPLING_IMPL(NAME, INV)                                                                     \
-  extern "C" int NAME(const float* x, float* y, float* logjac, const int32_t* idx1, int32_t n1,          \
-                      const int32_t* idx2, int32_t n2, const float* W, const float* c, int32_t D,        \
-                      int64_t N, int64_t ldx, int64_t ldy, int acc, void* stream) {                      \
+  extern "C" int NAME(const float* x, float* y, float* logjac, const int32_t* idx1, int32_t n1, int32_t row1, \
+                      const int32_t* idx2, int32_t n2, int32_t row2, const float* W, const float* c,        \
+                      int32_t D, int64_t N, int64_t ldx, int64_t ldy, int acc, void* workspace,             \
+                      size_t workspace_bytes, void* stream) {                                               \
     b2b_layer_desc d = mk(B2B_COUPLING_AFFINE, INV);                                                     \
     d.p0 = W;                                                                                            \
     d.p1 = c;                                                                                            \
@@ -279,7 +325,10 @@ B2B_RQS_IMPL(b2b_rqs_inv_f32, 1)
     d.i1 = idx2;                                                                                         \
     d.n0 = n1;                                                                                           \
     d.n1 = n2;                                                                                           \
-    return run1(d, x, y, logjac, D, N, ldx, ldy, acc, stream);                                           \
+    d.n2 = row1;                                                                                         \
+    d.n3 = row2;                                                                                         \
+    return b2b_chain_run_f32(&d, 1, x, y, logjac, nullptr, D, N, ldx, ldy, acc, workspace, workspace_bytes, \
+                             stream);                                                                    \
   }
 B2B_COUPLING_IMPL(b2b_coupling_affine_fwd_f32, 0)
 B2B_COUPLING_IMPL(b2b_coupling_affine_inv_f32, 1)

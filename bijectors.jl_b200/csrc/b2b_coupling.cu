@@ -26,14 +26,14 @@ template <bool INV>
 __global__ void __launch_bounds__(CP_THREADS) coupling_affine_kernel(
     const float* __restrict__ x, float* __restrict__ y, float* __restrict__ logjac,
     const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2, const float* __restrict__ W,
-    const float* __restrict__ cvec, int D, int n1, int n2, long long N, long long ldx, long long ldy,
-    int accumulate) {
+    const float* __restrict__ cvec, int D, int n1, int n2, int row1, int row2, long long N, long long ldx,
+    long long ldy, int accumulate) {
   extern __shared__ float smem[];
   float* X = smem;                                    // [D][CP_LD]
   float* red = X + (size_t)D * CP_LD;                 // [8][CP_TC]
   int* sidx2 = reinterpret_cast<int*>(red + 8 * CP_TC);  // [n2]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = threadIdx.x; k < n2; k += CP_THREADS) sidx2[k] = idx2[k];
+  for (int k = threadIdx.x; k < n2; k += CP_THREADS) sidx2[k] = idx2 ? idx2[k] : row2 + k;
   const bool wvec = ((n1 & 3) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const long long tiles = (N + CP_TC - 1) / CP_TC;
   const int ldw = 2 * n1;
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(CP_THREADS) coupling_affine_kernel(
         const int j = jb + q;
         if (j < n1) {
           const float cs = cvec ? __ldg(cvec + j) : 0.f, ct = cvec ? __ldg(cvec + n1 + j) : 0.f;
-          const int r1 = __ldg(idx1 + j);
+          const int r1 = idx1 ? __ldg(idx1 + j) : row1 + j;
           const float s_a = sA[q] + cs, s_b = sB[q] + cs, t_a = tA[q] + ct, t_b = tB[q] + ct;
           const float xa = X[r1 * CP_LD + cA], xb = X[r1 * CP_LD + cB];
           if (!INV) {
@@ -142,7 +142,8 @@ int b2b_launch_coupling_affine(const b2b_layer_desc& d, const float* x, float* y
                                cudaStream_t stream) {
   using namespace b2b;
   const int n1 = d.n0, n2 = d.n1;
-  if (n1 < 1 || n2 < 1 || n1 + n2 > D || !d.p0 || !d.i0 || !d.i1) return B2B_EINVAL;
+  if (n1 < 1 || n2 < 1 || n1 + n2 > D || !d.p0) return B2B_EINVAL;
+  if ((!d.i0 && d.n2 < 0) || (!d.i1 && d.n3 < 0)) return B2B_EINVAL;
   const size_t smem = ((size_t)D * CP_LD + 8 * CP_TC) * sizeof(float) + (size_t)n2 * sizeof(int);
   if (smem > 200 * 1024) return B2B_EUNSUPPORTED;
   auto kern = d.inverse ? coupling_affine_kernel<true> : coupling_affine_kernel<false>;
@@ -158,7 +159,7 @@ int b2b_launch_coupling_affine(const b2b_layer_desc& d, const float* x, float* y
   long long grid = (long long)sms * per_sm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
-  kern<<<(int)grid, CP_THREADS, smem, stream>>>(x, y, logjac, d.i0, d.i1, d.p0, d.p1, D, n1, n2, N, ldx, ldy,
-                                                accumulate);
+  kern<<<(int)grid, CP_THREADS, smem, stream>>>(x, y, logjac, d.i0, d.i1, d.p0, d.p1, D, n1, n2, d.n2, d.n3, N, ldx,
+                                                ldy, accumulate);
   return (int)cudaGetLastError();
 }

@@ -1,0 +1,446 @@
+// Affine coupling layer on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Reference: Coupling (src/bijectors/coupling.jl:206-228) with θ(x₂) = Shift(t) ∘ Scale(exp.(s)),
+// [s; t] = W·x₂ + c (scale.jl:13,31; shift.jl:14,21) mapped over the columns of the batch; see
+// b2b_coupling.cu for the exact-fp32 SIMT version this kernel is cross-checked against.
+//
+// The conditioner is a GEMM  [s;t](2·n1 x T) = W(2·n1 x n2) · X₂(n2 x T)  per tile of T = 64 columns:
+// 65.5 kFLOP per 2 KB sample at D = 256 (AI ≈ 32 FLOP/B), i.e. compute-bound on the fp32 CUDA cores at about
+// a third of the HBM roofline, hence tensor cores.  Plain TF32/BF16 cannot hold the 1e-5 parity bar, so both
+// operands are split into an fp16 "hi" and an fp16 "lo" half (22 mantissa bits together) after an EXACT
+// power-of-two rescale (W by one global 2^k, every x₂ column by its own 2^k, undone in the epilogue), and
+// three products hi·hi + hi·lo + lo·hi are accumulated in fp32 in TMEM (the dropped lo·lo term is 2^-22).
+//
+// Warp roles of the persistent CTA (288 threads, one CTA per SM):
+//   warps 0-3  epilogue : tcgen05.ld s/t rows out of TMEM (thread = row j), add c, read x₁ from global,
+//                         y₁ = exp(s)·x₁ + t (or the inverse) and store -- 512 B contiguous per column
+//   warps 4-7  producers: coalesced float4 loads of the x₂ rows, per-column scale, hi/lo split, store into the
+//                         K-major 128B-swizzled UMMA operand layout, logjac = wsum·x₂ + Σc in fp32
+//                         (Σ_j s_j = (Σ_j W_j)·x₂ + Σ_j c_j), pass-through rows when y != x
+//   warp  8    MMA      : one elected lane issues 48 tcgen05.mma (M128 N64 K16, kind::f16) per tile
+// W (both halves, both M tiles) stays resident in shared memory for the lifetime of the CTA (128 KB at
+// n2 = 128); x₂ operand stages and TMEM accumulator stages are double buffered and handed over with
+// mbarriers (tcgen05.commit on the MMA side).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "b2b_internal.h"
+
+namespace b2b {
+
+constexpr int TC_T = 64;              // batch columns per tile == UMMA N
+constexpr int TC_STAGES = 2;          // x₂ operand stages in shared memory
+constexpr int TC_ACC = 2;             // accumulator stages in TMEM
+constexpr int TC_SCALE_SLOTS = 4;     // per-column scale slots (producer may run 4 tiles ahead of the epilogue)
+constexpr int TC_ABLK = 128 * 128;    // one [128 rows x 64 k] fp16 block, 128B-swizzled, 16 KB
+constexpr int TC_BBLK = TC_T * 128;   // one [64 rows x 64 k] fp16 block, 8 KB
+constexpr int TC_THREADS = 288;
+constexpr int TC_TMEM_COLS = 256;     // 2 stages x (s: 64 + t: 64) fp32 columns
+
+struct TcParams {
+  const float* x;
+  float* y;
+  float* logjac;
+  const unsigned char* wimg;  // prepared fp16 hi/lo operand image of W (see coupling_prep_kernel)
+  const float* wsum;          // [n2]  Σ_j W[j, k] over the s rows
+  const float* meta;          // {1/scaleW, Σ_j c_j}
+  const float* cvec;          // [2 n1] or NULL
+  long long N, ldx, ldy, tiles;
+  int D, n1, n2, nkb, row1, row2, accumulate, inverse;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "TC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra TC_DONE;\n"
+      "bra TC_WAIT;\n"
+      "TC_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): K-major operand, 128-byte
+// swizzle, 8-row groups 1024 B apart: start>>4 | LBO(=1, unused)<<16 | SBO(1024>>4)<<32 | version 1<<46 | SW128(2)<<61
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// UMMA instruction descriptor (InstrDescriptor): D=f32 (1<<4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t TC_IDESC = (1u << 4) | ((uint32_t)(TC_T >> 3) << 17) | ((128u >> 4) << 24);
+
+// byte offset of the 8-byte group holding k' .. k'+3 of row `row` inside one 128B-swizzled [rows x 64] fp16 block
+__device__ __forceinline__ int sw128_off(int row, int kprime) {
+  return (row >> 3) * 1024 + (row & 7) * 128 + ((((kprime >> 3) ^ (row & 7)) & 7) << 4) + (kprime & 7) * 2;
+}
+
+// ---- W preparation (once per call, ~µs): global power-of-two scale, hi/lo fp16 split in operand layout --------
+// image blocks (16 KB each) are ordered [mt (0: s rows, 1: t rows)][part (0: hi, 1: lo)][kb]
+__global__ void __launch_bounds__(1024) coupling_prep_kernel(const float* __restrict__ W, const float* __restrict__ c,
+                                                             int n1, int n2, unsigned char* __restrict__ wimg,
+                                                             float* __restrict__ wsum, float* __restrict__ meta) {
+  __shared__ float red[32];
+  __shared__ float s_scale;
+  const int tid = threadIdx.x;
+  const int total = 2 * n1 * n2;
+  float m = 0.f;
+  for (int i = tid; i < total; i += 1024) m = fmaxf(m, fabsf(W[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) red[tid >> 5] = m;
+  __syncthreads();
+  if (tid < 32) {
+    float v = red[tid];
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (tid == 0) {
+      int e = (int)((__float_as_uint(v) >> 23) & 0xffu) - 127;  // floor(log2(max|W|))
+      e = max(-100, min(100, e));
+      s_scale = __uint_as_float((uint32_t)(127 + 9 - e) << 23);  // max|W|·scale in [2^9, 2^10)
+      meta[0] = __uint_as_float((uint32_t)(127 - 9 + e) << 23);  // 1/scale (exact)
+      float cs = 0.f;
+      if (c)
+        for (int j = 0; j < n1; ++j) cs += c[j];
+      meta[1] = cs;
+    }
+  }
+  __syncthreads();
+  const float scale = s_scale;
+  const int nkb = n2 / 64;
+  // one thread per (mt, m, group of 4 k)
+  const int groups = 2 * 128 * (n2 / 4);
+  for (int g = tid; g < groups; g += 1024) {
+    const int k4 = g % (n2 / 4), m_ = (g / (n2 / 4)) % 128, mt = g / ((n2 / 4) * 128);
+    __half hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 4 * k4 + e;
+      const float w = m_ < n1 ? W[(size_t)k * (2 * n1) + mt * n1 + m_] * scale : 0.f;
+      hi[e] = __float2half_rn(w);
+      lo[e] = __float2half_rn(w - __half2float(hi[e]));
+    }
+    const int kb = (4 * k4) / 64, kp = (4 * k4) % 64;
+    const int off = sw128_off(m_, kp);
+    *reinterpret_cast<uint2*>(wimg + (size_t)((mt * 2 + 0) * nkb + kb) * TC_ABLK + off) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(wimg + (size_t)((mt * 2 + 1) * nkb + kb) * TC_ABLK + off) = *reinterpret_cast<uint2*>(lo);
+  }
+  for (int k = tid; k < n2; k += 1024) {
+    float s = 0.f;
+    for (int j = 0; j < n1; ++j) s += W[(size_t)k * (2 * n1) + j];
+    wsum[k] = s;
+  }
+}
+
+// ---- main kernel -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = smem_dyn + ((1024u - (sm_u32(smem_dyn) & 1023u)) & 1023u);
+  const int nkb = P.nkb;
+  const int a_bytes = 4 * nkb * TC_ABLK;            // W image: 2 M tiles x {hi, lo} x nkb blocks
+  const int b_stage = 2 * nkb * TC_BBLK;            // x₂ stage: {hi, lo} x nkb blocks
+  unsigned char* sA = base;
+  unsigned char* sB = base + a_bytes;
+  float* colscale = reinterpret_cast<float*>(sB + TC_STAGES * b_stage);   // [TC_SCALE_SLOTS][TC_T]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(colscale + TC_SCALE_SLOTS * TC_T);
+  // bars: [0..1] b_full, [2..3] b_empty, [4..5] acc_full, [6..7] acc_empty, [8] w_ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      bar_init(sm_u32(&bars[0 + s]), 4);  // 4 producer warps
+      bar_init(sm_u32(&bars[2 + s]), 1);  // tcgen05.commit
+    }
+    for (int a = 0; a < TC_ACC; ++a) {
+      bar_init(sm_u32(&bars[4 + a]), 1);  // tcgen05.commit
+      bar_init(sm_u32(&bars[6 + a]), 4);  // 4 epilogue warps
+    }
+    bar_init(sm_u32(&bars[8]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_u32(tmem_slot)),
+                 "r"((uint32_t)TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long my_tiles = (P.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (warp == 8) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t wbar = sm_u32(&bars[8]);
+      bar_expect_tx(wbar, (uint32_t)a_bytes);
+      for (int off = 0; off < a_bytes; off += TC_ABLK) bulk_g2s(sm_u32(sA + off), P.wimg + off, TC_ABLK, wbar);
+      bar_wait(wbar, 0);
+      for (long long i = 0; i < my_tiles; ++i) {
+        const int s = (int)(i & 1), a = (int)(i & 1);
+        const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        bar_wait(sm_u32(&bars[0 + s]), ph);      // x₂ operand stage filled
+        bar_wait(sm_u32(&bars[6 + a]), ph ^ 1);  // accumulator stage drained by the epilogue
+        tc_fence_after();
+        const uint32_t bB = sm_u32(sB + s * b_stage);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(a * 2 * TC_T + mt * TC_T);
+          uint32_t acc = 0;
+          // smallest terms first: lo·hi, hi·lo, hi·hi
+#pragma unroll
+          for (int prod = 0; prod < 3; ++prod) {
+            const int pa = prod == 0 ? 1 : 0, pb = prod == 1 ? 1 : 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+              const uint32_t aaddr = sm_u32(sA) + (uint32_t)(((mt * 2 + pa) * nkb + kb) * TC_ABLK);
+              const uint32_t baddr = bB + (uint32_t)((pb * nkb + kb) * TC_BBLK);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {  // 4 K-steps of 16 fp16 (32 B) inside the 128-byte swizzle atom
+                tc_mma_f16(d_tmem, umma_desc_k_sw128(aaddr + 32 * j), umma_desc_k_sw128(baddr + 32 * j), TC_IDESC, acc);
+                acc = 1;
+              }
+            }
+          }
+        }
+        tc_commit(sm_u32(&bars[2 + s]));  // operand stage may be refilled
+        tc_commit(sm_u32(&bars[4 + a]));  // accumulators ready for the epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ producers ================================
+    const int p = warp - 4;
+    const bool active = 4 * lane < P.n2;
+    const float4 ws = active ? *reinterpret_cast<const float4*>(P.wsum + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float inv_scale_w = P.meta[0], csum = P.meta[1];
+    const int kb = (4 * lane) / 64, kp = (4 * lane) % 64;
+    for (long long i = 0; i < my_tiles; ++i) {
+      const int s = (int)(i & 1);
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      const long long tile = blockIdx.x + i * gridDim.x;
+      const long long col0 = tile * TC_T + p * 16;
+      bar_wait(sm_u32(&bars[2 + s]), ph ^ 1);  // stage free (MMAs that read it have completed)
+      unsigned char* stage = sB + s * b_stage;
+      float* cs = colscale + (int)(i & (TC_SCALE_SLOTS - 1)) * TC_T + p * 16;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float4 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const long long col = col0 + half * 8 + c;
+          v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (active && col < P.N)
+            v[c] = __ldcs(reinterpret_cast<const float4*>(P.x + col * P.ldx + P.row2) + lane);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const long long col = col0 + half * 8 + c;
+          const int n = p * 16 + half * 8 + c;  // row of the operand tile
+          float mx = fmaxf(fmaxf(fabsf(v[c].x), fabsf(v[c].y)), fmaxf(fabsf(v[c].z), fabsf(v[c].w)));
+          float dot = fmaf(v[c].x, ws.x, fmaf(v[c].y, ws.y, fmaf(v[c].z, ws.z, v[c].w * ws.w)));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          }
+          int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;
+          e = max(-100, min(100, e));
+          const float scale = __uint_as_float((uint32_t)(127 + 14 - e) << 23);  // max|x₂ col|·scale in [2^14, 2^15)
+          if (active) {
+            __half hi[4], lo[4];
+            const float q[4] = {v[c].x * scale, v[c].y * scale, v[c].z * scale, v[c].w * scale};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              hi[t] = __float2half_rn(q[t]);
+              lo[t] = __float2half_rn(q[t] - __half2float(hi[t]));
+            }
+            const int off = sw128_off(n, kp);
+            *reinterpret_cast<uint2*>(stage + (0 * nkb + kb) * TC_BBLK + off) = *reinterpret_cast<uint2*>(hi);
+            *reinterpret_cast<uint2*>(stage + (1 * nkb + kb) * TC_BBLK + off) = *reinterpret_cast<uint2*>(lo);
+            if (P.y && P.y != P.x && col < P.N)
+              __stcs(reinterpret_cast<float4*>(P.y + col * P.ldy + P.row2) + lane, v[c]);  // x₂ passes through
+          }
+          if (lane == 0) {
+            cs[half * 8 + c] = __uint_as_float((uint32_t)(127 - 14 + e) << 23) * inv_scale_w;  // undo both scales
+            if (P.logjac && col < P.N) {
+              const float ssum = dot + csum;  // Σ_j s_j = (Σ_j W_j)·x₂ + Σ_j c_j  (scale.jl:31)
+              const float b0 = P.accumulate ? P.logjac[col] : 0.f;
+              P.logjac[col] = P.inverse ? b0 - ssum : b0 + ssum;
+            }
+          }
+        }
+      }
+      // rows that belong to neither x₁ nor x₂ pass through when y != x
+      if (P.y && P.y != P.x && P.n1 + P.n2 < P.D) {
+        for (int c = 0; c < 16; ++c) {
+          const long long col = col0 + c;
+          if (col >= P.N) break;
+          for (int r = lane; r < P.D; r += 32) {
+            const bool in1 = r >= P.row1 && r < P.row1 + P.n1, in2 = r >= P.row2 && r < P.row2 + P.n2;
+            if (!in1 && !in2) P.y[col * P.ldy + r] = P.x[col * P.ldx + r];
+          }
+        }
+      }
+      fence_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) bar_arrive(sm_u32(&bars[0 + s]));
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int j = warp * 32 + lane;  // TMEM lane == row of s / t
+    const bool rowok = j < P.n1;
+    const float cs_j = (rowok && P.cvec) ? P.cvec[j] : 0.f;
+    const float ct_j = (rowok && P.cvec) ? P.cvec[P.n1 + j] : 0.f;
+    for (long long i = 0; i < my_tiles; ++i) {
+      const int a = (int)(i & 1);
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      const long long tile = blockIdx.x + i * gridDim.x;
+      const long long col0 = tile * TC_T;
+      const float* cs = colscale + (int)(i & (TC_SCALE_SLOTS - 1)) * TC_T;
+      bar_wait(sm_u32(&bars[4 + a]), ph);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 2 * TC_T);
+#pragma unroll 1
+      for (int ch = 0; ch < TC_T / 16; ++ch) {
+        uint32_t rs[16], rt[16];
+        tc_ld16(t_lane + ch * 16, rs);
+        tc_ld16(t_lane + TC_T + ch * 16, rt);
+        float x1[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+          const long long col = col0 + ch * 16 + n;
+          x1[n] = (rowok && col < P.N) ? __ldcs(P.x + col * P.ldx + P.row1 + j) : 0.f;
+        }
+        tc_wait_ld();
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+          const long long col = col0 + ch * 16 + n;
+          const float f = cs[ch * 16 + n];
+          const float sv = fmaf(__uint_as_float(rs[n]), f, cs_j);
+          const float tv = fmaf(__uint_as_float(rt[n]), f, ct_j);
+          float out;
+          if (!P.inverse) out = fmaf(expf(sv), x1[n], tv);  // exp(s)·x₁ + t  (scale.jl:13, shift.jl:14)
+          else out = (x1[n] - tv) / expf(sv);                // inv.(a) .* (y₁ + (−t))  (scale.jl:16, shift.jl:12)
+          if (P.y && rowok && col < P.N) __stcs(P.y + col * P.ldy + P.row1 + j, out);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) bar_arrive(sm_u32(&bars[6 + a]));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
+                 : "memory");
+  }
+}
+
+}  // namespace b2b
+
+size_t b2b_coupling_tc_workspace_bytes(int n1, int n2) {
+  if (n1 < 1 || n1 > 128 || (n2 != 64 && n2 != 128)) return 0;
+  return (size_t)4 * (n2 / 64) * b2b::TC_ABLK + (size_t)n2 * sizeof(float) + 64;
+}
+
+// Returns B2B_EUNSUPPORTED when the layer shape does not fit the tensor-core path (the caller then uses the
+// SIMT kernel).  The mask must be declared contiguous through desc.n2 / desc.n3 (first rows of idx1 / idx2).
+int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* x, float* y, float* logjac, int D,
+                                  long long N, long long ldx, long long ldy, int accumulate, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream) {
+  using namespace b2b;
+  const int n1 = d.n0, n2 = d.n1;
+  const size_t need = b2b_coupling_tc_workspace_bytes(n1, n2);
+  if (need == 0 || !workspace || workspace_bytes < need) return B2B_EUNSUPPORTED;
+  const int row1 = d.n2, row2 = d.n3;
+  if (row1 < 0 || row2 < 0 || row1 + n1 > D || row2 + n2 > D) return B2B_EUNSUPPORTED;
+  if ((row2 % 4) || (ldx % 4) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(d.p0) & 15))
+    return B2B_EUNSUPPORTED;
+  if (y && ((ldy % 4) || (reinterpret_cast<uintptr_t>(y) & 15))) return B2B_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023)) return B2B_EUNSUPPORTED;
+  const int nkb = n2 / 64;
+  unsigned char* wimg = static_cast<unsigned char*>(workspace);
+  float* wsum = reinterpret_cast<float*>(wimg + (size_t)4 * nkb * TC_ABLK);
+  float* meta = wsum + n2;
+  coupling_prep_kernel<<<1, 1024, 0, stream>>>(d.p0, d.p1, n1, n2, wimg, wsum, meta);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  TcParams P;
+  P.x = x;
+  P.y = y;
+  P.logjac = logjac;
+  P.wimg = wimg;
+  P.wsum = wsum;
+  P.meta = meta;
+  P.cvec = d.p1;
+  P.N = N;
+  P.ldx = ldx;
+  P.ldy = ldy;
+  P.tiles = (N + TC_T - 1) / TC_T;
+  P.D = D;
+  P.n1 = n1;
+  P.n2 = n2;
+  P.nkb = nkb;
+  P.row1 = row1;
+  P.row2 = row2;
+  P.accumulate = accumulate;
+  P.inverse = d.inverse;
+  const size_t smem = (size_t)4 * nkb * TC_ABLK + (size_t)TC_STAGES * 2 * nkb * TC_BBLK +
+                      TC_SCALE_SLOTS * TC_T * sizeof(float) + 16 * sizeof(uint64_t) + 1024;
+  e = cudaFuncSetAttribute(coupling_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = sms;
+  if (grid > P.tiles) grid = P.tiles;
+  if (grid < 1) grid = 1;
+  coupling_tc_kernel<<<(int)grid, TC_THREADS, smem, stream>>>(P);
+  return (int)cudaGetLastError();
+}

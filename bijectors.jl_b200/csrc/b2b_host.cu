@@ -24,7 +24,7 @@ struct b2b_host_ctx {
   long long hsum_cap;
 };
 
-static const size_t kWsBytes = 4096 * sizeof(double);
+static const size_t kWsBytes = 512 * 1024;  // batch-sum partials + tensor-core W image of a coupling layer
 
 extern "C" int b2b_host_ctx_create(b2b_host_ctx** out, int32_t D_max, int64_t chunk_cols, int32_t n_streams) {
   if (!out || D_max < 1 || chunk_cols < 1 || n_streams < 1 || n_streams > 16) return B2B_EINVAL;

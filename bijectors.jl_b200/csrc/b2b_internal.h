@@ -41,7 +41,12 @@ int b2b_launch_chain_v1(const B2BChainParams& p, cudaStream_t stream);
 int b2b_chain_grid_size(const B2BChainParams& p);
 // deterministic final sum of per-CTA partials into *sum_out
 int b2b_launch_sum_partials(const double* partials, int n, double* sum_out, cudaStream_t stream);
-// affine coupling (own kernel)
+// affine coupling, tensor-core path (B2B_EUNSUPPORTED when the shape / workspace does not fit)
+size_t b2b_coupling_tc_workspace_bytes(int n1, int n2);
+int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* x, float* y, float* logjac, int D,
+                                  long long N, long long ldx, long long ldy, int accumulate, void* workspace,
+                                  size_t workspace_bytes, cudaStream_t stream);
+// affine coupling, exact-fp32 CUDA-core kernel (any index lists)
 int b2b_launch_coupling_affine(const b2b_layer_desc& d, const float* x, float* y, float* logjac,
                                int D, long long N, long long ldx, long long ldy, int accumulate,
                                cudaStream_t stream);

@@ -246,6 +246,12 @@ class Coupling(_ParamLayer):
         self._idx1 = _dev_i32(np.asarray(mask.indices_1) - 1, θ.W.device)
         self._idx2 = _dev_i32(np.asarray(mask.indices_2) - 1, θ.W.device)
 
+        def first_row(idx):  # 0-based first row when the list is a contiguous increasing range, else -1
+            a = np.asarray(idx)
+            return int(a[0] - 1) if len(a) and np.array_equal(a, np.arange(a[0], a[0] + len(a))) else -1
+
+        self._row1, self._row2 = first_row(mask.indices_1), first_row(mask.indices_2)
+
     @property
     def device(self):
         return self.θ.W.device
@@ -257,7 +263,7 @@ class Coupling(_ParamLayer):
         if D != self.mask.n:
             raise ValueError(f"DimensionMismatch: Coupling mask has {self.mask.n} dims, input has {D}")
         return [_desc(_lib.COUPLING_AFFINE, inverse, p0=self.θ.W, p1=self.θ.c, i0=self._idx1, i1=self._idx2,
-                      n0=self.θ.n1, n1=self.θ.n2)]
+                      n0=self.θ.n1, n1=self.θ.n2, n2=self._row1, n3=self._row2)]
 
     def __eq__(self, o):
         return isinstance(o, Coupling) and self.mask == o.mask and torch.equal(self.θ.W, o.θ.W) and torch.equal(self.θ.c, o.θ.c)

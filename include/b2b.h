@@ -78,8 +78,11 @@ extern "C" {
  * RADIAL             α_[1]       β[1]        z_0[D]      -        -               -             -     -    -
  * RQS                widths      heights     derivatives -        -               -             K1    -    -
  *                    (each D x K1 column-major = the struct fields of rational_quadratic_spline.jl:75-79)
- * COUPLING_AFFINE    W[2n1 x n2] c[2n1]      -           -        idx1[n1]        idx2[n2]      n1    n2   -
- *                    (W column-major; rows 0..n1-1 give s, rows n1..2n1-1 give t; idx = PartitionMask rows)
+ * COUPLING_AFFINE    W[2n1 x n2] c[2n1]|NULL -           -        idx1[n1]        idx2[n2]      n1    n2   -
+ *                    (W column-major; rows 0..n1-1 give s, rows n1..2n1-1 give t; idx = PartitionMask rows.
+ *                     n2 / n3 = first row of idx1 / idx2 when that list is the contiguous range
+ *                     first..first+len-1 (then the pointer may be NULL), else -1.  Contiguous masks with
+ *                     n1 <= 128 and n2 in {64,128} run on the tensor cores (tcgen05) when workspace is given.)
  * BATCHNORM          b[D]        logs[D]     m[D]        v[D]     -               -             -     -    eps
  * PERMUTE            -           -           -           -        dst_of_src[D]   -             -     -    -
  *                    (y[dst_of_src[i]] = x[i], i.e. Permute(indices) of permute.jl:90-100, 0-based)
@@ -125,8 +128,10 @@ size_t b2b_chain_workspace_bytes(const b2b_layer_desc* layers, int32_t L, int32_
 /* Number of kernel launches the previous b2b_chain_run_f32 call on this thread enqueued. */
 int b2b_last_launch_count(void);
 
-/* Select the implementation of the fused column-local kernel: 0 = auto (default), 1 = lane-group
- * direct-global kernel (v0), 2 = TMA-staged thread-per-column kernel where available. */
+/* Select kernel implementations (testing / profiling).  Ones digit -- fused column-local kernel: 0 = auto
+ * (default), 1 = lane-group direct-global kernel (v0), 2 = TMA-staged thread-per-column kernel (v1) only.
+ * Tens digit -- coupling: 0 = auto (tensor cores when the mask is contiguous and workspace is given),
+ * 1 = always the exact-fp32 CUDA-core kernel. */
 int b2b_set_kernel_variant(int variant);
 
 /* ---- single layers (thin wrappers over a 1-element chain) --------------------------------------- */
@@ -151,15 +156,19 @@ int b2b_rqs_fwd_f32(const float* x, float* y, float* logjac, const float* widths
 int b2b_rqs_inv_f32(const float* x, float* y, float* logjac, const float* widths,
                     const float* heights, const float* derivs, int32_t K1, int32_t D, int64_t N,
                     int64_t ldx, int64_t ldy, int accumulate_logjac, void* stream);
-/* Coupling with the affine law: coupling.jl:206-215 (fwd), :217-228 (inverse) */
-int b2b_coupling_affine_fwd_f32(const float* x, float* y, float* logjac, const int32_t* idx1,
-                                int32_t n1, const int32_t* idx2, int32_t n2, const float* W,
+/* Coupling with the affine law: coupling.jl:206-215 (fwd), :217-228 (inverse).
+ * row1 / row2: first row of idx1 / idx2 when the list is a contiguous range (pointer may then be NULL), else -1.
+ * workspace: b2b_coupling_workspace_bytes(n1, n2) bytes, 1024-byte aligned, enables the tensor-core path
+ * (may be NULL: the exact-fp32 CUDA-core kernel is used). */
+int b2b_coupling_affine_fwd_f32(const float* x, float* y, float* logjac, const int32_t* idx1, int32_t n1,
+                                int32_t row1, const int32_t* idx2, int32_t n2, int32_t row2, const float* W,
                                 const float* c, int32_t D, int64_t N, int64_t ldx, int64_t ldy,
-                                int accumulate_logjac, void* stream);
-int b2b_coupling_affine_inv_f32(const float* x, float* y, float* logjac, const int32_t* idx1,
-                                int32_t n1, const int32_t* idx2, int32_t n2, const float* W,
+                                int accumulate_logjac, void* workspace, size_t workspace_bytes, void* stream);
+int b2b_coupling_affine_inv_f32(const float* x, float* y, float* logjac, const int32_t* idx1, int32_t n1,
+                                int32_t row1, const int32_t* idx2, int32_t n2, int32_t row2, const float* W,
                                 const float* c, int32_t D, int64_t N, int64_t ldx, int64_t ldy,
-                                int accumulate_logjac, void* stream);
+                                int accumulate_logjac, void* workspace, size_t workspace_bytes, void* stream);
+size_t b2b_coupling_workspace_bytes(int32_t n1, int32_t n2);
 /* InvertibleBatchNorm, eval mode: normalise.jl:61-67 (fwd), :74-86 (inverse) */
 int b2b_batchnorm_eval_fwd_f32(const float* x, float* y, float* logjac, const float* b,
                                const float* logs, const float* m, const float* v, float eps,
