@@ -1,0 +1,141 @@
+# B200Bijectors.jl -- the reference-side binding of libb2b.so (include/b2b.h).
+#
+# This is the file a Bijectors.jl maintainer adds (as a package extension on CUDA.jl, e.g.
+# ext/BijectorsB200Ext.jl) to make the batched flow path dispatch to the B200 kernels.  Bijectors.jl has no
+# FFI/plugin registry: "plugging in" = more specific methods of its own generic functions
+# (src/interface.jl:144,156,183,265).  NOT runnable in the build container (no Julia toolchain exists there);
+# the identical C ABI is exercised by the Python/ctypes harness in bijectors.jl_b200/ (tests/, bench.py).
+#
+# Conventions (include/b2b.h): D×N Float32 CuMatrix batches (Julia is column-major, so a column is one sample);
+# every pointer is a device pointer; the stream is CUDA.jl's task-local stream; non-zero status -> error(...).
+module B200Bijectors
+
+using CUDA
+using Bijectors
+using Bijectors: PlanarLayer, RadialLayer, RationalQuadraticSpline, Coupling, PartitionMask,
+                 InvertibleBatchNorm, Permute, Inverse, TransformedDistribution
+import Bijectors: transform, logabsdetjac, with_logabsdet_jacobian
+using Distributions: MvNormal
+using Functors: fmap
+
+const libb2b = get(ENV, "LIBB2B", "libb2b.so")
+
+# ---- b2b_layer_desc (include/b2b.h) ------------------------------------------------------------------
+struct LayerDesc
+    kind::Int32
+    inverse::Int32
+    n0::Int32; n1::Int32; n2::Int32; n3::Int32
+    f0::Float32; f1::Float32
+    p0::CuPtr{Float32}; p1::CuPtr{Float32}; p2::CuPtr{Float32}; p3::CuPtr{Float32}
+    i0::CuPtr{Int32}; i1::CuPtr{Int32}
+end
+const PLANAR, RADIAL, RQS, COUPLING_AFFINE, BATCHNORM, PERMUTE, STACKED_EW, MVNORMAL_DIAG = Int32.(1:8)
+const NULLF = CuPtr{Float32}(0)
+const NULLI = CuPtr{Int32}(0)
+
+check(rc::Cint) = rc == 0 ? nothing :
+    error(unsafe_string(ccall((:b2b_status_string, libb2b), Cstring, (Cint,), rc)))
+
+stream_handle() = CUDA.stream().handle
+
+# Device placement of a flow is the reference's own mechanism: Functors.fmap(cu, flow)
+# (Functors.@functor PlanarLayer / RadialLayer / InvertibleBatchNorm (b, logs) / Inverse; SURVEY §5).
+to_device(flow) = fmap(x -> x isa AbstractArray{<:Real} ? cu(Float32.(x)) : x, flow)
+
+# ---- layer -> descriptor ------------------------------------------------------------------------------
+# Parameters are passed RAW (the struct fields); û, wᵀû, softplus terms are derived on the device.
+desc(b::PlanarLayer{<:CuVector{Float32}}, inv::Bool) =
+    LayerDesc(PLANAR, inv, 0, 0, 0, 0, 0f0, 0f0, pointer(b.w), pointer(b.u), pointer(b.b), NULLF, NULLI, NULLI)
+desc(b::RadialLayer{<:CuVector{Float32}}, inv::Bool) =
+    LayerDesc(RADIAL, inv, 0, 0, 0, 0, 0f0, 0f0, pointer(b.α_), pointer(b.β), pointer(b.z_0), NULLF, NULLI, NULLI)
+desc(b::RationalQuadraticSpline{<:CuMatrix{Float32}}, inv::Bool) =       # fields are D×(K+1), column-major
+    LayerDesc(RQS, inv, size(b.widths, 2), 0, 0, 0, 0f0, 0f0,
+              pointer(b.widths), pointer(b.heights), pointer(b.derivatives), NULLF, NULLI, NULLI)
+desc(b::InvertibleBatchNorm{<:CuVector{Float32}}, inv::Bool) = begin
+    Bijectors.istraining() && error("InvertibleBatchNorm training mode is not on the device path")
+    LayerDesc(BATCHNORM, inv, 0, 0, 0, 0, Float32(b.eps), 0f0,
+              pointer(b.b), pointer(b.logs), pointer(b.m), pointer(b.v), NULLI, NULLI)
+end
+desc(b::Inverse, inv::Bool) = desc(b.orig, !inv)
+
+# The recognised coupling law θ(x₂) = Shift(t) ∘ Scale(exp.(s)), [s;t] = W*x₂ .+ c (SURVEY §8 a12).
+struct AffineConditioner{M<:CuMatrix{Float32},V<:CuVector{Float32}}
+    W::M   # (2n1 × n2)
+    c::V
+end
+(θ::AffineConditioner)(x₂) = (st = θ.W * x₂ .+ θ.c; n = length(st) ÷ 2;
+                              Bijectors.Shift(st[(n + 1):end]) ∘ Bijectors.Scale(exp.(st[1:n])))
+struct DeviceMask            # index lists of a PartitionMask (coupling.jl:51-118), 0-based on the device
+    idx1::CuVector{Int32}; idx2::CuVector{Int32}; row1::Int32; row2::Int32
+end
+function DeviceMask(m::PartitionMask)
+    rows(A) = Int32.(findnz(A)[1] .- 1)          # A_i[idx, j] = 1
+    first_row(r) = (length(r) > 0 && r == collect(r[1]:(r[1] + length(r) - 1))) ? r[1] : Int32(-1)
+    r1, r2 = rows(m.A_1), rows(m.A_2)
+    DeviceMask(cu(r1), cu(r2), first_row(r1), first_row(r2))
+end
+const MASKS = IdDict{Any,DeviceMask}()
+function desc(cl::Coupling{<:AffineConditioner}, inv::Bool)
+    dm = get!(() -> DeviceMask(cl.mask), MASKS, cl.mask)
+    LayerDesc(COUPLING_AFFINE, inv, length(dm.idx1), length(dm.idx2), dm.row1, dm.row2, 0f0, 0f0,
+              pointer(cl.θ.W), pointer(cl.θ.c), NULLF, NULLF, pointer(dm.idx1), pointer(dm.idx2))
+end
+desc(cl::Coupling, ::Bool) = error("Coupling: only AffineConditioner laws run on the device path (no CPU fallback)")
+
+# ---- chains: Base.ComposedFunction trees are flattened inner-most first ------------------------------
+flatten(f::ComposedFunction) = (flatten(f.inner)..., flatten(f.outer)...)
+flatten(f) = (f,)
+descs(f, inv::Bool) = inv ? [desc(b, true) for b in reverse(flatten(f))] : [desc(b, false) for b in flatten(f)]
+
+function run_chain(ds::Vector{LayerDesc}, x::CuMatrix{Float32}; y=similar(x), logjac=CUDA.zeros(Float32, size(x, 2)),
+                   sum_out=nothing, accumulate=false)
+    D, N = size(x)
+    ws_bytes = ccall((:b2b_chain_workspace_bytes, libb2b), Csize_t,
+                     (Ptr{LayerDesc}, Int32, Int32, Int64, Cint, Cint), ds, length(ds), D, N, y !== nothing, sum_out !== nothing)
+    ws = CuVector{UInt8}(undef, ws_bytes)
+    GC.@preserve ds ws begin
+        check(ccall((:b2b_chain_run_f32, libb2b), Cint,
+            (Ptr{LayerDesc}, Int32, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float64},
+             Int32, Int64, Int64, Int64, Cint, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+            ds, length(ds), pointer(x), y === nothing ? NULLF : pointer(y),
+            logjac === nothing ? NULLF : pointer(logjac),
+            sum_out === nothing ? CuPtr{Float64}(0) : pointer(sum_out),
+            D, N, stride(x, 2), y === nothing ? D : stride(y, 2), accumulate, pointer(ws), ws_bytes, stream_handle()))
+    end
+    return y, logjac
+end
+
+# ---- the methods Bijectors.jl dispatches to ------------------------------------------------------------
+const DeviceLayer = Union{PlanarLayer{<:CuVector{Float32}},RadialLayer{<:CuVector{Float32}},
+                          RationalQuadraticSpline{<:CuMatrix{Float32}},InvertibleBatchNorm{<:CuVector{Float32}},
+                          Coupling{<:AffineConditioner}}
+const DeviceTransform = Union{DeviceLayer,Inverse{<:DeviceLayer},ComposedFunction}
+
+with_logabsdet_jacobian(b::DeviceTransform, x::CuMatrix{Float32}) = run_chain(descs(b, false), x)
+transform(b::DeviceTransform, x::CuMatrix{Float32}) = first(run_chain(descs(b, false), x; logjac=nothing))
+logabsdetjac(b::DeviceTransform, x::CuMatrix{Float32}) = last(run_chain(descs(b, false), x; y=nothing))
+# in-place variants (src/interface.jl:175-176, 212-218): y aliases x, logjac accumulates
+Bijectors.with_logabsdet_jacobian!(b::DeviceTransform, x::CuMatrix{Float32}, y::CuMatrix{Float32}, logjac::CuVector{Float32}) =
+    run_chain(descs(b, false), x; y=y, logjac=logjac, accumulate=true)
+
+# logpdf(td::MvTransformed, y::Matrix) (src/transformed_distribution.jl:165-169): inverse chain + base
+# MvNormal + (optionally) the batch sum in ONE fused launch per fusable segment.
+function Distributions.logpdf(td::TransformedDistribution{<:MvNormal}, y::CuMatrix{Float32})
+    ds = descs(td.transform, true)
+    μ, σ = cu(Float32.(mean(td.dist))), cu(Float32.(sqrt.(var(td.dist))))
+    push!(ds, LayerDesc(MVNORMAL_DIAG, 0, 0, 0, 0, 0, 0f0, 0f0, pointer(μ), pointer(σ), NULLF, NULLF, NULLI, NULLI))
+    GC.@preserve μ σ last(run_chain(ds, y; y=nothing))
+end
+
+# ---- multi-GPU (one process per GPU): one NCCL sum of the batch log-density (SURVEY §8(e)) ------------
+mutable struct Comm; handle::Ptr{Cvoid}; end
+function Comm(nranks::Integer, rank::Integer, uid::Vector{UInt8})       # uid from b2b_comm_unique_id on rank 0
+    h = Ref{Ptr{Cvoid}}()
+    check(ccall((:b2b_comm_init_rank, libb2b), Cint, (Ptr{Ptr{Cvoid}}, Cint, Cint, Ptr{UInt8}), h, nranks, rank, uid))
+    Comm(h[])
+end
+allreduce_sum!(c::Comm, v::CuVector{Float64}) =
+    check(ccall((:b2b_allreduce_sum_f64, libb2b), Cint, (Ptr{Cvoid}, CuPtr{Float64}, Int32, Ptr{Cvoid}),
+                c.handle, pointer(v), length(v), stream_handle()))
+
+end # module
