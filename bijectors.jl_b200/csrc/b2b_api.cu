@@ -12,6 +12,7 @@ int b2b_chain_grid_size_v1(const B2BChainParams& p);
 
 static thread_local int g_last_launches = 0;
 static int g_variant = 0;           // fused chain kernel: 0 auto, 1 v0, 2 v1
+static int g_fold_bn = 1;            // fold BatchNorm neighbours into coupling launches (hundreds digit 1 disables)
 static int g_coupling_variant = 0;  // coupling: 0 auto (tensor cores when possible), 1 force the fp32 CUDA-core kernel
 
 extern "C" int b2b_version(void) { return B2B_VERSION; }
@@ -37,10 +38,11 @@ extern "C" int b2b_last_launch_count(void) { return g_last_launches; }
 
 extern "C" int b2b_set_kernel_variant(int variant) {
   // low decimal digit: fused chain kernel variant; tens digit: coupling variant (10 = force fp32 CUDA cores)
-  const int chain = variant % 10, cpl = variant / 10;
-  if (variant < 0 || chain > 2 || cpl > 1) return B2B_EINVAL;
+  const int chain = variant % 10, cpl = (variant / 10) % 10, nofold = variant / 100;
+  if (variant < 0 || chain > 2 || cpl > 1 || nofold > 1) return B2B_EINVAL;
   g_variant = chain;
   g_coupling_variant = cpl;
+  g_fold_bn = nofold ? 0 : 1;
   return B2B_OK;
 }
 
@@ -105,14 +107,28 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // workspace layout: [tensor-core W image (shared by all coupling layers; they run one after another)]
 //                   [D x N scratch when y == NULL and the chain has several segments] [batch-sum partials]
-static size_t chain_tc_bytes(const b2b_layer_desc* layers, int32_t L) {
+static size_t fold_bytes(int D) { return align_up((size_t)(4 * D + 4) * sizeof(float), 1024); }
+
+static bool chain_has_fold(const b2b_layer_desc* layers, int32_t L) {
+  for (int l = 0; l < L; ++l)
+    if (layers[l].kind == B2B_COUPLING_AFFINE &&
+        ((l > 0 && layers[l - 1].kind == B2B_BATCHNORM) || (l + 1 < L && layers[l + 1].kind == B2B_BATCHNORM)))
+      return true;
+  return false;
+}
+
+// [BatchNorm fold table (only when a BatchNorm neighbours a coupling)][tensor-core W image], each 1024-aligned,
+// + 1024 of alignment slack
+static size_t chain_tc_bytes(const b2b_layer_desc* layers, int32_t L, int D) {
   size_t tc = 0;
   for (int l = 0; l < L; ++l)
     if (layers[l].kind == B2B_COUPLING_AFFINE && layers[l].n2 >= 0 && layers[l].n3 >= 0) {
       const size_t b = b2b_coupling_tc_workspace_bytes(layers[l].n0, layers[l].n1);
       if (b > tc) tc = b;
     }
-  return tc ? align_up(tc, 1024) + 1024 : 0;
+  const size_t fb = chain_has_fold(layers, L) ? fold_bytes(D) : 0;
+  if (!tc && !fb) return 0;
+  return fb + (tc ? align_up(tc, 1024) : 0) + 1024;
 }
 
 extern "C" size_t b2b_coupling_workspace_bytes(int32_t n1, int32_t n2) {
@@ -122,7 +138,7 @@ extern "C" size_t b2b_coupling_workspace_bytes(int32_t n1, int32_t n2) {
 
 extern "C" size_t b2b_chain_workspace_bytes(const b2b_layer_desc* layers, int32_t L, int32_t D, int64_t N,
                                             int want_y, int want_sum) {
-  size_t bytes = chain_tc_bytes(layers, L);
+  size_t bytes = chain_tc_bytes(layers, L, D);
   bool has_coupling = false;
   for (int l = 0; l < L; ++l) has_coupling |= layers[l].kind == B2B_COUPLING_AFFINE;
   // a D x N scratch matrix is needed only when y == NULL but the chain has more than one segment
@@ -155,16 +171,17 @@ extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const 
   struct Seg {
     int begin, end;
     bool coupling;
+    int pre, post;  // layer index of a BatchNorm folded into this coupling launch (-1: none)
   };
   std::vector<Seg> segs;
   for (int l = 0; l < L;) {
     if (layers[l].kind == B2B_COUPLING_AFFINE) {
-      segs.push_back({l, l + 1, true});
+      segs.push_back({l, l + 1, true, -1, -1});
       ++l;
     } else {
       int e = l;
       while (e < L && fusable(layers[e].kind)) ++e;
-      segs.push_back({l, e, false});
+      segs.push_back({l, e, false, -1, -1});
       l = e;
     }
   }
@@ -173,15 +190,36 @@ extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const 
   size_t ws_left = workspace ? workspace_bytes : 0;
   void* tc_ws = nullptr;
   size_t tc_bytes = 0;
+  float* fold_ws = nullptr;
   {
-    const size_t want = chain_tc_bytes(layers, L);
+    const size_t want = chain_tc_bytes(layers, L, D);
     if (want && ws_left >= want) {
       const size_t pad = (1024 - (reinterpret_cast<uintptr_t>(ws) & 1023)) & 1023;
-      tc_ws = ws + pad;
-      tc_bytes = want - pad;
+      const size_t fb = chain_has_fold(layers, L) ? fold_bytes(D) : 0;
+      if (fb) fold_ws = reinterpret_cast<float*>(ws + pad);
+      if (want > fb + 1024) {
+        tc_ws = ws + pad + fb;
+        tc_bytes = want - pad - fb;
+      }
       ws += want;
       ws_left -= want;
     }
+  }
+  // fold BatchNorm neighbours (a per-row affine) into the coupling launches: removes their own pass over HBM
+  if (fold_ws && g_fold_bn) {
+    for (size_t s = 0; s < segs.size(); ++s) {
+      if (!segs[s].coupling) continue;
+      if (s + 1 < segs.size() && !segs[s + 1].coupling && segs[s + 1].end > segs[s + 1].begin &&
+          layers[segs[s + 1].begin].kind == B2B_BATCHNORM)
+        segs[s].post = segs[s + 1].begin++;
+      if (s > 0 && !segs[s - 1].coupling && segs[s - 1].end > segs[s - 1].begin &&
+          layers[segs[s - 1].end - 1].kind == B2B_BATCHNORM)
+        segs[s].pre = --segs[s - 1].end;
+    }
+    std::vector<Seg> kept;
+    for (const Seg& g : segs)
+      if (g.coupling || g.end > g.begin) kept.push_back(g);
+    segs.swap(kept);
   }
   float* scratch = nullptr;
   if (!y && segs.size() > 1) {
@@ -210,14 +248,22 @@ extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const 
     if (segs[s].coupling) {
       float* cdst = dst;
       // logjac-only call with a trailing coupling layer still needs no store
+      const float* fold = nullptr;
+      if (segs[s].pre >= 0 || segs[s].post >= 0) {
+        rc = b2b_launch_bn_fold_prep(segs[s].pre >= 0 ? &layers[segs[s].pre] : nullptr,
+                                     segs[s].post >= 0 ? &layers[segs[s].post] : nullptr, D, fold_ws, stream);
+        if (rc != B2B_OK) return rc;
+        ++g_last_launches;
+        fold = fold_ws;
+      }
       rc = B2B_EUNSUPPORTED;
       if (tc_ws && g_coupling_variant != 1) {
-        rc = b2b_launch_coupling_affine_tc(layers[segs[s].begin], cur, cdst, logjac, D, N, cur_ld, dst_ld,
+        rc = b2b_launch_coupling_affine_tc(layers[segs[s].begin], fold, cur, cdst, logjac, D, N, cur_ld, dst_ld,
                                            lj_started ? 1 : 0, tc_ws, tc_bytes, stream);
         if (rc == B2B_OK) g_last_launches += 2;  // W preparation + main kernel
       }
       if (rc == B2B_EUNSUPPORTED) {
-        rc = b2b_launch_coupling_affine(layers[segs[s].begin], cur, cdst, logjac, D, N, cur_ld, dst_ld,
+        rc = b2b_launch_coupling_affine(layers[segs[s].begin], fold, cur, cdst, logjac, D, N, cur_ld, dst_ld,
                                         lj_started ? 1 : 0, stream);
         if (rc == B2B_OK) ++g_last_launches;
       }

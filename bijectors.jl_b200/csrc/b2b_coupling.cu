@@ -14,6 +14,8 @@
 // lives in b2b_coupling_tc.cu and is cross-checked against this kernel.
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "b2b_internal.h"
 
 namespace b2b {
@@ -26,8 +28,8 @@ template <bool INV>
 __global__ void __launch_bounds__(CP_THREADS) coupling_affine_kernel(
     const float* __restrict__ x, float* __restrict__ y, float* __restrict__ logjac,
     const int32_t* __restrict__ idx1, const int32_t* __restrict__ idx2, const float* __restrict__ W,
-    const float* __restrict__ cvec, int D, int n1, int n2, int row1, int row2, long long N, long long ldx,
-    long long ldy, int accumulate) {
+    const float* __restrict__ cvec, const float* __restrict__ fold, int D, int n1, int n2, int row1, int row2,
+    long long N, long long ldx, long long ldy, int accumulate) {
   extern __shared__ float smem[];
   float* X = smem;                                    // [D][CP_LD]
   float* red = X + (size_t)D * CP_LD;                 // [8][CP_TC]
@@ -46,7 +48,11 @@ __global__ void __launch_bounds__(CP_THREADS) coupling_affine_kernel(
       const long long col = col0 + c;
       if (col < N) {
         const float* xc = x + col * ldx;
-        for (int r = lane; r < D; r += 32) X[r * CP_LD + c] = __ldcs(xc + r);
+        if (fold) {
+          for (int r = lane; r < D; r += 32) X[r * CP_LD + c] = fmaf(__ldcs(xc + r), fold[r], fold[D + r]);
+        } else {
+          for (int r = lane; r < D; r += 32) X[r * CP_LD + c] = __ldcs(xc + r);
+        }
       } else {
         for (int r = lane; r < D; r += 32) X[r * CP_LD + c] = 0.f;
       }
@@ -118,7 +124,11 @@ __global__ void __launch_bounds__(CP_THREADS) coupling_affine_kernel(
         const long long col = col0 + c;
         if (col < N) {
           float* yc = y + col * ldy;
-          for (int r = lane; r < D; r += 32) __stcs(yc + r, X[r * CP_LD + c]);
+          if (fold) {
+            for (int r = lane; r < D; r += 32) __stcs(yc + r, fmaf(X[r * CP_LD + c], fold[2 * D + r], fold[3 * D + r]));
+          } else {
+            for (int r = lane; r < D; r += 32) __stcs(yc + r, X[r * CP_LD + c]);
+          }
         }
       }
     }
@@ -128,17 +138,64 @@ __global__ void __launch_bounds__(CP_THREADS) coupling_affine_kernel(
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < CP_THREADS / 32; ++w) s += red[w * CP_TC + threadIdx.x];
-        const float base = accumulate ? logjac[col] : 0.f;
+        const float base = (accumulate ? logjac[col] : 0.f) + (fold ? fold[4 * D] : 0.f);
         logjac[col] = INV ? base - s : base + s;  // Σ log|exp(s)| = Σ s  (scale.jl:31)
       }
     }
   }
 }
 
+// Folded BatchNorm neighbours of a coupling layer (normalise.jl:61-67, :74-86): the per-row affine
+// x' = preA·x + preC is applied on the way in, y' = postA·y + postC on the way out, and the (column-independent)
+// log-Jacobian constants are summed into out[4D].  Layout: preA[D] | preC[D] | postA[D] | postC[D] | {lj}.
+__global__ void __launch_bounds__(256) bn_fold_prep_kernel(b2b_layer_desc pre, int has_pre, b2b_layer_desc post,
+                                                           int has_post, int D, float* __restrict__ out) {
+  __shared__ float red[8];
+  float lj = 0.f;
+  for (int i = threadIdx.x; i < D; i += 256) {
+    float A[2] = {1.f, 1.f}, C[2] = {0.f, 0.f};
+    for (int w = 0; w < 2; ++w) {
+      const b2b_layer_desc& d = w == 0 ? pre : post;
+      if (!(w == 0 ? has_pre : has_post)) continue;
+      const float ve = d.p3[i] + d.f0, sd = sqrtf(ve), sc = expf(d.p1[i]);
+      const float l = d.p1[i] - logf(ve) * 0.5f;
+      if (!d.inverse) {
+        A[w] = sc / sd;
+        C[w] = fmaf(-d.p2[i], A[w], d.p0[i]);
+        lj += l;
+      } else {
+        A[w] = sd / sc;
+        C[w] = fmaf(-d.p0[i], A[w], d.p2[i]);
+        lj -= l;
+      }
+    }
+    out[i] = A[0];
+    out[D + i] = C[0];
+    out[2 * D + i] = A[1];
+    out[3 * D + i] = C[1];
+  }
+  for (int o = 16; o > 0; o >>= 1) lj += __shfl_xor_sync(0xffffffffu, lj, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lj;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[4 * D] = t;
+  }
+}
+
 }  // namespace b2b
 
-int b2b_launch_coupling_affine(const b2b_layer_desc& d, const float* x, float* y, float* logjac, int D,
-                               long long N, long long ldx, long long ldy, int accumulate,
+int b2b_launch_bn_fold_prep(const b2b_layer_desc* pre, const b2b_layer_desc* post, int D, float* out,
+                            cudaStream_t stream) {
+  b2b_layer_desc z;
+  memset(&z, 0, sizeof(z));
+  b2b::bn_fold_prep_kernel<<<1, 256, 0, stream>>>(pre ? *pre : z, pre != nullptr, post ? *post : z, post != nullptr, D, out);
+  return (int)cudaGetLastError();
+}
+
+int b2b_launch_coupling_affine(const b2b_layer_desc& d, const float* fold, const float* x, float* y, float* logjac,
+                               int D, long long N, long long ldx, long long ldy, int accumulate,
                                cudaStream_t stream) {
   using namespace b2b;
   const int n1 = d.n0, n2 = d.n1;
@@ -159,7 +216,7 @@ int b2b_launch_coupling_affine(const b2b_layer_desc& d, const float* x, float* y
   long long grid = (long long)sms * per_sm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
-  kern<<<(int)grid, CP_THREADS, smem, stream>>>(x, y, logjac, d.i0, d.i1, d.p0, d.p1, D, n1, n2, d.n2, d.n3, N, ldx,
+  kern<<<(int)grid, CP_THREADS, smem, stream>>>(x, y, logjac, d.i0, d.i1, d.p0, d.p1, fold, D, n1, n2, d.n2, d.n3, N, ldx,
                                                 ldy, accumulate);
   return (int)cudaGetLastError();
 }

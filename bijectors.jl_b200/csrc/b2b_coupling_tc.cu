@@ -45,6 +45,7 @@ struct TcParams {
   const unsigned char* wimg;  // prepared fp16 hi/lo operand image of W (see coupling_prep_kernel)
   const float* wsum;          // [n2]  Σ_j W[j, k] over the s rows
   const float* meta;          // {1/scaleW, Σ_j c_j}
+  const float* fold;          // folded neighbouring BatchNorm layers: preA[D] | preC[D] | postA[D] | postC[D] | {Σ logjac}; or NULL
   const float* cvec;          // [2 n1] or NULL
   long long N, ldx, ldy, tiles;
   int D, n1, n2, nkb, row1, row2, accumulate, inverse;
@@ -252,75 +253,121 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
     }
   } else if (warp >= 4) {
     // ================================ producers ================================
+    // Warp p converts columns [16p, 16p+16) of every tile.  Lane l holds the float4 #l of a column (rows
+    // row2+4l..+3).  The 16 per-column maxima (operand scale) and the 16 dots with wsum (log-Jacobian) are reduced
+    // TOGETHER by a transposing butterfly (16 + 16 shuffles for 16 columns instead of 160); afterwards lane l owns
+    // column own(l) and does that column's scalar work once.  x₂ registers always hold the NEXT tile while the
+    // current one is being converted (refilled column by column), so DRAM latency hides behind a tile of work.
     const int p = warp - 4;
     const bool active = 4 * lane < P.n2;
     const float4 ws = active ? *reinterpret_cast<const float4*>(P.wsum + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float inv_scale_w = P.meta[0], csum = P.meta[1];
+    const float inv_scale_w = P.meta[0];
+    const float csum = P.meta[1] * (P.inverse ? -1.f : 1.f) + (P.fold ? P.fold[4 * P.D] : 0.f);
     const int kb = (4 * lane) / 64, kp = (4 * lane) % 64;
+    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool fold = P.fold != nullptr;
+    const float4 preA = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + P.row2 + 4 * lane) : one4;
+    const float4 preC = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + P.D + P.row2 + 4 * lane) : zero4;
+    const float4 postA = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + 2 * P.D + P.row2 + 4 * lane) : one4;
+    const float4 postC = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + 3 * P.D + P.row2 + 4 * lane) : zero4;
+    const bool write_y2 = P.y != nullptr && (P.y != P.x || fold);
+    // column owned by this lane after the transposing reduction, and the lane that owns column c
+    const int own = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const float* xlane = P.x + P.row2 + (active ? 4 * lane : 0);  // inactive lanes read a valid address, result unused
+    float4 v[16];
+    auto load_tile = [&](long long tile, int c) -> float4 {
+      long long col = tile * TC_T + p * 16 + c;
+      col = col < P.N ? col : P.N - 1;  // clamp instead of predicating; stores are predicated
+      return __ldcs(reinterpret_cast<const float4*>(xlane + col * P.ldx));
+    };
+    if (my_tiles > 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = load_tile(blockIdx.x, c);
+    }
     for (long long i = 0; i < my_tiles; ++i) {
       const int s = (int)(i & 1);
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
       const long long tile = blockIdx.x + i * gridDim.x;
       const long long col0 = tile * TC_T + p * 16;
+      const long long next_tile = (i + 1 < my_tiles) ? tile + gridDim.x : tile;
+      float mx[16], dt[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float4 vc = v[c];
+        if (fold)
+          vc = make_float4(fmaf(vc.x, preA.x, preC.x), fmaf(vc.y, preA.y, preC.y), fmaf(vc.z, preA.z, preC.z),
+                           fmaf(vc.w, preA.w, preC.w));
+        if (!active) vc = zero4;
+        v[c] = vc;
+        mx[c] = fmaxf(fmaxf(fabsf(vc.x), fabsf(vc.y)), fmaxf(fabsf(vc.z), fabsf(vc.w)));
+        dt[c] = fmaf(vc.x, ws.x, fmaf(vc.y, ws.y, fmaf(vc.z, ws.z, vc.w * ws.w)));
+      }
+      // transposing butterfly: 16 values over 32 lanes -> lane owns column `own`
+#pragma unroll
+      for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int q = 0; q < half; ++q) {
+          const float sm_ = up ? mx[q] : mx[q + half], km = up ? mx[q + half] : mx[q];
+          const float sd_ = up ? dt[q] : dt[q + half], kd = up ? dt[q + half] : dt[q];
+          mx[q] = fmaxf(km, __shfl_xor_sync(0xffffffffu, sm_, off));
+          dt[q] = kd + __shfl_xor_sync(0xffffffffu, sd_, off);
+        }
+      }
+      const float cmax = fmaxf(mx[0], __shfl_xor_sync(0xffffffffu, mx[0], 1));
+      const float cdot = dt[0] + __shfl_xor_sync(0xffffffffu, dt[0], 1);
+      int e = (int)((__float_as_uint(cmax) >> 23) & 0xffu) - 127;
+      e = max(-100, min(100, e));
+      const float my_scale = __uint_as_float((uint32_t)(127 + 14 - e) << 23);  // max|x₂ col|·scale in [2^14, 2^15)
       bar_wait(sm_u32(&bars[2 + s]), ph ^ 1);  // stage free (MMAs that read it have completed)
       unsigned char* stage = sB + s * b_stage;
-      float* cs = colscale + (int)(i & (TC_SCALE_SLOTS - 1)) * TC_T + p * 16;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float4 v[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const long long col = col0 + half * 8 + c;
-          v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (active && col < P.N)
-            v[c] = __ldcs(reinterpret_cast<const float4*>(P.x + col * P.ldx + P.row2) + lane);
+      if ((lane & 1) == 0) {
+        colscale[(int)(i & (TC_SCALE_SLOTS - 1)) * TC_T + p * 16 + own] =
+            __uint_as_float((uint32_t)(127 - 14 + e) << 23) * inv_scale_w;  // undoes both power-of-two scales
+        const long long col = col0 + own;
+        if (P.logjac && col < P.N) {
+          // Σ_j s_j = (Σ_j W_j)·x₂ + Σ_j c_j  (scale.jl:31); csum also carries the folded BatchNorm constants
+          const float b0 = P.accumulate ? P.logjac[col] : 0.f;
+          P.logjac[col] = b0 + (P.inverse ? -cdot : cdot) + csum;
         }
+      }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const long long col = col0 + half * 8 + c;
-          const int n = p * 16 + half * 8 + c;  // row of the operand tile
-          float mx = fmaxf(fmaxf(fabsf(v[c].x), fabsf(v[c].y)), fmaxf(fabsf(v[c].z), fabsf(v[c].w)));
-          float dot = fmaf(v[c].x, ws.x, fmaf(v[c].y, ws.y, fmaf(v[c].z, ws.z, v[c].w * ws.w)));
+      for (int c = 0; c < 16; ++c) {
+        // lane that owns column c: bits (c3 c2 c1 c0) -> lane bits (4 3 2 1)
+        const float scale = __shfl_sync(0xffffffffu, my_scale, (c & 8) * 2 + (c & 4) * 2 + (c & 2) * 2 + (c & 1) * 2);
+        const float4 vc = v[c];
+        const long long col = col0 + c;
+        v[c] = load_tile(next_tile, c);  // refill with the next tile's column
+        if (active) {
+          const int n = p * 16 + c;  // row of the operand tile
+          __half hi[4], lo[4];
+          const float q[4] = {vc.x * scale, vc.y * scale, vc.z * scale, vc.w * scale};
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          for (int t = 0; t < 4; ++t) {
+            hi[t] = __float2half_rn(q[t]);
+            lo[t] = __float2half_rn(q[t] - __half2float(hi[t]));
           }
-          int e = (int)((__float_as_uint(mx) >> 23) & 0xffu) - 127;
-          e = max(-100, min(100, e));
-          const float scale = __uint_as_float((uint32_t)(127 + 14 - e) << 23);  // max|x₂ col|·scale in [2^14, 2^15)
-          if (active) {
-            __half hi[4], lo[4];
-            const float q[4] = {v[c].x * scale, v[c].y * scale, v[c].z * scale, v[c].w * scale};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              hi[t] = __float2half_rn(q[t]);
-              lo[t] = __float2half_rn(q[t] - __half2float(hi[t]));
-            }
-            const int off = sw128_off(n, kp);
-            *reinterpret_cast<uint2*>(stage + (0 * nkb + kb) * TC_BBLK + off) = *reinterpret_cast<uint2*>(hi);
-            *reinterpret_cast<uint2*>(stage + (1 * nkb + kb) * TC_BBLK + off) = *reinterpret_cast<uint2*>(lo);
-            if (P.y && P.y != P.x && col < P.N)
-              __stcs(reinterpret_cast<float4*>(P.y + col * P.ldy + P.row2) + lane, v[c]);  // x₂ passes through
-          }
-          if (lane == 0) {
-            cs[half * 8 + c] = __uint_as_float((uint32_t)(127 - 14 + e) << 23) * inv_scale_w;  // undo both scales
-            if (P.logjac && col < P.N) {
-              const float ssum = dot + csum;  // Σ_j s_j = (Σ_j W_j)·x₂ + Σ_j c_j  (scale.jl:31)
-              const float b0 = P.accumulate ? P.logjac[col] : 0.f;
-              P.logjac[col] = P.inverse ? b0 - ssum : b0 + ssum;
-            }
-          }
+          const int off = sw128_off(n, kp);
+          *reinterpret_cast<uint2*>(stage + (0 * nkb + kb) * TC_BBLK + off) = *reinterpret_cast<uint2*>(hi);
+          *reinterpret_cast<uint2*>(stage + (1 * nkb + kb) * TC_BBLK + off) = *reinterpret_cast<uint2*>(lo);
+          if (write_y2 && col < P.N)  // x₂ passes through (plus the folded affines)
+            __stcs(reinterpret_cast<float4*>(P.y + col * P.ldy + P.row2) + lane,
+                   make_float4(fmaf(vc.x, postA.x, postC.x), fmaf(vc.y, postA.y, postC.y), fmaf(vc.z, postA.z, postC.z),
+                               fmaf(vc.w, postA.w, postC.w)));
         }
       }
       // rows that belong to neither x₁ nor x₂ pass through when y != x
-      if (P.y && P.y != P.x && P.n1 + P.n2 < P.D) {
+      if (write_y2 && P.n1 + P.n2 < P.D) {
         for (int c = 0; c < 16; ++c) {
           const long long col = col0 + c;
           if (col >= P.N) break;
           for (int r = lane; r < P.D; r += 32) {
             const bool in1 = r >= P.row1 && r < P.row1 + P.n1, in2 = r >= P.row2 && r < P.row2 + P.n2;
-            if (!in1 && !in2) P.y[col * P.ldy + r] = P.x[col * P.ldx + r];
+            if (!in1 && !in2) {
+              float xv = P.x[col * P.ldx + r];
+              if (fold) xv = fmaf(fmaf(xv, P.fold[r], P.fold[P.D + r]), P.fold[2 * P.D + r], P.fold[3 * P.D + r]);
+              P.y[col * P.ldy + r] = xv;
+            }
           }
         }
       }
@@ -330,42 +377,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
     }
   } else {
     // ================================ epilogue ================================
-    const int j = warp * 32 + lane;  // TMEM lane == row of s / t
+    // Thread = TMEM lane = row j of s / t.  x₁ of this row is prefetched TWO 16-column chunks ahead in two
+    // register buffers (A: even chunks, B: odd chunks); the loop body handles two chunks so that it stays
+    // small (instruction cache) while ~32 loads per thread are always in flight.
+    const int j = warp * 32 + lane;
     const bool rowok = j < P.n1;
+    const int jr = rowok ? j : 0;  // clamp: loads stay in bounds, stores are predicated
     const float cs_j = (rowok && P.cvec) ? P.cvec[j] : 0.f;
     const float ct_j = (rowok && P.cvec) ? P.cvec[P.n1 + j] : 0.f;
+    const bool efold = P.fold != nullptr && rowok;
+    const float preA_j = efold ? P.fold[P.row1 + j] : 1.f, preC_j = efold ? P.fold[P.D + P.row1 + j] : 0.f;
+    const float postA_j = efold ? P.fold[2 * P.D + P.row1 + j] : 1.f, postC_j = efold ? P.fold[3 * P.D + P.row1 + j] : 0.f;
+    const float* xrow = P.x + P.row1 + jr;
+    float* yrow = P.y ? P.y + P.row1 + jr : nullptr;
+    const bool do_store = P.y != nullptr && rowok;
+    const long long total_chunks = my_tiles * 4;
+    // first column of global chunk q (4 chunks of 16 columns per tile)
+    auto chunk_col = [&](long long q) -> long long { return (blockIdx.x + (q >> 2) * gridDim.x) * TC_T + (q & 3) * 16; };
+    auto load_chunk = [&](long long q, float (&buf)[16]) {
+      if (q >= total_chunks) return;
+      const long long c0 = chunk_col(q);
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        long long col = c0 + n;
+        col = col < P.N ? col : P.N - 1;
+        buf[n] = __ldcs(xrow + col * P.ldx);
+      }
+    };
+    float xa[16], xb[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) xa[n] = xb[n] = 0.f;
+    load_chunk(0, xa);
+    load_chunk(1, xb);
     for (long long i = 0; i < my_tiles; ++i) {
       const int a = (int)(i & 1);
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
-      const long long tile = blockIdx.x + i * gridDim.x;
-      const long long col0 = tile * TC_T;
       const float* cs = colscale + (int)(i & (TC_SCALE_SLOTS - 1)) * TC_T;
       bar_wait(sm_u32(&bars[4 + a]), ph);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 2 * TC_T);
 #pragma unroll 1
-      for (int ch = 0; ch < TC_T / 16; ++ch) {
-        uint32_t rs[16], rt[16];
-        tc_ld16(t_lane + ch * 16, rs);
-        tc_ld16(t_lane + TC_T + ch * 16, rt);
-        float x1[16];
-#pragma unroll
-        for (int n = 0; n < 16; ++n) {
-          const long long col = col0 + ch * 16 + n;
-          x1[n] = (rowok && col < P.N) ? __ldcs(P.x + col * P.ldx + P.row1 + j) : 0.f;
-        }
+      for (int pr = 0; pr < 2; ++pr) {
+        const long long q = i * 4 + pr * 2;
+        uint32_t rs0[16], rt0[16], rs1[16], rt1[16];
+        tc_ld16(t_lane + (pr * 2) * 16, rs0);
+        tc_ld16(t_lane + TC_T + (pr * 2) * 16, rt0);
+        tc_ld16(t_lane + (pr * 2 + 1) * 16, rs1);
+        tc_ld16(t_lane + TC_T + (pr * 2 + 1) * 16, rt1);
         tc_wait_ld();
+        auto finish = [&](const uint32_t (&rs)[16], const uint32_t (&rt)[16], float (&xbuf)[16], long long qq, int chl) {
+          const long long c0 = chunk_col(qq);
+          float outv[16];
 #pragma unroll
-        for (int n = 0; n < 16; ++n) {
-          const long long col = col0 + ch * 16 + n;
-          const float f = cs[ch * 16 + n];
-          const float sv = fmaf(__uint_as_float(rs[n]), f, cs_j);
-          const float tv = fmaf(__uint_as_float(rt[n]), f, ct_j);
-          float out;
-          if (!P.inverse) out = fmaf(expf(sv), x1[n], tv);  // exp(s)·x₁ + t  (scale.jl:13, shift.jl:14)
-          else out = (x1[n] - tv) / expf(sv);                // inv.(a) .* (y₁ + (−t))  (scale.jl:16, shift.jl:12)
-          if (P.y && rowok && col < P.N) __stcs(P.y + col * P.ldy + P.row1 + j, out);
-        }
+          for (int n = 0; n < 16; ++n) {
+            const float f = cs[chl * 16 + n];
+            const float sv = fmaf(__uint_as_float(rs[n]), f, cs_j);
+            const float tv = fmaf(__uint_as_float(rt[n]), f, ct_j);
+            const float xv = fmaf(xbuf[n], preA_j, preC_j);
+            float out;
+            if (!P.inverse) out = fmaf(__expf(sv), xv, tv);  // exp(s)·x₁ + t  (scale.jl:13, shift.jl:14)
+            else out = (xv - tv) * __expf(-sv);               // inv.(a) .* (y₁ + (−t))  (scale.jl:16, shift.jl:12)
+            outv[n] = fmaf(out, postA_j, postC_j);
+          }
+          load_chunk(qq + 2, xbuf);  // refill this buffer two chunks ahead
+          if (do_store) {
+#pragma unroll
+            for (int n = 0; n < 16; ++n)
+              if (c0 + n < P.N) __stcs(yrow + (c0 + n) * P.ldy, outv[n]);
+          }
+        };
+        finish(rs0, rt0, xa, q, pr * 2);
+        finish(rs1, rt1, xb, q + 1, pr * 2 + 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -391,15 +473,16 @@ size_t b2b_coupling_tc_workspace_bytes(int n1, int n2) {
 
 // Returns B2B_EUNSUPPORTED when the layer shape does not fit the tensor-core path (the caller then uses the
 // SIMT kernel).  The mask must be declared contiguous through desc.n2 / desc.n3 (first rows of idx1 / idx2).
-int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* x, float* y, float* logjac, int D,
-                                  long long N, long long ldx, long long ldy, int accumulate, void* workspace,
-                                  size_t workspace_bytes, cudaStream_t stream) {
+int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* fold, const float* x, float* y,
+                                  float* logjac, int D, long long N, long long ldx, long long ldy, int accumulate,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   using namespace b2b;
   const int n1 = d.n0, n2 = d.n1;
   const size_t need = b2b_coupling_tc_workspace_bytes(n1, n2);
   if (need == 0 || !workspace || workspace_bytes < need) return B2B_EUNSUPPORTED;
   const int row1 = d.n2, row2 = d.n3;
   if (row1 < 0 || row2 < 0 || row1 + n1 > D || row2 + n2 > D) return B2B_EUNSUPPORTED;
+  if (fold && ((D % 4) || (reinterpret_cast<uintptr_t>(fold) & 15))) return B2B_EUNSUPPORTED;
   if ((row2 % 4) || (ldx % 4) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(d.p0) & 15))
     return B2B_EUNSUPPORTED;
   if (y && ((ldy % 4) || (reinterpret_cast<uintptr_t>(y) & 15))) return B2B_EUNSUPPORTED;
@@ -418,6 +501,7 @@ int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* x, float
   P.wimg = wimg;
   P.wsum = wsum;
   P.meta = meta;
+  P.fold = fold;
   P.cvec = d.p1;
   P.N = N;
   P.ldx = ldx;

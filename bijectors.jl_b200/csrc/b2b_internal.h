@@ -43,10 +43,13 @@ int b2b_chain_grid_size(const B2BChainParams& p);
 int b2b_launch_sum_partials(const double* partials, int n, double* sum_out, cudaStream_t stream);
 // affine coupling, tensor-core path (B2B_EUNSUPPORTED when the shape / workspace does not fit)
 size_t b2b_coupling_tc_workspace_bytes(int n1, int n2);
-int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* x, float* y, float* logjac, int D,
-                                  long long N, long long ldx, long long ldy, int accumulate, void* workspace,
-                                  size_t workspace_bytes, cudaStream_t stream);
+// `fold` (device, 4*D+1 floats, or NULL): folded BatchNorm neighbours, see bn_fold_prep_kernel
+int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* fold, const float* x, float* y,
+                                  float* logjac, int D, long long N, long long ldx, long long ldy, int accumulate,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int b2b_launch_bn_fold_prep(const b2b_layer_desc* pre, const b2b_layer_desc* post, int D, float* out,
+                            cudaStream_t stream);
 // affine coupling, exact-fp32 CUDA-core kernel (any index lists)
-int b2b_launch_coupling_affine(const b2b_layer_desc& d, const float* x, float* y, float* logjac,
-                               int D, long long N, long long ldx, long long ldy, int accumulate,
+int b2b_launch_coupling_affine(const b2b_layer_desc& d, const float* fold, const float* x, float* y,
+                               float* logjac, int D, long long N, long long ldx, long long ldy, int accumulate,
                                cudaStream_t stream);

@@ -111,7 +111,8 @@ const char* b2b_status_string(int status);
  * ChangesOfVariables rule for ComposedFunction) ----------------------------------------------------
  * Applies layers[0], layers[1], ... in order (inner-most first), accumulating per-column log-Jacobians.
  * Consecutive column-local layers are fused into ONE kernel launch (each column is read once and
- * written once for the whole fused run); COUPLING_AFFINE layers run in their own GEMM kernel.
+ * written once for the whole fused run); COUPLING_AFFINE layers run in their own GEMM kernel, which also
+ * absorbs a BATCHNORM layer directly before and/or after it as a per-row affine (needs workspace).
  * If the last element is B2B_MVNORMAL_DIAG, `logjac` receives logpdf[n] = logpdf(MvNormal)(x_n) +
  * accumulated logjac (transformed_distribution.jl:165-169 when the preceding layers are the inverse
  * chain) and, when sum_out != NULL, *sum_out (device double) receives Σ_n logpdf[n] (fixed summation
@@ -131,7 +132,8 @@ int b2b_last_launch_count(void);
 /* Select kernel implementations (testing / profiling).  Ones digit -- fused column-local kernel: 0 = auto
  * (default), 1 = lane-group direct-global kernel (v0), 2 = TMA-staged thread-per-column kernel (v1) only.
  * Tens digit -- coupling: 0 = auto (tensor cores when the mask is contiguous and workspace is given),
- * 1 = always the exact-fp32 CUDA-core kernel. */
+ * 1 = always the exact-fp32 CUDA-core kernel.  Hundreds digit -- 1 = do not fold BatchNorm layers into
+ * neighbouring coupling launches. */
 int b2b_set_kernel_variant(int variant);
 
 /* ---- single layers (thin wrappers over a 1-element chain) --------------------------------------- */

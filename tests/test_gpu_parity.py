@@ -521,5 +521,25 @@ def test_realnvp_config5_shape(B):
     tot, lp2 = B.logpdf_sum(td, yd)
     assert abs(float(tot) - lpo.sum()) <= 1e-5 * abs(lpo.sum())
     xs, ljf = B.with_logabsdet_jacobian(flow, yd)
+    n_folded = B.lib().b2b_last_launch_count()
     xo, ljo = O.chain_forward(ora_layers, yv.astype(np.float64))
     assert rel(B.to_numpy(xs), xo) <= RTOL and rel(B.to_numpy(ljf), ljo) <= RTOL
+    # BatchNorm layers ride inside the coupling launches: 4 x (fold table + W image + tcgen05 kernel), no BN launch
+    assert n_folded == 12, n_folded
+    B.lib().b2b_set_kernel_variant(100)  # same chain with the BatchNorm layers as their own launches
+    try:
+        xs2, ljf2 = B.with_logabsdet_jacobian(flow, yd)
+        assert B.lib().b2b_last_launch_count() == 12  # 4 x (W image + kernel) + 4 BatchNorm launches
+        lp3 = B.to_numpy(B.logpdf(td, yd))
+    finally:
+        B.lib().b2b_set_kernel_variant(0)
+    assert rel(B.to_numpy(xs), B.to_numpy(xs2)) <= 2e-6 and rel(B.to_numpy(ljf), B.to_numpy(ljf2)) <= 2e-6
+    assert rel(lp, lp3) <= 2e-6
+    # the fp32 CUDA-core coupling kernel folds BatchNorm the same way
+    B.lib().b2b_set_kernel_variant(10)
+    try:
+        xs3, ljf3 = B.with_logabsdet_jacobian(flow, yd)
+        assert B.lib().b2b_last_launch_count() == 8  # 4 x (fold table + kernel)
+    finally:
+        B.lib().b2b_set_kernel_variant(0)
+    assert rel(B.to_numpy(xs3), xo) <= RTOL and rel(B.to_numpy(ljf3), ljo) <= RTOL
