@@ -235,10 +235,7 @@ __global__ void __launch_bounds__(256) chain_v0_kernel(const __grid_constant__ B
           lj += d.inverse ? -ljc : ljc;
         } break;
         case B2B_RQS: {
-          const int K1 = d.n0;
-          const float* W = sp;
-          const float* H = sp + K1 * Dp;
-          const float* Dv = sp + 2 * K1 * Dp;
+          const int K1 = d.n0, KP = rqs_kp(K1);
           float p[C];
 #pragma unroll
           for (int c = 0; c < C; ++c) {
@@ -250,8 +247,8 @@ __global__ void __launch_bounds__(256) chain_v0_kernel(const __grid_constant__ B
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 float o = e[q], l1 = 0.f;
-                if (d.inverse) rqs_element<true>(W, H, Dv, K1, Dp, r0 + q, e[q], o, l1);
-                else rqs_element<false>(W, H, Dv, K1, Dp, r0 + q, e[q], o, l1);
+                if (d.inverse) rqs_element<true>(sp, K1, KP, Dp, r0 + q, e[q], o, l1);
+                else rqs_element<false>(sp, K1, KP, Dp, r0 + q, e[q], o, l1);
                 e[q] = o;
                 acc += l1;
               }

@@ -214,17 +214,15 @@ template <int D, int TPC>
 __device__ __forceinline__ void rqs_apply(float2 (&x)[D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp, int K1,
                                           bool inverse, float& lj) {
   using C = ColCtx<D, TPC>;
-  const float* W = sp;
-  const float* H = sp + K1 * D;
-  const float* Dv = sp + 2 * K1 * D;
   float acc = 0.f;
+  const int KP = rqs_kp(K1);
   B2B_FOR_SLOTS {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float& xe = (e & 1) ? x[(ql * 8 + r) * 2 + (e >> 1)].y : x[(ql * 8 + r) * 2 + (e >> 1)].x;
       float o = xe, l1 = 0.f;
-      if (inverse) rqs_element<true>(W, H, Dv, K1, D, c.row(ql, r, e), xe, o, l1);
-      else rqs_element<false>(W, H, Dv, K1, D, c.row(ql, r, e), xe, o, l1);
+      if (inverse) rqs_element<true>(sp, K1, KP, D, c.row(ql, r, e), xe, o, l1);
+      else rqs_element<false>(sp, K1, KP, D, c.row(ql, r, e), xe, o, l1);
       xe = o;
       acc += l1;
     }
@@ -490,16 +488,21 @@ static int plan_v1(B2BChainParams& p, V1Plan& plan) {
   bool per_row = false;  // RQS / Stacked are unrolled per row: only built for <= 64 rows per thread
   for (int l = 0; l < p.L; ++l) per_row |= p.layers[l].kind == B2B_RQS || p.layers[l].kind == B2B_STACKED_EW;
   int nw, tpc;
-  if (D == 256) { plan.kernel = chain_v1_kernel<256, 4, 16>; nw = 16; tpc = 4; }
+  // warps per CTA are chosen so that the per-thread register budget (65536 / threads) holds the column fragment
+  // without spilling: 64 data registers need ~170 (12 warps), 128 need 255 (8 warps), 32 fit in 128 (16 warps)
+  static const int cfg = getenv("B2B_V1_CFG") ? atoi(getenv("B2B_V1_CFG")) : 0;
+  if (D == 256) { plan.kernel = chain_v1_kernel<256, 4, 12>; nw = 12; tpc = 4; }
   else if (D == 128) {
-    // default: one thread per column (128 data registers, 8 warps).  B2B_V1_CFG=216 / 212 select the
-    // 2-lanes-per-column builds (16 warps capped at 128 registers / 12 warps at 170) for experiments.
-    static const int cfg = getenv("B2B_V1_CFG") ? atoi(getenv("B2B_V1_CFG")) : 108;
-    if (cfg == 216 || (per_row && cfg != 212)) { plan.kernel = chain_v1_kernel<128, 2, 16>; nw = 16; tpc = 2; }
-    else if (cfg == 212) { plan.kernel = chain_v1_kernel<128, 2, 12>; nw = 12; tpc = 2; }
+    // default: one thread per column (128 data registers, 8 warps); chains with per-row layers (RQS, Stacked) use
+    // two lanes per column.  B2B_V1_CFG=216 / 212 force the 2-lane builds (16 / 12 warps) for experiments.
+    if (cfg == 216) { plan.kernel = chain_v1_kernel<128, 2, 16>; nw = 16; tpc = 2; }
+    else if (cfg == 212 || per_row) { plan.kernel = chain_v1_kernel<128, 2, 12>; nw = 12; tpc = 2; }
     else { plan.kernel = chain_v1_kernel<128, 1, 8>; nw = 8; tpc = 1; }
   }
-  else if (D == 64) { plan.kernel = chain_v1_kernel<64, 1, 16>; nw = 16; tpc = 1; }
+  else if (D == 64) {
+    if (cfg == 116) { plan.kernel = chain_v1_kernel<64, 1, 16>; nw = 16; tpc = 1; }
+    else { plan.kernel = chain_v1_kernel<64, 1, 12>; nw = 12; tpc = 1; }
+  }
   else { plan.kernel = chain_v1_kernel<32, 1, 16>; nw = 16; tpc = 1; }
   plan.cols = 32 / tpc;
   const int tile_bytes = D * 4 * plan.cols;

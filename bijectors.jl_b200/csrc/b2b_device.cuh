@@ -61,52 +61,54 @@ __device__ __forceinline__ float find_alpha(float t, float c, float b) {
 }
 
 // One RQS element (rational_quadratic_spline.jl:317-357 forward, :183-220 inverse + the forward
-// log-Jacobian at the recovered point, interface.jl:276-281).  Tables are knot-major [k][Dp].
-// `k` below is the reference's 1-based bin index (searchsortedfirst − 1).
+// log-Jacobian at the recovered point, interface.jl:276-281).
+// Staged tables (see stage_layer), ROW-major so that lanes that work on the same row but land in different bins
+// hit different banks: knots Sw[row][KP] (widths) and Sh[row][KP] (heights), padded with +inf up to KP = the next
+// power of two >= K1 (a branch-free binary search needs no bound checks), and per (row, bin) the eight per-bin
+// constants the reference recomputes for every element:
+//   {w_k, 1/w, w, h_k | Δy, s = Δy/w, d_k, d_{k+1} + d_k − 2s}
+// Bin k is the reference's 1-based index (searchsortedfirst − 1); bin 0 is the k == 0 branch (:331-343) that
+// only raw three-argument-constructor knots can reach.
+__host__ __device__ inline int rqs_kp(int K1) {
+  int kp = 2;
+  while (kp < K1) kp <<= 1;
+  return kp;
+}
+
 template <bool INV>
-__device__ __forceinline__ void rqs_element(const float* __restrict__ W, const float* __restrict__ H,
-                                            const float* __restrict__ Dv, int K1, int Dp, int row,
-                                            float v, float& out, float& lj) {
-  const float* S = INV ? H : W;  // table searched: heights for the inverse (:191), widths otherwise (:328)
-  const float Bs = S[(K1 - 1) * Dp + row];
-  if ((v <= -Bs) || (v >= Bs)) {  // identity outside the box, :322-324 / :186-188
-    out = v;
-    lj = 0.0f;
-    return;
-  }
+__device__ __forceinline__ void rqs_element(const float* __restrict__ tab, int K1, int KP, int Dp, int row, float v,
+                                            float& out, float& lj) {
+  const float* S = tab + (INV ? Dp * KP : 0) + row * KP;  // heights for the inverse (:191), widths otherwise (:328)
+  const float Bs = S[K1 - 1];
+  const bool outside = (v <= -Bs) || (v >= Bs);  // identity outside the box, :322-324 / :186-188
+  // k = number of knots < v  (searchsortedfirst − 1): branch-free binary search over the padded knots
   int k = 0;
-  for (int q = 0; q < K1; ++q) k += (S[q * Dp + row] < v) ? 1 : 0;
-  const int km = (k > 0 ? k : 1) - 1;
-  const float w_k = (k == 0) ? -W[(K1 - 1) * Dp + row] : W[km * Dp + row];  // :331
-  const float w = W[k * Dp + row] - w_k;
-  const float h_k = (k == 0) ? -H[(K1 - 1) * Dp + row] : H[km * Dp + row];  // :335
-  const float dy = H[k * Dp + row] - h_k;
-  const float s = dy / w;  // :339
-  const float d_k = (k == 0) ? 1.0f : Dv[km * Dp + row];        // :342
-  const float d_k1 = (k == K1 - 1) ? 1.0f : Dv[k * Dp + row];   // :343
-  float xi;
+  for (int st = KP >> 1; st >= 1; st >>= 1) k += (S[k + st - 1] < v) ? st : 0;
+  k = min(k, K1 - 1);
+  const float4* cf = reinterpret_cast<const float4*>(tab + 2 * Dp * KP) + (size_t)(row * K1 + k) * 2;
+  const float4 c0 = cf[0], c1 = cf[1];
+  const float w_k = c0.x, inv_w = c0.y, w = c0.z, h_k = c0.w;
+  const float dy = c1.x, sl = c1.y, d_k = c1.z, ds = c1.w;
+  const float d_k1 = ds - d_k + 2.0f * sl;
+  float xi, res;
   if (INV) {
-    const float ds = d_k1 + d_k - 2.0f * s;            // :205
     const float yh = v - h_k;
-    const float a1 = dy * (s - d_k) + yh * ds;         // :208
-    const float a2 = dy * d_k - yh * ds;               // :210
-    const float a3 = -s * yh;                          // :212
-    xi = (-2.0f * a3) / (a2 + sqrtf(a2 * a2 - 4.0f * a1 * a3));  // :215-217
-    out = xi * w + w_k;                                // :219
+    const float a1 = fmaf(dy, sl - d_k, yh * ds);   // :208
+    const float a2 = fmaf(dy, d_k, -yh * ds);       // :210
+    const float a3 = -sl * yh;                      // :212
+    xi = __fdividef(-2.0f * a3, a2 + sqrtf(fmaf(a2, a2, -4.0f * a1 * a3)));  // :215-217
+    res = fmaf(xi, w, w_k);                         // :219
   } else {
-    xi = (v - w_k) / w;  // :340
+    xi = (v - w_k) * inv_w;  // :340
   }
-  const float omx = 1.0f - xi;
-  const float den = s + (d_k1 + d_k - 2.0f * s) * xi * omx;  // :346
-  const float rden = 1.0f / den;
-  const float num = s * s * (d_k1 * xi * xi + 2.0f * s * xi * omx + d_k * omx * omx);  // :349
-  const float l = logf(num * rden * rden);  // = log(num) − 2·log(den), :350
-  if (INV) {
-    lj = -l;
-  } else {
-    lj = l;
-    out = h_k + dy * (s * xi * xi + d_k * xi * omx) * rden;  // :353-354
-  }
+  const float omx = 1.0f - xi, xo = xi * omx;
+  const float den = fmaf(ds, xo, sl);               // :346
+  const float rden = __fdividef(1.0f, den);
+  const float num = sl * sl * fmaf(d_k1 * xi, xi, fmaf(2.0f * sl, xo, d_k * omx * omx));  // :349
+  const float l = __logf(num * rden * rden);        // = log(num) − 2·log(den), :350
+  if (!INV) res = fmaf(dy * fmaf(sl * xi, xi, d_k * xo), rden, h_k);  // :353-354
+  out = outside ? v : res;
+  lj = outside ? 0.0f : (INV ? -l : l);
 }
 
 // ---- parameter staging (once per CTA) --------------------------------------------------------------
@@ -114,7 +116,7 @@ __device__ __forceinline__ void rqs_element(const float* __restrict__ W, const f
 //   PLANAR    : w[Dp] | û[Dp] | {c = wᵀû, b, -, -}                      (get_u_hat, planar_layer.jl:65-70)
 //   RADIAL    : z0[Dp] | {α, β̂, α+β̂, -}                                 (radial_layer.jl:44-45,91-92)
 //   BATCHNORM : A[Dp] | C[Dp] | iA[Dp] | iC[Dp] | {Σ(logs − log(v+eps)/2)}   y = A·x + C, x = iA·y + iC
-//   RQS       : W[K1][Dp] | H[K1][Dp] | Dv[K1][Dp]
+//   RQS       : Sw[Dp][KP] | Sh[Dp][KP] | per-(row,bin) constants float4 x 2 [Dp][K1]  ((2·KP + 8·K1)·Dp floats)
 //   PERMUTE   : src_of_dst[Dp] (int)
 //   STACKED_EW: code[Dp] (int) | a[Dp]
 //   MVNORMAL  : mu[Dp] | 1/sigma[Dp] | {−(D·log2π + Σ log σ²)/2}
@@ -183,12 +185,34 @@ __device__ inline void stage_layer(const b2b_layer_desc& d, float* sm, int D, in
       if (lane == 0) sm[4 * Dp] = lj;
     } break;
     case B2B_RQS: {
-      const int K1 = d.n0;
-      for (int t = 0; t < 3; ++t) {
-        const float* src = t == 0 ? d.p0 : (t == 1 ? d.p1 : d.p2);
-        float* dst = sm + t * K1 * Dp;
-        for (int k = 0; k < K1; ++k)
-          for (int i = lane; i < Dp; i += 32) dst[k * Dp + i] = i < D ? src[(size_t)k * D + i] : 0.f;
+      // row-major knots (padded with +inf) for the bin search + per-(row,bin) constants (see rqs_element); padded
+      // rows get a zero-width box, i.e. the identity with zero log-Jacobian
+      const int K1 = d.n0, KP = rqs_kp(K1);
+      float* Sw = sm;
+      float* Sh = sm + Dp * KP;
+      float4* cf = reinterpret_cast<float4*>(sm + 2 * Dp * KP);
+      const float inf = __int_as_float(0x7f800000);
+      for (int i = lane; i < Dp; i += 32) {
+        const bool in = i < D;
+        for (int k = 0; k < KP; ++k) {
+          const bool kin = k < K1;
+          Sw[i * KP + k] = kin ? (in ? d.p0[(size_t)k * D + i] : 0.f) : inf;
+          Sh[i * KP + k] = kin ? (in ? d.p1[(size_t)k * D + i] : 0.f) : inf;
+          if (!kin) continue;
+          float w_k = 0.f, w = 1.f, h_k = 0.f, dy = 1.f, d_k = 1.f, d_k1 = 1.f;
+          if (in) {
+            const float Wl = d.p0[(size_t)(K1 - 1) * D + i], Hl = d.p1[(size_t)(K1 - 1) * D + i];
+            w_k = k == 0 ? -Wl : d.p0[(size_t)(k - 1) * D + i];              // :331
+            w = d.p0[(size_t)k * D + i] - w_k;                               // :332
+            h_k = k == 0 ? -Hl : d.p1[(size_t)(k - 1) * D + i];              // :335
+            dy = d.p1[(size_t)k * D + i] - h_k;                              // :336
+            d_k = k == 0 ? 1.0f : d.p2[(size_t)(k - 1) * D + i];             // :342
+            d_k1 = k == K1 - 1 ? 1.0f : d.p2[(size_t)k * D + i];             // :343
+          }
+          const float sl = dy / w;                                           // :339
+          cf[(size_t)(i * K1 + k) * 2 + 0] = make_float4(w_k, 1.0f / w, w, h_k);
+          cf[(size_t)(i * K1 + k) * 2 + 1] = make_float4(dy, sl, d_k, d_k1 + d_k - 2.0f * sl);
+        }
       }
     } break;
     case B2B_PERMUTE: {

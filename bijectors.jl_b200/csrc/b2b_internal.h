@@ -24,7 +24,11 @@ static inline int b2b_layer_smem_floats(const b2b_layer_desc& d, int Dp) {
     case B2B_PLANAR: return 2 * Dp + 4;
     case B2B_RADIAL: return Dp + 4;
     case B2B_BATCHNORM: return 4 * Dp + 4;
-    case B2B_RQS: return 3 * d.n0 * Dp;
+    case B2B_RQS: {
+      int kp = 2;
+      while (kp < d.n0) kp <<= 1;  // knots padded to a power of two (rqs_kp)
+      return (2 * kp + 8 * d.n0) * Dp;
+    }
     case B2B_PERMUTE: return Dp;
     case B2B_STACKED_EW: return 2 * Dp;
     case B2B_MVNORMAL_DIAG: return 2 * Dp + 4;
