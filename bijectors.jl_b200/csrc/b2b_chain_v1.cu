@@ -83,11 +83,13 @@ struct V1Extra {
   long long tiles;
 };
 
-// Register layout of one thread: it owns rows [h*EPT, (h+1)*EPT) of its column (h = part index, TPC parts
-// per column) as float2 pairs so that the packed sm_100 FP32 pipe (FFMA2 / FADD2: two fp32 results per
-// issue slot) does the per-row work.  Box ql (of NQT = EPT/32 boxes) slot r holds the LOGICAL 16-byte
-// chunk r ^ rot (rot = h * 8/TPC keeps the TPC parts of a quarter-warp on different bank groups); pair
-// index = (ql*8 + r)*2 + {0,1}.  prm() returns the float4 index of the parameters matching slot (ql, r).
+// Register layout of one thread: it owns rows [h*EPT, (h+1)*EPT) (h = part index, TPC parts per column) of CPT
+// columns, as float2 pairs so that the packed sm_100 FP32 pipe (FFMA2: two fp32 results per issue slot) does
+// the per-row work.  Every layer parameter that is loaded from shared memory is used for all CPT columns of the
+// thread: at D = 128 (TPC = 2, CPT = 2) that halves the LDS wavefronts per column, which is what bounds the
+// one-column-per-thread mapping.  Box ql (of NQT = EPT/32 boxes) slot r holds the LOGICAL 16-byte chunk r ^ rot
+// (rot = h * 8/TPC keeps the TPC parts of a quarter-warp on different bank groups); pair index =
+// (ql*8 + r)*2 + {0,1}.  prm() returns the float4 index of the parameters matching slot (ql, r).
 template <int D, int TPC>
 struct ColCtx {
   static constexpr int EPT = D / TPC;
@@ -106,96 +108,114 @@ __device__ __forceinline__ float part_sum(float v) {
 
 #define B2B_FOR_SLOTS                        \
   _Pragma("unroll") for (int ql = 0; ql < C::NQT; ++ql) _Pragma("unroll") for (int r = 0; r < 8; ++r)
+#define B2B_FOR_COLS _Pragma("unroll") for (int cc = 0; cc < CPT; ++cc)
 
-template <int D, int TPC>
-__device__ __forceinline__ void planar_apply(float2 (&x)[D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp,
-                                             bool inverse, float& lj) {
+template <int D, int TPC, int CPT>
+__device__ __forceinline__ void planar_apply(float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp,
+                                             bool inverse, float (&lj)[CPT]) {
   using C = ColCtx<D, TPC>;
   const float4* w4 = reinterpret_cast<const float4*>(sp);
   const float4* u4 = reinterpret_cast<const float4*>(sp + D);
-  const float cc = sp[2 * D], bb = sp[2 * D + 1];
-  float2 acc[4];
+  const float cc_ = sp[2 * D], bb = sp[2 * D + 1];
+  float2 acc[CPT][4];
+  B2B_FOR_COLS {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < 4; ++i) acc[cc][i] = make_float2(0.f, 0.f);
+  }
   B2B_FOR_SLOTS {
     const float4 w = w4[c.prm(ql, r)];
     const int i = (ql * 8 + r) * 2;
-    acc[(r & 1) * 2 + 0] = __ffma2_rn(make_float2(w.x, w.y), x[i], acc[(r & 1) * 2 + 0]);
-    acc[(r & 1) * 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), x[i + 1], acc[(r & 1) * 2 + 1]);
+    B2B_FOR_COLS {
+      acc[cc][(r & 1) * 2 + 0] = __ffma2_rn(make_float2(w.x, w.y), x[cc][i], acc[cc][(r & 1) * 2 + 0]);
+      acc[cc][(r & 1) * 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), x[cc][i + 1], acc[cc][(r & 1) * 2 + 1]);
+    }
   }
-  const float2 s01 = __fadd2_rn(acc[0], acc[1]), s23 = __fadd2_rn(acc[2], acc[3]);
-  const float2 s = __fadd2_rn(s01, s23);
-  const float wz = part_sum<TPC>(s.x + s.y);  // aT_b(w, z), utils.jl:2
-  float t, s2;
-  if (!inverse) {
-    tanh_sech2(wz + bb, t, s2);
-    lj += log1pf(cc * s2);  // planar_layer.jl:107
-  } else {
-    const float alpha = find_alpha(wz, cc, bb);  // planar_layer.jl:121
-    tanh_sech2(alpha + bb, t, s2);
-    lj -= log1pf(cc * s2);
-    t = -t;
+  float2 t2[CPT];
+  B2B_FOR_COLS {
+    const float2 s = __fadd2_rn(__fadd2_rn(acc[cc][0], acc[cc][1]), __fadd2_rn(acc[cc][2], acc[cc][3]));
+    const float wz = part_sum<TPC>(s.x + s.y);  // aT_b(w, z), utils.jl:2
+    float t, s2;
+    if (!inverse) {
+      tanh_sech2(wz + bb, t, s2);
+      lj[cc] += log1pf(cc_ * s2);  // planar_layer.jl:107
+    } else {
+      const float alpha = find_alpha(wz, cc_, bb);  // planar_layer.jl:121
+      tanh_sech2(alpha + bb, t, s2);
+      lj[cc] -= log1pf(cc_ * s2);
+      t = -t;
+    }
+    t2[cc] = make_float2(t, t);
   }
-  const float2 t2 = make_float2(t, t);
   B2B_FOR_SLOTS {
     const float4 u = u4[c.prm(ql, r)];
     const int i = (ql * 8 + r) * 2;
-    x[i] = __ffma2_rn(make_float2(u.x, u.y), t2, x[i]);  // planar_layer.jl:78 / :124
-    x[i + 1] = __ffma2_rn(make_float2(u.z, u.w), t2, x[i + 1]);
+    B2B_FOR_COLS {
+      x[cc][i] = __ffma2_rn(make_float2(u.x, u.y), t2[cc], x[cc][i]);  // planar_layer.jl:78 / :124
+      x[cc][i + 1] = __ffma2_rn(make_float2(u.z, u.w), t2[cc], x[cc][i + 1]);
+    }
   }
 }
 
-template <int D, int TPC>
-__device__ __forceinline__ void radial_apply(float2 (&x)[D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp,
-                                             bool inverse, float& lj) {
+template <int D, int TPC, int CPT>
+__device__ __forceinline__ void radial_apply(float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp,
+                                             bool inverse, float (&lj)[CPT]) {
   using C = ColCtx<D, TPC>;
   const float4* z4 = reinterpret_cast<const float4*>(sp);
   const float alpha = sp[D], bhat = sp[D + 1], apb = sp[D + 2];
   const float2 m1 = make_float2(-1.f, -1.f);
-  float2 acc[4];
+  float2 acc[CPT][4];
+  B2B_FOR_COLS {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int i = 0; i < 4; ++i) acc[cc][i] = make_float2(0.f, 0.f);
+  }
   B2B_FOR_SLOTS {
     const float4 z0 = z4[c.prm(ql, r)];
     const int i = (ql * 8 + r) * 2;
-    const float2 d0 = __ffma2_rn(make_float2(z0.x, z0.y), m1, x[i]);
-    const float2 d1 = __ffma2_rn(make_float2(z0.z, z0.w), m1, x[i + 1]);
-    acc[(r & 1) * 2 + 0] = __ffma2_rn(d0, d0, acc[(r & 1) * 2 + 0]);
-    acc[(r & 1) * 2 + 1] = __ffma2_rn(d1, d1, acc[(r & 1) * 2 + 1]);
+    B2B_FOR_COLS {
+      const float2 d0 = __ffma2_rn(make_float2(z0.x, z0.y), m1, x[cc][i]);
+      const float2 d1 = __ffma2_rn(make_float2(z0.z, z0.w), m1, x[cc][i + 1]);
+      acc[cc][(r & 1) * 2 + 0] = __ffma2_rn(d0, d0, acc[cc][(r & 1) * 2 + 0]);
+      acc[cc][(r & 1) * 2 + 1] = __ffma2_rn(d1, d1, acc[cc][(r & 1) * 2 + 1]);
+    }
   }
-  const float2 s = __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
-  const float nrm = sqrtf(part_sum<TPC>(s.x + s.y));  // radial_layer.jl:49 / :125
-  float r_ = nrm;
-  if (inverse) {
-    const float a = apb - nrm;  // radial_layer.jl:126-127
-    const float sq = sqrtf(fmaf(a, a, 4.0f * alpha * nrm));
-    r_ = a > 0.f ? (2.0f * alpha * nrm) / (sq + a) : 0.5f * (sq - a);
+  float2 g2[CPT];
+  B2B_FOR_COLS {
+    const float2 s = __fadd2_rn(__fadd2_rn(acc[cc][0], acc[cc][1]), __fadd2_rn(acc[cc][2], acc[cc][3]));
+    const float nrm = sqrtf(part_sum<TPC>(s.x + s.y));  // radial_layer.jl:49 / :125
+    float r_ = nrm;
+    if (inverse) {
+      const float a = apb - nrm;  // radial_layer.jl:126-127
+      const float sq = sqrtf(fmaf(a, a, 4.0f * alpha * nrm));
+      r_ = a > 0.f ? (2.0f * alpha * nrm) / (sq + a) : 0.5f * (sq - a);
+    }
+    const float hh = 1.0f / (alpha + r_);
+    const float bh = bhat * hh;
+    const float ljf = (float)(D - 1) * log1pf(bh) + log1pf(bh * alpha * hh);  // radial_layer.jl:68-70
+    float g;
+    if (!inverse) {
+      g = bh;
+      lj[cc] += ljf;
+    } else {
+      g = -bhat / (apb + r_);  // (α+r)/(α+β̂+r) − 1, radial_layer.jl:96
+      lj[cc] -= ljf;
+    }
+    g2[cc] = make_float2(g, g);
   }
-  const float hh = 1.0f / (alpha + r_);
-  const float bh = bhat * hh;
-  const float ljf = (float)(D - 1) * log1pf(bh) + log1pf(bh * alpha * hh);  // radial_layer.jl:68-70
-  float g;
-  if (!inverse) {
-    g = bh;
-    lj += ljf;
-  } else {
-    g = -bhat / (apb + r_);  // (α+r)/(α+β̂+r) − 1, radial_layer.jl:96
-    lj -= ljf;
-  }
-  const float2 g2 = make_float2(g, g);
   B2B_FOR_SLOTS {
     const float4 z0 = z4[c.prm(ql, r)];
     const int i = (ql * 8 + r) * 2;
-    const float2 d0 = __ffma2_rn(make_float2(z0.x, z0.y), m1, x[i]);
-    const float2 d1 = __ffma2_rn(make_float2(z0.z, z0.w), m1, x[i + 1]);
-    x[i] = __ffma2_rn(g2, d0, x[i]);
-    x[i + 1] = __ffma2_rn(g2, d1, x[i + 1]);
+    B2B_FOR_COLS {
+      const float2 d0 = __ffma2_rn(make_float2(z0.x, z0.y), m1, x[cc][i]);
+      const float2 d1 = __ffma2_rn(make_float2(z0.z, z0.w), m1, x[cc][i + 1]);
+      x[cc][i] = __ffma2_rn(g2[cc], d0, x[cc][i]);
+      x[cc][i + 1] = __ffma2_rn(g2[cc], d1, x[cc][i + 1]);
+    }
   }
 }
 
-template <int D, int TPC>
-__device__ __forceinline__ void batchnorm_apply(float2 (&x)[D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp,
-                                                bool inverse, float& lj) {
+template <int D, int TPC, int CPT>
+__device__ __forceinline__ void batchnorm_apply(float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& c,
+                                                const float* sp, bool inverse, float (&lj)[CPT]) {
   using C = ColCtx<D, TPC>;
   // staged as y = A·x + C (fwd) / x = iA·y + iC (inverse): normalise.jl:66 / :84 with the constants folded
   const float4* A4 = reinterpret_cast<const float4*>(sp + (inverse ? 2 * D : 0));
@@ -203,95 +223,110 @@ __device__ __forceinline__ void batchnorm_apply(float2 (&x)[D / TPC / 2], const 
   B2B_FOR_SLOTS {
     const float4 a = A4[c.prm(ql, r)], k = C4[c.prm(ql, r)];
     const int i = (ql * 8 + r) * 2;
-    x[i] = __ffma2_rn(x[i], make_float2(a.x, a.y), make_float2(k.x, k.y));
-    x[i + 1] = __ffma2_rn(x[i + 1], make_float2(a.z, a.w), make_float2(k.z, k.w));
+    B2B_FOR_COLS {
+      x[cc][i] = __ffma2_rn(x[cc][i], make_float2(a.x, a.y), make_float2(k.x, k.y));
+      x[cc][i + 1] = __ffma2_rn(x[cc][i + 1], make_float2(a.z, a.w), make_float2(k.z, k.w));
+    }
   }
   const float ljc = sp[4 * D];
-  lj += inverse ? -ljc : ljc;
+  B2B_FOR_COLS lj[cc] += inverse ? -ljc : ljc;
 }
 
-template <int D, int TPC>
-__device__ __forceinline__ void rqs_apply(float2 (&x)[D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp, int K1,
-                                          bool inverse, float& lj) {
+template <int D, int TPC, int CPT>
+__device__ __forceinline__ void rqs_apply(float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp,
+                                          int K1, bool inverse, float (&lj)[CPT]) {
   using C = ColCtx<D, TPC>;
-  float acc = 0.f;
   const int KP = rqs_kp(K1);
+  float acc[CPT];
+  B2B_FOR_COLS acc[cc] = 0.f;
   B2B_FOR_SLOTS {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float& xe = (e & 1) ? x[(ql * 8 + r) * 2 + (e >> 1)].y : x[(ql * 8 + r) * 2 + (e >> 1)].x;
-      float o = xe, l1 = 0.f;
-      if (inverse) rqs_element<true>(sp, K1, KP, D, c.row(ql, r, e), xe, o, l1);
-      else rqs_element<false>(sp, K1, KP, D, c.row(ql, r, e), xe, o, l1);
-      xe = o;
-      acc += l1;
+      const int row = c.row(ql, r, e);
+      B2B_FOR_COLS {
+        float& xe = (e & 1) ? x[cc][(ql * 8 + r) * 2 + (e >> 1)].y : x[cc][(ql * 8 + r) * 2 + (e >> 1)].x;
+        float o = xe, l1 = 0.f;
+        if (inverse) rqs_element<true>(sp, K1, KP, D, row, xe, o, l1);
+        else rqs_element<false>(sp, K1, KP, D, row, xe, o, l1);
+        xe = o;
+        acc[cc] += l1;
+      }
     }
   }
-  lj += part_sum<TPC>(acc);  // sum over dimensions, rational_quadratic_spline.jl:304-309
+  B2B_FOR_COLS lj[cc] += part_sum<TPC>(acc[cc]);  // sum over dimensions, rational_quadratic_spline.jl:304-309
 }
 
-template <int D, int TPC>
-__device__ __forceinline__ void stacked_apply(float2 (&x)[D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp,
-                                              bool inverse, float& lj) {
+template <int D, int TPC, int CPT>
+__device__ __forceinline__ void stacked_apply(float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp,
+                                              bool inverse, float (&lj)[CPT]) {
   using C = ColCtx<D, TPC>;
   const int* code = reinterpret_cast<const int*>(sp);
   const float* av = sp + D;
-  float acc = 0.f;
+  float acc[CPT];
+  B2B_FOR_COLS acc[cc] = 0.f;
   B2B_FOR_SLOTS {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float& xe = (e & 1) ? x[(ql * 8 + r) * 2 + (e >> 1)].y : x[(ql * 8 + r) * 2 + (e >> 1)].x;
       const int row = c.row(ql, r, e);
       int op = code[row];
       const float a = av[row];
       if (inverse) op = op == B2B_EW_EXP ? B2B_EW_LOG : (op == B2B_EW_LOG ? B2B_EW_EXP : op);
-      const float xv = xe;
-      if (op == B2B_EW_EXP) {
-        xe = expf(xv);
-        acc += xv;
-      } else if (op == B2B_EW_LOG) {
-        const float lg = logf(xv);
-        xe = lg;
-        acc -= lg;
-      } else if (op == B2B_EW_SHIFT) {
-        xe = inverse ? xv - a : a + xv;
-      } else if (op == B2B_EW_SCALE) {
-        xe = inverse ? xv / a : a * xv;
-        const float la = logf(fabsf(a));
-        acc += inverse ? -la : la;
+      B2B_FOR_COLS {
+        float& xe = (e & 1) ? x[cc][(ql * 8 + r) * 2 + (e >> 1)].y : x[cc][(ql * 8 + r) * 2 + (e >> 1)].x;
+        const float xv = xe;
+        if (op == B2B_EW_EXP) {
+          xe = expf(xv);
+          acc[cc] += xv;
+        } else if (op == B2B_EW_LOG) {
+          const float lg = logf(xv);
+          xe = lg;
+          acc[cc] -= lg;
+        } else if (op == B2B_EW_SHIFT) {
+          xe = inverse ? xv - a : a + xv;
+        } else if (op == B2B_EW_SCALE) {
+          xe = inverse ? xv / a : a * xv;
+          const float la = logf(fabsf(a));
+          acc[cc] += inverse ? -la : la;
+        }
       }
     }
   }
-  lj += part_sum<TPC>(acc);
+  B2B_FOR_COLS lj[cc] += part_sum<TPC>(acc[cc]);
 }
 
-template <int D, int TPC>
-__device__ __forceinline__ void mvnormal_apply(const float2 (&x)[D / TPC / 2], const ColCtx<D, TPC>& c,
-                                               const float* sp, float& lj) {
+template <int D, int TPC, int CPT>
+__device__ __forceinline__ void mvnormal_apply(const float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& c,
+                                               const float* sp, float (&lj)[CPT]) {
   using C = ColCtx<D, TPC>;
   const float4* mu4 = reinterpret_cast<const float4*>(sp);
   const float4* is4 = reinterpret_cast<const float4*>(sp + D);
   const float2 m1 = make_float2(-1.f, -1.f);
-  float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  float2 acc[CPT][2];
+  B2B_FOR_COLS acc[cc][0] = acc[cc][1] = make_float2(0.f, 0.f);
   B2B_FOR_SLOTS {
     const float4 mu = mu4[c.prm(ql, r)], is = is4[c.prm(ql, r)];
     const int i = (ql * 8 + r) * 2;
-    const float2 z0 = __fmul2_rn(__ffma2_rn(make_float2(mu.x, mu.y), m1, x[i]), make_float2(is.x, is.y));
-    const float2 z1 = __fmul2_rn(__ffma2_rn(make_float2(mu.z, mu.w), m1, x[i + 1]), make_float2(is.z, is.w));
-    acc[0] = __ffma2_rn(z0, z0, acc[0]);
-    acc[1] = __ffma2_rn(z1, z1, acc[1]);
+    B2B_FOR_COLS {
+      const float2 z0 = __fmul2_rn(__ffma2_rn(make_float2(mu.x, mu.y), m1, x[cc][i]), make_float2(is.x, is.y));
+      const float2 z1 = __fmul2_rn(__ffma2_rn(make_float2(mu.z, mu.w), m1, x[cc][i + 1]), make_float2(is.z, is.w));
+      acc[cc][0] = __ffma2_rn(z0, z0, acc[cc][0]);
+      acc[cc][1] = __ffma2_rn(z1, z1, acc[cc][1]);
+    }
   }
-  const float2 s = __fadd2_rn(acc[0], acc[1]);
-  lj += sp[2 * D] - 0.5f * part_sum<TPC>(s.x + s.y);
+  B2B_FOR_COLS {
+    const float2 s = __fadd2_rn(acc[cc][0], acc[cc][1]);
+    lj[cc] += sp[2 * D] - 0.5f * part_sum<TPC>(s.x + s.y);
+  }
 }
 
-template <int D, int TPC, int NW>
+template <int D, int TPC, int CPT, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
     chain_v1_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
                     const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y) {
   using C = ColCtx<D, TPC>;
   constexpr int NQ = D / 32;                 // boxes per tile
-  constexpr int COLS = 32 / TPC;             // columns per tile (= per warp)
+  constexpr int LPC = 32 / TPC;              // lane groups per warp
+  constexpr int COLS = LPC * CPT;            // columns per tile (= per warp)
   constexpr int BOX_BYTES = COLS * 128;      // COLS lines of 128 B
   constexpr int TILE_BYTES = NQ * BOX_BYTES;
   extern __shared__ unsigned char smem_dyn[];
@@ -331,12 +366,13 @@ __global__ void __launch_bounds__(NW * 32, 1)
   __syncthreads();
 
   C ctx;
-  const int t = lane / TPC;
+  const int t = lane / TPC;  // lane group: columns t, t + LPC, ... of the tile
   ctx.h = lane % TPC;
   ctx.rot = ctx.h * (8 / TPC);
   unsigned char* my_out = out_base + (size_t)warp * TILE_BYTES;
-  const int sw = (((t & 7) ^ ctx.rot) & 7) * 16;  // byte XOR: physical slot = r ^ rot ^ (line & 7)
-  const int line = t * 128 + ctx.h * C::NQT * BOX_BYTES;  // this thread's line inside its first box
+  // byte XOR: physical slot = r ^ rot ^ (line & 7); LPC is a multiple of 8, so it is the same for all CPT columns
+  const int sw = (((t & 7) ^ ctx.rot) & 7) * 16;
+  const int line = t * 128 + ctx.h * C::NQT * BOX_BYTES;  // this thread's first line inside its first box
   double dsum = 0.0;
   bool store_pending = false;
 
@@ -348,13 +384,16 @@ __global__ void __launch_bounds__(NW * 32, 1)
     while (armed[buf] != (int)j) __nanosleep(20);
     mbar_wait(smem_u32(&bars[buf]), parity);
 
-    float2 x[C::EPT / 2];
+    float2 x[CPT][C::EPT / 2];
     {
       const unsigned char* src = in_base + (size_t)buf * TILE_BYTES + line;
-      B2B_FOR_SLOTS {
-        const float4 v = *reinterpret_cast<const float4*>(src + ql * BOX_BYTES + ((r * 16) ^ sw));
-        x[(ql * 8 + r) * 2] = make_float2(v.x, v.y);
-        x[(ql * 8 + r) * 2 + 1] = make_float2(v.z, v.w);
+      B2B_FOR_COLS {
+        B2B_FOR_SLOTS {
+          const float4 v =
+              *reinterpret_cast<const float4*>(src + cc * (LPC * 128) + ql * BOX_BYTES + ((r * 16) ^ sw));
+          x[cc][(ql * 8 + r) * 2] = make_float2(v.x, v.y);
+          x[cc][(ql * 8 + r) * 2 + 1] = make_float2(v.z, v.w);
+        }
       }
     }
     __syncwarp();
@@ -371,22 +410,26 @@ __global__ void __launch_bounds__(NW * 32, 1)
       armed[buf] = (int)(j + E.n_in);
     }
 
-    float lj = (P.accumulate && P.logjac && col < P.N) ? P.logjac[col] : 0.0f;
+    float lj[CPT];
+    B2B_FOR_COLS {
+      const long long cl = col + cc * LPC;
+      lj[cc] = (P.accumulate && P.logjac && cl < P.N) ? P.logjac[cl] : 0.0f;
+    }
 #pragma unroll 1
     for (int l = 0; l < P.L; ++l) {
       const b2b_layer_desc& d = P.layers[l];
       const float* sp = params + P.soff[l];
       switch (d.kind) {
-        case B2B_PLANAR: planar_apply<D, TPC>(x, ctx, sp, d.inverse != 0, lj); break;
-        case B2B_RADIAL: radial_apply<D, TPC>(x, ctx, sp, d.inverse != 0, lj); break;
-        case B2B_BATCHNORM: batchnorm_apply<D, TPC>(x, ctx, sp, d.inverse != 0, lj); break;
+        case B2B_PLANAR: planar_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj); break;
+        case B2B_RADIAL: radial_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj); break;
+        case B2B_BATCHNORM: batchnorm_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj); break;
         case B2B_RQS:
-          if constexpr (C::EPT <= 64) rqs_apply<D, TPC>(x, ctx, sp, d.n0, d.inverse != 0, lj);
+          if constexpr (C::EPT * CPT <= 64) rqs_apply<D, TPC, CPT>(x, ctx, sp, d.n0, d.inverse != 0, lj);
           break;
         case B2B_STACKED_EW:
-          if constexpr (C::EPT <= 64) stacked_apply<D, TPC>(x, ctx, sp, d.inverse != 0, lj);
+          if constexpr (C::EPT * CPT <= 64) stacked_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj);
           break;
-        case B2B_MVNORMAL_DIAG: mvnormal_apply<D, TPC>(x, ctx, sp, lj); break;
+        case B2B_MVNORMAL_DIAG: mvnormal_apply<D, TPC, CPT>(x, ctx, sp, lj); break;
         default: break;
       }
     }
@@ -397,9 +440,12 @@ __global__ void __launch_bounds__(NW * 32, 1)
         __syncwarp();
       }
       unsigned char* dst = my_out + line;
-      B2B_FOR_SLOTS {
-        const float2 a = x[(ql * 8 + r) * 2], b = x[(ql * 8 + r) * 2 + 1];
-        *reinterpret_cast<float4*>(dst + ql * BOX_BYTES + ((r * 16) ^ sw)) = make_float4(a.x, a.y, b.x, b.y);
+      B2B_FOR_COLS {
+        B2B_FOR_SLOTS {
+          const float2 a = x[cc][(ql * 8 + r) * 2], b = x[cc][(ql * 8 + r) * 2 + 1];
+          *reinterpret_cast<float4*>(dst + cc * (LPC * 128) + ql * BOX_BYTES + ((r * 16) ^ sw)) =
+              make_float4(a.x, a.y, b.x, b.y);
+        }
       }
       fence_proxy_async();
       __syncwarp();
@@ -411,9 +457,14 @@ __global__ void __launch_bounds__(NW * 32, 1)
       }
       store_pending = true;
     }
-    if (ctx.h == 0 && col < P.N) {
-      if (P.logjac) P.logjac[col] = lj;
-      dsum += (double)lj;
+    if (ctx.h == 0) {
+      B2B_FOR_COLS {
+        const long long cl = col + cc * LPC;
+        if (cl < P.N) {
+          if (P.logjac) P.logjac[cl] = lj[cc];
+          dsum += (double)lj[cc];
+        }
+      }
     }
   }
   if (lane == 0 && store_pending) tma_wait_all0();  // smem must stay valid until the stores have drained
@@ -487,24 +538,27 @@ static int plan_v1(B2BChainParams& p, V1Plan& plan) {
   p.scratch_off = -1;
   bool per_row = false;  // RQS / Stacked are unrolled per row: only built for <= 64 rows per thread
   for (int l = 0; l < p.L; ++l) per_row |= p.layers[l].kind == B2B_RQS || p.layers[l].kind == B2B_STACKED_EW;
-  int nw, tpc;
-  // warps per CTA are chosen so that the per-thread register budget (65536 / threads) holds the column fragment
-  // without spilling: 64 data registers need ~170 (12 warps), 128 need 255 (8 warps), 32 fit in 128 (16 warps)
+  // <D, lanes per column, columns per thread, warps>: warps are chosen so that the per-thread register budget
+  // (65536 / threads) holds the fragment without spilling: 64 data registers need ~170 (12 warps), 128 need 255
+  // (8 warps), 32 fit in 128 (16 warps).  B2B_V1_CFG selects alternative builds for experiments.
   static const int cfg = getenv("B2B_V1_CFG") ? atoi(getenv("B2B_V1_CFG")) : 0;
-  if (D == 256) { plan.kernel = chain_v1_kernel<256, 4, 12>; nw = 12; tpc = 4; }
+  int nw, tpc, cpt = 1;
+  if (D == 256) { plan.kernel = chain_v1_kernel<256, 4, 1, 12>; nw = 12; tpc = 4; }
   else if (D == 128) {
-    // default: one thread per column (128 data registers, 8 warps); chains with per-row layers (RQS, Stacked) use
-    // two lanes per column.  B2B_V1_CFG=216 / 212 force the 2-lane builds (16 / 12 warps) for experiments.
-    if (cfg == 216) { plan.kernel = chain_v1_kernel<128, 2, 16>; nw = 16; tpc = 2; }
-    else if (cfg == 212 || per_row) { plan.kernel = chain_v1_kernel<128, 2, 12>; nw = 12; tpc = 2; }
-    else { plan.kernel = chain_v1_kernel<128, 1, 8>; nw = 8; tpc = 1; }
+    // default: one thread per column (measured fastest: 4.4-4.5 G samples/s on C2).  Chains with per-row layers
+    // (RQS, Stacked) use two lanes per column.  B2B_V1_CFG=2218 selects the build with two lanes per column and
+    // TWO columns per thread (every parameter load serves two columns: LDS wavefronts -36 %, but more scalar work
+    // per warp; measured 4.06 G samples/s), 2112 the 2-lane / 12-warp build (3.7 G samples/s).
+    if (cfg == 2218 && !per_row) { plan.kernel = chain_v1_kernel<128, 2, 2, 8>; nw = 8; tpc = 2; cpt = 2; }
+    else if (cfg == 2112 || per_row) { plan.kernel = chain_v1_kernel<128, 2, 1, 12>; nw = 12; tpc = 2; }
+    else { plan.kernel = chain_v1_kernel<128, 1, 1, 8>; nw = 8; tpc = 1; }
   }
   else if (D == 64) {
-    if (cfg == 116) { plan.kernel = chain_v1_kernel<64, 1, 16>; nw = 16; tpc = 1; }
-    else { plan.kernel = chain_v1_kernel<64, 1, 12>; nw = 12; tpc = 1; }
+    if (cfg == 1128 && !per_row) { plan.kernel = chain_v1_kernel<64, 1, 2, 8>; nw = 8; tpc = 1; cpt = 2; }
+    else { plan.kernel = chain_v1_kernel<64, 1, 1, 12>; nw = 12; tpc = 1; }
   }
-  else { plan.kernel = chain_v1_kernel<32, 1, 16>; nw = 16; tpc = 1; }
-  plan.cols = 32 / tpc;
+  else { plan.kernel = chain_v1_kernel<32, 1, 1, 16>; nw = 16; tpc = 1; }
+  plan.cols = (32 / tpc) * cpt;
   const int tile_bytes = D * 4 * plan.cols;
   const size_t param_bytes = (size_t)off * sizeof(float);
   const size_t budget = 225 * 1024;
