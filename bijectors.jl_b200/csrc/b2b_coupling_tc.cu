@@ -11,19 +11,23 @@
 // power-of-two rescale (W by one global 2^k, every x₂ column by its own 2^k, undone in the epilogue), and
 // three products hi·hi + hi·lo + lo·hi are accumulated in fp32 in TMEM (the dropped lo·lo term is 2^-22).
 //
-// Warp roles of the persistent CTA (288 threads, one CTA per SM):
-//   warps 0-3  epilogue : tcgen05.ld s/t rows out of TMEM (thread = row j), add c, read x₁ from global,
+// Warp roles of the persistent CTA (544 threads, one CTA per SM; the roles are latency-bound, so each gets 8 warps):
+//   warps 0-7  epilogue : tcgen05.ld s/t rows out of TMEM (thread = row j = 32·(warp%4)+lane, columns
+//                         32·(warp/4)..+31 of the tile), add c, read x₁ from global (prefetched one chunk ahead),
 //                         y₁ = exp(s)·x₁ + t (or the inverse) and store -- 512 B contiguous per column
-//   warps 4-7  producers: coalesced float4 loads of the x₂ rows, per-column scale, hi/lo split, store into the
-//                         K-major 128B-swizzled UMMA operand layout, logjac = wsum·x₂ + Σc in fp32
-//                         (Σ_j s_j = (Σ_j W_j)·x₂ + Σ_j c_j), pass-through rows when y != x
-//   warp  8    MMA      : one elected lane issues 48 tcgen05.mma (M128 N64 K16, kind::f16) per tile
+//   warps 8-15 producers: coalesced float4 loads of the x₂ rows (prefetched one tile ahead), per-column scale
+//                         (REDUX max of the float bit patterns), hi/lo split, store into the K-major 128B-swizzled
+//                         UMMA operand layout, logjac = wsum·x₂ + Σc in fp32 (Σ_j s_j = (Σ_j W_j)·x₂ + Σ_j c_j),
+//                         pass-through rows when y != x
+//   warp  16   MMA      : one elected lane issues 48 tcgen05.mma (M128 N64 K16, kind::f16) per tile
 // W (both halves, both M tiles) stays resident in shared memory for the lifetime of the CTA (128 KB at
 // n2 = 128); x₂ operand stages and TMEM accumulator stages are double buffered and handed over with
 // mbarriers (tcgen05.commit on the MMA side).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "b2b_internal.h"
 
@@ -35,7 +39,8 @@ constexpr int TC_ACC = 2;             // accumulator stages in TMEM
 constexpr int TC_SCALE_SLOTS = 4;     // per-column scale slots (producer may run 4 tiles ahead of the epilogue)
 constexpr int TC_ABLK = 128 * 128;    // one [128 rows x 64 k] fp16 block, 128B-swizzled, 16 KB
 constexpr int TC_BBLK = TC_T * 128;   // one [64 rows x 64 k] fp16 block, 8 KB
-constexpr int TC_THREADS = 288;
+constexpr int TC_THREADS = 544;
+constexpr int TC_PROD_WARPS = 8, TC_EPI_WARPS = 8, TC_MMA_WARP = 16;
 constexpr int TC_TMEM_COLS = 256;     // 2 stages x (s: 64 + t: 64) fp32 columns
 
 struct TcParams {
@@ -49,6 +54,7 @@ struct TcParams {
   const float* cvec;          // [2 n1] or NULL
   long long N, ldx, ldy, tiles;
   int D, n1, n2, nkb, row1, row2, accumulate, inverse;
+  int debug;  // B2B_TC_DEBUG bit mask (profiling only): 1 epilogue no global I/O, 2 producers no global I/O, 4 no MMA
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------
@@ -192,17 +198,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
-      bar_init(sm_u32(&bars[0 + s]), 4);  // 4 producer warps
+      bar_init(sm_u32(&bars[0 + s]), TC_PROD_WARPS);
       bar_init(sm_u32(&bars[2 + s]), 1);  // tcgen05.commit
     }
     for (int a = 0; a < TC_ACC; ++a) {
       bar_init(sm_u32(&bars[4 + a]), 1);  // tcgen05.commit
-      bar_init(sm_u32(&bars[6 + a]), 4);  // 4 epilogue warps
+      bar_init(sm_u32(&bars[6 + a]), TC_EPI_WARPS);
     }
     bar_init(sm_u32(&bars[8]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm_u32(tmem_slot)),
                  "r"((uint32_t)TC_TMEM_COLS)
                  : "memory");
@@ -214,7 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
   const long long my_tiles = (P.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
       const uint32_t wbar = sm_u32(&bars[8]);
@@ -241,7 +247,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
               const uint32_t baddr = bB + (uint32_t)((pb * nkb + kb) * TC_BBLK);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {  // 4 K-steps of 16 fp16 (32 B) inside the 128-byte swizzle atom
-                tc_mma_f16(d_tmem, umma_desc_k_sw128(aaddr + 32 * j), umma_desc_k_sw128(baddr + 32 * j), TC_IDESC, acc);
+                if (!(P.debug & 4))
+                  tc_mma_f16(d_tmem, umma_desc_k_sw128(aaddr + 32 * j), umma_desc_k_sw128(baddr + 32 * j), TC_IDESC, acc);
                 acc = 1;
               }
             }
@@ -251,14 +258,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
         tc_commit(sm_u32(&bars[4 + a]));  // accumulators ready for the epilogue
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= TC_EPI_WARPS) {
     // ================================ producers ================================
-    // Warp p converts columns [16p, 16p+16) of every tile.  Lane l holds the float4 #l of a column (rows
-    // row2+4l..+3).  The 16 per-column maxima (operand scale) and the 16 dots with wsum (log-Jacobian) are reduced
-    // TOGETHER by a transposing butterfly (16 + 16 shuffles for 16 columns instead of 160); afterwards lane l owns
-    // column own(l) and does that column's scalar work once.  x₂ registers always hold the NEXT tile while the
+    // Warp p converts columns [8p, 8p+8) of every tile.  Lane l holds the float4 #l of a column (rows
+    // row2+4l..+3).  The per-column maximum (operand scale) is ONE redux.sync on the float bit patterns (monotonic
+    // for non-negative floats); the 8 dots with wsum (log-Jacobian) are reduced together by a transposing butterfly
+    // (7+2 shuffles), after which lane l owns column (l>>2)&7.  x₂ registers always hold the NEXT tile while the
     // current one is being converted (refilled column by column), so DRAM latency hides behind a tile of work.
-    const int p = warp - 4;
+    constexpr int CW = TC_T / TC_PROD_WARPS;  // 8 columns per producer warp
+    const int p = warp - TC_EPI_WARPS;
     const bool active = 4 * lane < P.n2;
     const float4 ws = active ? *reinterpret_cast<const float4*>(P.wsum + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float inv_scale_w = P.meta[0];
@@ -270,60 +278,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
     const float4 preC = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + P.D + P.row2 + 4 * lane) : zero4;
     const float4 postA = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + 2 * P.D + P.row2 + 4 * lane) : one4;
     const float4 postC = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + 3 * P.D + P.row2 + 4 * lane) : zero4;
-    const bool write_y2 = P.y != nullptr && (P.y != P.x || fold);
-    // column owned by this lane after the transposing reduction, and the lane that owns column c
-    const int own = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const bool write_y2 = P.y != nullptr && (P.y != P.x || fold) && !(P.debug & 2);
+    const int own = (lane >> 2) & 7;  // column owned by this lane after the transposing reduction
     const float* xlane = P.x + P.row2 + (active ? 4 * lane : 0);  // inactive lanes read a valid address, result unused
-    float4 v[16];
+    float4 v[CW];
     auto load_tile = [&](long long tile, int c) -> float4 {
-      long long col = tile * TC_T + p * 16 + c;
+      long long col = tile * TC_T + p * CW + c;
       col = col < P.N ? col : P.N - 1;  // clamp instead of predicating; stores are predicated
+      if (P.debug & 2) return make_float4(1.f, 2.f, 3.f, 4.f);
       return __ldcs(reinterpret_cast<const float4*>(xlane + col * P.ldx));
     };
     if (my_tiles > 0) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) v[c] = load_tile(blockIdx.x, c);
+      for (int c = 0; c < CW; ++c) v[c] = load_tile(blockIdx.x, c);
     }
     for (long long i = 0; i < my_tiles; ++i) {
       const int s = (int)(i & 1);
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
       const long long tile = blockIdx.x + i * gridDim.x;
-      const long long col0 = tile * TC_T + p * 16;
+      const long long col0 = tile * TC_T + p * CW;
       const long long next_tile = (i + 1 < my_tiles) ? tile + gridDim.x : tile;
-      float mx[16], dt[16];
+      float dt[CW];
+      unsigned emax[CW];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
+      for (int c = 0; c < CW; ++c) {
         float4 vc = v[c];
         if (fold)
           vc = make_float4(fmaf(vc.x, preA.x, preC.x), fmaf(vc.y, preA.y, preC.y), fmaf(vc.z, preA.z, preC.z),
                            fmaf(vc.w, preA.w, preC.w));
         if (!active) vc = zero4;
         v[c] = vc;
-        mx[c] = fmaxf(fmaxf(fabsf(vc.x), fabsf(vc.y)), fmaxf(fabsf(vc.z), fabsf(vc.w)));
+        const float mx = fmaxf(fmaxf(fabsf(vc.x), fabsf(vc.y)), fmaxf(fabsf(vc.z), fabsf(vc.w)));
+        emax[c] = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));  // bits of max|x₂ column|
         dt[c] = fmaf(vc.x, ws.x, fmaf(vc.y, ws.y, fmaf(vc.z, ws.z, vc.w * ws.w)));
       }
-      // transposing butterfly: 16 values over 32 lanes -> lane owns column `own`
+      // transposing butterfly: 8 dots over 32 lanes -> lane owns column `own`
 #pragma unroll
-      for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+      for (int half = CW / 2, off = 16; half >= 1; half >>= 1, off >>= 1) {
         const bool up = (lane & off) != 0;
 #pragma unroll
         for (int q = 0; q < half; ++q) {
-          const float sm_ = up ? mx[q] : mx[q + half], km = up ? mx[q + half] : mx[q];
           const float sd_ = up ? dt[q] : dt[q + half], kd = up ? dt[q + half] : dt[q];
-          mx[q] = fmaxf(km, __shfl_xor_sync(0xffffffffu, sm_, off));
           dt[q] = kd + __shfl_xor_sync(0xffffffffu, sd_, off);
         }
       }
-      const float cmax = fmaxf(mx[0], __shfl_xor_sync(0xffffffffu, mx[0], 1));
-      const float cdot = dt[0] + __shfl_xor_sync(0xffffffffu, dt[0], 1);
-      int e = (int)((__float_as_uint(cmax) >> 23) & 0xffu) - 127;
-      e = max(-100, min(100, e));
-      const float my_scale = __uint_as_float((uint32_t)(127 + 14 - e) << 23);  // max|x₂ col|·scale in [2^14, 2^15)
+      float cdot = dt[0] + __shfl_xor_sync(0xffffffffu, dt[0], 2);
+      cdot += __shfl_xor_sync(0xffffffffu, cdot, 1);
       bar_wait(sm_u32(&bars[2 + s]), ph ^ 1);  // stage free (MMAs that read it have completed)
       unsigned char* stage = sB + s * b_stage;
-      if ((lane & 1) == 0) {
-        colscale[(int)(i & (TC_SCALE_SLOTS - 1)) * TC_T + p * 16 + own] =
-            __uint_as_float((uint32_t)(127 - 14 + e) << 23) * inv_scale_w;  // undoes both power-of-two scales
+      float* cslot = colscale + (int)(i & (TC_SCALE_SLOTS - 1)) * TC_T + p * CW;
+      if ((lane & 3) == 0) {
         const long long col = col0 + own;
         if (P.logjac && col < P.N) {
           // Σ_j s_j = (Σ_j W_j)·x₂ + Σ_j c_j  (scale.jl:31); csum also carries the folded BatchNorm constants
@@ -332,24 +336,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
         }
       }
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        // lane that owns column c: bits (c3 c2 c1 c0) -> lane bits (4 3 2 1)
-        const float scale = __shfl_sync(0xffffffffu, my_scale, (c & 8) * 2 + (c & 4) * 2 + (c & 2) * 2 + (c & 1) * 2);
+      for (int c = 0; c < CW; ++c) {
+        int e = (int)((emax[c] >> 23) & 0xffu) - 127;
+        e = max(-100, min(100, e));
+        const float scale = __uint_as_float((uint32_t)(127 + 14 - e) << 23);  // max|x₂ col|·scale in [2^14, 2^15)
+        if (lane == 0) cslot[c] = __uint_as_float((uint32_t)(127 - 14 + e) << 23) * inv_scale_w;  // undoes both scales
         const float4 vc = v[c];
         const long long col = col0 + c;
         v[c] = load_tile(next_tile, c);  // refill with the next tile's column
         if (active) {
-          const int n = p * 16 + c;  // row of the operand tile
-          __half hi[4], lo[4];
-          const float q[4] = {vc.x * scale, vc.y * scale, vc.z * scale, vc.w * scale};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            hi[t] = __float2half_rn(q[t]);
-            lo[t] = __float2half_rn(q[t] - __half2float(hi[t]));
-          }
+          const int n = p * CW + c;  // row of the operand tile
+          const float q0 = vc.x * scale, q1 = vc.y * scale, q2 = vc.z * scale, q3 = vc.w * scale;
+          const __half2 h01 = __floats2half2_rn(q0, q1), h23 = __floats2half2_rn(q2, q3);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(q0 - f01.x, q1 - f01.y), l23 = __floats2half2_rn(q2 - f23.x, q3 - f23.y);
           const int off = sw128_off(n, kp);
-          *reinterpret_cast<uint2*>(stage + (0 * nkb + kb) * TC_BBLK + off) = *reinterpret_cast<uint2*>(hi);
-          *reinterpret_cast<uint2*>(stage + (1 * nkb + kb) * TC_BBLK + off) = *reinterpret_cast<uint2*>(lo);
+          uint2 hi2, lo2;
+          hi2.x = *reinterpret_cast<const unsigned*>(&h01);
+          hi2.y = *reinterpret_cast<const unsigned*>(&h23);
+          lo2.x = *reinterpret_cast<const unsigned*>(&l01);
+          lo2.y = *reinterpret_cast<const unsigned*>(&l23);
+          *reinterpret_cast<uint2*>(stage + (0 * nkb + kb) * TC_BBLK + off) = hi2;
+          *reinterpret_cast<uint2*>(stage + (1 * nkb + kb) * TC_BBLK + off) = lo2;
           if (write_y2 && col < P.N)  // x₂ passes through (plus the folded affines)
             __stcs(reinterpret_cast<float4*>(P.y + col * P.ldy + P.row2) + lane,
                    make_float4(fmaf(vc.x, postA.x, postC.x), fmaf(vc.y, postA.y, postC.y), fmaf(vc.z, postA.z, postC.z),
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
       }
       // rows that belong to neither x₁ nor x₂ pass through when y != x
       if (write_y2 && P.n1 + P.n2 < P.D) {
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < CW; ++c) {
           const long long col = col0 + c;
           if (col >= P.N) break;
           for (int r = lane; r < P.D; r += 32) {
@@ -377,10 +385,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
     }
   } else {
     // ================================ epilogue ================================
-    // Thread = TMEM lane = row j of s / t.  x₁ of this row is prefetched TWO 16-column chunks ahead in two
-    // register buffers (A: even chunks, B: odd chunks); the loop body handles two chunks so that it stays
-    // small (instruction cache) while ~32 loads per thread are always in flight.
-    const int j = warp * 32 + lane;
+    // Thread = TMEM lane = row j of s / t; warp w covers rows 32·(w%4)..+31 and columns 32·(w/4)..+31 of the tile
+    // as two chunks of 16 columns.  x₁ of the row is prefetched ONE chunk ahead (buffers A/B alternate).
+    const int j = (warp & 3) * 32 + lane;
+    const int chalf = warp >> 2;  // which 32-column half of the tile
     const bool rowok = j < P.n1;
     const int jr = rowok ? j : 0;  // clamp: loads stay in bounds, stores are predicated
     const float cs_j = (rowok && P.cvec) ? P.cvec[j] : 0.f;
@@ -390,12 +398,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
     const float postA_j = efold ? P.fold[2 * P.D + P.row1 + j] : 1.f, postC_j = efold ? P.fold[3 * P.D + P.row1 + j] : 0.f;
     const float* xrow = P.x + P.row1 + jr;
     float* yrow = P.y ? P.y + P.row1 + jr : nullptr;
-    const bool do_store = P.y != nullptr && rowok;
-    const long long total_chunks = my_tiles * 4;
-    // first column of global chunk q (4 chunks of 16 columns per tile)
-    auto chunk_col = [&](long long q) -> long long { return (blockIdx.x + (q >> 2) * gridDim.x) * TC_T + (q & 3) * 16; };
+    const bool do_store = P.y != nullptr && rowok && !(P.debug & 1);
+    const long long total_chunks = my_tiles * 2;  // this warp's chunks: 2 per tile
+    // first column of this warp's chunk q
+    auto chunk_col = [&](long long q) -> long long {
+      return (blockIdx.x + (q >> 1) * gridDim.x) * TC_T + chalf * 32 + (q & 1) * 16;
+    };
     auto load_chunk = [&](long long q, float (&buf)[16]) {
-      if (q >= total_chunks) return;
+      if (q >= total_chunks || (P.debug & 1)) return;
       const long long c0 = chunk_col(q);
 #pragma unroll
       for (int n = 0; n < 16; ++n) {
@@ -412,42 +422,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
     for (long long i = 0; i < my_tiles; ++i) {
       const int a = (int)(i & 1);
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
-      const float* cs = colscale + (int)(i & (TC_SCALE_SLOTS - 1)) * TC_T;
+      const float* cs = colscale + (int)(i & (TC_SCALE_SLOTS - 1)) * TC_T + chalf * 32;
       bar_wait(sm_u32(&bars[4 + a]), ph);
       tc_fence_after();
-      const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 2 * TC_T);
-#pragma unroll 1
-      for (int pr = 0; pr < 2; ++pr) {
-        const long long q = i * 4 + pr * 2;
-        uint32_t rs0[16], rt0[16], rs1[16], rt1[16];
-        tc_ld16(t_lane + (pr * 2) * 16, rs0);
-        tc_ld16(t_lane + TC_T + (pr * 2) * 16, rt0);
-        tc_ld16(t_lane + (pr * 2 + 1) * 16, rs1);
-        tc_ld16(t_lane + TC_T + (pr * 2 + 1) * 16, rt1);
-        tc_wait_ld();
-        auto finish = [&](const uint32_t (&rs)[16], const uint32_t (&rt)[16], float (&xbuf)[16], long long qq, int chl) {
-          const long long c0 = chunk_col(qq);
-          float outv[16];
+      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * 2 * TC_T + chalf * 32);
+      auto finish = [&](const uint32_t (&rs)[16], const uint32_t (&rt)[16], float (&xbuf)[16], long long qq, int chl) {
+        const long long c0 = chunk_col(qq);
+        float outv[16];
 #pragma unroll
-          for (int n = 0; n < 16; ++n) {
-            const float f = cs[chl * 16 + n];
-            const float sv = fmaf(__uint_as_float(rs[n]), f, cs_j);
-            const float tv = fmaf(__uint_as_float(rt[n]), f, ct_j);
+        for (int n4 = 0; n4 < 4; ++n4) {
+          const float4 f4 = *reinterpret_cast<const float4*>(cs + chl * 16 + n4 * 4);
+          const float ff[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int n = n4 * 4 + m;
+            const float sv = fmaf(__uint_as_float(rs[n]), ff[m], cs_j);
+            const float tv = fmaf(__uint_as_float(rt[n]), ff[m], ct_j);
             const float xv = fmaf(xbuf[n], preA_j, preC_j);
             float out;
             if (!P.inverse) out = fmaf(__expf(sv), xv, tv);  // exp(s)·x₁ + t  (scale.jl:13, shift.jl:14)
             else out = (xv - tv) * __expf(-sv);               // inv.(a) .* (y₁ + (−t))  (scale.jl:16, shift.jl:12)
             outv[n] = fmaf(out, postA_j, postC_j);
           }
-          load_chunk(qq + 2, xbuf);  // refill this buffer two chunks ahead
-          if (do_store) {
+        }
+        load_chunk(qq + 2, xbuf);  // refill this buffer with the same chunk of the next tile
+        if (do_store) {
 #pragma unroll
-            for (int n = 0; n < 16; ++n)
-              if (c0 + n < P.N) __stcs(yrow + (c0 + n) * P.ldy, outv[n]);
-          }
-        };
-        finish(rs0, rt0, xa, q, pr * 2);
-        finish(rs1, rt1, xb, q + 1, pr * 2 + 1);
+          for (int n = 0; n < 16; ++n)
+            if (c0 + n < P.N) __stcs(yrow + (c0 + n) * P.ldy, outv[n]);
+        }
+      };
+      {
+        uint32_t rs[16], rt[16];
+        tc_ld16(t_lane, rs);
+        tc_ld16(t_lane + TC_T, rt);
+        tc_wait_ld();
+        finish(rs, rt, xa, i * 2, 0);
+      }
+      {
+        uint32_t rs[16], rt[16];
+        tc_ld16(t_lane + 16, rs);
+        tc_ld16(t_lane + TC_T + 16, rt);
+        tc_wait_ld();
+        finish(rs, rt, xb, i * 2 + 1, 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -458,7 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) {
+  if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TC_TMEM_COLS)
                  : "memory");
   }
@@ -515,6 +532,7 @@ int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* fold, co
   P.row2 = row2;
   P.accumulate = accumulate;
   P.inverse = d.inverse;
+  P.debug = getenv("B2B_TC_DEBUG") ? atoi(getenv("B2B_TC_DEBUG")) : 0;
   const size_t smem = (size_t)4 * nkb * TC_ABLK + (size_t)TC_STAGES * 2 * nkb * TC_BBLK +
                       TC_SCALE_SLOTS * TC_T * sizeof(float) + 16 * sizeof(uint64_t) + 1024;
   e = cudaFuncSetAttribute(coupling_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
