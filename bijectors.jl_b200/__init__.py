@@ -5,12 +5,13 @@ repository root registers this package under that name).
 """
 from ._lib import B2BError, LIB_PATH, exported_symbols, lib  # noqa: F401
 from .interface import (  # noqa: F401
-    Bijector, Composed, ComposedFunction, Inverse, Transform, colmajor_empty, compose, flatten, from_numpy,
+    Bijector, Columnwise, Composed, ComposedFunction, Inverse, Transform, colmajor_empty, columnwise, compose, flatten,
+    from_numpy,
     inverse, isclosedform, isinvertible, logabsdetjac, logabsdetjac_, run_chain, to_numpy, transform, transform_,
     with_logabsdet_jacobian, with_logabsdet_jacobian_,
 )
 from .layers import (  # noqa: F401
-    AffineConditioner, Coupling, Elementwise, InvertibleBatchNorm, PartitionMask, Permute, PlanarLayer, RadialLayer,
+    AffineConditioner, Coupling, Elementwise, InvertibleBatchNorm, LeakyReLU, PartitionMask, Permute, PlanarLayer, RadialLayer,
     RationalQuadraticSpline, Scale, Shift, Stacked, coupling, elementwise,
 )
 from .transformed_distribution import (  # noqa: F401

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb2b.so")
 B2B_OK = 0
 B2B_EINVAL, B2B_EUNSUPPORTED, B2B_EWORKSPACE, B2B_ENONCCL = -1, -2, -3, -4
 PLANAR, RADIAL, RQS, COUPLING_AFFINE, BATCHNORM, PERMUTE, STACKED_EW, MVNORMAL_DIAG = 1, 2, 3, 4, 5, 6, 7, 8
-EW_IDENTITY, EW_EXP, EW_LOG, EW_SHIFT, EW_SCALE = 0, 1, 2, 3, 4
+EW_IDENTITY, EW_EXP, EW_LOG, EW_SHIFT, EW_SCALE, EW_LEAKY_RELU = 0, 1, 2, 3, 4, 5
 MAX_CHAIN = 24
 
 
@@ -71,6 +71,9 @@ _SIGS = {
     "b2b_coupling_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "b2b_batchnorm_eval_fwd_f32": (c_int, [_F32P] * 7 + [c_float, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b2b_batchnorm_eval_inv_f32": (c_int, [_F32P] * 7 + [c_float, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "b2b_batchnorm_train_fwd_f32": (c_int, [_F32P] * 7 + [c_float, c_float, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p,
+                                            c_void_p, c_size_t, c_void_p]),
+    "b2b_batchnorm_train_workspace_bytes": (c_size_t, [c_int32]),
     "b2b_permute_rows_f32": (c_int, [_F32P] * 3 + [c_void_p, c_int, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b2b_stacked_elementwise_f32": (c_int, [_F32P] * 3 + [c_void_p, _F32P, c_int, c_int32, c_int64, c_int64, c_int64,
                                             c_int, c_void_p]),

@@ -289,6 +289,13 @@ __global__ void __launch_bounds__(256) chain_v0_kernel(const __grid_constant__ B
                   e[q] = d.inverse ? xv / a : a * xv;  // scale.jl:13,15
                   const float la = logf(fabsf(a));
                   p[c] += d.inverse ? -la : la;  // scale.jl:26
+                } else if (op == B2B_EW_LEAKY_RELU) {
+                  // J = x < 0 ? α : 1 (leaky_relu.jl:18-22); inverse(b) = LeakyReLU(inv(α)) (:16)
+                  const float al = d.inverse ? 1.0f / a : a;
+                  if (xv < 0.f) {
+                    e[q] = al * xv;
+                    p[c] += logf(fabsf(al));
+                  }
                 }
               }
             }

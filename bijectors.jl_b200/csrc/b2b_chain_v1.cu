@@ -287,6 +287,12 @@ __device__ __forceinline__ void stacked_apply(float2 (&x)[CPT][D / TPC / 2], con
           xe = inverse ? xv / a : a * xv;
           const float la = logf(fabsf(a));
           acc[cc] += inverse ? -la : la;
+        } else if (op == B2B_EW_LEAKY_RELU) {
+          const float al = inverse ? 1.0f / a : a;  // leaky_relu.jl:16,18-22
+          if (xv < 0.f) {
+            xe = al * xv;
+            acc[cc] += logf(fabsf(al));
+          }
         }
       }
     }

@@ -38,7 +38,15 @@ __device__ __forceinline__ float find_alpha(float t, float c, float b) {
   const float delta = 2.0f * fabsf(c);
   float lo = t - delta, hi = t + delta;
   if (lo == hi) return lo;  // empty bracket, planar_layer.jl:171-173
+  // stop when the Newton step is below one ulp of the bracket's magnitude (a purely relative test never fires
+  // for roots near zero and would burn all iterations)
+  const float tol = 1.2e-7f * (fabsf(t) + delta) + 1e-30f;
   float x = t;
+  if (fabsf(c) < 1.0f) {  // contraction: one fixed-point step is a better start than the bracket centre
+    float th, s2;
+    tanh_sech2(t + b, th, s2);
+    x = fminf(fmaxf(fmaf(-c, th, t), lo), hi);
+  }
 #pragma unroll 1
   for (int it = 0; it < 64; ++it) {
     float th, s2;
@@ -47,7 +55,7 @@ __device__ __forceinline__ float find_alpha(float t, float c, float b) {
     if (f == 0.0f) break;
     if (f < 0.0f) lo = x; else hi = x;
     float xn = x - f / fmaf(c, s2, 1.0f);
-    if (fabsf(xn - x) <= 1.2e-7f * fabsf(x) + 1e-30f) {  // Newton step below one ulp: converged
+    if (fabsf(xn - x) <= tol) {  // converged
       if (xn >= lo && xn <= hi) x = xn;
       break;
     }

@@ -179,6 +179,29 @@ class Composed(Transform):
         return tuple(k for b in self.layers for k in b._keepalive())
 
 
+class Columnwise(Transform):
+    """columnwise(f) = Base.Fix1(eachcolmaphcat, f) (src/interface.jl:41,71-78): `f` applied to every column; its
+    `logabsdetjac` / `with_logabsdet_jacobian` return the SUM of the per-column log-Jacobians (interface.jl:75-78).
+    On the device the batched kernels already work column by column, so this only adds the fixed-order batch sum
+    (returned as a float64 device scalar)."""
+
+    def __init__(self, f):
+        self.x = f  # Fix1 field name
+
+    def _descs(self, inverse_, D):
+        return self.x._descs(inverse_, D)
+
+    def _keepalive(self):
+        return self.x._keepalive()
+
+    def _inverse(self):
+        return Columnwise(inverse(self.x))  # inverse(f::Columnwise) = columnwise(inverse(f.x)), interface.jl:72
+
+
+def columnwise(f):
+    return Columnwise(f)
+
+
 def compose(*fs):
     """compose(fn, ..., f2, f1) == fn ∘ … ∘ f2 ∘ f1."""
     out = fs[-1]
@@ -306,6 +329,12 @@ def with_logabsdet_jacobian(t, x):
     """(transform(t, x), logabsdetjac(t, x)) in one fused pass (src/interface.jl:144)."""
     if hasattr(t, "_host_wladj") and not (isinstance(x, torch.Tensor) and x.is_cuda):
         return t._host_wladj(x)
+    if isinstance(t, Columnwise):
+        total = torch.zeros((), dtype=torch.float64, device=x.device if x.is_cuda else "cpu")
+        y, _ = run_chain(t, x, sum_out=total)
+        return y, total
+    if getattr(t, "training", False) and hasattr(t, "train_forward"):  # istraining() == true, normalise.jl:51-60
+        return t.train_forward(x)
     return run_chain(t, x)
 
 
@@ -320,6 +349,10 @@ def logabsdetjac(t, x):
     """logabsdetjac(b, x) (src/interface.jl:183-192): no D×N store is issued."""
     if hasattr(t, "_host_wladj") and not (isinstance(x, torch.Tensor) and x.is_cuda):
         return t._host_wladj(x)[1]
+    if isinstance(t, Columnwise):  # sum over columns, interface.jl:75-77
+        total = torch.zeros((), dtype=torch.float64, device=x.device if x.is_cuda else "cpu")
+        run_chain(t, x, want_y=False, sum_out=total)
+        return total
     return run_chain(t, x, want_y=False)[1]
 
 

@@ -8,6 +8,7 @@ launch of the matching libb2b.so kernel (include/b2b.h).  No arithmetic on the b
   InvertibleBatchNorm                src/bijectors/normalise.jl:9-37
   Permute                            src/bijectors/permute.jl:84-157
   Stacked / elementwise / Shift / Scale   src/bijectors/stacked.jl, exp_log.jl, shift.jl, scale.jl
+  LeakyReLU                          src/bijectors/leaky_relu.jl
 """
 from __future__ import annotations
 
@@ -279,8 +280,8 @@ def coupling(cl: Coupling):
 # --------------------------------------------------------------------------------------------------
 class InvertibleBatchNorm(_ParamLayer):
     """InvertibleBatchNorm(chs; eps=1f-5, mtm=1f-1) (normalise.jl:9-37); eval mode (:61-67,:74-86).
-    The reference's global `istraining()` switch (:7) is an explicit argument here; training mode is
-    not part of the v1 device path and raises."""
+    The reference's global `istraining()` switch (:7) is the explicit `training` flag here: a training-mode layer
+    computes batch statistics and updates its moving statistics in place (`train_forward`, :51-60)."""
 
     _fields = ("b", "logs", "m", "v")
 
@@ -296,8 +297,30 @@ class InvertibleBatchNorm(_ParamLayer):
             # error text of normalise.jl:43-45
             raise RuntimeError(f"InvertibleBatchNorm expected {self.b.numel()} channels, got {D}")
         if self.training:
-            raise B2BError(_lib.B2B_EUNSUPPORTED, "InvertibleBatchNorm training mode")
+            raise B2BError(_lib.B2B_EUNSUPPORTED, "InvertibleBatchNorm in training mode cannot be fused into a chain "
+                                                  "or inverted (normalise.jl:75); call it on its own")
         return [_desc(_lib.BATCHNORM, inverse, p0=self.b, p1=self.logs, p2=self.m, p3=self.v, f0=self.eps)]
+
+    def train_forward(self, x, comm=None):
+        """with_logabsdet_jacobian(bn, x) with istraining() == true (normalise.jl:51-69): batch statistics (over all
+        ranks of `comm`, a distributed.Communicator, when given), in-place moving-average update of self.m / self.v,
+        output and logjac from the batch statistics."""
+        from .interface import _batch_view, _stream, colmajor_empty
+        from ._lib import check, lib
+
+        D, N, ldx = _batch_view(x)
+        if D != self.b.numel():
+            raise RuntimeError(f"InvertibleBatchNorm expected {self.b.numel()} channels, got {D}")
+        y = colmajor_empty(D, N, x.device)
+        lj = torch.empty((N,), dtype=torch.float32, device=x.device)
+        nbytes = lib().b2b_batchnorm_train_workspace_bytes(D)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+        handle = comm.handle if (comm is not None and getattr(comm, "handle", None) is not None) else None
+        check(lib().b2b_batchnorm_train_fwd_f32(x.data_ptr(), y.data_ptr(), lj.data_ptr(), self.b.data_ptr(),
+                                                self.logs.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.eps,
+                                                self.mtm, D, N, ldx, D, 0, handle, ws.data_ptr(), nbytes, _stream()),
+              "b2b_batchnorm_train_fwd_f32")
+        return y, lj
 
 
 # --------------------------------------------------------------------------------------------------
@@ -465,6 +488,30 @@ class Scale(Bijector):
     __hash__ = object.__hash__
 
 
+class LeakyReLU(Bijector):
+    """LeakyReLU(α): x ↦ x if x ≥ 0 else αx, α > 0 (leaky_relu.jl:9-29); inverse = LeakyReLU(1/α) (:16).
+    Batched logjac is per column (the reference sums over the whole array)."""
+
+    def __init__(self, α):
+        self.a = float(α)
+        if not self.a > 0:
+            raise ValueError("LeakyReLU needs α > 0")
+
+    code = _lib.EW_LEAKY_RELU
+    α = property(lambda s: s.a)
+
+    def _inverse(self):
+        return LeakyReLU(1.0 / self.a)
+
+    def _descs(self, inverse, D):
+        return _as_stacked(self, D)._descs(inverse, D)
+
+    def __eq__(self, o):
+        return isinstance(o, LeakyReLU) and o.a == self.a
+
+    __hash__ = object.__hash__
+
+
 class Stacked(Transform):
     """Stacked(bs, ranges): bs[i] applied to rows ranges[i] (1-based inclusive (lo, hi) like Julia
     UnitRanges; stacked.jl:25-59).  Device scope: elementwise blocks (exp, log, identity, Shift, Scale)."""
@@ -477,7 +524,7 @@ class Stacked(Transform):
         if len(bs) != len(ranges):
             raise ValueError("length(bs) == length(ranges) needs to be true")
         for b in bs:
-            if not isinstance(b, (Elementwise, Shift, Scale)) and b is not None:
+            if not isinstance(b, (Elementwise, Shift, Scale, LeakyReLU)) and b is not None:
                 raise B2BError(_lib.B2B_EUNSUPPORTED, f"Stacked block {type(b).__name__}")
         self.bs, self.ranges_in = bs, ranges
         self.length_in = sum(hi - lo + 1 for lo, hi in ranges)

@@ -68,6 +68,7 @@ extern "C" {
 #define B2B_EW_LOG 2   /* elementwise(log): y=log(x), logjac -= log(x)     exp_log.jl:8-9  */
 #define B2B_EW_SHIFT 3 /* Shift(a): y = a + x                              shift.jl:14,21  */
 #define B2B_EW_SCALE 4 /* Scale(a): y = a * x, logjac += log|a|            scale.jl:13,26  */
+#define B2B_EW_LEAKY_RELU 5 /* LeakyReLU(a): y = x >= 0 ? x : a*x, logjac += x < 0 ? log|a| : 0   leaky_relu.jl:18-29 */
 
 /*
  * One element of a chain.  `inverse != 0` evaluates Inverse(layer) and its log-Jacobian
@@ -180,6 +181,15 @@ int b2b_batchnorm_eval_inv_f32(const float* x, float* y, float* logjac, const fl
                                const float* logs, const float* m, const float* v, float eps,
                                int32_t D, int64_t N, int64_t ldx, int64_t ldy, int accumulate_logjac,
                                void* stream);
+/* InvertibleBatchNorm, TRAINING mode: normalise.jl:51-60 (the reference's global istraining() switch is this
+ * separate entry point).  Batch mean / variance over the N columns -- over ALL ranks when comm != NULL, which costs
+ * one all-reduce of 2D+1 doubles -- then the moving statistics m, v are updated IN PLACE (momentum mtm, n/(n-1)
+ * correction) and y / logjac are computed with the batch statistics.  workspace: b2b_batchnorm_train_workspace_bytes(D). */
+int b2b_batchnorm_train_fwd_f32(const float* x, float* y, float* logjac, const float* b, const float* logs,
+                                float* m, float* v, float eps, float mtm, int32_t D, int64_t N, int64_t ldx,
+                                int64_t ldy, int accumulate_logjac, struct b2b_comm* comm, void* workspace,
+                                size_t workspace_bytes, void* stream);
+size_t b2b_batchnorm_train_workspace_bytes(int32_t D);
 /* Permute rows (also serves PartitionMask / Stacked range movement): permute.jl:152-155. Bit-exact. */
 int b2b_permute_rows_f32(const float* x, float* y, float* logjac, const int32_t* dst_of_src,
                          int inverse, int32_t D, int64_t N, int64_t ldx, int64_t ldy,

