@@ -153,7 +153,12 @@ extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const 
                                  size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   g_last_launches = 0;
-  if (!layers || L < 1 || L > B2B_MAX_CHAIN || !x || D < 1 || N < 0 || ldx < D) return B2B_EINVAL;
+  if (!layers || L < 1 || L > B2B_MAX_CHAIN || D < 1 || N < 0 || ldx < D) return B2B_EINVAL;
+  if (N == 0) {  // empty batch: nothing to launch (pointers may be NULL)
+    if (sum_out) return (int)cudaMemsetAsync(sum_out, 0, sizeof(double), stream);
+    return B2B_OK;
+  }
+  if (!x) return B2B_EINVAL;
   if (y && ldy < D) return B2B_EINVAL;
   if (!y && !logjac && !sum_out) return B2B_EINVAL;
   for (int l = 0; l < L; ++l) {

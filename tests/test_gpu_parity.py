@@ -586,3 +586,96 @@ def test_batchnorm_training_mode(B, D, N):
     assert rel(B.to_numpy(y2), ye) <= RTOL
     with pytest.raises(RuntimeError, match="channels"):
         B.InvertibleBatchNorm(D + 1, training=True).train_forward(B.from_numpy(x))
+
+
+@pytest.mark.parametrize("D", [128, 64, 10])
+def test_edge_shapes_strides_alignment(B, D):
+    """Empty / single-column / ragged batches, padded leading dimension, misaligned base pointers (these take the
+    scalar-load build of the lane-group kernel), in-place evaluation, NaN columns staying local."""
+    import torch
+
+    rng = np.random.default_rng(D + 1)
+    pairs = [make_case(k, D, rng) for k in ("planar", "radial", "batchnorm")]
+    flow = B.Composed(*[p[0] for p in pairs])
+    olayers = [p[1] for p in pairs]
+    # N = 0: nothing is launched, empty outputs
+    y0, lj0 = B.with_logabsdet_jacobian(flow, B.colmajor_empty(D, 0))
+    assert y0.shape == (D, 0) and lj0.shape == (0,)
+    for N in (1, 31, 33, 257):
+        x = rng.standard_normal((D, N)).astype(f32)
+        y, lj = B.with_logabsdet_jacobian(flow, B.from_numpy(x))
+        yo, ljo = O.chain_forward(olayers, x.astype(np.float64))
+        assert rel(B.to_numpy(y).reshape(D, N), yo) <= RTOL and rel(B.to_numpy(lj), ljo) <= RTOL, N
+    N = 515
+    x = rng.standard_normal((D, N)).astype(f32)
+    yo, ljo = O.chain_forward(olayers, x.astype(np.float64))
+    for pad in (4, 1):  # ld = D + 4 keeps 16-byte alignment; ld = D + 1 does not
+        buf = torch.zeros((N, D + pad), device="cuda")
+        xv = buf[:, :D].t()  # shape (D, N), strides (1, D + pad)
+        xv.copy_(B.from_numpy(x))
+        obuf = torch.full((N, D + pad), 7.0, device="cuda")
+        yv = obuf[:, :D].t()
+        y, lj = B.run_chain(flow, xv, y=yv)
+        assert rel(B.to_numpy(yv), yo) <= RTOL and rel(B.to_numpy(lj), ljo) <= RTOL, pad
+        assert bool((obuf[:, D:] == 7.0).all()), "padding between columns was overwritten"
+    # misaligned base pointer (offset by one float)
+    flat = torch.zeros(D * N + 1, device="cuda")
+    xm = flat[1:].view(N, D).t()
+    xm.copy_(B.from_numpy(x))
+    y, lj = B.with_logabsdet_jacobian(flow, xm)
+    assert rel(B.to_numpy(y), yo) <= RTOL and rel(B.to_numpy(lj), ljo) <= RTOL
+    # in place (y aliases x)
+    xi = B.from_numpy(x)
+    y, lj = B.with_logabsdet_jacobian_(flow, xi)
+    assert y.data_ptr() == xi.data_ptr() and rel(B.to_numpy(xi), yo) <= RTOL
+    # a NaN column stays a NaN column and does not leak into its neighbours
+    xn = x.copy()
+    xn[:, 100] = np.nan
+    y, lj = B.with_logabsdet_jacobian(flow, B.from_numpy(xn))
+    yh, ljh = B.to_numpy(y), B.to_numpy(lj)
+    assert np.isnan(yh[:, 100]).all() and np.isnan(ljh[100])
+    keep = np.arange(N) != 100
+    assert rel(yh[:, keep], yo[:, keep]) <= RTOL and rel(ljh[keep], ljo[keep]) <= RTOL
+
+
+@pytest.mark.parametrize("N", [1, 63, 64, 65, 200])
+def test_coupling_tc_ragged_batches(B, N):
+    rng = np.random.default_rng(N)
+    D = 256
+    idx1, idx2 = list(range(1, 129)), list(range(129, 257))
+    W = (rng.standard_normal((256, 128)) * 0.2 / np.sqrt(128)).astype(f32)
+    c = (rng.standard_normal(256) * 0.1).astype(f32)
+    cl = B.Coupling(B.AffineConditioner(W, c), B.PartitionMask(D, idx1, idx2))
+    ol = O.Layer("coupling_affine", dict(idx1=np.asarray(idx1), idx2=np.asarray(idx2), W=W, c=c))
+    x = rng.standard_normal((D, N)).astype(f32)
+    y, lj = B.with_logabsdet_jacobian(cl, B.from_numpy(x))
+    assert B.lib().b2b_last_launch_count() == 2
+    yo, ljo = ol.forward(x.astype(np.float64))
+    assert rel(B.to_numpy(y).reshape(D, N), yo) <= RTOL and rel(B.to_numpy(lj), ljo) <= RTOL
+
+
+@pytest.mark.parametrize("D", [32, 64, 128, 256])
+def test_tma_kernel_matches_lane_group_kernel_on_ragged_batches(B, D):
+    """The TMA-staged kernel (several tiles per warp, input ring shallower than the warp count, tail tiles) against the
+    direct-load kernel, repeated to catch hand-off races (regression test for the buffer re-arm flags)."""
+    import torch
+
+    rng = np.random.default_rng(D)
+    lay = [make_case("radial", D, rng)[0], make_case("batchnorm", D, rng)[0], make_case("planar", D, rng)[0]]
+    flow = B.Composed(*lay)
+    for N in (3001, 5000, 100_000):
+        x = B.from_numpy(rng.standard_normal((D, N)).astype(f32))
+        B.lib().b2b_set_kernel_variant(1)
+        try:
+            y0, l0 = B.with_logabsdet_jacobian(flow, x)
+            t0 = torch.zeros((), dtype=torch.float64, device="cuda")
+            B.run_chain(flow, x, want_y=False, sum_out=t0)
+        finally:
+            B.lib().b2b_set_kernel_variant(0)
+        for _ in range(10):
+            y1, l1 = B.with_logabsdet_jacobian(flow, x)
+            t1 = torch.zeros((), dtype=torch.float64, device="cuda")
+            B.run_chain(flow, x, want_y=False, sum_out=t1)
+            assert float((y1 - y0).norm() / y0.norm()) <= 2e-6
+            assert float((l1 - l0).norm() / l0.norm()) <= 2e-6
+            assert abs(float(t1 - t0)) <= 1e-7 * abs(float(t0))

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Tiny invocation of every kernel family, meant to run under compute-sanitizer on the GPU box:
+   compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bijectors_jl_b200 as B
+
+f32 = np.float32
+rng = np.random.default_rng(0)
+
+
+def run(D, N, variant):
+    B.lib().b2b_set_kernel_variant(variant)
+    n1 = D // 2
+    layers = [
+        B.PlanarLayer((rng.standard_normal(D) / np.sqrt(D)).astype(f32), (rng.standard_normal(D) / np.sqrt(D)).astype(f32), f32([0.1])),
+        B.InvertibleBatchNorm(b=np.zeros(D, f32), logs=np.zeros(D, f32), m=np.zeros(D, f32), v=np.ones(D, f32)),
+        B.RadialLayer(f32([0.2]), f32([0.3]), rng.standard_normal(D).astype(f32)),
+        B.RationalQuadraticSpline(rng.standard_normal((D, 8)).astype(f32), rng.standard_normal((D, 8)).astype(f32),
+                                  rng.standard_normal((D, 7)).astype(f32), 3.0),
+        B.Coupling(B.AffineConditioner((rng.standard_normal((2 * n1, D - n1)) * 0.1).astype(f32)),
+                   B.PartitionMask(D, list(range(1, n1 + 1)), list(range(n1 + 1, D + 1)))),
+        B.LeakyReLU(0.2),
+        B.Permute((rng.permutation(D) + 1).tolist()),
+    ]
+    flow = B.Composed(*layers)
+    x = B.from_numpy(rng.standard_normal((D, N)).astype(f32))
+    y, lj = B.with_logabsdet_jacobian(flow, x)
+    xi, lji = B.with_logabsdet_jacobian(B.inverse(flow), y)
+    td = B.transformed(B.MvNormal(D), flow)
+    tot, lp = B.logpdf_sum(td, y)
+    torch.cuda.synchronize()
+    err = float((xi - x).norm() / x.norm())
+    print(f"D={D} N={N} variant={variant}: roundtrip {err:.2e} total {float(tot):.4f}")
+    assert err < 1e-3
+
+
+for D, N in [(128, 200), (64, 100), (32, 70), (256, 130), (10, 50)]:
+    for variant in (0, 1, 10):
+        run(D, N, variant)
+bn = B.InvertibleBatchNorm(32, training=True)
+bn.train_forward(B.from_numpy(rng.standard_normal((32, 300)).astype(f32)))
+xh = B.from_numpy(rng.standard_normal((64, 1000)).astype(f32), device="cpu", pin_memory=True)
+B.with_logabsdet_jacobian(B.PlanarLayer(64), xh)
+torch.cuda.synchronize()
+print("sanitize smoke done")
