@@ -679,3 +679,79 @@ def test_tma_kernel_matches_lane_group_kernel_on_ragged_batches(B, D):
             assert float((y1 - y0).norm() / y0.norm()) <= 2e-6
             assert float((l1 - l0).norm() / l0.norm()) <= 2e-6
             assert abs(float(t1 - t0)) <= 1e-7 * abs(float(t0))
+
+
+def _full_size_props(B, flow, olayers, D, N, sample=2048, rt_tol=1e-4):
+    """Size-independent properties at a BASELINE config's FULL size + an oracle check on a column sample."""
+    import torch
+
+    gen = torch.Generator(device="cuda").manual_seed(D + 3)
+    x = torch.randn((N, D), device="cuda", generator=gen).t()
+    y, lj = B.with_logabsdet_jacobian(flow, x)
+    assert bool(torch.isfinite(y).all()) and bool(torch.isfinite(lj).all())
+    cols = np.sort(np.random.default_rng(D).choice(N, sample, replace=False))
+    ct = torch.as_tensor(cols, device="cuda")
+    yo, ljo = O.chain_forward(olayers, x[:, ct].cpu().numpy().astype(np.float64))
+    assert rel(y[:, ct].cpu().numpy(), yo) <= RTOL and rel(lj[ct].cpu().numpy(), ljo) <= RTOL
+    xi, lji = B.with_logabsdet_jacobian(B.inverse(flow), y)
+    assert float((xi - x).norm() / x.norm()) <= rt_tol  # inverse∘forward ≈ id
+    assert float((lji + lj).norm()) <= rt_tol * max(float(lj.norm()), 1.0)  # ires == (x, −logjac)
+    td = B.transformed(B.MvNormal(D), flow)
+    tot, lp = B.logpdf_sum(td, y)
+    # logpdf(td, y) = logpdf(base, x) − logjac(x)  (test/normalising_flows.jl:97-111), here for the whole batch
+    base = -0.5 * (D * math.log(2 * math.pi)) - 0.5 * (x.double() ** 2).sum(0)
+    ref = (base - lj.double())
+    assert float((lp.double() - ref).norm() / ref.norm()) <= rt_tol
+    assert abs(float(tot) - float(lp.double().sum())) <= 1e-9 * abs(float(tot))
+    return x, y, lj
+
+
+def test_full_size_properties_config3_radial(B):
+    """BASELINE config 3 at full size: 6 x RadialLayer, D = 64, N = 2^20, forward + inverse."""
+    rng = np.random.default_rng(200)
+    pairs = [make_case("radial", 64, np.random.default_rng(200 + l)) for l in range(6)]
+    _full_size_props(B, B.Composed(*[p[0] for p in pairs]), [p[1] for p in pairs], 64, 1 << 20, rt_tol=2e-3)
+
+
+def test_full_size_properties_config4_rqs(B):
+    """BASELINE config 4 at full size: RationalQuadraticSpline K = 8, D = 32, N = 2^19 (about 5 % of the elements
+    outside the box)."""
+    import torch
+
+    lay, olay = make_case("rqs", 32, np.random.default_rng(300))
+    D, N = 32, 1 << 19
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    x = (torch.randn((N, D), device="cuda", generator=gen) * 1.5).t()
+    y, lj = B.with_logabsdet_jacobian(lay, x)
+    outside = (x.abs() >= 3.0)
+    assert 0.02 < float(outside.float().mean()) < 0.08
+    assert bool((y[outside] == x[outside]).all())  # identity outside the box, bit for bit
+    cols = np.sort(np.random.default_rng(1).choice(N, 4096, replace=False))
+    ct = torch.as_tensor(cols, device="cuda")
+    yo, ljo = olay.forward(x[:, ct].cpu().numpy().astype(np.float64))
+    assert rel(y[:, ct].cpu().numpy(), yo) <= RTOL and rel(lj[ct].cpu().numpy(), ljo) <= RTOL
+    xi, lji = B.with_logabsdet_jacobian(B.inverse(lay), y)
+    assert float((xi - x).norm() / x.norm()) <= 1e-4 and float((lji + lj).norm() / lj.norm()) <= 1e-4
+    # monotone: the spline preserves the order of any two inputs of the same row
+    assert bool(((y[:, 1:] - y[:, :-1]) * (x[:, 1:] - x[:, :-1]) >= 0).all())
+
+
+def test_full_size_properties_config5_realnvp_share(B):
+    """BASELINE config 5, one GPU's share at 8-way sharding: 4 x (affine Coupling + InvertibleBatchNorm), D = 256,
+    N = 2^19 columns."""
+    rng = np.random.default_rng(400)
+    D = 256
+    dev_layers, ora_layers = [], []
+    for l in range(4):
+        first = l % 2 == 0
+        idx1 = list(range(1, 129)) if first else list(range(129, 257))
+        idx2 = list(range(129, 257)) if first else list(range(1, 129))
+        W = (rng.standard_normal((256, 128)) * 0.05 / np.sqrt(128)).astype(f32)
+        c = np.zeros(256, f32)
+        dev_layers.append(B.Coupling(B.AffineConditioner(W, c), B.PartitionMask(D, idx1, idx2)))
+        ora_layers.append(O.Layer("coupling_affine", dict(idx1=np.asarray(idx1), idx2=np.asarray(idx2), W=W, c=c)))
+        b, logs, m = (rng.standard_normal(D) * 0.1).astype(f32), (rng.standard_normal(D) * 0.1).astype(f32), (rng.standard_normal(D) * 0.1).astype(f32)
+        v = rng.uniform(0.5, 1.5, D).astype(f32)
+        dev_layers.append(B.InvertibleBatchNorm(b=b, logs=logs, m=m, v=v))
+        ora_layers.append(O.Layer("batchnorm", dict(bn=O.BatchNormParams(b, logs, m, v, f32(1e-5), f32(0.1)))))
+    _full_size_props(B, B.Composed(*dev_layers), ora_layers, D, 1 << 19, sample=1024)
