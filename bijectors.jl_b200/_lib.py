@@ -58,6 +58,8 @@ _SIGS = {
     "b2b_set_kernel_variant": (c_int, [c_int]),
     "b2b_planar_fwd_f32": (c_int, [_F32P] * 6 + [c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b2b_planar_inv_f32": (c_int, [_F32P] * 6 + [c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "b2b_planar_chain_hostparams_f32": (c_int, [_F32P] * 3 + [c_int32, c_int] + [_F32P] * 3 +
+                                        [c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b2b_radial_fwd_f32": (c_int, [_F32P] * 6 + [c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b2b_radial_inv_f32": (c_int, [_F32P] * 6 + [c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b2b_rqs_fwd_f32": (c_int, [_F32P] * 6 + [c_int32, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),

@@ -1,6 +1,7 @@
 // C ABI of libb2b.so (include/b2b.h): argument validation, chain segmentation, launch bookkeeping.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -436,4 +437,67 @@ extern "C" int b2b_mvnormal_diag_logpdf_f32(const float* x, const float* mu, con
   }
   return b2b_chain_run_f32(&d, 1, x, nullptr, logpdf_out, sum_out, D, N, ldx, D, acc, workspace,
                            workspace_bytes, stream);
+}
+
+// ---- planar chains with HOST-resident parameters ---------------------------------------------------------
+// get_u_hat (planar_layer.jl:65-70) on the host: û = u + (m(wᵀu) − wᵀu)·w/‖w‖², m(x) = −1 + softplus(x); c = wᵀû.
+static void planar_derive_host(const float* w, const float* u, int D, float* uh, float* c) {
+  double wu = 0.0, ww = 0.0;
+  for (int i = 0; i < D; ++i) {
+    wu += (double)w[i] * u[i];
+    ww += (double)w[i] * w[i];
+  }
+  const float wuf = (float)wu;
+  const float sp = wuf > 0.f ? wuf + log1pf(expf(-wuf)) : log1pf(expf(wuf));
+  const float scale = ((-1.0f + sp) - wuf) / (float)ww;
+  double cc = 0.0;
+  for (int i = 0; i < D; ++i) {
+    uh[i] = u[i] + scale * w[i];
+    cc += (double)w[i] * uh[i];
+  }
+  *c = (float)cc;
+}
+
+extern "C" int b2b_planar_chain_hostparams_f32(const float* w_host, const float* u_host, const float* b_host,
+                                               int32_t L, int inverse, const float* x, float* y, float* logjac,
+                                               int32_t D, int64_t N, int64_t ldx, int64_t ldy,
+                                               int accumulate_logjac, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  g_last_launches = 0;
+  if (L < 1 || D < 1 || N < 0) return B2B_EINVAL;
+  if (N == 0) return B2B_OK;
+  if (!w_host || !u_host || !b_host || !x || (!y && !logjac) || ldx < D || (y && ldy < D)) return B2B_EINVAL;
+  if (!(D == 32 || D == 64 || D == 128)) return B2B_EUNSUPPORTED;
+  if (!y && L > 8) return B2B_EUNSUPPORTED;  // several launches need the D x N intermediate
+  // launches take 1, 2, 4 or 8 layers: the tail is padded with identity layers (w = û = 0: y = x, logjac += 0),
+  // which costs a little arithmetic but no extra pass over the batch
+  const int Lp = (L + 7) / 8 * 8;
+  std::vector<float> wp((size_t)Lp * D, 0.f), uh((size_t)Lp * D, 0.f), c(Lp, 0.f), bp(Lp, 0.f);
+  memcpy(wp.data(), w_host, sizeof(float) * (size_t)L * D);
+  memcpy(bp.data(), b_host, sizeof(float) * L);
+  for (int l = 0; l < L; ++l) planar_derive_host(w_host + (size_t)l * D, u_host + (size_t)l * D, D, &uh[(size_t)l * D], &c[l]);
+  B2BChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.D = D;
+  p.N = N;
+  p.logjac = logjac;
+  p.scratch_off = -1;
+  int done = 0;
+  while (done < L) {
+    int n = 1;
+    while (n < L - done && n < 8) n <<= 1;
+    const bool last = done + n >= L;
+    p.x = done == 0 ? x : y;
+    p.ldx = done == 0 ? ldx : ldy;
+    p.y = y;
+    p.ldy = ldy;
+    p.accumulate = (done == 0) ? (accumulate_logjac != 0) : 1;
+    (void)last;
+    const int rc = b2b_launch_planar_hostparams(p, n, &wp[(size_t)done * D], &uh[(size_t)done * D], &c[done],
+                                                &bp[done], inverse, stream);
+    if (rc != B2B_OK) return rc;
+    ++g_last_launches;
+    done += n;
+  }
+  return B2B_OK;
 }

@@ -69,6 +69,20 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
                "r"(c0), "r"(c1), "r"(src)
                : "memory");
 }
+// 3-D forms: the tensor map views a batch as {32 floats, N columns, D/32 row-blocks} so that ONE instruction moves
+// a whole [row-block][column][32 floats] tile (the 128-byte swizzle limits the innermost box extent to 32 floats)
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(src)
+               : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -88,6 +102,7 @@ struct V1Extra {
   int param_off;   // byte offset of the staged parameters in dynamic smem
   int bar_off;     // byte offset of the mbarriers
   int nwarps;
+  int tma3d;       // 1: the tensor maps are 3-D (one TMA instruction per tile), 0: 2-D (one per 32-row block)
   long long tiles;
 };
 
@@ -333,10 +348,11 @@ __device__ __forceinline__ void mvnormal_apply(const float2 (&x)[CPT][D / TPC / 
   }
 }
 
-template <int D, int TPC, int CPT, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
-    chain_v1_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
-                    const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y) {
+// The pipeline (TMA tile ring, register-resident fragments, per-warp TMA store) is independent of WHAT is applied
+// to the fragments: `prog.stage()` prepares per-CTA state, `prog.apply()` maps the fragments and accumulates logjac.
+template <int D, int TPC, int CPT, int NW, class Prog>
+__device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E, const CUtensorMap& map_x,
+                                       const CUtensorMap& map_y, const Prog& prog) {
   using C = ColCtx<D, TPC>;
   constexpr int NQ = D / 32;                 // boxes per tile
   constexpr int LPC = 32 / TPC;              // lane groups per warp
@@ -357,8 +373,18 @@ __global__ void __launch_bounds__(NW * 32, 1)
   // polling load against the releasing store -- that pairing is the synchronisation itself)
   int* armed = reinterpret_cast<int*>(bars + 8);
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int l = warp; l < P.L; l += NW) stage_layer(P.layers[l], params + P.soff[l], D, D, lane);
+  // the warp index is made provably warp-uniform: tile / buffer / barrier addresses then live in uniform registers
+  // and the TMA instructions take them directly (no per-instruction R2UR + BRA.U.ANY uniformisation loop)
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  auto load_tile = [&](uint32_t dst, int col0, uint32_t bar) {
+    if (E.tma3d) {
+      tma_load_3d(dst, &map_x, 0, col0, 0, bar);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) tma_load_2d(dst + q * BOX_BYTES, &map_x, q * 32, col0, bar);
+    }
+  };
+  prog.stage(params, warp, lane, NW);
   if (threadIdx.x == 0) {
     for (int i = 0; i < E.n_in; ++i) mbar_init(smem_u32(&bars[i]), 1);
     fence_mbar_init();
@@ -372,10 +398,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
       const uint32_t bar = smem_u32(&bars[j]);
       mbar_expect_tx(bar, TILE_BYTES);
       const long long tile = blockIdx.x + (long long)j * gridDim.x;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        tma_load_2d(smem_u32(in_base + (size_t)j * TILE_BYTES + q * BOX_BYTES), &map_x, q * 32,
-                    (int)(tile * COLS), bar);
+      load_tile(smem_u32(in_base + (size_t)j * TILE_BYTES), (int)(tile * COLS), bar);
       flag_store_release(&armed[j], j);
     }
   }
@@ -418,10 +441,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
       const uint32_t bar = smem_u32(&bars[buf]);
       mbar_expect_tx(bar, TILE_BYTES);
       const long long nt = blockIdx.x + (j + E.n_in) * gridDim.x;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        tma_load_2d(smem_u32(in_base + (size_t)buf * TILE_BYTES + q * BOX_BYTES), &map_x, q * 32,
-                    (int)(nt * COLS), bar);
+      load_tile(smem_u32(in_base + (size_t)buf * TILE_BYTES), (int)(nt * COLS), bar);
       flag_store_release(&armed[buf], (int)(j + E.n_in));
     }
 
@@ -430,24 +450,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
       const long long cl = col + cc * LPC;
       lj[cc] = (P.accumulate && P.logjac && cl < P.N) ? P.logjac[cl] : 0.0f;
     }
-#pragma unroll 1
-    for (int l = 0; l < P.L; ++l) {
-      const b2b_layer_desc& d = P.layers[l];
-      const float* sp = params + P.soff[l];
-      switch (d.kind) {
-        case B2B_PLANAR: planar_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj); break;
-        case B2B_RADIAL: radial_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj); break;
-        case B2B_BATCHNORM: batchnorm_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj); break;
-        case B2B_RQS:
-          if constexpr (C::EPT * CPT <= 64) rqs_apply<D, TPC, CPT>(x, ctx, sp, d.n0, d.inverse != 0, lj);
-          break;
-        case B2B_STACKED_EW:
-          if constexpr (C::EPT * CPT <= 64) stacked_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj);
-          break;
-        case B2B_MVNORMAL_DIAG: mvnormal_apply<D, TPC, CPT>(x, ctx, sp, lj); break;
-        default: break;
-      }
-    }
+    prog.apply(x, ctx, params, lj);
 
     if (P.y) {
       if (store_pending) {
@@ -465,9 +468,13 @@ __global__ void __launch_bounds__(NW * 32, 1)
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
+        if (E.tma3d) {
+          tma_store_3d(&map_y, 0, (int)(tile * COLS), 0, smem_u32(my_out));
+        } else {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q)
-          tma_store_2d(&map_y, q * 32, (int)(tile * COLS), smem_u32(my_out + q * BOX_BYTES));
+          for (int q = 0; q < NQ; ++q)
+            tma_store_2d(&map_y, q * 32, (int)(tile * COLS), smem_u32(my_out + q * BOX_BYTES));
+        }
         tma_commit();
       }
       store_pending = true;
@@ -498,6 +505,111 @@ __global__ void __launch_bounds__(NW * 32, 1)
   }
 }
 
+// Program 1: the layer-descriptor interpreter (parameters staged in shared memory from DEVICE pointers).
+template <int D, int TPC, int CPT>
+struct InterpProg {
+  const B2BChainParams& P;
+  __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
+    for (int l = warp; l < P.L; l += nw) stage_layer(P.layers[l], params + P.soff[l], D, D, lane);
+  }
+  __device__ __forceinline__ void apply(float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& ctx, const float* params,
+                                        float (&lj)[CPT]) const {
+    using C = ColCtx<D, TPC>;
+#pragma unroll 1
+    for (int l = 0; l < P.L; ++l) {
+      const b2b_layer_desc& d = P.layers[l];
+      const float* sp = params + P.soff[l];
+      switch (d.kind) {
+        case B2B_PLANAR: planar_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj); break;
+        case B2B_RADIAL: radial_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj); break;
+        case B2B_BATCHNORM: batchnorm_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj); break;
+        case B2B_RQS:
+          if constexpr (C::EPT * CPT <= 64) rqs_apply<D, TPC, CPT>(x, ctx, sp, d.n0, d.inverse != 0, lj);
+          break;
+        case B2B_STACKED_EW:
+          if constexpr (C::EPT * CPT <= 64) stacked_apply<D, TPC, CPT>(x, ctx, sp, d.inverse != 0, lj);
+          break;
+        case B2B_MVNORMAL_DIAG: mvnormal_apply<D, TPC, CPT>(x, ctx, sp, lj); break;
+        default: break;
+      }
+    }
+  }
+};
+
+template <int D, int TPC, int CPT, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+    chain_v1_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
+                    const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y) {
+  const InterpProg<D, TPC, CPT> prog{P};
+  v1_run<D, TPC, CPT, NW>(P, E, map_x, map_y, prog);
+}
+
+// Program 2: a chain of L PlanarLayers whose (derived) parameters arrive BY VALUE as kernel arguments, i.e. in the
+// constant bank: every w / û element is read with a uniform LDCU into a uniform register and used directly as an
+// FFMA2 operand -- no shared-memory traffic for parameters at all (the LSU broadcast of parameters is what bounds the
+// interpreter at ~70 % of the roofline).  This is the reference's own parameter residency: PlanarLayer fields are
+// host Arrays (planar_layer.jl:13-18); û and wᵀû (get_u_hat, :65-70) are computed on the host at launch time.
+template <int D, int L>
+struct PlanarHP {
+  float w[L][D];
+  float uh[L][D];
+  float c[L];
+  float b[L];
+  int inverse;
+};
+
+template <int D, int L, int U>
+struct PlanarHPProg {
+  const PlanarHP<D, L>& H;
+  __device__ __forceinline__ void stage(float*, int, int, int) const {}
+  __device__ __forceinline__ void apply(float2 (&x)[1][D / 2], const ColCtx<D, 1>&, const float*, float (&lj)[1]) const {
+    // U layers are unrolled; the outer loop is kept rolled (constant-bank addresses indexed by a uniform register)
+#pragma unroll 1
+    for (int l0 = 0; l0 < L; l0 += U)
+#pragma unroll
+    for (int lu = 0; lu < U; ++lu) {
+      const int l = l0 + lu;
+      float2 acc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) {
+        acc[(i & 1) * 2 + 0] = __ffma2_rn(make_float2(H.w[l][4 * i], H.w[l][4 * i + 1]), x[0][2 * i], acc[(i & 1) * 2 + 0]);
+        acc[(i & 1) * 2 + 1] =
+            __ffma2_rn(make_float2(H.w[l][4 * i + 2], H.w[l][4 * i + 3]), x[0][2 * i + 1], acc[(i & 1) * 2 + 1]);
+      }
+      const float2 s = __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
+      const float wz = s.x + s.y;  // aT_b(w, z), utils.jl:2
+      const float cc_ = H.c[l], bb = H.b[l];
+      float t, s2;
+      if (!H.inverse) {
+        tanh_sech2(wz + bb, t, s2);
+        lj[0] += log1pf(cc_ * s2);  // planar_layer.jl:107
+      } else {
+        const float alpha = find_alpha(wz, cc_, bb);  // planar_layer.jl:121
+        tanh_sech2(alpha + bb, t, s2);
+        lj[0] -= log1pf(cc_ * s2);
+        t = -t;
+      }
+      const float2 t2 = make_float2(t, t);
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) {
+        x[0][2 * i] = __ffma2_rn(make_float2(H.uh[l][4 * i], H.uh[l][4 * i + 1]), t2, x[0][2 * i]);  // :78 / :124
+        x[0][2 * i + 1] = __ffma2_rn(make_float2(H.uh[l][4 * i + 2], H.uh[l][4 * i + 3]), t2, x[0][2 * i + 1]);
+      }
+    }
+  }
+};
+
+template <int D, int L, int U, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+    planar_hp_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
+                     const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+                     const __grid_constant__ PlanarHP<D, L> H) {
+  const PlanarHPProg<D, L, U> prog{H};
+  v1_run<D, 1, 1, NW>(P, E, map_x, map_y, prog);
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -516,16 +628,41 @@ static encode_tiled_fn get_encode() {
   return fn;
 }
 
-static bool make_map(CUtensorMap* m, const float* base, int D, long long N, long long ld, int cols) {
+static bool make_map(CUtensorMap* m, const float* base, int D, long long N, long long ld, int cols, bool three_d) {
   encode_tiled_fn enc = get_encode();
   if (!enc) return false;
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (three_d) {
+    // {32 floats, N columns, D/32 row-blocks}: the row-block stride (128 B) is SMALLER than the column stride
+    const cuuint64_t dims[3] = {32, (cuuint64_t)N, (cuuint64_t)(D / 32)};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(float), 128};
+    const cuuint32_t box[3] = {32, (cuuint32_t)cols, (cuuint32_t)(D / 32)};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
   const cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)N};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   const cuuint32_t box[2] = {32, (cuuint32_t)cols};
-  const cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Both maps of a launch; 3-D when the driver accepts them (B2B_V1_TMA=2 forces the 2-D form)
+static bool make_maps(const B2BChainParams& q, int cols, CUtensorMap* mx, CUtensorMap* my, int* tma3d) {
+  static const int force2d = getenv("B2B_V1_TMA") && atoi(getenv("B2B_V1_TMA")) == 2;
+  for (int three_d = force2d ? 0 : 1; three_d >= 0; --three_d) {
+    if (three_d && q.D == 32) continue;  // one row-block: the 2-D form already is one instruction
+    bool ok = make_map(mx, q.x, q.D, q.N, q.ldx, cols, three_d != 0);
+    if (ok && q.y) ok = make_map(my, q.y, q.D, q.N, q.ldy, cols, three_d != 0);
+    if (ok) {
+      if (!q.y) *my = *mx;
+      *tma3d = three_d;
+      return true;
+    }
+  }
+  return false;
 }
 
 typedef void (*v1_kernel_t)(const B2BChainParams, const V1Extra, const CUtensorMap, const CUtensorMap);
@@ -537,7 +674,7 @@ struct V1Plan {
   V1Extra extra;
 };
 
-static int plan_v1(B2BChainParams& p, V1Plan& plan) {
+static int plan_v1(B2BChainParams& p, V1Plan& plan, int nw_override = 0) {
   const int D = p.D;
   if (!(D == 32 || D == 64 || D == 128 || D == 256)) return B2B_EUNSUPPORTED;
   if (p.N >= (1ll << 31) - 64) return B2B_EUNSUPPORTED;
@@ -573,6 +710,7 @@ static int plan_v1(B2BChainParams& p, V1Plan& plan) {
     else { plan.kernel = chain_v1_kernel<64, 1, 1, 12>; nw = 12; tpc = 1; }
   }
   else { plan.kernel = chain_v1_kernel<32, 1, 1, 16>; nw = 16; tpc = 1; }
+  if (nw_override) nw = nw_override;
   plan.cols = (32 / tpc) * cpt;
   const int tile_bytes = D * 4 * plan.cols;
   const size_t param_bytes = (size_t)off * sizeof(float);
@@ -615,14 +753,73 @@ int b2b_launch_chain_v1(const B2BChainParams& p, cudaStream_t stream) {
   const int rc = plan_v1(q, plan);
   if (rc != 0) return rc;
   CUtensorMap mx, my;
-  if (!make_map(&mx, q.x, q.D, q.N, q.ldx, plan.cols)) return B2B_EUNSUPPORTED;
-  if (q.y) {
-    if (!make_map(&my, q.y, q.D, q.N, q.ldy, plan.cols)) return B2B_EUNSUPPORTED;
-  } else {
-    my = mx;
-  }
+  if (!make_maps(q, plan.cols, &mx, &my, &plan.extra.tma3d)) return B2B_EUNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(plan.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
   if (e != cudaSuccess) return (int)e;
   plan.kernel<<<plan.grid, plan.nw * 32, plan.smem, stream>>>(q, plan.extra, mx, my);
   return (int)cudaGetLastError();
+}
+
+// ---- host-parameter planar chains ------------------------------------------------------------------------
+namespace b2b {
+
+template <int D, int L, int U, int NW>
+static int launch_planar_hp(const B2BChainParams& q, const V1Plan& plan, const CUtensorMap& mx, const CUtensorMap& my,
+                            const float* w, const float* uh, const float* c, const float* b, int inverse,
+                            cudaStream_t stream) {
+  static PlanarHP<D, L> H;  // 2·L·D+2·L+1 floats; filled and copied into the launch's parameter buffer
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  memcpy(H.w, w, sizeof(float) * L * D);
+  memcpy(H.uh, uh, sizeof(float) * L * D);
+  memcpy(H.c, c, sizeof(float) * L);
+  memcpy(H.b, b, sizeof(float) * L);
+  H.inverse = inverse;
+  auto kernel = planar_hp_kernel<D, L, U, NW>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+  if (e != cudaSuccess) return (int)e;
+  kernel<<<plan.grid, NW * 32, plan.smem, stream>>>(q, plan.extra, mx, my, H);  // arguments are copied at launch
+  return (int)cudaGetLastError();
+}
+
+template <int D, int NW>
+static int launch_planar_hp_L(int L, const B2BChainParams& q, const V1Plan& plan, const CUtensorMap& mx,
+                              const CUtensorMap& my, const float* w, const float* uh, const float* c, const float* b,
+                              int inverse, cudaStream_t stream) {
+  static const int u_env = getenv("B2B_HP_U") ? atoi(getenv("B2B_HP_U")) : 0;
+  if (D == 128 && L == 8) {
+    if (u_env == 1) return launch_planar_hp<D, 8, 1, NW>(q, plan, mx, my, w, uh, c, b, inverse, stream);
+    if (u_env == 2) return launch_planar_hp<D, 8, 2, NW>(q, plan, mx, my, w, uh, c, b, inverse, stream);
+    if (u_env == 4) return launch_planar_hp<D, 8, 4, NW>(q, plan, mx, my, w, uh, c, b, inverse, stream);
+  }
+  switch (L) {
+    case 8: return launch_planar_hp<D, 8, 8, NW>(q, plan, mx, my, w, uh, c, b, inverse, stream);
+    case 4: return launch_planar_hp<D, 4, 4, NW>(q, plan, mx, my, w, uh, c, b, inverse, stream);
+    case 2: return launch_planar_hp<D, 2, 2, NW>(q, plan, mx, my, w, uh, c, b, inverse, stream);
+    case 1: return launch_planar_hp<D, 1, 1, NW>(q, plan, mx, my, w, uh, c, b, inverse, stream);
+    default: return B2B_EINVAL;
+  }
+}
+
+}  // namespace b2b
+
+// One launch of `L` (1, 2, 4 or 8) planar layers with derived parameters (w, û, c = wᵀû, b) in HOST memory.
+int b2b_launch_planar_hostparams(const B2BChainParams& p, int L, const float* w, const float* uh, const float* c,
+                                 const float* b, int inverse, cudaStream_t stream) {
+  using namespace b2b;
+  B2BChainParams q = p;
+  q.L = 0;
+  V1Plan plan;
+  // warps per CTA of the host-parameter kernels (registers: 185 at D = 128 -> 10 warps fit)
+  static const int nw128 = getenv("B2B_HP_NW") ? atoi(getenv("B2B_HP_NW")) : 8;
+  const int rc = plan_v1(q, plan, q.D == 128 ? nw128 : 0);
+  if (rc != 0) return rc;
+  if (q.D > 128) return B2B_EUNSUPPORTED;
+  CUtensorMap mx, my;
+  if (!make_maps(q, plan.cols, &mx, &my, &plan.extra.tma3d)) return B2B_EUNSUPPORTED;
+  if (q.D == 128 && nw128 == 10) return launch_planar_hp_L<128, 10>(L, q, plan, mx, my, w, uh, c, b, inverse, stream);
+  if (q.D == 128 && nw128 == 12) return launch_planar_hp_L<128, 12>(L, q, plan, mx, my, w, uh, c, b, inverse, stream);
+  if (q.D == 128) return launch_planar_hp_L<128, 8>(L, q, plan, mx, my, w, uh, c, b, inverse, stream);
+  if (q.D == 64) return launch_planar_hp_L<64, 12>(L, q, plan, mx, my, w, uh, c, b, inverse, stream);
+  return launch_planar_hp_L<32, 16>(L, q, plan, mx, my, w, uh, c, b, inverse, stream);
 }

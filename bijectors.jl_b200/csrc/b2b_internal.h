@@ -41,6 +41,9 @@ static inline int b2b_layer_smem_floats(const b2b_layer_desc& d, int Dp) {
 int b2b_launch_chain_v0(const B2BChainParams& p, cudaStream_t stream);
 // v1: TMA-staged thread-per-column fused interpreter (D in {32,64,128}); returns B2B_EUNSUPPORTED otherwise
 int b2b_launch_chain_v1(const B2BChainParams& p, cudaStream_t stream);
+// L (1,2,4,8) planar layers, derived parameters w, û, c, b in HOST memory -> kernel arguments (constant bank)
+int b2b_launch_planar_hostparams(const B2BChainParams& p, int L, const float* w, const float* uh, const float* c,
+                                 const float* b, int inverse, cudaStream_t stream);
 // number of CTAs the v0/v1 launch of `p` will use (size of the partials array)
 int b2b_chain_grid_size(const B2BChainParams& p);
 // deterministic final sum of per-CTA partials into *sum_out

@@ -257,6 +257,8 @@ def run_chain(t, x: torch.Tensor, *, want_y=True, want_logjac=True, y: Optional[
     descs = list(t._descs(False, D)) + list(extra_descs)
     if not descs:
         raise ValueError("empty chain")
+    if any(hasattr(d, "_host_planar") for d in descs):
+        return _run_planar_hostparams(descs, x, D, N, ldx, want_y, want_logjac, y, logjac, accumulate, sum_out)
     arr = _desc_array(descs)
     L = len(descs)
     if not x.is_cuda:
@@ -291,6 +293,45 @@ def run_chain(t, x: torch.Tensor, *, want_y=True, want_logjac=True, y: Optional[
     if lj_out is not None and x.dim() == 1:
         lj_out = lj_out.reshape(())
     return y, lj_out
+
+
+def _run_planar_hostparams(descs, x, D, N, ldx, want_y, want_logjac, y, logjac, accumulate, sum_out):
+    """∘-chains of PlanarLayers whose parameters are HOST tensors, on a device batch:
+    b2b_planar_chain_hostparams_f32 (parameters travel as kernel arguments, include/b2b.h)."""
+    if not all(hasattr(d, "_host_planar") for d in descs):
+        raise B2BError(_lib.B2B_EUNSUPPORTED,
+                       "mixed parameter residency: host-resident parameters are supported for chains made of "
+                       "PlanarLayers only; move the flow to the device with .to('cuda')")
+    inv = {int(d.inverse) for d in descs}
+    if len(inv) != 1 or sum_out is not None or not x.is_cuda or x.dim() != 2:
+        raise B2BError(_lib.B2B_EUNSUPPORTED,
+                       "host-parameter planar chains take a device matrix, one direction, no batch sum; "
+                       "move the flow to the device with .to('cuda')")
+    L = len(descs)
+    w = torch.stack([d._host_planar[0] for d in descs]).contiguous()
+    u = torch.stack([d._host_planar[1] for d in descs]).contiguous()
+    b = torch.stack([d._host_planar[2].reshape(-1)[0] for d in descs]).contiguous()
+    if want_y:
+        if y is None:
+            y = colmajor_empty(D, N, x.device)
+        Dy, Ny, ldy = _batch_view(y)
+        if (Dy, Ny) != (D, N) or not y.is_cuda:
+            raise ValueError("output shape mismatch")
+    else:
+        y, ldy = None, D
+    if want_logjac:
+        if logjac is None:
+            logjac = torch.empty((N,), dtype=torch.float32, device=x.device)
+        elif logjac.numel() != N or logjac.dtype != torch.float32 or not logjac.is_contiguous():
+            raise ValueError("logjac must be a contiguous float32 vector of length N")
+    else:
+        logjac = None
+    rc = lib().b2b_planar_chain_hostparams_f32(
+        w.data_ptr(), u.data_ptr(), b.data_ptr(), L, inv.pop(), x.data_ptr(),
+        y.data_ptr() if y is not None else None, logjac.data_ptr() if logjac is not None else None,
+        D, N, ldx, ldy, 1 if accumulate else 0, _stream())
+    check(rc, "b2b_planar_chain_hostparams_f32")
+    return y, logjac
 
 
 def _run_chain_host(arr, L, x, D, N, want_y, want_logjac, sum_out):

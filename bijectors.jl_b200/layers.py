@@ -101,7 +101,12 @@ class PlanarLayer(_ParamLayer):
     def _descs(self, inverse, D):
         if D != self.w.numel():
             raise ValueError(f"DimensionMismatch: PlanarLayer has {self.w.numel()} dims, input has {D}")
-        return [_desc(_lib.PLANAR, inverse, p0=self.w, p1=self.u, p2=self.b)]
+        d = _desc(_lib.PLANAR, inverse, p0=self.w, p1=self.u, p2=self.b)
+        if not self.w.is_cuda:
+            # host-resident parameters (the reference's own residency: plain Arrays, planar_layer.jl:13-18):
+            # run_chain routes all-planar host-parameter chains to b2b_planar_chain_hostparams_f32
+            d._host_planar = (self.w, self.u, self.b)
+        return [d]
 
 
 class RadialLayer(_ParamLayer):

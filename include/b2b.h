@@ -145,6 +145,17 @@ int b2b_planar_fwd_f32(const float* x, float* y, float* logjac, const float* w, 
 int b2b_planar_inv_f32(const float* x, float* y, float* logjac, const float* w, const float* u,
                        const float* b, int32_t D, int64_t N, int64_t ldx, int64_t ldy,
                        int accumulate_logjac, void* stream);
+/* A ∘-chain of L PlanarLayers whose parameters live in HOST memory -- which is where the reference keeps them
+ * (PlanarLayer's fields are host Arrays, planar_layer.jl:13-18; a flow that was never moved with fmap(cu, .)).
+ * `w_host`, `u_host` are L x D (layer l at offset l*D, application order), `b_host` has L entries.  û = get_u_hat
+ * (planar_layer.jl:65-70) is derived on the host; the derived parameters travel as KERNEL ARGUMENTS (constant bank),
+ * so the kernel spends no shared-memory bandwidth on them.  `inverse` != 0 applies inverse(layer l) for every l in
+ * the given order (the caller passes the layers reversed, as inverse(f∘g) = inverse(g)∘inverse(f)).
+ * `x`, `y`, `logjac` are DEVICE pointers as everywhere else.  D in {32, 64, 128}; B2B_EUNSUPPORTED otherwise (use
+ * b2b_chain_run_f32 with device-resident parameters). */
+int b2b_planar_chain_hostparams_f32(const float* w_host, const float* u_host, const float* b_host, int32_t L,
+                                    int inverse, const float* x, float* y, float* logjac, int32_t D, int64_t N,
+                                    int64_t ldx, int64_t ldy, int accumulate_logjac, void* stream);
 /* RadialLayer: radial_layer.jl:58-72 (fwd), :88-102,124-129 (inverse) */
 int b2b_radial_fwd_f32(const float* x, float* y, float* logjac, const float* alpha_raw,
                        const float* beta, const float* z0, int32_t D, int64_t N, int64_t ldx,

@@ -755,3 +755,50 @@ def test_full_size_properties_config5_realnvp_share(B):
         dev_layers.append(B.InvertibleBatchNorm(b=b, logs=logs, m=m, v=v))
         ora_layers.append(O.Layer("batchnorm", dict(bn=O.BatchNormParams(b, logs, m, v, f32(1e-5), f32(0.1)))))
     _full_size_props(B, B.Composed(*dev_layers), ora_layers, D, 1 << 19, sample=1024)
+
+
+@pytest.mark.parametrize("D", [128, 64, 32])
+@pytest.mark.parametrize("L", [1, 3, 8, 11])
+def test_planar_chain_with_host_resident_parameters(B, D, L):
+    """PlanarLayers whose parameters stay in HOST memory (the reference's residency) on a device batch:
+    b2b_planar_chain_hostparams_f32 -- same results as the device-parameter chain and the oracle."""
+    import torch
+
+    rng = np.random.default_rng(1000 * D + L)
+    N = 2500 + L  # ragged: not a multiple of the 32-column tile
+    pairs = [make_case("planar", D, rng) for _ in range(L)]
+    dev_flow = B.Composed(*[p[0] for p in pairs])
+    host_flow = B.Composed(*[p[0].to("cpu") for p in pairs])
+    x = rng.standard_normal((D, N)).astype(f32)
+    xd = B.from_numpy(x)
+    y, lj = B.with_logabsdet_jacobian(host_flow, xd)
+    assert B.lib().b2b_last_launch_count() == {1: 1, 3: 1, 8: 1, 11: 2}[L]
+    yo, ljo = O.chain_forward([p[1] for p in pairs], x.astype(np.float64))
+    assert rel(B.to_numpy(y), yo) <= RTOL and rel(B.to_numpy(lj), ljo) <= RTOL
+    yd, ljd = B.with_logabsdet_jacobian(dev_flow, xd)
+    assert rel(B.to_numpy(y), B.to_numpy(yd)) <= 2e-6 and rel(B.to_numpy(lj), B.to_numpy(ljd)) <= 2e-6
+    # transform-only / logabsdetjac-only (the latter needs one launch: L <= 8)
+    assert np.array_equal(B.to_numpy(B.transform(host_flow, xd)), B.to_numpy(y))
+    if L <= 8:
+        assert np.array_equal(B.to_numpy(B.logabsdetjac(host_flow, xd)), B.to_numpy(lj))
+    # inverse chain (find_alpha per layer), in place + accumulating
+    xi, lji = B.with_logabsdet_jacobian(B.inverse(host_flow), y)
+    xid, ljid = B.with_logabsdet_jacobian(B.inverse(dev_flow), y)
+    assert rel(B.to_numpy(xi), B.to_numpy(xid)) <= 2e-6 and rel(B.to_numpy(lji), B.to_numpy(ljid)) <= 2e-6
+    assert rel(B.to_numpy(xi), x) <= 1e-4 and rel(B.to_numpy(lji), -ljo) <= 1e-4
+    buf, acc = B.from_numpy(x), torch.full((N,), 0.5, dtype=torch.float32, device="cuda")
+    buf, acc = B.with_logabsdet_jacobian_(host_flow, buf, None, acc)
+    assert np.array_equal(B.to_numpy(buf), B.to_numpy(y))
+    assert rel(B.to_numpy(acc), B.to_numpy(lj) + 0.5) <= 2e-6
+
+
+def test_host_resident_parameters_unsupported_cases_fail_loudly(B):
+    rng = np.random.default_rng(5)
+    pl, _ = make_case("planar", 128, rng)
+    rd, _ = make_case("radial", 128, rng)
+    xd = B.from_numpy(rng.standard_normal((128, 64)).astype(f32))
+    with pytest.raises(B.B2BError):  # mixed residency / non-planar layers
+        B.with_logabsdet_jacobian(B.Composed(pl.to("cpu"), rd), xd)
+    pl10, _ = make_case("planar", 10, rng)
+    with pytest.raises(B.B2BError):  # D outside {32, 64, 128}: no silent fallback
+        B.with_logabsdet_jacobian(pl10.to("cpu"), B.from_numpy(rng.standard_normal((10, 64)).astype(f32)))
