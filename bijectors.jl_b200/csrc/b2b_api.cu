@@ -12,7 +12,7 @@ int b2b_chain_grid_size_v0(const B2BChainParams& p);
 int b2b_chain_grid_size_v1(const B2BChainParams& p);
 
 static thread_local int g_last_launches = 0;
-static int g_variant = 0;           // fused chain kernel: 0 auto, 1 v0, 2 v1
+static int g_variant = 0;           // fused chain kernel: 0 auto, 1 v0, 2 v1 interpreter, 3 constant-bank planar
 static int g_fold_bn = 1;            // fold BatchNorm neighbours into coupling launches (hundreds digit 1 disables)
 static int g_coupling_variant = 0;  // coupling: 0 auto (tensor cores when possible), 1 force the fp32 CUDA-core kernel
 
@@ -40,7 +40,7 @@ extern "C" int b2b_last_launch_count(void) { return g_last_launches; }
 extern "C" int b2b_set_kernel_variant(int variant) {
   // low decimal digit: fused chain kernel variant; tens digit: coupling variant (10 = force fp32 CUDA cores)
   const int chain = variant % 10, cpl = (variant / 10) % 10, nofold = variant / 100;
-  if (variant < 0 || chain > 2 || cpl > 1 || nofold > 1) return B2B_EINVAL;
+  if (variant < 0 || chain > 3 || cpl > 1 || nofold > 1) return B2B_EINVAL;
   g_variant = chain;
   g_coupling_variant = cpl;
   g_fold_bn = nofold ? 0 : 1;
@@ -86,8 +86,21 @@ static int validate_layer(const b2b_layer_desc& d, int D, bool last) {
   return B2B_OK;
 }
 
+// number of kernel launches the last launch_fused enqueued (the constant-bank path adds a prep kernel and a copy)
+static thread_local int g_fused_launches = 1;
+
 static int launch_fused(B2BChainParams& p, cudaStream_t stream) {
   int rc = B2B_EUNSUPPORTED;
+  g_fused_launches = 1;
+  // segments made of <= 8 PlanarLayers: parameters through the constant bank (variant 3 forces, 1 / 2 disable)
+  if ((g_variant == 0 || g_variant == 3) && !p.partials) {
+    rc = b2b_launch_planar_chain_const(p, stream);
+    if (rc == B2B_OK) {
+      g_fused_launches = 2;  // parameter preparation kernel + main kernel (plus one 8 KB device-to-device copy)
+      return rc;
+    }
+    if (g_variant == 3 || rc != B2B_EUNSUPPORTED) return rc;
+  }
   if (g_variant != 1) {
     rc = b2b_launch_chain_v1(p, stream);
     if (rc == B2B_OK) return rc;
@@ -295,7 +308,7 @@ extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const 
       }
       rc = launch_fused(p, stream);
       if (rc != B2B_OK) return rc;
-      ++g_last_launches;
+      g_last_launches += g_fused_launches;
       if (sum_out && last_seg) {
         rc = b2b_launch_sum_partials(partials, grid, sum_out, stream);
         if (rc != B2B_OK) return rc;
@@ -441,21 +454,18 @@ extern "C" int b2b_mvnormal_diag_logpdf_f32(const float* x, const float* mu, con
 
 // ---- planar chains with HOST-resident parameters ---------------------------------------------------------
 // get_u_hat (planar_layer.jl:65-70) on the host: û = u + (m(wᵀu) − wᵀu)·w/‖w‖², m(x) = −1 + softplus(x); c = wᵀû.
+static float softplus_host(float x) { return x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x)); }
+
 static void planar_derive_host(const float* w, const float* u, int D, float* uh, float* c) {
   double wu = 0.0, ww = 0.0;
   for (int i = 0; i < D; ++i) {
     wu += (double)w[i] * u[i];
     ww += (double)w[i] * w[i];
   }
-  const float wuf = (float)wu;
-  const float sp = wuf > 0.f ? wuf + log1pf(expf(-wuf)) : log1pf(expf(wuf));
-  const float scale = ((-1.0f + sp) - wuf) / (float)ww;
-  double cc = 0.0;
-  for (int i = 0; i < D; ++i) {
-    uh[i] = u[i] + scale * w[i];
-    cc += (double)w[i] * uh[i];
-  }
-  *c = (float)cc;
+  const float s = (float)wu;
+  const float k = (softplus_host(-s) - 1.0f) / (float)ww;  // (m(wᵀu) − wᵀu)/‖w‖², planar_layer.jl:67
+  for (int i = 0; i < D; ++i) uh[i] = fmaf(k, w[i], u[i]);
+  *c = softplus_host(s) - 1.0f;  // wᵀû = m(wᵀu), planar_layer.jl:68
 }
 
 extern "C" int b2b_planar_chain_hostparams_f32(const float* w_host, const float* u_host, const float* b_host,
@@ -471,10 +481,7 @@ extern "C" int b2b_planar_chain_hostparams_f32(const float* w_host, const float*
   if (!y && L > 8) return B2B_EUNSUPPORTED;  // several launches need the D x N intermediate
   // launches take 1, 2, 4 or 8 layers: the tail is padded with identity layers (w = û = 0: y = x, logjac += 0),
   // which costs a little arithmetic but no extra pass over the batch
-  const int Lp = (L + 7) / 8 * 8;
-  std::vector<float> wp((size_t)Lp * D, 0.f), uh((size_t)Lp * D, 0.f), c(Lp, 0.f), bp(Lp, 0.f);
-  memcpy(wp.data(), w_host, sizeof(float) * (size_t)L * D);
-  memcpy(bp.data(), b_host, sizeof(float) * L);
+  std::vector<float> uh((size_t)L * D), c(L), packed;
   for (int l = 0; l < L; ++l) planar_derive_host(w_host + (size_t)l * D, u_host + (size_t)l * D, D, &uh[(size_t)l * D], &c[l]);
   B2BChainParams p;
   memset(&p, 0, sizeof(p));
@@ -486,15 +493,18 @@ extern "C" int b2b_planar_chain_hostparams_f32(const float* w_host, const float*
   while (done < L) {
     int n = 1;
     while (n < L - done && n < 8) n <<= 1;
-    const bool last = done + n >= L;
+    const int real = L - done < n ? L - done : n;
+    packed.assign((size_t)2 * n * D + 2 * n, 0.f);  // w[n][D] | û[n][D] | c[n] | b[n]
+    memcpy(&packed[0], w_host + (size_t)done * D, sizeof(float) * (size_t)real * D);
+    memcpy(&packed[(size_t)n * D], &uh[(size_t)done * D], sizeof(float) * (size_t)real * D);
+    memcpy(&packed[(size_t)2 * n * D], &c[done], sizeof(float) * real);
+    memcpy(&packed[(size_t)2 * n * D + n], b_host + done, sizeof(float) * real);
     p.x = done == 0 ? x : y;
     p.ldx = done == 0 ? ldx : ldy;
     p.y = y;
     p.ldy = ldy;
     p.accumulate = (done == 0) ? (accumulate_logjac != 0) : 1;
-    (void)last;
-    const int rc = b2b_launch_planar_hostparams(p, n, &wp[(size_t)done * D], &uh[(size_t)done * D], &c[done],
-                                                &bp[done], inverse, stream);
+    const int rc = b2b_launch_planar_hostparams(p, n, packed.data(), inverse ? (1 << n) - 1 : 0, stream);
     if (rc != B2B_OK) return rc;
     ++g_last_launches;
     done += n;

@@ -41,9 +41,13 @@ static inline int b2b_layer_smem_floats(const b2b_layer_desc& d, int Dp) {
 int b2b_launch_chain_v0(const B2BChainParams& p, cudaStream_t stream);
 // v1: TMA-staged thread-per-column fused interpreter (D in {32,64,128}); returns B2B_EUNSUPPORTED otherwise
 int b2b_launch_chain_v1(const B2BChainParams& p, cudaStream_t stream);
-// L (1,2,4,8) planar layers, derived parameters w, û, c, b in HOST memory -> kernel arguments (constant bank)
-int b2b_launch_planar_hostparams(const B2BChainParams& p, int L, const float* w, const float* uh, const float* c,
-                                 const float* b, int inverse, cudaStream_t stream);
+// constant-bank planar chains (b2b_planar_const.cu).  hostparams: `L` in {1,2,4,8} layers, derived parameters packed
+// w[L][D] | û[L][D] | c[L] | b[L] in HOST memory, bit l of invmask = inverse of layer l.
+int b2b_launch_planar_hostparams(const B2BChainParams& p, int L, const float* packed, int invmask,
+                                 cudaStream_t stream);
+// device-resident parameters: p.layers must be 1..8 PLANAR layers; B2B_EUNSUPPORTED when not applicable
+int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream);
+int b2b_planar_const_grid_size(const B2BChainParams& p);
 // number of CTAs the v0/v1 launch of `p` will use (size of the partials array)
 int b2b_chain_grid_size(const B2BChainParams& p);
 // deterministic final sum of per-CTA partials into *sum_out

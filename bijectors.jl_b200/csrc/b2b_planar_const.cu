@@ -1,0 +1,301 @@
+// Chains of PlanarLayers with their (derived) parameters in the CONSTANT BANK.
+//
+// Why: in the layer interpreter (b2b_chain_v1.cu) every parameter element is a warp-uniform LDS broadcast and the
+// 8-layer D = 128 headline chain is bound by LSU wavefronts (~70 % of the HBM roofline).  A constant-bank operand
+// reaches FFMA2 through a uniform register (LDCU -> UR) and costs no LSU work, but the first-level constant cache
+// only holds ~4 KB.  So: chains whose w and û fit in 4 KB read both from the constant bank (MODE 0); the 8-layer
+// D = 128 chain (8 KB) keeps w in shared memory and û in the constant bank (MODE 2), splitting the operand traffic
+// over both paths -- 86 % of the roofline instead of 72 %.
+//
+// Two parameter sources share the per-tile program:
+//   ArgSrc  parameters in HOST memory (b2b_planar_chain_hostparams_f32): derived on the host, passed BY VALUE as
+//           kernel arguments (bank 0).  No device-side preparation at all.
+//   SymSrc  parameters in DEVICE memory (b2b_chain_run_f32 segments made of PlanarLayers only): a one-CTA kernel
+//           derives û / wᵀû into a staging buffer, cudaMemcpyToSymbolAsync moves it into a __constant__ array
+//           (stream-ordered, so the constant cache is coherent), then the main kernel runs.  The symbol is per-device
+//           library state: launches that use it are serialised by an event (same stream: free).
+//
+// Reference semantics: planar_layer.jl:65-80 (get_u_hat, forward), :102-110 (logabsdetjac), :112-127 + :160-185
+// (inverse through find_alpha).
+#include <cstring>
+
+#include "b2b_v1_pipeline.cuh"
+
+namespace b2b {
+
+constexpr int HP_MAX_L = 8;
+constexpr int HP_MAX_D = 128;
+// packed layout for (D, L): w[L][D] | û[L][D] | c[L] | b[L]
+constexpr int HP_MAX_FLOATS = 2 * HP_MAX_L * HP_MAX_D + 2 * HP_MAX_L;
+
+__constant__ float c_planar[HP_MAX_FLOATS];
+__device__ float g_planar_stage[HP_MAX_FLOATS];
+
+template <int D, int L>
+struct PlanarHP {
+  float v[2 * L * D + 2 * L];
+};
+
+template <int D, int L>
+struct ArgSrc {
+  const PlanarHP<D, L>& H;
+  int invmask;
+  __device__ __forceinline__ float w(int l, int i) const { return H.v[l * D + i]; }
+  __device__ __forceinline__ float uh(int l, int i) const { return H.v[L * D + l * D + i]; }
+  __device__ __forceinline__ float c(int l) const { return H.v[2 * L * D + l]; }
+  __device__ __forceinline__ float b(int l) const { return H.v[2 * L * D + L + l]; }
+  __device__ __forceinline__ bool inv(int l) const { return (invmask >> l) & 1; }
+  __device__ __forceinline__ float raw(int i) const { return H.v[i]; }  // dynamic index: staging only
+};
+
+template <int D, int L>
+struct SymSrc {
+  const float* stage;  // the same packed parameters in global memory (source of the shared-memory half)
+  int invmask;
+  __device__ __forceinline__ float w(int l, int i) const { return c_planar[l * D + i]; }
+  __device__ __forceinline__ float uh(int l, int i) const { return c_planar[L * D + l * D + i]; }
+  __device__ __forceinline__ float c(int l) const { return c_planar[2 * L * D + l]; }
+  __device__ __forceinline__ float b(int l) const { return c_planar[2 * L * D + L + l]; }
+  __device__ __forceinline__ bool inv(int l) const { return (invmask >> l) & 1; }
+  __device__ __forceinline__ float raw(int i) const { return stage[i]; }
+};
+
+// MODE 0: w and û from the constant bank; MODE 1: û staged in shared memory (LDS broadcast), w from the constant
+// bank; MODE 2: w in shared memory, û from the constant bank.
+template <int D, int L, int MODE, class Src>
+struct PlanarConstProg {
+  const Src src;
+  __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
+    if (MODE == 0) return;
+    for (int i = warp * 32 + lane; i < L * D; i += nw * 32) params[i] = src.raw((MODE == 1 ? L * D : 0) + i);
+  }
+  __device__ __forceinline__ void apply(float2 (&x)[1][D / 2], const ColCtx<D, 1>&, const float* params,
+                                        float (&lj)[1]) const {
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const float4* sp4 = reinterpret_cast<const float4*>(params + l * D);
+      float2 acc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) {
+        float4 w;
+        if (MODE == 2) w = sp4[i];
+        else w = make_float4(src.w(l, 4 * i), src.w(l, 4 * i + 1), src.w(l, 4 * i + 2), src.w(l, 4 * i + 3));
+        acc[(i & 1) * 2 + 0] = __ffma2_rn(make_float2(w.x, w.y), x[0][2 * i], acc[(i & 1) * 2 + 0]);
+        acc[(i & 1) * 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), x[0][2 * i + 1], acc[(i & 1) * 2 + 1]);
+      }
+      const float2 s = __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
+      const float wz = s.x + s.y;  // aT_b(w, z), utils.jl:2
+      const float cc_ = src.c(l), bb = src.b(l);
+      float t, s2;
+      if (!src.inv(l)) {
+        tanh_sech2(wz + bb, t, s2);
+        lj[0] += log1pf(cc_ * s2);  // planar_layer.jl:107
+      } else {
+        const float alpha = find_alpha(wz, cc_, bb);  // planar_layer.jl:121
+        tanh_sech2(alpha + bb, t, s2);
+        lj[0] -= log1pf(cc_ * s2);
+        t = -t;
+      }
+      const float2 t2 = make_float2(t, t);
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) {
+        float4 u;
+        if (MODE == 1) u = sp4[i];
+        else u = make_float4(src.uh(l, 4 * i), src.uh(l, 4 * i + 1), src.uh(l, 4 * i + 2), src.uh(l, 4 * i + 3));
+        x[0][2 * i] = __ffma2_rn(make_float2(u.x, u.y), t2, x[0][2 * i]);  // planar_layer.jl:78 / :124
+        x[0][2 * i + 1] = __ffma2_rn(make_float2(u.z, u.w), t2, x[0][2 * i + 1]);
+      }
+    }
+  }
+};
+
+template <int D, int L, int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32, 1)
+    planar_arg_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
+                      const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+                      const __grid_constant__ PlanarHP<D, L> H, const int invmask) {
+  const PlanarConstProg<D, L, MODE, ArgSrc<D, L>> prog{{H, invmask}};
+  v1_run<D, 1, 1, NW>(P, E, map_x, map_y, prog);
+}
+
+template <int D, int L, int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32, 1)
+    planar_sym_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
+                      const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+                      const float* stage, const int invmask) {
+  const PlanarConstProg<D, L, MODE, SymSrc<D, L>> prog{{stage, invmask}};
+  v1_run<D, 1, 1, NW>(P, E, map_x, map_y, prog);
+}
+
+// get_u_hat (planar_layer.jl:65-70) for Lp layers (the last Lp - L are identity padding), one warp per layer,
+// packed for (D, Lp) into `out`.
+__global__ void __launch_bounds__(HP_MAX_L * 32)
+    planar_prep_kernel(const __grid_constant__ B2BChainParams P, int L, int Lp, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, l = threadIdx.x >> 5, D = P.D;
+  if (l >= Lp) return;
+  float* w_out = out + l * D;
+  float* u_out = out + Lp * D + l * D;
+  if (l >= L) {
+    for (int i = lane; i < D; i += 32) w_out[i] = u_out[i] = 0.f;
+    if (lane == 0) out[2 * Lp * D + l] = out[2 * Lp * D + Lp + l] = 0.f;
+    return;
+  }
+  const b2b_layer_desc& d = P.layers[l];
+  float s = 0.f, q = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float w = d.p0[i], u = d.p1[i];
+    s = fmaf(w, u, s);
+    q = fmaf(w, w, q);
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  const float k = (softplus(-s) - 1.0f) / q;  // planar_layer.jl:67
+  for (int i = lane; i < D; i += 32) {
+    const float w = d.p0[i];
+    w_out[i] = w;
+    u_out[i] = fmaf(k, w, d.p1[i]);
+  }
+  if (lane == 0) {
+    out[2 * Lp * D + l] = softplus(s) - 1.0f;  // wᵀû, planar_layer.jl:68
+    out[2 * Lp * D + Lp + l] = d.p2[0];        // first(flow.b), :75
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+struct HPShape {
+  int nw, mode;
+};
+
+// warps per CTA as in the interpreter (register budget); MODE 2 when w and û exceed ~4 KB of constants
+static HPShape hp_shape(int D, int L) {
+  static const int mode_env = getenv("B2B_HP_MODE") ? atoi(getenv("B2B_HP_MODE")) : -1;
+  HPShape s;
+  s.nw = D == 128 ? 8 : (D == 64 ? 12 : 16);
+  s.mode = (2 * D * L * 4 > 4096) ? 2 : 0;
+  if (mode_env == 0) s.mode = 0;  // experiments: force the all-constant form
+  return s;
+}
+
+template <int D, int L, int NW, int MODE>
+static int launch_arg(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
+                      const float* packed, int invmask, cudaStream_t stream) {
+  static PlanarHP<D, L> H;  // copied into the launch's argument buffer by <<<>>>
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  memcpy(H.v, packed, sizeof(H.v));
+  auto kernel = planar_arg_kernel<D, L, NW, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) return (int)e;
+  kernel<<<g.grid, NW * 32, g.smem, stream>>>(q, g.extra, mx, my, H, invmask);
+  return (int)cudaGetLastError();
+}
+
+template <int D, int L, int NW, int MODE>
+static int launch_sym(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
+                      const float* stage, int invmask, cudaStream_t stream) {
+  auto kernel = planar_sym_kernel<D, L, NW, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) return (int)e;
+  kernel<<<g.grid, NW * 32, g.smem, stream>>>(q, g.extra, mx, my, stage, invmask);
+  return (int)cudaGetLastError();
+}
+
+// dispatch over (D, L, MODE) for either source
+template <bool SYM, int D, int NW>
+static int dispatch_L(int L, int mode, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx,
+                      const CUtensorMap& my, const float* params, int invmask, cudaStream_t stream) {
+#define B2B_HP_CASE(LL, MM)                                                                          \
+  if (L == LL && mode == MM)                                                                         \
+    return SYM ? launch_sym<D, LL, NW, MM>(q, g, mx, my, params, invmask, stream)                    \
+               : launch_arg<D, LL, NW, MM>(q, g, mx, my, params, invmask, stream);
+  B2B_HP_CASE(1, 0)
+  B2B_HP_CASE(2, 0)
+  B2B_HP_CASE(4, 0)
+  if (2 * D * 8 * 4 > 4096) {
+    B2B_HP_CASE(8, 2)
+  }
+  B2B_HP_CASE(8, 0)
+#undef B2B_HP_CASE
+  return B2B_EUNSUPPORTED;
+}
+
+template <bool SYM>
+static int launch_planar_const(const B2BChainParams& p, int L, const float* params, int invmask, cudaStream_t stream) {
+  B2BChainParams q = p;
+  q.L = 0;
+  q.scratch_off = -1;
+  if (!(q.D == 32 || q.D == 64 || q.D == 128)) return B2B_EUNSUPPORTED;
+  if (v1_check_io(q) != 0) return B2B_EUNSUPPORTED;
+  const HPShape sh = hp_shape(q.D, L);
+  V1Geom g;
+  const int rc = v1_geometry(q.D, q.N, sh.nw, 32, sh.mode ? (size_t)L * q.D : 0, g);
+  if (rc != 0) return rc;
+  CUtensorMap mx, my;
+  if (!make_maps(q, g.cols, &mx, &my, &g.extra.tma3d)) return B2B_EUNSUPPORTED;
+  if (q.D == 128) return dispatch_L<SYM, 128, 8>(L, sh.mode, q, g, mx, my, params, invmask, stream);
+  if (q.D == 64) return dispatch_L<SYM, 64, 12>(L, sh.mode, q, g, mx, my, params, invmask, stream);
+  return dispatch_L<SYM, 32, 16>(L, sh.mode, q, g, mx, my, params, invmask, stream);
+}
+
+// per-device state of the __constant__ slot
+struct SlotState {
+  std::mutex mu;
+  cudaEvent_t free_ev = nullptr;
+  float* stage = nullptr;
+};
+static SlotState g_slots[64];
+
+}  // namespace b2b
+
+int b2b_planar_const_grid_size(const B2BChainParams& p) {
+  using namespace b2b;
+  if (!(p.D == 32 || p.D == 64 || p.D == 128)) return 0;
+  V1Geom g;
+  const HPShape sh = hp_shape(p.D, 8);
+  if (v1_geometry(p.D, p.N, sh.nw, 32, 0, g) != 0) return 0;
+  return g.grid;
+}
+
+// `L` (1, 2, 4 or 8) planar layers, derived parameters packed for (D, L) in HOST memory -> kernel arguments
+int b2b_launch_planar_hostparams(const B2BChainParams& p, int L, const float* packed, int invmask,
+                                 cudaStream_t stream) {
+  return b2b::launch_planar_const<false>(p, L, packed, invmask, stream);
+}
+
+// A fusable segment made only of PlanarLayers (device-resident parameters), at most 8 of them:
+// prep kernel -> staging buffer -> __constant__ symbol -> main kernel.  B2B_EUNSUPPORTED when not applicable.
+int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream) {
+  using namespace b2b;
+  if (p.L < 1 || p.L > HP_MAX_L || !(p.D == 32 || p.D == 64 || p.D == 128)) return B2B_EUNSUPPORTED;
+  int invmask = 0;
+  for (int l = 0; l < p.L; ++l) {
+    if (p.layers[l].kind != B2B_PLANAR) return B2B_EUNSUPPORTED;
+    if (p.layers[l].inverse) invmask |= 1 << l;
+  }
+  if (v1_check_io(p) != 0) return B2B_EUNSUPPORTED;
+  int Lp = 1;
+  while (Lp < p.L) Lp <<= 1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return B2B_EUNSUPPORTED;
+  SlotState& st = g_slots[dev];
+  std::lock_guard<std::mutex> lock(st.mu);
+  cudaError_t e;
+  if (!st.free_ev) {
+    if ((e = cudaEventCreateWithFlags(&st.free_ev, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+    if ((e = cudaGetSymbolAddress(reinterpret_cast<void**>(&st.stage), g_planar_stage)) != cudaSuccess) return (int)e;
+    if ((e = cudaEventRecord(st.free_ev, stream)) != cudaSuccess) return (int)e;
+  }
+  // the previous user of the slot (possibly on another stream) must have finished
+  if ((e = cudaStreamWaitEvent(stream, st.free_ev, 0)) != cudaSuccess) return (int)e;
+  planar_prep_kernel<<<1, HP_MAX_L * 32, 0, stream>>>(p, p.L, Lp, st.stage);
+  if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+  const size_t bytes = sizeof(float) * (size_t)(2 * Lp * p.D + 2 * Lp);
+  if ((e = cudaMemcpyToSymbolAsync(c_planar, st.stage, bytes, 0, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess)
+    return (int)e;
+  const int rc = launch_planar_const<true>(p, Lp, st.stage, invmask, stream);
+  if (rc != B2B_OK) return rc;
+  if ((e = cudaEventRecord(st.free_ev, stream)) != cudaSuccess) return (int)e;
+  return B2B_OK;
+}

@@ -131,7 +131,8 @@ size_t b2b_chain_workspace_bytes(const b2b_layer_desc* layers, int32_t L, int32_
 int b2b_last_launch_count(void);
 
 /* Select kernel implementations (testing / profiling).  Ones digit -- fused column-local kernel: 0 = auto
- * (default), 1 = lane-group direct-global kernel (v0), 2 = TMA-staged thread-per-column kernel (v1) only.
+ * (default), 1 = lane-group direct-global kernel (v0), 2 = TMA-staged thread-per-column interpreter (v1) only,
+ * 3 = constant-bank planar-chain kernel only (segments of <= 8 PlanarLayers, D in {32,64,128}; else B2B_EUNSUPPORTED).
  * Tens digit -- coupling: 0 = auto (tensor cores when the mask is contiguous and workspace is given),
  * 1 = always the exact-fp32 CUDA-core kernel.  Hundreds digit -- 1 = do not fold BatchNorm layers into
  * neighbouring coupling launches. */

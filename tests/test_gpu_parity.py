@@ -802,3 +802,75 @@ def test_host_resident_parameters_unsupported_cases_fail_loudly(B):
     pl10, _ = make_case("planar", 10, rng)
     with pytest.raises(B.B2BError):  # D outside {32, 64, 128}: no silent fallback
         B.with_logabsdet_jacobian(pl10.to("cpu"), B.from_numpy(rng.standard_normal((10, 64)).astype(f32)))
+
+
+@pytest.mark.parametrize("D", [128, 64, 32])
+@pytest.mark.parametrize("L", [1, 3, 8])
+def test_constant_bank_planar_chain_matches_interpreter_and_oracle(B, D, L):
+    """Segments of <= 8 PlanarLayers with device-resident parameters run through the constant bank
+    (b2b_planar_const.cu): same results as the shared-memory interpreter and the oracle, mixed directions."""
+    rng = np.random.default_rng(77 * D + L)
+    N = 4000 + 3 * L
+    pairs = [make_case("planar", D, rng) for _ in range(L)]
+    # mix forward and inverse layers in one chain
+    flow = B.Composed(*[B.inverse(p[0]) if i % 3 == 1 else p[0] for i, p in enumerate(pairs)])
+    x = rng.standard_normal((D, N)).astype(f32)
+    xd = B.from_numpy(x)
+    lib = B.lib()
+    try:
+        assert lib.b2b_set_kernel_variant(3) == 0
+        y3, lj3 = B.with_logabsdet_jacobian(flow, xd)
+        assert lib.b2b_last_launch_count() == 2
+        assert lib.b2b_set_kernel_variant(2) == 0
+        y2, lj2 = B.with_logabsdet_jacobian(flow, xd)
+        assert lib.b2b_last_launch_count() == 1
+    finally:
+        lib.b2b_set_kernel_variant(0)
+    y0, lj0 = B.with_logabsdet_jacobian(flow, xd)  # auto picks the constant-bank path
+    assert np.array_equal(B.to_numpy(y0), B.to_numpy(y3)) and np.array_equal(B.to_numpy(lj0), B.to_numpy(lj3))
+    assert rel(B.to_numpy(y3), B.to_numpy(y2)) <= 2e-6 and rel(B.to_numpy(lj3), B.to_numpy(lj2)) <= 2e-6
+    # oracle: forward layers forward, inverse layers through the float64 inverse
+    z, ljo = x.astype(np.float64), np.zeros(N)
+    for i, p in enumerate(pairs):
+        if i % 3 == 1:
+            z, l1 = O.chain_inverse([p[1]], z)
+        else:
+            z, l1 = O.chain_forward([p[1]], z)
+        ljo = ljo + l1
+    assert rel(B.to_numpy(y3), z) <= 5e-5 and rel(B.to_numpy(lj3), ljo) <= 5e-5
+    if L != 3 or True:
+        fwd = B.Composed(*[p[0] for p in pairs])
+        yf, ljf = B.with_logabsdet_jacobian(fwd, xd)
+        yo, lo = O.chain_forward([p[1] for p in pairs], x.astype(np.float64))
+        assert rel(B.to_numpy(yf), yo) <= RTOL and rel(B.to_numpy(ljf), lo) <= RTOL
+
+
+def test_constant_bank_slot_is_safe_across_streams(B):
+    """The __constant__ parameter slot is per-device state: launches from different streams with different flows
+    are ordered by the library (event), results never mix."""
+    import torch
+
+    rng = np.random.default_rng(99)
+    D, N = 128, 1 << 16
+    flows, outs, refs = [], [], []
+    x = B.from_numpy(rng.standard_normal((D, N)).astype(f32))
+    for k in range(4):
+        pairs = [make_case("planar", D, rng) for _ in range(8)]
+        flows.append(B.Composed(*[p[0] for p in pairs]))
+    lib = B.lib()
+    lib.b2b_set_kernel_variant(2)
+    try:
+        for f in flows:
+            refs.append(tuple(B.to_numpy(t) for t in B.with_logabsdet_jacobian(f, x)))
+    finally:
+        lib.b2b_set_kernel_variant(0)
+    streams = [torch.cuda.Stream() for _ in flows]
+    torch.cuda.synchronize()
+    for rep in range(5):
+        outs = []
+        for f, s in zip(flows, streams):
+            with torch.cuda.stream(s):
+                outs.append(B.with_logabsdet_jacobian(f, x))
+        torch.cuda.synchronize()
+        for (y, lj), (yr, ljr) in zip(outs, refs):
+            assert rel(B.to_numpy(y), yr) <= 2e-6 and rel(B.to_numpy(lj), ljr) <= 2e-6
