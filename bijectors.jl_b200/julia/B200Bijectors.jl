@@ -118,6 +118,23 @@ logabsdetjac(b::DeviceTransform, x::CuMatrix{Float32}) = last(run_chain(descs(b,
 Bijectors.with_logabsdet_jacobian!(b::DeviceTransform, x::CuMatrix{Float32}, y::CuMatrix{Float32}, logjac::CuVector{Float32}) =
     run_chain(descs(b, false), x; y=y, logjac=logjac, accumulate=true)
 
+# Host-resident PlanarLayer chains (fields are plain Arrays) on a device batch: parameters travel as kernel arguments.
+const HostPlanar = PlanarLayer{<:Vector{Float32}}
+all_host_planar(f) = all(b -> b isa HostPlanar, flatten(f))
+function planar_hostparams(f, x::CuMatrix{Float32}; inv::Bool=false)
+    ls = inv ? reverse(collect(flatten(f))) : collect(flatten(f))
+    w, u, b = reduce(hcat, [l.w for l in ls]), reduce(hcat, [l.u for l in ls]), Float32[first(l.b) for l in ls]
+    y, logjac = similar(x), CUDA.zeros(Float32, size(x, 2))
+    check(ccall((:b2b_planar_chain_hostparams_f32, libb2b), Cint,
+        (Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Int32, Cint, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32},
+         Int32, Int64, Int64, Int64, Cint, Ptr{Cvoid}),
+        w, u, b, length(ls), inv, pointer(x), pointer(y), pointer(logjac),
+        size(x, 1), size(x, 2), stride(x, 2), stride(y, 2), false, stream_handle()))
+    return y, logjac
+end
+with_logabsdet_jacobian(b::Union{HostPlanar,ComposedFunction}, x::CuMatrix{Float32}) =
+    all_host_planar(b) ? planar_hostparams(b, x) : run_chain(descs(b, false), x)
+
 # logpdf(td::MvTransformed, y::Matrix) (src/transformed_distribution.jl:165-169): inverse chain + base
 # MvNormal + (optionally) the batch sum in ONE fused launch per fusable segment.
 function Distributions.logpdf(td::TransformedDistribution{<:MvNormal}, y::CuMatrix{Float32})
