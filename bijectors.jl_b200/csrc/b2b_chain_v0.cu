@@ -146,8 +146,7 @@ __global__ void __launch_bounds__(256) chain_v0_kernel(const __grid_constant__ B
             tanh_sech2(wz + bb, t, s2);
             lj += log1pf(cc * s2);  // :107
           } else {
-            const float alpha = find_alpha(wz, cc, bb);  // :121
-            tanh_sech2(alpha + bb, t, s2);
+            find_alpha_ts(wz, cc, bb, t, s2);  // :121; t = tanh(α+b), s2 = sech²(α+b)
             lj -= log1pf(cc * s2);  // interface.jl:276-281 with wᵀz + b = α + b
             t = -t;
           }

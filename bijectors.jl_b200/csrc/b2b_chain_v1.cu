@@ -57,8 +57,7 @@ __device__ __forceinline__ void planar_apply(float2 (&x)[CPT][D / TPC / 2], cons
       tanh_sech2(wz + bb, t, s2);
       lj[cc] += log1pf(cc_ * s2);  // planar_layer.jl:107
     } else {
-      const float alpha = find_alpha(wz, cc_, bb);  // planar_layer.jl:121
-      tanh_sech2(alpha + bb, t, s2);
+      find_alpha_ts(wz, cc_, bb, t, s2);  // planar_layer.jl:121; t = tanh(α+b), s2 = sech²(α+b)
       lj[cc] -= log1pf(cc_ * s2);
       t = -t;
     }

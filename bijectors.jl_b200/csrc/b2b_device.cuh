@@ -31,41 +31,75 @@ __device__ __forceinline__ void tanh_sech2(float a, float& t, float& s2) {
   s2 = 4.0f * e * r * r;
 }
 
-// find_alpha (planar_layer.jl:160-185): root of f(α) = α + c·tanh(α+b) − t in [t−2|c|, t+2|c|].
+// find_alpha (planar_layer.jl:160-185): root of f(α) = α + c·tanh(α+b) − t in [t−2|c|, t+2|c|]; also returns
+// tanh(α+b) and sech²(α+b), which the inverse needs next (planar_layer.jl:122-124, interface.jl:276-281).
 // The reference narrows a bracket with Roots.A42; results are pinned by the equation residual
-// (test/normalising_flows.jl:47-71), so a bisection-safeguarded Newton on the monotone f is admissible.
-__device__ __forceinline__ float find_alpha(float t, float c, float b) {
+// (test/normalising_flows.jl:47-71), so any bracketed iteration on the monotone f is admissible.  Here:
+//  * start from one fixed-point step x0 = t − c·tanh(t+b) (always inside the bracket since |tanh| < 1);
+//  * Chebyshev steps x ← x − N(1 + N·A), N = f/f1, A = f2/(2·f1) (cubic; tanh and sech² give f and its first three
+//    derivatives f1, f2, f3 for free), falling back to Newton when the series is not trustworthy and to bisection
+//    when a step leaves the bracket;
+//  * stop as soon as the PREDICTED error of the new iterate, |2A² − f3/(6·f1)|·|N|³ (+ a quartic bound), is below
+//    one ulp of the bracket's magnitude -- no extra evaluation just to observe a tiny step;
+//  * tanh / sech² at the final iterate come from their second-order expansion around the last evaluation point
+//    (the last step d satisfies |d|³ ≲ tol), so the caller does not re-evaluate them.
+// Typical cost: 3 exponentials per root (the Newton version with re-evaluation needed 5-6).
+__device__ __forceinline__ float find_alpha_ts(float t, float c, float b, float& th, float& s2) {
   const float delta = 2.0f * fabsf(c);
   float lo = t - delta, hi = t + delta;
+  tanh_sech2(t + b, th, s2);
   if (lo == hi) return lo;  // empty bracket, planar_layer.jl:171-173
-  // stop when the Newton step is below one ulp of the bracket's magnitude (a purely relative test never fires
-  // for roots near zero and would burn all iterations)
   const float tol = 1.2e-7f * (fabsf(t) + delta) + 1e-30f;
-  float x = t;
-  if (fabsf(c) < 1.0f) {  // contraction: one fixed-point step is a better start than the bracket centre
-    float th, s2;
-    tanh_sech2(t + b, th, s2);
-    x = fminf(fmaxf(fmaf(-c, th, t), lo), hi);
-  }
+  float x = fminf(fmaxf(fmaf(-c, th, t), lo), hi);
+  float d = 0.0f;  // x − (point at which th, s2 were evaluated)
+  bool stale = true;
 #pragma unroll 1
   for (int it = 0; it < 64; ++it) {
-    float th, s2;
     tanh_sech2(x + b, th, s2);
     const float f = fmaf(c, th, x) - t;
+    stale = false;
     if (f == 0.0f) break;
     if (f < 0.0f) lo = x; else hi = x;
-    float xn = x - f / fmaf(c, s2, 1.0f);
-    if (fabsf(xn - x) <= tol) {  // converged
-      if (xn >= lo && xn <= hi) x = xn;
+    const float r = __frcp_rn(fmaf(c, s2, 1.0f));  // 1/f1 (f1 > 0: wᵀû > −1)
+    const float n = f * r;
+    const float cs = c * s2 * r;
+    const float a = -cs * th;                                          // f2/(2 f1)
+    const float b3 = -cs * fmaf(-2.0f * th, th, s2) * (1.0f / 3.0f);   // f3/(6 f1)
+    const float na = n * a;
+    const bool series_ok = fabsf(na) <= 0.25f;
+    float xn = series_ok ? fmaf(-n, 1.0f + na, x) : x - n;
+    // predicted error of xn: the cubic term of the Chebyshev iteration plus a bound of the quartic one
+    // (|d⁴tanh| <= 4.1); only trusted for steps well inside tanh's unit length scale (far out in the saturated
+    // region all local derivatives vanish although the root is elsewhere)
+    const float n2 = n * n;
+    const float err = fmaf(fabsf(fmaf(2.0f * a, a, -b3)), fabsf(n2 * n), 0.2f * fabsf(c) * r * n2 * n2);
+    const bool inside = xn > lo && xn < hi;
+    if (inside && series_ok && fabsf(n) <= 0.25f && err <= tol) {  // converged: accept without re-evaluating
+      d = xn - x;
+      x = xn;
       break;
     }
-    if (!(xn > lo && xn < hi)) {
+    if (!inside) {
       xn = 0.5f * (lo + hi);
       if (!(xn > lo && xn < hi)) break;  // bracket is adjacent floats
     }
     x = xn;
+    stale = true;
+  }
+  if (stale) {  // iteration cap reached (never observed): th, s2 must match the returned point
+    tanh_sech2(x + b, th, s2);
+  } else {
+    const float ts = th * s2;                       // d/dx tanh = sech², d²/dx² tanh = −2·tanh·sech²
+    const float q = s2 * fmaf(-2.0f * th, th, s2);  // −(d²/dx² sech²)/2 = sech²(sech² − 2tanh²)
+    th = fmaf(d, fmaf(-d, ts, s2), th);
+    s2 = fmaf(-d, fmaf(d, q, 2.0f * ts), s2);
   }
   return x;
+}
+
+__device__ __forceinline__ float find_alpha(float t, float c, float b) {
+  float th, s2;
+  return find_alpha_ts(t, c, b, th, s2);
 }
 
 // One RQS element (rational_quadratic_spline.jl:317-357 forward, :183-220 inverse + the forward

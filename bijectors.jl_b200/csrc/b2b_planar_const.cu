@@ -62,7 +62,10 @@ struct SymSrc {
 
 // MODE 0: w and û from the constant bank; MODE 1: û staged in shared memory (LDS broadcast), w from the constant
 // bank; MODE 2: w in shared memory, û from the constant bank.
-template <int D, int L, int MODE, class Src>
+// DIR 0: every layer forward, 1: every layer inverse, 2: per-layer direction from the mask.  The unrolled program of
+// 8 layers is large; carrying the (unused) root-finder of the other direction in the hot path costs a quarter of the
+// forward throughput in instruction-cache misses, so the pure directions get their own kernels.
+template <int D, int L, int MODE, int DIR, class Src>
 struct PlanarConstProg {
   const Src src;
   __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
@@ -89,12 +92,11 @@ struct PlanarConstProg {
       const float wz = s.x + s.y;  // aT_b(w, z), utils.jl:2
       const float cc_ = src.c(l), bb = src.b(l);
       float t, s2;
-      if (!src.inv(l)) {
+      if (DIR == 0 || (DIR == 2 && !src.inv(l))) {
         tanh_sech2(wz + bb, t, s2);
         lj[0] += log1pf(cc_ * s2);  // planar_layer.jl:107
       } else {
-        const float alpha = find_alpha(wz, cc_, bb);  // planar_layer.jl:121
-        tanh_sech2(alpha + bb, t, s2);
+        find_alpha_ts(wz, cc_, bb, t, s2);  // planar_layer.jl:121; t = tanh(α+b), s2 = sech²(α+b)
         lj[0] -= log1pf(cc_ * s2);
         t = -t;
       }
@@ -111,21 +113,21 @@ struct PlanarConstProg {
   }
 };
 
-template <int D, int L, int NW, int MODE>
+template <int D, int L, int NW, int MODE, int DIR>
 __global__ void __launch_bounds__(NW * 32, 1)
     planar_arg_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
                       const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                       const __grid_constant__ PlanarHP<D, L> H, const int invmask) {
-  const PlanarConstProg<D, L, MODE, ArgSrc<D, L>> prog{{H, invmask}};
+  const PlanarConstProg<D, L, MODE, DIR, ArgSrc<D, L>> prog{{H, invmask}};
   v1_run<D, 1, 1, NW>(P, E, map_x, map_y, prog);
 }
 
-template <int D, int L, int NW, int MODE>
+template <int D, int L, int NW, int MODE, int DIR>
 __global__ void __launch_bounds__(NW * 32, 1)
     planar_sym_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
                       const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                       const float* stage, const int invmask) {
-  const PlanarConstProg<D, L, MODE, SymSrc<D, L>> prog{{stage, invmask}};
+  const PlanarConstProg<D, L, MODE, DIR, SymSrc<D, L>> prog{{stage, invmask}};
   v1_run<D, 1, 1, NW>(P, E, map_x, map_y, prog);
 }
 
@@ -170,54 +172,64 @@ struct HPShape {
 
 // warps per CTA as in the interpreter (register budget); MODE 2 when w and û exceed ~4 KB of constants
 static HPShape hp_shape(int D, int L) {
-  static const int mode_env = getenv("B2B_HP_MODE") ? atoi(getenv("B2B_HP_MODE")) : -1;
   HPShape s;
   s.nw = D == 128 ? 8 : (D == 64 ? 12 : 16);
   s.mode = (2 * D * L * 4 > 4096) ? 2 : 0;
-  if (mode_env == 0) s.mode = 0;  // experiments: force the all-constant form
   return s;
 }
 
-template <int D, int L, int NW, int MODE>
+template <int D, int L, int NW, int MODE, int DIR>
 static int launch_arg(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
                       const float* packed, int invmask, cudaStream_t stream) {
   static PlanarHP<D, L> H;  // copied into the launch's argument buffer by <<<>>>
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
   memcpy(H.v, packed, sizeof(H.v));
-  auto kernel = planar_arg_kernel<D, L, NW, MODE>;
+  auto kernel = planar_arg_kernel<D, L, NW, MODE, DIR>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
   kernel<<<g.grid, NW * 32, g.smem, stream>>>(q, g.extra, mx, my, H, invmask);
   return (int)cudaGetLastError();
 }
 
-template <int D, int L, int NW, int MODE>
+template <int D, int L, int NW, int MODE, int DIR>
 static int launch_sym(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
                       const float* stage, int invmask, cudaStream_t stream) {
-  auto kernel = planar_sym_kernel<D, L, NW, MODE>;
+  auto kernel = planar_sym_kernel<D, L, NW, MODE, DIR>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
   kernel<<<g.grid, NW * 32, g.smem, stream>>>(q, g.extra, mx, my, stage, invmask);
   return (int)cudaGetLastError();
 }
 
-// dispatch over (D, L, MODE) for either source
+// dispatch over (D, L, MODE, DIR) for either source
+template <bool SYM, int D, int NW, int LL, int MM>
+static int dispatch_dir(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
+                        const float* params, int invmask, cudaStream_t stream) {
+  const int all = (1 << LL) - 1;
+  const int dir = (invmask & all) == 0 ? 0 : ((invmask & all) == all ? 1 : 2);
+#define B2B_HP_DIR(DD)                                                                                   \
+  if (dir == DD)                                                                                         \
+    return SYM ? launch_sym<D, LL, NW, MM, DD>(q, g, mx, my, params, invmask, stream)                    \
+               : launch_arg<D, LL, NW, MM, DD>(q, g, mx, my, params, invmask, stream);
+  B2B_HP_DIR(0)
+  B2B_HP_DIR(1)
+  B2B_HP_DIR(2)
+#undef B2B_HP_DIR
+  return B2B_EUNSUPPORTED;
+}
+
 template <bool SYM, int D, int NW>
 static int dispatch_L(int L, int mode, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx,
                       const CUtensorMap& my, const float* params, int invmask, cudaStream_t stream) {
-#define B2B_HP_CASE(LL, MM)                                                                          \
-  if (L == LL && mode == MM)                                                                         \
-    return SYM ? launch_sym<D, LL, NW, MM>(q, g, mx, my, params, invmask, stream)                    \
-               : launch_arg<D, LL, NW, MM>(q, g, mx, my, params, invmask, stream);
-  B2B_HP_CASE(1, 0)
-  B2B_HP_CASE(2, 0)
-  B2B_HP_CASE(4, 0)
-  if (2 * D * 8 * 4 > 4096) {
-    B2B_HP_CASE(8, 2)
+  if (L == 1 && mode == 0) return dispatch_dir<SYM, D, NW, 1, 0>(q, g, mx, my, params, invmask, stream);
+  if (L == 2 && mode == 0) return dispatch_dir<SYM, D, NW, 2, 0>(q, g, mx, my, params, invmask, stream);
+  if (L == 4 && mode == 0) return dispatch_dir<SYM, D, NW, 4, 0>(q, g, mx, my, params, invmask, stream);
+  if constexpr (2 * D * 8 * 4 > 4096) {
+    if (L == 8 && mode == 2) return dispatch_dir<SYM, D, NW, 8, 2>(q, g, mx, my, params, invmask, stream);
+  } else {
+    if (L == 8 && mode == 0) return dispatch_dir<SYM, D, NW, 8, 0>(q, g, mx, my, params, invmask, stream);
   }
-  B2B_HP_CASE(8, 0)
-#undef B2B_HP_CASE
   return B2B_EUNSUPPORTED;
 }
 
