@@ -112,6 +112,13 @@ def main():
         inv = B.inverse(flow)
         ms = time_ms(lambda: B.run_chain(inv, y, y=x, logjac=lj), max(args.iters // 2, 3), world=world)
         report("C2_planar8_D128_inverse", world * N, ms, world * N * 4 * (2 * D + 1))
+        # logpdf(transformed(MvNormal, flow), y) + batch sum: inverse chain + base density, no D x N store
+        r = np.random.Generator(np.random.PCG64(199))
+        td = B.transformed(B.MvNormal(D, (r.standard_normal(D) * 0.1).astype(f32), r.uniform(0.5, 2.0, D).astype(f32)), flow)
+        B.run_chain(flow, x, y=y, logjac=lj)
+        ms = time_ms(lambda: B.logpdf_sum(td, y), max(args.iters // 2, 3), world=world)
+        report("C2_planar8_D128_logpdf_sum", world * N, ms, world * N * 4 * (D + 1),
+               extra={"accounting": "read column + write logpdf: 4*(D+1) B/sample"})
         del x, y
 
     # ---- C3: 6 x Radial, D=64, N=2^20 per GPU, forward + inverse ------------------------------------------

@@ -93,7 +93,7 @@ static int launch_fused(B2BChainParams& p, cudaStream_t stream) {
   int rc = B2B_EUNSUPPORTED;
   g_fused_launches = 1;
   // segments made of <= 8 PlanarLayers: parameters through the constant bank (variant 3 forces, 1 / 2 disable)
-  if ((g_variant == 0 || g_variant == 3) && !p.partials) {
+  if (g_variant == 0 || g_variant == 3) {
     rc = b2b_launch_planar_chain_const(p, stream);
     if (rc == B2B_OK) {
       g_fused_launches = 2;  // parameter preparation kernel + main kernel (plus one 8 KB device-to-device copy)
@@ -110,6 +110,10 @@ static int launch_fused(B2BChainParams& p, cudaStream_t stream) {
 }
 
 static int fused_grid(const B2BChainParams& p) {
+  if ((g_variant == 0 || g_variant == 3) && b2b_planar_const_layers(p) > 0) {
+    const int g = b2b_planar_const_grid_size(p);
+    if (g > 0 || g_variant == 3) return g;
+  }
   if (g_variant != 1) {
     const int g = b2b_chain_grid_size_v1(p);
     if (g > 0) return g;

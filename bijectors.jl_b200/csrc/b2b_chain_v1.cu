@@ -217,31 +217,6 @@ __device__ __forceinline__ void stacked_apply(float2 (&x)[CPT][D / TPC / 2], con
   B2B_FOR_COLS lj[cc] += part_sum<TPC>(acc[cc]);
 }
 
-template <int D, int TPC, int CPT>
-__device__ __forceinline__ void mvnormal_apply(const float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& c,
-                                               const float* sp, float (&lj)[CPT]) {
-  using C = ColCtx<D, TPC>;
-  const float4* mu4 = reinterpret_cast<const float4*>(sp);
-  const float4* is4 = reinterpret_cast<const float4*>(sp + D);
-  const float2 m1 = make_float2(-1.f, -1.f);
-  float2 acc[CPT][2];
-  B2B_FOR_COLS acc[cc][0] = acc[cc][1] = make_float2(0.f, 0.f);
-  B2B_FOR_SLOTS {
-    const float4 mu = mu4[c.prm(ql, r)], is = is4[c.prm(ql, r)];
-    const int i = (ql * 8 + r) * 2;
-    B2B_FOR_COLS {
-      const float2 z0 = __fmul2_rn(__ffma2_rn(make_float2(mu.x, mu.y), m1, x[cc][i]), make_float2(is.x, is.y));
-      const float2 z1 = __fmul2_rn(__ffma2_rn(make_float2(mu.z, mu.w), m1, x[cc][i + 1]), make_float2(is.z, is.w));
-      acc[cc][0] = __ffma2_rn(z0, z0, acc[cc][0]);
-      acc[cc][1] = __ffma2_rn(z1, z1, acc[cc][1]);
-    }
-  }
-  B2B_FOR_COLS {
-    const float2 s = __fadd2_rn(acc[cc][0], acc[cc][1]);
-    lj[cc] += sp[2 * D] - 0.5f * part_sum<TPC>(s.x + s.y);
-  }
-}
-
 // Program 1: the layer-descriptor interpreter (parameters staged in shared memory from DEVICE pointers).
 template <int D, int TPC, int CPT>
 struct InterpProg {

@@ -48,6 +48,8 @@ int b2b_launch_planar_hostparams(const B2BChainParams& p, int L, const float* pa
 // device-resident parameters: p.layers must be 1..8 PLANAR layers; B2B_EUNSUPPORTED when not applicable
 int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream);
 int b2b_planar_const_grid_size(const B2BChainParams& p);
+// number of planar layers when the constant-bank path applies to the segment `p`, else 0
+int b2b_planar_const_layers(const B2BChainParams& p);
 // number of CTAs the v0/v1 launch of `p` will use (size of the partials array)
 int b2b_chain_grid_size(const B2BChainParams& p);
 // deterministic final sum of per-CTA partials into *sum_out

@@ -65,14 +65,18 @@ struct SymSrc {
 // DIR 0: every layer forward, 1: every layer inverse, 2: per-layer direction from the mask.  The unrolled program of
 // 8 layers is large; carrying the (unused) root-finder of the other direction in the hot path costs a quarter of the
 // forward throughput in instruction-cache misses, so the pure directions get their own kernels.
-template <int D, int L, int MODE, int DIR, class Src>
+// MVN: the chain ends in the base MvNormal log-density (P.layers[0] holds its descriptor): logpdf(td, y).
+template <int D, int L, int MODE, int DIR, bool MVN, class Src>
 struct PlanarConstProg {
   const Src src;
+  const B2BChainParams& P;
+  static constexpr int MVN_OFF = MODE ? L * D : 0;
   __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
+    if (MVN && warp == nw - 1) stage_layer(P.layers[0], params + MVN_OFF, D, D, lane);
     if (MODE == 0) return;
     for (int i = warp * 32 + lane; i < L * D; i += nw * 32) params[i] = src.raw((MODE == 1 ? L * D : 0) + i);
   }
-  __device__ __forceinline__ void apply(float2 (&x)[1][D / 2], const ColCtx<D, 1>&, const float* params,
+  __device__ __forceinline__ void apply(float2 (&x)[1][D / 2], const ColCtx<D, 1>& ctx, const float* params,
                                         float (&lj)[1]) const {
 #pragma unroll
     for (int l = 0; l < L; ++l) {
@@ -110,6 +114,7 @@ struct PlanarConstProg {
         x[0][2 * i + 1] = __ffma2_rn(make_float2(u.z, u.w), t2, x[0][2 * i + 1]);
       }
     }
+    if (MVN) mvnormal_apply<D, 1, 1>(x, ctx, params + MVN_OFF, lj);
   }
 };
 
@@ -118,16 +123,16 @@ __global__ void __launch_bounds__(NW * 32, 1)
     planar_arg_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
                       const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                       const __grid_constant__ PlanarHP<D, L> H, const int invmask) {
-  const PlanarConstProg<D, L, MODE, DIR, ArgSrc<D, L>> prog{{H, invmask}};
+  const PlanarConstProg<D, L, MODE, DIR, false, ArgSrc<D, L>> prog{{H, invmask}, P};
   v1_run<D, 1, 1, NW>(P, E, map_x, map_y, prog);
 }
 
-template <int D, int L, int NW, int MODE, int DIR>
+template <int D, int L, int NW, int MODE, int DIR, bool MVN>
 __global__ void __launch_bounds__(NW * 32, 1)
     planar_sym_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
                       const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
                       const float* stage, const int invmask) {
-  const PlanarConstProg<D, L, MODE, DIR, SymSrc<D, L>> prog{{stage, invmask}};
+  const PlanarConstProg<D, L, MODE, DIR, MVN, SymSrc<D, L>> prog{{stage, invmask}, P};
   v1_run<D, 1, 1, NW>(P, E, map_x, map_y, prog);
 }
 
@@ -192,10 +197,10 @@ static int launch_arg(const B2BChainParams& q, const V1Geom& g, const CUtensorMa
   return (int)cudaGetLastError();
 }
 
-template <int D, int L, int NW, int MODE, int DIR>
+template <int D, int L, int NW, int MODE, int DIR, bool MVN = false>
 static int launch_sym(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
                       const float* stage, int invmask, cudaStream_t stream) {
-  auto kernel = planar_sym_kernel<D, L, NW, MODE, DIR>;
+  auto kernel = planar_sym_kernel<D, L, NW, MODE, DIR, MVN>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
   kernel<<<g.grid, NW * 32, g.smem, stream>>>(q, g.extra, mx, my, stage, invmask);
@@ -208,6 +213,12 @@ static int dispatch_dir(const B2BChainParams& q, const V1Geom& g, const CUtensor
                         const float* params, int invmask, cudaStream_t stream) {
   const int all = (1 << LL) - 1;
   const int dir = (invmask & all) == 0 ? 0 : ((invmask & all) == all ? 1 : 2);
+  if (q.L == 1) {  // terminal MvNormal (device-resident parameters, all-inverse chains only)
+    if constexpr (SYM) {
+      if (dir == 1) return launch_sym<D, LL, NW, MM, 1, true>(q, g, mx, my, params, invmask, stream);
+    }
+    return B2B_EUNSUPPORTED;
+  }
 #define B2B_HP_DIR(DD)                                                                                   \
   if (dir == DD)                                                                                         \
     return SYM ? launch_sym<D, LL, NW, MM, DD>(q, g, mx, my, params, invmask, stream)                    \
@@ -235,14 +246,13 @@ static int dispatch_L(int L, int mode, const B2BChainParams& q, const V1Geom& g,
 
 template <bool SYM>
 static int launch_planar_const(const B2BChainParams& p, int L, const float* params, int invmask, cudaStream_t stream) {
-  B2BChainParams q = p;
-  q.L = 0;
+  B2BChainParams q = p;  // q.L: 0, or 1 when q.layers[0] is the terminal MvNormal
   q.scratch_off = -1;
   if (!(q.D == 32 || q.D == 64 || q.D == 128)) return B2B_EUNSUPPORTED;
   if (v1_check_io(q) != 0) return B2B_EUNSUPPORTED;
   const HPShape sh = hp_shape(q.D, L);
   V1Geom g;
-  const int rc = v1_geometry(q.D, q.N, sh.nw, 32, sh.mode ? (size_t)L * q.D : 0, g);
+  const int rc = v1_geometry(q.D, q.N, sh.nw, 32, (sh.mode ? (size_t)L * q.D : 0) + (q.L ? 2 * q.D + 4 : 0), g);
   if (rc != 0) return rc;
   CUtensorMap mx, my;
   if (!make_maps(q, g.cols, &mx, &my, &g.extra.tma3d)) return B2B_EUNSUPPORTED;
@@ -273,22 +283,40 @@ int b2b_planar_const_grid_size(const B2BChainParams& p) {
 // `L` (1, 2, 4 or 8) planar layers, derived parameters packed for (D, L) in HOST memory -> kernel arguments
 int b2b_launch_planar_hostparams(const B2BChainParams& p, int L, const float* packed, int invmask,
                                  cudaStream_t stream) {
-  return b2b::launch_planar_const<false>(p, L, packed, invmask, stream);
+  B2BChainParams q = p;
+  q.L = 0;
+  return b2b::launch_planar_const<false>(q, L, packed, invmask, stream);
 }
 
-// A fusable segment made only of PlanarLayers (device-resident parameters), at most 8 of them:
+// Applicability of the constant-bank path to a fusable segment: 1..8 PlanarLayers, optionally followed by the
+// terminal MvNormal when every planar layer is inverse (= logpdf(td, y)); D in {32,64,128}; 16-byte aligned batches.
+// Returns the number of planar layers, 0 when not applicable.
+int b2b_planar_const_layers(const B2BChainParams& p) {
+  using namespace b2b;
+  if (!(p.D == 32 || p.D == 64 || p.D == 128) || p.L < 1) return 0;
+  const bool mvn = p.layers[p.L - 1].kind == B2B_MVNORMAL_DIAG;
+  const int n = p.L - (mvn ? 1 : 0);
+  if (n < 1 || n > HP_MAX_L) return 0;
+  for (int l = 0; l < n; ++l) {
+    if (p.layers[l].kind != B2B_PLANAR) return 0;
+    if (mvn && !p.layers[l].inverse) return 0;
+  }
+  if (v1_check_io(p) != 0) return 0;
+  return n;
+}
+
 // prep kernel -> staging buffer -> __constant__ symbol -> main kernel.  B2B_EUNSUPPORTED when not applicable.
 int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream) {
   using namespace b2b;
-  if (p.L < 1 || p.L > HP_MAX_L || !(p.D == 32 || p.D == 64 || p.D == 128)) return B2B_EUNSUPPORTED;
+  const int n = b2b_planar_const_layers(p);
+  if (n == 0) return B2B_EUNSUPPORTED;
   int invmask = 0;
-  for (int l = 0; l < p.L; ++l) {
-    if (p.layers[l].kind != B2B_PLANAR) return B2B_EUNSUPPORTED;
+  for (int l = 0; l < n; ++l)
     if (p.layers[l].inverse) invmask |= 1 << l;
-  }
-  if (v1_check_io(p) != 0) return B2B_EUNSUPPORTED;
   int Lp = 1;
-  while (Lp < p.L) Lp <<= 1;
+  while (Lp < n) Lp <<= 1;
+  // identity padding is its own inverse: an all-inverse chain stays all-inverse (the single-direction kernel)
+  if (invmask == (1 << n) - 1) invmask = (1 << Lp) - 1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return B2B_EUNSUPPORTED;
   SlotState& st = g_slots[dev];
@@ -301,12 +329,18 @@ int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream) 
   }
   // the previous user of the slot (possibly on another stream) must have finished
   if ((e = cudaStreamWaitEvent(stream, st.free_ev, 0)) != cudaSuccess) return (int)e;
-  planar_prep_kernel<<<1, HP_MAX_L * 32, 0, stream>>>(p, p.L, Lp, st.stage);
+  planar_prep_kernel<<<1, HP_MAX_L * 32, 0, stream>>>(p, n, Lp, st.stage);
   if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
   const size_t bytes = sizeof(float) * (size_t)(2 * Lp * p.D + 2 * Lp);
   if ((e = cudaMemcpyToSymbolAsync(c_planar, st.stage, bytes, 0, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess)
     return (int)e;
-  const int rc = launch_planar_const<true>(p, Lp, st.stage, invmask, stream);
+  B2BChainParams q = p;
+  q.L = 0;
+  if (p.L > n) {
+    q.L = 1;
+    q.layers[0] = p.layers[p.L - 1];
+  }
+  const int rc = launch_planar_const<true>(q, Lp, st.stage, invmask, stream);
   if (rc != B2B_OK) return rc;
   if ((e = cudaEventRecord(st.free_ev, stream)) != cudaSuccess) return (int)e;
   return B2B_OK;

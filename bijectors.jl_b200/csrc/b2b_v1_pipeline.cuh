@@ -110,6 +110,33 @@ __device__ __forceinline__ float part_sum(float v) {
   _Pragma("unroll") for (int ql = 0; ql < C::NQT; ++ql) _Pragma("unroll") for (int r = 0; r < 8; ++r)
 #define B2B_FOR_COLS _Pragma("unroll") for (int cc = 0; cc < CPT; ++cc)
 
+// Terminal op of logpdf(td, y): lj += const − ½·Σ((x−μ)/σ)² (transformed_distribution.jl:165-169 + MvNormal logpdf);
+// parameters staged by stage_layer(B2B_MVNORMAL_DIAG): μ | 1/σ | const.
+template <int D, int TPC, int CPT>
+__device__ __forceinline__ void mvnormal_apply(const float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& c,
+                                               const float* sp, float (&lj)[CPT]) {
+  using C = ColCtx<D, TPC>;
+  const float4* mu4 = reinterpret_cast<const float4*>(sp);
+  const float4* is4 = reinterpret_cast<const float4*>(sp + D);
+  const float2 m1 = make_float2(-1.f, -1.f);
+  float2 acc[CPT][2];
+  B2B_FOR_COLS acc[cc][0] = acc[cc][1] = make_float2(0.f, 0.f);
+  B2B_FOR_SLOTS {
+    const float4 mu = mu4[c.prm(ql, r)], is = is4[c.prm(ql, r)];
+    const int i = (ql * 8 + r) * 2;
+    B2B_FOR_COLS {
+      const float2 z0 = __fmul2_rn(__ffma2_rn(make_float2(mu.x, mu.y), m1, x[cc][i]), make_float2(is.x, is.y));
+      const float2 z1 = __fmul2_rn(__ffma2_rn(make_float2(mu.z, mu.w), m1, x[cc][i + 1]), make_float2(is.z, is.w));
+      acc[cc][0] = __ffma2_rn(z0, z0, acc[cc][0]);
+      acc[cc][1] = __ffma2_rn(z1, z1, acc[cc][1]);
+    }
+  }
+  B2B_FOR_COLS {
+    const float2 s = __fadd2_rn(acc[cc][0], acc[cc][1]);
+    lj[cc] += sp[2 * D] - 0.5f * part_sum<TPC>(s.x + s.y);
+  }
+}
+
 // The pipeline (TMA tile ring, register-resident fragments, per-warp TMA store) is independent of WHAT is applied
 // to the fragments: `prog.stage()` prepares per-CTA state, `prog.apply()` maps the fragments and accumulates logjac.
 template <int D, int TPC, int CPT, int NW, class Prog>

@@ -874,3 +874,37 @@ def test_constant_bank_slot_is_safe_across_streams(B):
         torch.cuda.synchronize()
         for (y, lj), (yr, ljr) in zip(outs, refs):
             assert rel(B.to_numpy(y), yr) <= 2e-6 and rel(B.to_numpy(lj), ljr) <= 2e-6
+
+
+@pytest.mark.parametrize("D,L", [(128, 8), (64, 5), (32, 2)])
+def test_constant_bank_logpdf_of_planar_flow(B, D, L):
+    """logpdf(transformed(MvNormal, planar flow), y) (transformed_distribution.jl:165-169): the all-inverse planar
+    chain + base log-density (+ batch sum) through the constant-bank kernel = interpreter = oracle."""
+    rng = np.random.default_rng(31 * D + L)
+    N = 3000 + L
+    pairs = [make_case("planar", D, rng) for _ in range(L)]
+    flow = B.Composed(*[p[0] for p in pairs])
+    mu, sigma = (rng.standard_normal(D) * 0.1).astype(f32), rng.uniform(0.5, 2.0, D).astype(f32)
+    td = B.transformed(B.MvNormal(D, mu, sigma), flow)
+    x = rng.standard_normal((D, N)).astype(f32)
+    yo, ljo = O.chain_forward([p[1] for p in pairs], x.astype(np.float64))
+    y = B.from_numpy(yo.astype(f32))
+    lib = B.lib()
+    res = {}
+    try:
+        for variant in (3, 2):
+            assert lib.b2b_set_kernel_variant(variant) == 0
+            lp = B.logpdf(td, y)
+            n_launch = lib.b2b_last_launch_count()
+            tot, lp2 = B.logpdf_sum(td, y)
+            res[variant] = (B.to_numpy(lp), float(tot), B.to_numpy(lp2), n_launch)
+    finally:
+        lib.b2b_set_kernel_variant(0)
+    assert res[3][3] == 2 and res[2][3] == 1
+    assert rel(res[3][0], res[2][0]) <= 2e-6
+    assert np.array_equal(res[3][0], res[3][2])
+    assert abs(res[3][1] - float(res[3][0].astype(np.float64).sum())) <= 1e-9 * abs(res[3][1]) + 1e-6
+    # oracle: y was produced from x in float64, so x is the exact preimage up to the float32 rounding of y
+    lpo = O.mvnormal_diag_logpdf(mu.astype(np.float64), sigma.astype(np.float64), x.astype(np.float64)) - ljo
+    assert rel(res[3][0], lpo) <= 1e-4
+    assert np.array_equal(B.to_numpy(B.logpdf(td, y)), res[3][0])  # auto = constant-bank path

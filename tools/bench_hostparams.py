@@ -9,6 +9,7 @@ import torch
 
 import bijectors_jl_b200 as B
 
+B.lib().b2b_set_kernel_variant(int(os.environ.get('B2B_VARIANT', '0')))
 D, N, L = int(sys.argv[1]) if len(sys.argv) > 1 else 128, 1 << 20, int(sys.argv[2]) if len(sys.argv) > 2 else 8
 rng = np.random.default_rng(0)
 layers = [B.PlanarLayer((rng.standard_normal(D) / np.sqrt(D)).astype(np.float32),
