@@ -515,3 +515,49 @@ extern "C" int b2b_planar_chain_hostparams_f32(const float* w_host, const float*
   }
   return B2B_OK;
 }
+
+// ---- reverse mode of forward planar chains ----------------------------------------------------------------
+extern "C" size_t b2b_planar_chain_vjp_workspace_bytes(int32_t L, int32_t D, int64_t N) {
+  if (L < 1 || L > 8 || D < 1 || N < 0) return 0;
+  return b2b_planar_vjp_workspace(L, D, N);
+}
+
+extern "C" int b2b_planar_chain_vjp_f32(const b2b_layer_desc* layers, int32_t L, const float* x, const float* ybar,
+                                        const float* ljbar, float* xbar, float* wbar, float* ubar, float* bbar,
+                                        int32_t D, int64_t N, int64_t ldx, int64_t ldybar, int64_t ldxbar,
+                                        void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  g_last_launches = 0;
+  if (!layers || L < 1 || D < 1 || N < 0) return B2B_EINVAL;
+  if (L > 8) return B2B_EUNSUPPORTED;
+  const bool want_params = wbar || ubar || bbar;
+  if (want_params && !(wbar && ubar && bbar)) return B2B_EINVAL;
+  if (N == 0) {
+    if (want_params) {
+      cudaMemsetAsync(wbar, 0, sizeof(float) * (size_t)L * D, stream);
+      cudaMemsetAsync(ubar, 0, sizeof(float) * (size_t)L * D, stream);
+      return (int)cudaMemsetAsync(bbar, 0, sizeof(float) * L, stream);
+    }
+    return B2B_OK;
+  }
+  if (!x || !ybar || !xbar || ldx < D || ldybar < D || ldxbar < D) return B2B_EINVAL;
+  for (int l = 0; l < L; ++l) {
+    if (layers[l].kind != B2B_PLANAR) return B2B_EUNSUPPORTED;
+    const int rc = validate_layer(layers[l], D, false);
+    if (rc != B2B_OK) return rc;
+    if (layers[l].inverse) return B2B_EUNSUPPORTED;
+  }
+  B2BChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x;
+  p.N = N;
+  p.ldx = ldx;
+  p.D = D;
+  p.L = L;
+  for (int l = 0; l < L; ++l) p.layers[l] = layers[l];
+  int launches = 0;
+  const int rc = b2b_launch_planar_chain_vjp(p, ybar, ldybar, ljbar, xbar, ldxbar, wbar, ubar, bbar, workspace,
+                                             workspace_bytes, &launches, stream);
+  if (rc == B2B_OK) g_last_launches = launches;
+  return rc;
+}

@@ -220,6 +220,7 @@ __device__ __forceinline__ void stacked_apply(float2 (&x)[CPT][D / TPC / 2], con
 // Program 1: the layer-descriptor interpreter (parameters staged in shared memory from DEVICE pointers).
 template <int D, int TPC, int CPT>
 struct InterpProg {
+  using State = V1NoState;
   const B2BChainParams& P;
   __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
     for (int l = warp; l < P.L; l += nw) stage_layer(P.layers[l], params + P.soff[l], D, D, lane);

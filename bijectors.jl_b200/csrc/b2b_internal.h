@@ -50,6 +50,11 @@ int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream);
 int b2b_planar_const_grid_size(const B2BChainParams& p);
 // number of planar layers when the constant-bank path applies to the segment `p`, else 0
 int b2b_planar_const_layers(const B2BChainParams& p);
+// reverse mode of a forward planar chain (b2b_planar_const.cu)
+size_t b2b_planar_vjp_workspace(int L, int D, long long N);
+int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long long ldyb, const float* ljbar,
+                                float* xbar, long long ldxb, float* wbar, float* ubar, float* bbar, void* workspace,
+                                size_t workspace_bytes, int* launches, cudaStream_t stream);
 // number of CTAs the v0/v1 launch of `p` will use (size of the partials array)
 int b2b_chain_grid_size(const B2BChainParams& p);
 // deterministic final sum of per-CTA partials into *sum_out

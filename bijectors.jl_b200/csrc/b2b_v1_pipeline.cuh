@@ -139,20 +139,29 @@ __device__ __forceinline__ void mvnormal_apply(const float2 (&x)[CPT][D / TPC / 
 
 // The pipeline (TMA tile ring, register-resident fragments, per-warp TMA store) is independent of WHAT is applied
 // to the fragments: `prog.stage()` prepares per-CTA state, `prog.apply()` maps the fragments and accumulates logjac.
-template <int D, int TPC, int CPT, int NW, class Prog>
+//
+// NIN = 2 (reverse-mode kernels): every input slot holds the tile of a SECOND D x N tensor (map_x2) behind the first.
+// The program first consumes the fragment of the first tensor (`prog.phase1`), then the SAME registers are reloaded
+// with the second tensor's fragment for `prog.apply` -- the register budget stays that of one column.  Per-tile
+// program state travels in `Prog::State`; `apply` also receives the tile's first column index.
+struct V1NoState {};
+
+template <int D, int TPC, int CPT, int NW, class Prog, int NIN = 1>
 __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E, const CUtensorMap& map_x,
-                                       const CUtensorMap& map_y, const Prog& prog) {
+                                       const CUtensorMap& map_y, const Prog& prog,
+                                       const CUtensorMap* map_x2 = nullptr) {
   using C = ColCtx<D, TPC>;
   constexpr int NQ = D / 32;                 // boxes per tile
   constexpr int LPC = 32 / TPC;              // lane groups per warp
   constexpr int COLS = LPC * CPT;            // columns per tile (= per warp)
   constexpr int BOX_BYTES = COLS * 128;      // COLS lines of 128 B
   constexpr int TILE_BYTES = NQ * BOX_BYTES;
+  constexpr int SLOT_BYTES = NIN * TILE_BYTES;  // one input slot
   extern __shared__ unsigned char smem_dyn[];
   // the 128-byte swizzle pattern repeats every 1024 B: align the tile area by hand (1 KB of slack is allocated)
   unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* in_base = smem_raw;                                    // n_in tiles
-  unsigned char* out_base = smem_raw + (size_t)E.n_in * TILE_BYTES;     // NW tiles
+  unsigned char* out_base = smem_raw + (size_t)E.n_in * SLOT_BYTES;     // NW tiles
   float* params = reinterpret_cast<float*>(smem_raw + E.param_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + E.bar_off);
   // armed[b] = index j of the tile whose load has been issued into input buffer b.  A warp may only wait on
@@ -168,9 +177,14 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
   auto load_tile = [&](uint32_t dst, int col0, uint32_t bar) {
     if (E.tma3d) {
       tma_load_3d(dst, &map_x, 0, col0, 0, bar);
+      if (NIN == 2) tma_load_3d(dst + TILE_BYTES, map_x2, 0, col0, 0, bar);
     } else {
 #pragma unroll
       for (int q = 0; q < NQ; ++q) tma_load_2d(dst + q * BOX_BYTES, &map_x, q * 32, col0, bar);
+      if (NIN == 2) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) tma_load_2d(dst + TILE_BYTES + q * BOX_BYTES, map_x2, q * 32, col0, bar);
+      }
     }
   };
   prog.stage(params, warp, lane, NW);
@@ -185,9 +199,9 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
   if (threadIdx.x == 0) {
     for (int j = 0; j < E.n_in && j < my_tiles; ++j) {
       const uint32_t bar = smem_u32(&bars[j]);
-      mbar_expect_tx(bar, TILE_BYTES);
+      mbar_expect_tx(bar, SLOT_BYTES);
       const long long tile = blockIdx.x + (long long)j * gridDim.x;
-      load_tile(smem_u32(in_base + (size_t)j * TILE_BYTES), (int)(tile * COLS), bar);
+      load_tile(smem_u32(in_base + (size_t)j * SLOT_BYTES), (int)(tile * COLS), bar);
       flag_store_release(&armed[j], j);
     }
   }
@@ -213,8 +227,7 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
     mbar_wait(smem_u32(&bars[buf]), parity);
 
     float2 x[CPT][C::EPT / 2];
-    {
-      const unsigned char* src = in_base + (size_t)buf * TILE_BYTES + line;
+    auto load_fragment = [&](const unsigned char* src) {
       B2B_FOR_COLS {
         B2B_FOR_SLOTS {
           const float4 v =
@@ -223,14 +236,25 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
           x[cc][(ql * 8 + r) * 2 + 1] = make_float2(v.z, v.w);
         }
       }
+    };
+    load_fragment(in_base + (size_t)buf * SLOT_BYTES + line);
+    typename Prog::State st;
+    if constexpr (NIN == 2) {
+      prog.phase1(x, ctx, params, st);
+      load_fragment(in_base + (size_t)buf * SLOT_BYTES + TILE_BYTES + line);
     }
+    // The slot is about to be overwritten through the ASYNC proxy (TMA) after having been read through the generic
+    // proxy (LDS): every lane orders its reads before later async-proxy accesses, then the warp converges.  Without
+    // the proxy fence the refill can overtake reads that are still in flight (observed with the two-tensor slots:
+    // torn tiles in the first refilled slot).
+    fence_proxy_async();
     __syncwarp();
     // re-arm this input buffer with the tile P steps ahead
     if (lane == 0 && j + E.n_in < my_tiles) {
       const uint32_t bar = smem_u32(&bars[buf]);
-      mbar_expect_tx(bar, TILE_BYTES);
+      mbar_expect_tx(bar, SLOT_BYTES);
       const long long nt = blockIdx.x + (j + E.n_in) * gridDim.x;
-      load_tile(smem_u32(in_base + (size_t)buf * TILE_BYTES), (int)(nt * COLS), bar);
+      load_tile(smem_u32(in_base + (size_t)buf * SLOT_BYTES), (int)(nt * COLS), bar);
       flag_store_release(&armed[buf], (int)(j + E.n_in));
     }
 
@@ -239,7 +263,8 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
       const long long cl = col + cc * LPC;
       lj[cc] = (P.accumulate && P.logjac && cl < P.N) ? P.logjac[cl] : 0.0f;
     }
-    prog.apply(x, ctx, params, lj);
+    if constexpr (NIN == 2) prog.apply(x, ctx, params, lj, st, col);
+    else prog.apply(x, ctx, params, lj);
 
     if (P.y) {
       if (store_pending) {
@@ -272,7 +297,7 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
       B2B_FOR_COLS {
         const long long cl = col + cc * LPC;
         if (cl < P.N) {
-          if (P.logjac) P.logjac[cl] = lj[cc];
+          if (P.logjac && !(P.accumulate & 2)) P.logjac[cl] = lj[cc];  // accumulate bit 1: logjac is read-only
           dsum += (double)lj[cc];
         }
       }
@@ -364,20 +389,22 @@ static inline int v1_check_io(const B2BChainParams& p) {
   return 0;
 }
 
-static inline int v1_geometry(int D, long long N, int nw, int cols, size_t param_floats, V1Geom& g) {
+static inline int v1_geometry(int D, long long N, int nw, int cols, size_t param_floats, V1Geom& g,
+                              int in_tiles = 1) {
   const int tile_bytes = D * 4 * cols;
   const size_t param_bytes = param_floats * sizeof(float);
   const size_t budget = 225 * 1024;
   const size_t fixed = (size_t)nw * tile_bytes + ((param_bytes + 15) & ~(size_t)15) + 16 * sizeof(uint64_t) + 1024;
-  if (fixed + 2 * (size_t)tile_bytes > budget) return B2B_EUNSUPPORTED;
-  int n_in = (int)((budget - fixed) / tile_bytes);
+  const size_t slot_bytes = (size_t)in_tiles * tile_bytes;
+  if (fixed + 2 * slot_bytes > budget) return B2B_EUNSUPPORTED;
+  int n_in = (int)((budget - fixed) / slot_bytes);
   if (n_in > 8) n_in = 8;
   g.nw = nw;
   g.cols = cols;
   g.extra.n_in = n_in;
   g.extra.nwarps = nw;
   g.extra.tma3d = 0;
-  g.extra.param_off = (n_in + nw) * tile_bytes;
+  g.extra.param_off = n_in * (int)slot_bytes + nw * tile_bytes;
   g.extra.bar_off = g.extra.param_off + (int)((param_bytes + 15) & ~(size_t)15);
   g.extra.tiles = (N + cols - 1) / cols;
   g.smem = (size_t)g.extra.bar_off + 16 * sizeof(uint64_t) + 1024;  // +1024: base alignment slack

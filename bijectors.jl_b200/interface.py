@@ -413,6 +413,46 @@ def logabsdetjac_(t, x, logjac=None):
     return run_chain(t, x, want_y=False, logjac=logjac, accumulate=logjac is not None)[1]
 
 
+def planar_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[torch.Tensor] = None,
+                     want_param_grads: bool = True):
+    """Vector-Jacobian product of ``with_logabsdet_jacobian(t, x)`` for a ∘-chain ``t`` of (≤ 8) PlanarLayers:
+    what the reference's reverse-mode AD computes in a training step (docs/src/flows.md:93-100,
+    ext/BijectorsChainRulesCoreExt.jl).  ``ybar`` (D×N) / ``ljbar`` (N) are the cotangents of the two outputs.
+
+    Returns ``(xbar, grads)``: ``xbar`` (D×N) and ``grads`` = list of ``{"w": …, "u": …, "b": …}`` per layer
+    (summed over the columns of this batch), or ``None`` when ``want_param_grads`` is false."""
+    D, N, ldx = _batch_view(x)
+    Dy, Ny, ldyb = _batch_view(ybar)
+    if (Dy, Ny) != (D, N) or not x.is_cuda or not ybar.is_cuda or x.dim() != 2:
+        raise ValueError("planar_chain_vjp: x and ybar must be device matrices of the same D×N shape")
+    descs = list(t._descs(False, D))
+    if any(d.kind != _lib.PLANAR or d.inverse or hasattr(d, "_host_planar") for d in descs):
+        raise B2BError(_lib.B2B_EUNSUPPORTED, "planar_chain_vjp: forward PlanarLayers with device parameters only")
+    L = len(descs)
+    arr = _desc_array(descs)
+    if ljbar is not None and (ljbar.numel() != N or ljbar.dtype != torch.float32 or not ljbar.is_contiguous()):
+        raise ValueError("ljbar must be a contiguous float32 vector of length N")
+    xbar = colmajor_empty(D, N, x.device)
+    wbar = ubar = bbar = None
+    if want_param_grads:
+        wbar = torch.empty((L, D), dtype=torch.float32, device=x.device)
+        ubar = torch.empty((L, D), dtype=torch.float32, device=x.device)
+        bbar = torch.empty((L,), dtype=torch.float32, device=x.device)
+    L_ = lib()
+    ws_bytes = L_.b2b_planar_chain_vjp_workspace_bytes(L, D, N)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=x.device)
+    rc = L_.b2b_planar_chain_vjp_f32(
+        arr, L, x.data_ptr(), ybar.data_ptr(), ljbar.data_ptr() if ljbar is not None else None, xbar.data_ptr(),
+        wbar.data_ptr() if wbar is not None else None, ubar.data_ptr() if ubar is not None else None,
+        bbar.data_ptr() if bbar is not None else None, D, N, ldx, ldyb, _batch_view(xbar)[2],
+        ws.data_ptr(), ws_bytes, _stream())
+    check(rc, "b2b_planar_chain_vjp_f32")
+    grads = None
+    if want_param_grads:
+        grads = [{"w": wbar[l], "u": ubar[l], "b": bbar[l:l + 1]} for l in range(L)]
+    return xbar, grads
+
+
 def isinvertible(t) -> bool:
     return isinstance(t, Transform)
 

@@ -157,6 +157,20 @@ int b2b_planar_inv_f32(const float* x, float* y, float* logjac, const float* w, 
 int b2b_planar_chain_hostparams_f32(const float* w_host, const float* u_host, const float* b_host, int32_t L,
                                     int inverse, const float* x, float* y, float* logjac, int32_t D, int64_t N,
                                     int64_t ldx, int64_t ldy, int accumulate_logjac, void* stream);
+/* Reverse mode (vector-Jacobian product) of with_logabsdet_jacobian through a ∘-chain of L <= 8 PlanarLayers, forward
+ * direction -- the computation the reference obtains from its AD rules when a flow is trained
+ * (docs/src/flows.md:93-100; ext/BijectorsChainRulesCoreExt.jl; get_u_hat planar_layer.jl:65-70 is differentiated
+ * through).  Inputs: the batch `x` the chain was applied to, the cotangents `ybar` (D x N, of the transformed batch)
+ * and `ljbar` (N, of the accumulated logjac; NULL = zeros).  Outputs: `xbar` (D x N cotangent of x, required) and --
+ * when all three are non-NULL -- the parameter cotangents `wbar`, `ubar` (L x D, layer l at offset l*D) and `bbar` (L),
+ * summed over the N columns (a multi-GPU caller all-reduces them, see b2b_allreduce_sum_f64).  D in {32, 64, 128};
+ * `layers` are B2B_PLANAR descriptors with inverse == 0.  `xbar` may alias `ybar` only when no parameter cotangents
+ * are requested.  Workspace: b2b_planar_chain_vjp_workspace_bytes. */
+size_t b2b_planar_chain_vjp_workspace_bytes(int32_t L, int32_t D, int64_t N);
+int b2b_planar_chain_vjp_f32(const b2b_layer_desc* layers, int32_t L, const float* x, const float* ybar,
+                             const float* ljbar, float* xbar, float* wbar, float* ubar, float* bbar, int32_t D,
+                             int64_t N, int64_t ldx, int64_t ldybar, int64_t ldxbar, void* workspace,
+                             size_t workspace_bytes, void* stream);
 /* RadialLayer: radial_layer.jl:58-72 (fwd), :88-102,124-129 (inverse) */
 int b2b_radial_fwd_f32(const float* x, float* y, float* logjac, const float* alpha_raw,
                        const float* beta, const float* z0, int32_t D, int64_t N, int64_t ldx,

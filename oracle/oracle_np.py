@@ -104,6 +104,61 @@ def planar_forward(w, u, b, z):
     return y.astype(dt), np.asarray(logjac, dtype=dt)[()]
 
 
+def find_alpha_partials(alpha, wt_u_hat, b):
+    """Partials (∂α/∂wt_y, ∂α/∂wt_u_hat, ∂α/∂b) of find_alpha by the implicit-function theorem --
+    ext/BijectorsChainRulesCoreExt.jl:42-46: x = inv(1 + wt_u_hat·sech(α+b)²) -> (x, −tanh(α+b)·x, x − 1)."""
+    x = 1.0 / (1.0 + wt_u_hat / np.cosh(alpha + b) ** 2)
+    return x, -np.tanh(alpha + b) * x, x - 1.0
+
+
+def planar_chain_vjp(params, x, ybar, ljbar):
+    """Vector-Jacobian product of a ∘-chain of PlanarLayers (forward direction) -- what reverse-mode AD of
+    with_logabsdet_jacobian (src/bijectors/planar_layer.jl:73-80,102-110 through get_u_hat :65-70) yields; the
+    reference trains flows this way (docs/src/flows.md:93-100).
+
+    params: list of (w, u, b); x (D, N); ybar (D, N) cotangent of the transformed batch; ljbar (N,) cotangent of the
+    accumulated logjac.  Returns (xbar (D, N), [(wbar, ubar, bbar), ...]).  Written layer by layer with stored
+    activations (the plain restatement); the device kernels use the algebraically equal reorganisation described
+    in DESIGN.md."""
+    dt = x.dtype
+    zs, cache = [x], []
+    for (w, u, b) in params:
+        w, u = w.astype(dt), u.astype(dt)
+        bb = dt.type(np.asarray(b).reshape(-1)[0])
+        u_hat, c = get_u_hat(u, w)
+        a = w @ zs[-1] + bb
+        t = np.tanh(a)
+        with np.errstate(over="ignore"):
+            s2 = (dt.type(1) / np.cosh(a)) ** 2
+        zs.append(zs[-1] + u_hat[:, None] * t[None, :])
+        cache.append((w, u, u_hat, c, t, s2))
+    yb = ybar.astype(dt).copy()
+    grads = [None] * len(params)
+    for l in range(len(params) - 1, -1, -1):
+        w, u, u_hat, c, t, s2 = cache[l]
+        z = zs[l]
+        den = dt.type(1) + c * s2
+        d = u_hat @ yb                                   # cotangent of tanh(a)
+        g = s2 * d + ljbar * (-2 * c * t * s2 / den)     # cotangent of a = wᵀz + b
+        uhat_bar = yb @ t                                # Σ_n t_n ȳ_n
+        c_bar = np.sum(ljbar * s2 / den)                 # ∂ log1p(c·s2)/∂c
+        w_bar = z @ g                                    # direct dependence a = wᵀz + b
+        b_bar = np.sum(g)
+        yb = yb + w[:, None] * g[None, :]
+        # through get_u_hat: û = u + k(s, q)·w, k = (log1pexp(−s) − 1)/q, s = wᵀu, q = wᵀw; c = log1pexp(s) − 1
+        s_ = dt.type(np.dot(w, u))
+        q_ = dt.type(np.sum(w * w))
+        sig = lambda v: dt.type(1) / (dt.type(1) + np.exp(-v))
+        k = (log1pexp(-s_) - dt.type(1)) / q_
+        dk_ds = -sig(-s_) / q_
+        dk_dq = -k / q_
+        uw = dt.type(np.dot(uhat_bar, w))
+        u_bar = uhat_bar + (uw * dk_ds + c_bar * sig(s_)) * w
+        w_bar = w_bar + k * uhat_bar + uw * (dk_ds * u + dk_dq * 2 * w) + c_bar * sig(s_) * u
+        grads[l] = (w_bar.astype(dt), u_bar.astype(dt), dt.type(b_bar))
+    return yb.astype(dt), grads
+
+
 def find_alpha(wt_y, wt_u_hat, b):
     """src/bijectors/planar_layer.jl:160-185, vectorised over ``wt_y``.
 

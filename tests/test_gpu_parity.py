@@ -908,3 +908,41 @@ def test_constant_bank_logpdf_of_planar_flow(B, D, L):
     lpo = O.mvnormal_diag_logpdf(mu.astype(np.float64), sigma.astype(np.float64), x.astype(np.float64)) - ljo
     assert rel(res[3][0], lpo) <= 1e-4
     assert np.array_equal(B.to_numpy(B.logpdf(td, y)), res[3][0])  # auto = constant-bank path
+
+
+@pytest.mark.parametrize("D", [128, 64, 32])
+@pytest.mark.parametrize("L", [1, 3, 8])
+def test_planar_chain_vjp_matches_oracle(B, D, L):
+    """b2b_planar_chain_vjp_f32 (reverse mode of with_logabsdet_jacobian through a planar chain) against the
+    float64 oracle VJP, which is itself pinned by finite differences of the forward oracle (CPU suite)."""
+    import torch
+
+    rng = np.random.default_rng(500 * D + L)
+    N = 6000 + 7 * L  # ragged
+    pairs = [make_case("planar", D, rng) for _ in range(L)]
+    flow = B.Composed(*[p[0] for p in pairs])
+    params = [(p[1].params["w"], p[1].params["u"], p[1].params["b"]) for p in pairs]
+    x = rng.standard_normal((D, N)).astype(f32)
+    ybar = rng.standard_normal((D, N)).astype(f32)
+    ljbar = rng.standard_normal(N).astype(f32)
+    xb_o, grads_o = O.planar_chain_vjp([(w.astype(np.float64), u.astype(np.float64), b.astype(np.float64)) for w, u, b in params],
+                                       x.astype(np.float64), ybar.astype(np.float64), ljbar.astype(np.float64))
+    xd, ybd, ljd = B.from_numpy(x), B.from_numpy(ybar), torch.from_numpy(ljbar).cuda()
+    xbar, grads = B.planar_chain_vjp(flow, xd, ybd, ljd)
+    assert B.lib().b2b_last_launch_count() == 7
+    assert rel(B.to_numpy(xbar), xb_o) <= RTOL
+    for l in range(L):
+        # parameter cotangents are sums of N float32 products: 2e-5 norm-wise
+        assert rel(grads[l]["w"].cpu().numpy(), grads_o[l][0]) <= 2e-5, (l, "w")
+        assert rel(grads[l]["u"].cpu().numpy(), grads_o[l][1]) <= 2e-5, (l, "u")
+        assert abs(float(grads[l]["b"]) - float(grads_o[l][2])) <= 2e-5 * max(abs(float(grads_o[l][2])), np.sqrt(N))
+    # inputs untouched; xbar-only call (no parameter cotangents), ljbar = None
+    assert np.array_equal(B.to_numpy(xd), x) and np.array_equal(B.to_numpy(ybd), ybar)
+    xbar2, g2 = B.planar_chain_vjp(flow, xd, ybd, None, want_param_grads=False)
+    assert g2 is None and B.lib().b2b_last_launch_count() == 2
+    xb_o2, _ = O.planar_chain_vjp([(w.astype(np.float64), u.astype(np.float64), b.astype(np.float64)) for w, u, b in params],
+                                  x.astype(np.float64), ybar.astype(np.float64), np.zeros(N))
+    assert rel(B.to_numpy(xbar2), xb_o2) <= RTOL
+    # determinism of the reductions
+    xbar3, grads3 = B.planar_chain_vjp(flow, xd, ybd, ljd)
+    assert all(torch.equal(grads3[l][k], grads[l][k]) for l in range(L) for k in ("w", "u", "b"))

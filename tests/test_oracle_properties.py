@@ -133,3 +133,59 @@ def test_log1pexp_tails():
     for x in [-100.0, -37.0, -10.0, -1.0, 0.0, 1.0, 10.0, 18.0, 33.3, 50.0, 700.0]:
         ref = float(mp.log1p(mp.e ** mp.mpf(x)))
         assert float(O.log1pexp(np.float64(x))) == pytest.approx(ref, rel=1e-14, abs=1e-300)
+
+
+def test_planar_chain_vjp_matches_finite_differences():
+    """The oracle VJP (reverse-mode restatement) against central finite differences of the pinned forward oracle."""
+    rng = np.random.default_rng(11)
+    D, N, L = 6, 5, 3
+    params = [(rng.standard_normal(D) / np.sqrt(D), rng.standard_normal(D) / np.sqrt(D), rng.standard_normal(1)) for _ in range(L)]
+    x = rng.standard_normal((D, N))
+    ybar, ljbar = rng.standard_normal((D, N)), rng.standard_normal(N)
+
+    def loss(ps, xx):
+        z, lj = xx, np.zeros(N)
+        for (w, u, b) in ps:
+            z, l1 = O.planar_forward(w, u, b, z)
+            lj = lj + l1
+        return float(np.sum(z * ybar) + np.sum(lj * ljbar))
+
+    xbar, grads = O.planar_chain_vjp(params, x, ybar, ljbar)
+    eps = 1e-6
+    fd = np.zeros_like(x)
+    for i in range(D):
+        for n in range(N):
+            xp, xm = x.copy(), x.copy()
+            xp[i, n] += eps
+            xm[i, n] -= eps
+            fd[i, n] = (loss(params, xp) - loss(params, xm)) / (2 * eps)
+    assert np.allclose(xbar, fd, rtol=1e-6, atol=1e-8)
+    for l in range(L):
+        for k, name in enumerate(("w", "u", "b")):
+            base = np.asarray(params[l][k], dtype=np.float64)
+            fdp = np.zeros_like(base)
+            for i in range(base.size):
+                pp, pm = base.copy(), base.copy()
+                pp[i] += eps
+                pm[i] -= eps
+                ps_p = [tuple(pp if (ll == l and kk == k) else params[ll][kk] for kk in range(3)) for ll in range(L)]
+                ps_m = [tuple(pm if (ll == l and kk == k) else params[ll][kk] for kk in range(3)) for ll in range(L)]
+                fdp[i] = (loss(ps_p, x) - loss(ps_m, x)) / (2 * eps)
+            got = np.atleast_1d(np.asarray(grads[l][k], dtype=np.float64))
+            assert np.allclose(got, fdp, rtol=1e-5, atol=1e-7), (l, name, got, fdp)
+
+
+def test_find_alpha_partials_match_finite_differences():
+    """ext/BijectorsChainRulesCoreExt.jl:42-46 (the implicit-function rule the reference registers)."""
+    rng = np.random.default_rng(12)
+    for _ in range(20):
+        t, c, b = rng.standard_normal() * 2, rng.uniform(-0.9, 2.0), rng.standard_normal()
+        a = float(O.find_alpha(np.float64(t), np.float64(c), np.float64(b)))
+        px = O.find_alpha_partials(a, c, b)
+        eps = 1e-6
+        fd = [
+            (float(O.find_alpha(np.float64(t + eps), np.float64(c), np.float64(b))) - float(O.find_alpha(np.float64(t - eps), np.float64(c), np.float64(b)))) / (2 * eps),
+            (float(O.find_alpha(np.float64(t), np.float64(c + eps), np.float64(b))) - float(O.find_alpha(np.float64(t), np.float64(c - eps), np.float64(b)))) / (2 * eps),
+            (float(O.find_alpha(np.float64(t), np.float64(c), np.float64(b + eps))) - float(O.find_alpha(np.float64(t), np.float64(c), np.float64(b - eps)))) / (2 * eps),
+        ]
+        assert np.allclose(px, fd, rtol=1e-5, atol=1e-7)
