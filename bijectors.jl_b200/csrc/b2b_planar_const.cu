@@ -303,19 +303,47 @@ __global__ void __launch_bounds__(PG_THREADS)
 #pragma unroll
   for (int l = 0; l < L; ++l) a1[l] = a2[l] = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long gw = (long long)blockIdx.x * nwarps + warp, stride = (long long)gridDim.x * nwarps;
-  for (long long c0 = gw * CPW; c0 < N; c0 += stride * CPW) {
-    const long long col = c0 + sub;
-    if (col < N) {
-      const float4 xv = __ldcs(reinterpret_cast<const float4*>(x + col * ldx) + chunk);
-      const float4 yv = __ldcs(reinterpret_cast<const float4*>(yb + col * ldyb) + chunk);
-      const float* sc = scal + col * (3 * L);
+  // UNR column groups per iteration: all loads are issued before the FMAs (2·UNR 16-byte loads in flight per lane)
+  constexpr int UNR = 4;
+  for (long long c0 = gw * (CPW * UNR); c0 < N; c0 += stride * (CPW * UNR)) {
+    float4 xv[UNR], yv[UNR];
+    float g[UNR][L], t[UNR][L];
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
+      const long long col = c0 + k * CPW + sub;
+      const bool ok = col < N;
+      const long long cs = ok ? col : 0;
+      xv[k] = __ldcs(reinterpret_cast<const float4*>(x + cs * ldx) + chunk);
+      yv[k] = __ldcs(reinterpret_cast<const float4*>(yb + cs * ldyb) + chunk);
+      const float* sc = scal + cs * (3 * L);
+      if constexpr (L % 4 == 0) {
+#pragma unroll
+        for (int l = 0; l < L; l += 4) {
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(sc + l));
+          const float4 tv = __ldg(reinterpret_cast<const float4*>(sc + L + l));
+          g[k][l] = gv.x; g[k][l + 1] = gv.y; g[k][l + 2] = gv.z; g[k][l + 3] = gv.w;
+          t[k][l] = tv.x; t[k][l + 1] = tv.y; t[k][l + 2] = tv.z; t[k][l + 3] = tv.w;
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          g[k][l] = __ldg(sc + l);
+          t[k][l] = __ldg(sc + L + l);
+        }
+      }
+      if (!ok) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) g[k][l] = t[k][l] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < UNR; ++k) {
 #pragma unroll
       for (int l = 0; l < L; ++l) {
-        const float g = __ldg(sc + l), t = __ldg(sc + L + l);
-        a1[l].x = fmaf(g, xv.x, a1[l].x); a1[l].y = fmaf(g, xv.y, a1[l].y);
-        a1[l].z = fmaf(g, xv.z, a1[l].z); a1[l].w = fmaf(g, xv.w, a1[l].w);
-        a2[l].x = fmaf(t, yv.x, a2[l].x); a2[l].y = fmaf(t, yv.y, a2[l].y);
-        a2[l].z = fmaf(t, yv.z, a2[l].z); a2[l].w = fmaf(t, yv.w, a2[l].w);
+        a1[l].x = fmaf(g[k][l], xv[k].x, a1[l].x); a1[l].y = fmaf(g[k][l], xv[k].y, a1[l].y);
+        a1[l].z = fmaf(g[k][l], xv[k].z, a1[l].z); a1[l].w = fmaf(g[k][l], xv[k].w, a1[l].w);
+        a2[l].x = fmaf(t[k][l], yv[k].x, a2[l].x); a2[l].y = fmaf(t[k][l], yv[k].y, a2[l].y);
+        a2[l].z = fmaf(t[k][l], yv[k].z, a2[l].z); a2[l].w = fmaf(t[k][l], yv[k].w, a2[l].w);
       }
     }
   }
@@ -349,13 +377,18 @@ __global__ void __launch_bounds__(PG_THREADS)
   for (int i = threadIdx.x; i < 2 * L * D; i += PG_THREADS) partials[(size_t)blockIdx.x * (2 * L * D) + i] = red[i];
 }
 
-// fixed-order sum of per-CTA partials: out[i] = Σ_b partials[b][i]
+// fixed-order sum of per-CTA partials: out[i] = Σ_b partials[b][i].  One warp per output: lane k adds the partials
+// b ≡ k (mod 32) in increasing order, then a fixed shuffle tree combines the lanes (deterministic, and the nblk
+// dependent loads of a serial sum become nblk/32).
 __global__ void __launch_bounds__(256) planar_psum_kernel(const float* __restrict__ partials, int nblk, int n,
                                                           float* __restrict__ out) {
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
     float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += partials[(size_t)b * n + i];
-    out[i] = s;
+    for (int b = lane; b < nblk; b += 32) s += partials[(size_t)b * n + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[i] = s;
   }
 }
 
@@ -401,7 +434,7 @@ __global__ void __launch_bounds__(SS_THREADS)
   }
 }
 
-// K4 (one CTA): w̄, ū, b̄ of the `nreal` layers.  `packed` = the prep kernel's w | û | c | b for (D, Lp); A = A1 | A2
+// K4 (one CTA per layer): w̄, ū, b̄ of the `nreal` layers.  `packed` = the prep kernel's w | û | c | b for (D, Lp); A = A1 | A2
 // (Lp x D each); SS = S | gb | gc.  Chain rule through get_u_hat: û = u + k·w, k = (log1pexp(−s) − 1)/q, s = wᵀu,
 // q = wᵀw, c = log1pexp(s) − 1 (planar_layer.jl:65-70).
 __device__ __forceinline__ float block_sum_256(float v, float* sh) {
@@ -427,16 +460,24 @@ __global__ void __launch_bounds__(256)
   const float* S = SS;
   const float* gb = SS + Lp * Lp;
   const float* gc = gb + Lp;
-  for (int l = 0; l < nreal; ++l) {
+  const int l = blockIdx.x;  // one CTA per layer
+  {
     const b2b_layer_desc& d = P.layers[l];
     float uhb = 0.f, wdir = 0.f, w = 0.f, u = 0.f;
     if (i < D) {
       w = d.p0[i];
       u = d.p1[i];
       uhb = A[Lp * D + l * D + i];
-      for (int k = l + 1; k < nreal; ++k) uhb = fmaf(S[k * Lp + l], W[k * D + i], uhb);
       wdir = A[l * D + i];
-      for (int k = 0; k < l; ++k) wdir = fmaf(S[l * Lp + k], UH[k * D + i], wdir);
+#pragma unroll
+      for (int k = 0; k < HP_MAX_L; ++k) {  // independent loads first, short FMA chains after
+        const float s_kl = (k > l && k < nreal) ? S[k * Lp + l] : 0.f;
+        const float w_k = (k > l && k < nreal) ? W[k * D + i] : 0.f;
+        const float s_lk = (k < l) ? S[l * Lp + k] : 0.f;
+        const float uh_k = (k < l) ? UH[k * D + i] : 0.f;
+        uhb = fmaf(s_kl, w_k, uhb);
+        wdir = fmaf(s_lk, uh_k, wdir);
+      }
     }
     const float s = block_sum_256(w * u, sh);
     const float q = block_sum_256(w * w, sh);
@@ -744,7 +785,10 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
 
   const HPShape sh = hp_shape(D, Lp);
   V1Geom g;
-  int rc = v1_geometry(D, p.N, sh.nw, 32, sh.mode ? (size_t)Lp * D : 0, g, 2);
+  static const int vjp_nw = getenv("B2B_VJP_NW") ? atoi(getenv("B2B_VJP_NW")) : 0;
+  // D = 128 x 8 layers: two-tensor slots are 32 KB; 7 warps leave room for 3 of them (8 warps: 2, 40 % slower)
+  const int nw = (D == 128 && Lp == 8) ? ((vjp_nw == 6 || vjp_nw == 8) ? vjp_nw : 7) : sh.nw;
+  int rc = v1_geometry(D, p.N, nw, 32, sh.mode ? (size_t)Lp * D : 0, g, 2);
   if (rc != 0) return rc;
   CUtensorMap mx, mxb, myb;
   if (!make_maps(q, g.cols, &mx, &mxb, &g.extra.tma3d)) return B2B_EUNSUPPORTED;
@@ -766,7 +810,9 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
   const size_t bytes = sizeof(float) * (size_t)(2 * Lp * D + 2 * Lp);
   if ((e = cudaMemcpyToSymbolAsync(c_planar, st.stage, bytes, 0, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess)
     return (int)e;
-  if (D == 128) rc = dispatch_vjp_main<128, 8>(Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
+  if (D == 128 && Lp == 8 && g.nw == 6) rc = launch_vjp_main<128, 8, 6, 2>(q, g, mx, myb, mxb, st.stage, ws.scal, stream);
+  else if (D == 128 && Lp == 8 && g.nw == 7) rc = launch_vjp_main<128, 8, 7, 2>(q, g, mx, myb, mxb, st.stage, ws.scal, stream);
+  else if (D == 128) rc = dispatch_vjp_main<128, 8>(Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
   else if (D == 64) rc = dispatch_vjp_main<64, 12>(Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
   else rc = dispatch_vjp_main<32, 16>(Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
   if (rc != B2B_OK) return rc;
@@ -779,12 +825,12 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
     else if (D == 64) rc = launch_pgrad<64>(Lp, p.x, ybar, ws.scal, p.N, p.ldx, ldyb, ws.pg_partials, stream);
     else rc = launch_pgrad<32>(Lp, p.x, ybar, ws.scal, p.N, p.ldx, ldyb, ws.pg_partials, stream);
     if (rc != B2B_OK) return rc;
-    planar_psum_kernel<<<(2 * Lp * D + 255) / 256, 256, 0, stream>>>(ws.pg_partials, VJP_PG_GRID, 2 * Lp * D, ws.A);
+    planar_psum_kernel<<<(2 * Lp * D + 7) / 8, 256, 0, stream>>>(ws.pg_partials, VJP_PG_GRID, 2 * Lp * D, ws.A);
     rc = launch_sstat(Lp, ws.scal, p.N, ws.ss_partials, stream);
     if (rc != B2B_OK) return rc;
     const int ns = Lp * Lp + 2 * Lp;
-    planar_psum_kernel<<<1, 256, 0, stream>>>(ws.ss_partials, VJP_SS_GRID, ns, ws.SS);
-    planar_vjp_finalize_kernel<<<1, 256, 0, stream>>>(p, n, Lp, st.stage, ws.A, ws.SS, wbar, ubar, bbar);
+    planar_psum_kernel<<<(ns + 7) / 8, 256, 0, stream>>>(ws.ss_partials, VJP_SS_GRID, ns, ws.SS);
+    planar_vjp_finalize_kernel<<<n, 256, 0, stream>>>(p, n, Lp, st.stage, ws.A, ws.SS, wbar, ubar, bbar);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     nl += 5;
   }
