@@ -17,6 +17,6 @@ from .layers import (  # noqa: F401
 from .transformed_distribution import (  # noqa: F401
     MvNormal, TransformedDistribution, logpdf, logpdf_sum, rand, transformed,
 )
-from . import distributed  # noqa: F401
+from . import autograd, distributed  # noqa: F401
 
 lib()  # fail loudly at import time when libb2b.so has not been built

@@ -1,0 +1,76 @@
+"""torch.autograd glue for planar flows: makes ``with_logabsdet_jacobian`` of a PlanarLayer chain (either direction)
+differentiable by routing the backward pass to ``b2b_planar_chain_vjp_f32`` -- the role the AD extensions play for the
+reference (ext/BijectorsChainRulesCoreExt.jl, docs/src/flows.md:93-100).  No arithmetic on batches happens here."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+
+from .interface import Composed, colmajor_empty, inverse, planar_chain_vjp, run_chain
+from .layers import PlanarLayer
+
+
+def _colmajor(t: torch.Tensor) -> torch.Tensor:
+    """A (D, N) tensor with strides (1, D) (no copy when it already has them)."""
+    if t.dim() == 2 and t.stride(0) == 1 and (t.shape[1] == 1 or t.stride(1) == t.shape[0]):
+        return t
+    out = colmajor_empty(t.shape[0], t.shape[1], t.device)
+    out.copy_(t)
+    return out
+
+
+class _PlanarChainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inv: bool, *wub):
+        L = len(wub) // 3
+        layers = [PlanarLayer(wub[3 * l].detach(), wub[3 * l + 1].detach(), wub[3 * l + 2].detach()) for l in range(L)]
+        flow = Composed(*layers)
+        t = inverse(flow) if inv else flow
+        xc = _colmajor(x.detach())
+        y, lj = run_chain(t, xc)
+        ctx.t, ctx.inv, ctx.L = t, inv, L
+        ctx.save_for_backward(xc)
+        return y, lj
+
+    @staticmethod
+    def backward(ctx, ybar, ljbar):
+        (xc,) = ctx.saved_tensors
+        D, N = xc.shape
+        yb = _colmajor(ybar) if ybar is not None else _colmajor(torch.zeros((D, N), device=xc.device))
+        lb = ljbar.contiguous() if ljbar is not None else None
+        xbar, grads = planar_chain_vjp(ctx.t, xc, yb, lb)
+        if ctx.inv:  # application order of inverse(flow) is the flow's layers reversed
+            grads = grads[::-1]
+        flat: List[torch.Tensor] = []
+        for g in grads:
+            flat += [g["w"], g["u"], g["b"]]
+        return (xbar, None, *flat)
+
+
+class PlanarFlow(torch.nn.Module):
+    """A trainable ∘-chain of L PlanarLayers (planar_layer.jl:13-28: randn-initialised w, u, b) on the device."""
+
+    def __init__(self, dims: int, n_layers: int, device="cuda", generator=None, scale: float = 1.0):
+        super().__init__()
+        mk = lambda n: torch.nn.Parameter((torch.randn(n, generator=generator) * scale).to(device))
+        self.w = torch.nn.ParameterList([mk(dims) for _ in range(n_layers)])
+        self.u = torch.nn.ParameterList([mk(dims) for _ in range(n_layers)])
+        self.b = torch.nn.ParameterList([mk(1) for _ in range(n_layers)])
+
+    def _wub(self) -> Sequence[torch.Tensor]:
+        out = []
+        for w, u, b in zip(self.w, self.u, self.b):
+            out += [w, u, b]
+        return out
+
+    def layers(self) -> List[PlanarLayer]:
+        return [PlanarLayer(w.detach(), u.detach(), b.detach()) for w, u, b in zip(self.w, self.u, self.b)]
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """with_logabsdet_jacobian(flow, x), differentiable w.r.t. x and the parameters."""
+        return _PlanarChainFn.apply(x, False, *self._wub())
+
+    def inverse(self, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """with_logabsdet_jacobian(inverse(flow), y), differentiable (find_alpha through its implicit rule)."""
+        return _PlanarChainFn.apply(y, True, *self._wub())

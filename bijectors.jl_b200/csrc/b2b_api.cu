@@ -545,7 +545,7 @@ extern "C" int b2b_planar_chain_vjp_f32(const b2b_layer_desc* layers, int32_t L,
     if (layers[l].kind != B2B_PLANAR) return B2B_EUNSUPPORTED;
     const int rc = validate_layer(layers[l], D, false);
     if (rc != B2B_OK) return rc;
-    if (layers[l].inverse) return B2B_EUNSUPPORTED;
+    if ((layers[l].inverse != 0) != (layers[0].inverse != 0)) return B2B_EUNSUPPORTED;  // one direction per call
   }
   B2BChainParams p;
   memset(&p, 0, sizeof(p));

@@ -190,7 +190,11 @@ struct VjpState {
   float t[L], s2[L];
 };
 
-template <int D, int L, int MODE>
+// DIR 0: forward layers; DIR 1: inverse layers in application order (the logpdf / NLL path): α from find_alpha,
+// differentiated with the implicit-function rule ext/BijectorsChainRulesCoreExt.jl:42-46
+// (∂α/∂(wᵀy) = X, ∂α/∂c = −tanh(α+b)·X, ∂α/∂b = X − 1, X = 1/(1 + c·sech²(α+b))):
+//   u_{k+1} = u_k − û_k th_k,  g_k = X·(−s_k·û_kᵀζ_{k+1} + 2 c th_k·l̄ s_k X),  ζ_k = ζ_{k+1} + w_k g_k.
+template <int D, int L, int MODE, int DIR>
 struct PlanarVjpProg {
   using State = VjpState<L>;
   using Src = SymSrc<D, L>;
@@ -220,9 +224,11 @@ struct PlanarVjpProg {
         acc[(i & 1) * 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), x[0][2 * i + 1], acc[(i & 1) * 2 + 1]);
       }
       const float2 s = __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
-      tanh_sech2(s.x + s.y + src.b(l), st.t[l], st.s2[l]);
+      if (DIR == 0) tanh_sech2(s.x + s.y + src.b(l), st.t[l], st.s2[l]);
+      else find_alpha_ts(s.x + s.y, src.c(l), src.b(l), st.t[l], st.s2[l]);  // planar_layer.jl:121
       if (l + 1 < L) {  // the last layer's output is not needed
-        const float2 t2 = make_float2(st.t[l], st.t[l]);
+        const float tt = DIR == 0 ? st.t[l] : -st.t[l];
+        const float2 t2 = make_float2(tt, tt);
 #pragma unroll
         for (int i = 0; i < D / 4; ++i) {
           x[0][2 * i] = __ffma2_rn(make_float2(src.uh(l, 4 * i), src.uh(l, 4 * i + 1)), t2, x[0][2 * i]);
@@ -252,7 +258,8 @@ struct PlanarVjpProg {
       const float c = src.c(l), s2 = st.s2[l], t = st.t[l];
       const float rden = __frcp_rn(fmaf(c, s2, 1.0f));
       cb[l] = lj[0] * s2 * rden;
-      g[l] = fmaf(s2, d, -2.0f * c * t * cb[l]);
+      if (DIR == 0) g[l] = fmaf(s2, d, -2.0f * c * t * cb[l]);
+      else g[l] = rden * fmaf(-s2, d, 2.0f * c * t * cb[l]);
       const float2 g2 = make_float2(g[l], g[l]);
       const float4* sp4 = reinterpret_cast<const float4*>(params + l * D);
 #pragma unroll
@@ -276,13 +283,13 @@ struct PlanarVjpProg {
   }
 };
 
-template <int D, int L, int NW, int MODE>
+template <int D, int L, int NW, int MODE, int DIR>
 __global__ void __launch_bounds__(NW * 32, 1)
     planar_vjp_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
                       const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_yb,
                       const __grid_constant__ CUtensorMap map_xb, const float* stage, float* scal) {
-  const PlanarVjpProg<D, L, MODE> prog{{stage, 0}, scal, P.N};
-  v1_run<D, 1, 1, NW, PlanarVjpProg<D, L, MODE>, 2>(P, E, map_x, map_xb, prog, &map_yb);
+  const PlanarVjpProg<D, L, MODE, DIR> prog{{stage, 0}, scal, P.N};
+  v1_run<D, 1, 1, NW, PlanarVjpProg<D, L, MODE, DIR>, 2>(P, E, map_x, map_xb, prog, &map_yb);
 }
 
 // K2: A1[l][r] = Σ_n g[l,n]·x[r,n],  A2[l][r] = Σ_n t[l,n]·ȳ[r,n].  A warp handles 128/D columns at a time (lane ->
@@ -450,7 +457,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
 }
 
 __global__ void __launch_bounds__(256)
-    planar_vjp_finalize_kernel(const __grid_constant__ B2BChainParams P, int nreal, int Lp, const float* __restrict__ packed,
+    planar_vjp_finalize_kernel(const __grid_constant__ B2BChainParams P, int nreal, int Lp, int dir, const float* __restrict__ packed,
                                const float* __restrict__ A, const float* __restrict__ SS, float* __restrict__ wbar,
                                float* __restrict__ ubar, float* __restrict__ bbar) {
   __shared__ float sh[8];
@@ -476,8 +483,9 @@ __global__ void __launch_bounds__(256)
         const float s_lk = (k < l) ? S[l * Lp + k] : 0.f;
         const float uh_k = (k < l) ? UH[k * D + i] : 0.f;
         uhb = fmaf(s_kl, w_k, uhb);
-        wdir = fmaf(s_lk, uh_k, wdir);
+        wdir = fmaf(dir ? -s_lk : s_lk, uh_k, wdir);
       }
+      if (dir) uhb = -uhb;  // inverse layers subtract û·tanh
     }
     const float s = block_sum_256(w * u, sh);
     const float q = block_sum_256(w * w, sh);
@@ -485,7 +493,7 @@ __global__ void __launch_bounds__(256)
     const float kk = (softplus(-s) - 1.0f) / q;
     const float sig_s = 1.0f / (1.0f + expf(-s)), sig_ms = 1.0f / (1.0f + expf(s));
     const float dk_ds = -sig_ms / q, dk_dq = -kk / q;
-    const float cbar = gc[l];
+    const float cbar = dir ? -S[l * Lp + l] - gc[l] : gc[l];  // inverse: Σ(−th·g) − Σ l̄ s X
     if (i < D) {
       ubar[l * D + i] = fmaf(fmaf(uw, dk_ds, cbar * sig_s), w, uhb);
       wbar[l * D + i] = wdir + kk * uhb + uw * fmaf(dk_ds, u, dk_dq * 2.0f * w) + cbar * sig_s * u;
@@ -700,9 +708,9 @@ static VjpWs vjp_carve(char* base, int Lp, int D, long long N) {
 }
 
 template <int D, int L, int NW, int MODE>
-static int launch_vjp_main(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& myb,
+static int launch_vjp_main(int dir, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& myb,
                            const CUtensorMap& mxb, const float* stage, float* scal, cudaStream_t stream) {
-  auto kernel = planar_vjp_kernel<D, L, NW, MODE>;
+  auto kernel = dir ? planar_vjp_kernel<D, L, NW, MODE, 1> : planar_vjp_kernel<D, L, NW, MODE, 0>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
   kernel<<<g.grid, NW * 32, g.smem, stream>>>(q, g.extra, mx, myb, mxb, stage, scal);
@@ -710,16 +718,16 @@ static int launch_vjp_main(const B2BChainParams& q, const V1Geom& g, const CUten
 }
 
 template <int D, int NW>
-static int dispatch_vjp_main(int L, int mode, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx,
+static int dispatch_vjp_main(int dir, int L, int mode, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx,
                              const CUtensorMap& myb, const CUtensorMap& mxb, const float* stage, float* scal,
                              cudaStream_t stream) {
-  if (L == 1) return launch_vjp_main<D, 1, NW, 0>(q, g, mx, myb, mxb, stage, scal, stream);
-  if (L == 2) return launch_vjp_main<D, 2, NW, 0>(q, g, mx, myb, mxb, stage, scal, stream);
-  if (L == 4) return launch_vjp_main<D, 4, NW, 0>(q, g, mx, myb, mxb, stage, scal, stream);
+  if (L == 1) return launch_vjp_main<D, 1, NW, 0>(dir, q, g, mx, myb, mxb, stage, scal, stream);
+  if (L == 2) return launch_vjp_main<D, 2, NW, 0>(dir, q, g, mx, myb, mxb, stage, scal, stream);
+  if (L == 4) return launch_vjp_main<D, 4, NW, 0>(dir, q, g, mx, myb, mxb, stage, scal, stream);
   if constexpr (2 * D * 8 * 4 > 4096) {
-    if (L == 8 && mode == 2) return launch_vjp_main<D, 8, NW, 2>(q, g, mx, myb, mxb, stage, scal, stream);
+    if (L == 8 && mode == 2) return launch_vjp_main<D, 8, NW, 2>(dir, q, g, mx, myb, mxb, stage, scal, stream);
   } else {
-    if (L == 8 && mode == 0) return launch_vjp_main<D, 8, NW, 0>(q, g, mx, myb, mxb, stage, scal, stream);
+    if (L == 8 && mode == 0) return launch_vjp_main<D, 8, NW, 0>(dir, q, g, mx, myb, mxb, stage, scal, stream);
   }
   return B2B_EUNSUPPORTED;
 }
@@ -764,8 +772,9 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
   using namespace b2b;
   const int n = p.L, D = p.D;
   if (n < 1 || n > HP_MAX_L || !(D == 32 || D == 64 || D == 128)) return B2B_EUNSUPPORTED;
+  const int dir = p.layers[0].inverse ? 1 : 0;  // all layers forward, or all inverse (application order)
   for (int l = 0; l < n; ++l)
-    if (p.layers[l].kind != B2B_PLANAR || p.layers[l].inverse) return B2B_EUNSUPPORTED;
+    if (p.layers[l].kind != B2B_PLANAR || (p.layers[l].inverse ? 1 : 0) != dir) return B2B_EUNSUPPORTED;
   int Lp = 1;
   while (Lp < n) Lp <<= 1;
   B2BChainParams q = p;  // main kernel: x -> (fragment 1), ybar -> (fragment 2), xbar out, ljbar read-only
@@ -810,11 +819,11 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
   const size_t bytes = sizeof(float) * (size_t)(2 * Lp * D + 2 * Lp);
   if ((e = cudaMemcpyToSymbolAsync(c_planar, st.stage, bytes, 0, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess)
     return (int)e;
-  if (D == 128 && Lp == 8 && g.nw == 6) rc = launch_vjp_main<128, 8, 6, 2>(q, g, mx, myb, mxb, st.stage, ws.scal, stream);
-  else if (D == 128 && Lp == 8 && g.nw == 7) rc = launch_vjp_main<128, 8, 7, 2>(q, g, mx, myb, mxb, st.stage, ws.scal, stream);
-  else if (D == 128) rc = dispatch_vjp_main<128, 8>(Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
-  else if (D == 64) rc = dispatch_vjp_main<64, 12>(Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
-  else rc = dispatch_vjp_main<32, 16>(Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
+  if (D == 128 && Lp == 8 && g.nw == 6) rc = launch_vjp_main<128, 8, 6, 2>(dir, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
+  else if (D == 128 && Lp == 8 && g.nw == 7) rc = launch_vjp_main<128, 8, 7, 2>(dir, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
+  else if (D == 128) rc = dispatch_vjp_main<128, 8>(dir, Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
+  else if (D == 64) rc = dispatch_vjp_main<64, 12>(dir, Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
+  else rc = dispatch_vjp_main<32, 16>(dir, Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
   if (rc != B2B_OK) return rc;
   // parameter gradients: skinny reductions over the ORIGINAL x and ybar.  NOTE: xbar may alias ybar, in which case
   // ybar has been overwritten -- aliasing is therefore only allowed when the caller does not want parameter gradients.
@@ -830,7 +839,7 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
     if (rc != B2B_OK) return rc;
     const int ns = Lp * Lp + 2 * Lp;
     planar_psum_kernel<<<(ns + 7) / 8, 256, 0, stream>>>(ws.ss_partials, VJP_SS_GRID, ns, ws.SS);
-    planar_vjp_finalize_kernel<<<n, 256, 0, stream>>>(p, n, Lp, st.stage, ws.A, ws.SS, wbar, ubar, bbar);
+    planar_vjp_finalize_kernel<<<n, 256, 0, stream>>>(p, n, Lp, dir, st.stage, ws.A, ws.SS, wbar, ubar, bbar);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     nl += 5;
   }

@@ -419,15 +419,22 @@ def planar_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[tor
     what the reference's reverse-mode AD computes in a training step (docs/src/flows.md:93-100,
     ext/BijectorsChainRulesCoreExt.jl).  ``ybar`` (D×N) / ``ljbar`` (N) are the cotangents of the two outputs.
 
-    Returns ``(xbar, grads)``: ``xbar`` (D×N) and ``grads`` = list of ``{"w": …, "u": …, "b": …}`` per layer
-    (summed over the columns of this batch), or ``None`` when ``want_param_grads`` is false."""
+    ``t`` may also be ``inverse(flow)`` (the chain ``logpdf(transformed(d, flow), y)`` evaluates,
+    docs/src/flows.md:66-100): ``x`` is then the observed batch and ``find_alpha`` is differentiated with the reference's
+    implicit-function rule (ext/BijectorsChainRulesCoreExt.jl:42-46).
+
+    Returns ``(xbar, grads)``: ``xbar`` (D×N) and ``grads`` = list of ``{"w": …, "u": …, "b": …}``, one entry per layer
+    in APPLICATION order (``flatten(t)``; for ``inverse(flow)`` that is the flow's layers reversed), summed over the
+    columns of this batch -- or ``None`` when ``want_param_grads`` is false."""
     D, N, ldx = _batch_view(x)
     Dy, Ny, ldyb = _batch_view(ybar)
     if (Dy, Ny) != (D, N) or not x.is_cuda or not ybar.is_cuda or x.dim() != 2:
         raise ValueError("planar_chain_vjp: x and ybar must be device matrices of the same D×N shape")
     descs = list(t._descs(False, D))
-    if any(d.kind != _lib.PLANAR or d.inverse or hasattr(d, "_host_planar") for d in descs):
-        raise B2BError(_lib.B2B_EUNSUPPORTED, "planar_chain_vjp: forward PlanarLayers with device parameters only")
+    if any(d.kind != _lib.PLANAR or hasattr(d, "_host_planar") for d in descs) or len({int(d.inverse) for d in descs}) != 1:
+        raise B2BError(_lib.B2B_EUNSUPPORTED,
+                       "planar_chain_vjp: PlanarLayers with device parameters, one direction per chain "
+                       "(a flow, or inverse(flow))")
     L = len(descs)
     arr = _desc_array(descs)
     if ljbar is not None and (ljbar.numel() != N or ljbar.dtype != torch.float32 or not ljbar.is_contiguous()):

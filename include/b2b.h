@@ -164,7 +164,10 @@ int b2b_planar_chain_hostparams_f32(const float* w_host, const float* u_host, co
  * and `ljbar` (N, of the accumulated logjac; NULL = zeros).  Outputs: `xbar` (D x N cotangent of x, required) and --
  * when all three are non-NULL -- the parameter cotangents `wbar`, `ubar` (L x D, layer l at offset l*D) and `bbar` (L),
  * summed over the N columns (a multi-GPU caller all-reduces them, see b2b_allreduce_sum_f64).  D in {32, 64, 128};
- * `layers` are B2B_PLANAR descriptors with inverse == 0.  `xbar` may alias `ybar` only when no parameter cotangents
+ * `layers` are B2B_PLANAR descriptors in application order, either all with inverse == 0 (the forward chain) or all
+ * with inverse == 1 (the chain inverse(flow) that logpdf(td, y) evaluates, docs/src/flows.md:66-100: `x` is then the
+ * observed batch y, `ybar` the cotangent of the recovered x; find_alpha is differentiated with the reference's
+ * implicit-function rule, ext/BijectorsChainRulesCoreExt.jl:42-46); cotangent l of wbar/ubar/bbar belongs to layers[l].  `xbar` may alias `ybar` only when no parameter cotangents
  * are requested.  Workspace: b2b_planar_chain_vjp_workspace_bytes. */
 size_t b2b_planar_chain_vjp_workspace_bytes(int32_t L, int32_t D, int64_t N);
 int b2b_planar_chain_vjp_f32(const b2b_layer_desc* layers, int32_t L, const float* x, const float* ybar,

@@ -159,6 +159,67 @@ def planar_chain_vjp(params, x, ybar, ljbar):
     return yb.astype(dt), grads
 
 
+def _get_u_hat_pullback(w, u, uhat_bar, c_bar, dt):
+    """Cotangents (w̄, ū) contributed through get_u_hat (planar_layer.jl:65-70): û = u + k(s, q)·w,
+    k = (log1pexp(−s) − 1)/q, s = wᵀu, q = wᵀw; c = wᵀû = log1pexp(s) − 1."""
+    s_ = dt.type(np.dot(w, u))
+    q_ = dt.type(np.sum(w * w))
+    sig = lambda v: dt.type(1) / (dt.type(1) + np.exp(-v))
+    k = (log1pexp(-s_) - dt.type(1)) / q_
+    dk_ds = -sig(-s_) / q_
+    dk_dq = -k / q_
+    uw = dt.type(np.dot(uhat_bar, w))
+    u_bar = uhat_bar + (uw * dk_ds + c_bar * sig(s_)) * w
+    w_bar = k * uhat_bar + uw * (dk_ds * u + dk_dq * 2 * w) + c_bar * sig(s_) * u
+    return w_bar, u_bar
+
+
+def planar_inverse_chain_vjp(params, y, xbar, ljbar):
+    """Vector-Jacobian product of with_logabsdet_jacobian(inverse(f_L ∘ … ∘ f_1), y) -- the computation under
+    ``logpdf(transformed(d, flow), y)`` that the reference's training example differentiates
+    (docs/src/flows.md:66-100).  Inverse layers are applied in the order L, L−1, …, 1 (planar_layer.jl:112-127); α comes
+    from find_alpha and is differentiated with the reference's implicit-function rule
+    (ext/BijectorsChainRulesCoreExt.jl:42-46, restated in find_alpha_partials).
+
+    params: [(w, u, b)] in FORWARD order; y (D, N); xbar (D, N) cotangent of the recovered x; ljbar (N,) cotangent of the
+    accumulated (inverse) logjac.  Returns (ybar, [(wbar, ubar, bbar), ...]) in forward order."""
+    dt = y.dtype
+    L = len(params)
+    us, cache = [y], []
+    for l in range(L - 1, -1, -1):
+        w, u = params[l][0].astype(dt), params[l][1].astype(dt)
+        bb = dt.type(np.asarray(params[l][2]).reshape(-1)[0])
+        u_hat, c = get_u_hat(u, w)
+        t_in = w @ us[-1]
+        alpha = find_alpha(t_in, c, bb).astype(dt)
+        a = alpha + bb
+        th = np.tanh(a)
+        with np.errstate(over="ignore"):
+            s2 = (dt.type(1) / np.cosh(a)) ** 2
+        us.append(us[-1] - u_hat[:, None] * th[None, :])   # planar_layer.jl:124
+        cache.append((l, w, u, u_hat, c, bb, alpha, th, s2))
+    zb = xbar.astype(dt).copy()
+    grads = [None] * L
+    for k in range(L - 1, -1, -1):          # reverse over the applied inverse layers
+        l, w, u, u_hat, c, bb, alpha, th, s2 = cache[k]
+        inp = us[k]
+        pt, pc, pb = find_alpha_partials(alpha, c, bb)      # ∂α/∂(wᵀy), ∂α/∂c, ∂α/∂b
+        X = pt
+        th_bar = -(u_hat @ zb)
+        uhat_bar = -(zb @ th)
+        # logjac of the inverse layer: −log1p(c·sech²(α+b))  (interface.jl:276-281)
+        a_bar = s2 * th_bar + ljbar * (2 * c * th * s2 * X)
+        c_bar_direct = np.sum(ljbar * (-s2 * X))
+        t_bar = a_bar * pt
+        c_bar = np.sum(a_bar * pc) + c_bar_direct
+        b_bar = np.sum(a_bar * (1 + pb))                    # a = α + b: direct + through α
+        w_bar = inp @ t_bar
+        zb = zb + w[:, None] * t_bar[None, :]
+        gw, gu = _get_u_hat_pullback(w, u, uhat_bar, c_bar, dt)
+        grads[l] = ((w_bar + gw).astype(dt), gu.astype(dt), dt.type(b_bar))
+    return zb.astype(dt), grads
+
+
 def find_alpha(wt_y, wt_u_hat, b):
     """src/bijectors/planar_layer.jl:160-185, vectorised over ``wt_y``.
 
