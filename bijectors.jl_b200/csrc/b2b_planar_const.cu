@@ -384,6 +384,118 @@ __global__ void __launch_bounds__(PG_THREADS)
   for (int i = threadIdx.x; i < 2 * L * D; i += PG_THREADS) partials[(size_t)blockIdx.x * (2 * L * D) + i] = red[i];
 }
 
+// K2 for dense batches (ld == D): chunks of PGB_CH columns of x, ȳ and the per-column scalars are contiguous in global
+// memory, so one elected thread streams them into a 4-stage shared-memory ring with three 1-D bulk copies per chunk
+// (cp.async.bulk + mbarrier full/empty pairs); the 8 warps consume from shared memory.  This keeps ~100 KB in flight
+// per SM -- the register-staged kernel above is bound by load latency (3 TB/s).
+constexpr int PGB_CH = 16;      // columns per chunk
+constexpr int PGB_STAGES = 4;
+template <int D, int L>
+__global__ void __launch_bounds__(PG_THREADS)
+    planar_pgrad_bulk_kernel(const float* __restrict__ x, const float* __restrict__ yb, const float* __restrict__ scal,
+                             long long N, float* __restrict__ partials) {
+  constexpr int LPCOL = D / 4, CPW = 32 / LPCOL, NWARPS = PG_THREADS / 32;
+  constexpr int XB = PGB_CH * D * 4, SB = PGB_CH * 3 * L * 4, STAGE = 2 * XB + SB;
+  extern __shared__ __align__(128) unsigned char pg_smem[];
+  __shared__ uint64_t full[PGB_STAGES], empty[PGB_STAGES];
+  __shared__ float red[2 * L * D];
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int sub = lane / LPCOL, chunk = lane % LPCOL;
+  for (int i = threadIdx.x; i < 2 * L * D; i += PG_THREADS) red[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PGB_STAGES; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), NWARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const long long nchunks = (N + PGB_CH - 1) / PGB_CH;
+  const long long mine = (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x;  // chunks blockIdx.x + k*gridDim.x
+  auto issue = [&](long long k) {
+    const int s = (int)(k % PGB_STAGES);
+    const long long c0 = (blockIdx.x + k * gridDim.x) * PGB_CH;
+    const int cols = (int)((N - c0 < PGB_CH) ? (N - c0) : PGB_CH);
+    const uint32_t bar = smem_u32(&full[s]);
+    unsigned char* st = pg_smem + (size_t)s * STAGE;
+    // bulk copies move multiples of 16 bytes: the scalar block of a ragged last chunk is rounded up (the bytes past
+    // it belong to the same workspace allocation and are never used)
+    const uint32_t sbytes = ((uint32_t)cols * 3 * L * 4 + 15u) & ~15u;
+    mbar_expect_tx(bar, (uint32_t)cols * (2 * D * 4) + sbytes);
+    bulk_load_1d(smem_u32(st), x + c0 * D, (uint32_t)cols * D * 4, bar);
+    bulk_load_1d(smem_u32(st + XB), yb + c0 * D, (uint32_t)cols * D * 4, bar);
+    bulk_load_1d(smem_u32(st + 2 * XB), scal + c0 * (3 * L), sbytes, bar);
+  };
+  if (threadIdx.x == 0)
+    for (long long k = 0; k < PGB_STAGES - 1 && k < mine; ++k) issue(k);
+
+  float4 a1[L], a2[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) a1[l] = a2[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long k = 0; k < mine; ++k) {
+    const int s = (int)(k % PGB_STAGES);
+    // refill the stage that was consumed in the previous iteration with chunk k + STAGES − 1
+    if (threadIdx.x == 0 && k + PGB_STAGES - 1 < mine) {
+      const long long kn = k + PGB_STAGES - 1;
+      if (kn >= PGB_STAGES) mbar_wait(smem_u32(&empty[kn % PGB_STAGES]), (uint32_t)(((kn / PGB_STAGES) - 1) & 1));
+      issue(kn);
+    }
+    mbar_wait(smem_u32(&full[s]), (uint32_t)((k / PGB_STAGES) & 1));
+    const long long c0 = (blockIdx.x + k * gridDim.x) * PGB_CH;
+    const int cols = (int)((N - c0 < PGB_CH) ? (N - c0) : PGB_CH);
+    const unsigned char* st = pg_smem + (size_t)s * STAGE;
+    const float4* xs = reinterpret_cast<const float4*>(st);
+    const float4* ys = reinterpret_cast<const float4*>(st + XB);
+    const float* sc = reinterpret_cast<const float*>(st + 2 * XB);
+#pragma unroll
+    for (int cc = 0; cc < PGB_CH / (NWARPS * CPW) + (PGB_CH % (NWARPS * CPW) ? 1 : 0); ++cc) {
+      const int col = (cc * NWARPS + warp) * CPW + sub;
+      if (col < cols) {
+        const float4 xv = xs[col * LPCOL + chunk], yv = ys[col * LPCOL + chunk];
+        const float* sp = sc + col * (3 * L);
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+          const float g = sp[l], t = sp[L + l];
+          a1[l].x = fmaf(g, xv.x, a1[l].x); a1[l].y = fmaf(g, xv.y, a1[l].y);
+          a1[l].z = fmaf(g, xv.z, a1[l].z); a1[l].w = fmaf(g, xv.w, a1[l].w);
+          a2[l].x = fmaf(t, yv.x, a2[l].x); a2[l].y = fmaf(t, yv.y, a2[l].y);
+          a2[l].z = fmaf(t, yv.z, a2[l].z); a2[l].w = fmaf(t, yv.w, a2[l].w);
+        }
+      }
+    }
+    // this warp is done with the stage: order its generic-proxy reads before the async refill, then release
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&empty[s]));
+  }
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+#pragma unroll
+    for (int o = LPCOL; o < 32; o <<= 1) {
+      a1[l].x += __shfl_xor_sync(0xffffffffu, a1[l].x, o); a1[l].y += __shfl_xor_sync(0xffffffffu, a1[l].y, o);
+      a1[l].z += __shfl_xor_sync(0xffffffffu, a1[l].z, o); a1[l].w += __shfl_xor_sync(0xffffffffu, a1[l].w, o);
+      a2[l].x += __shfl_xor_sync(0xffffffffu, a2[l].x, o); a2[l].y += __shfl_xor_sync(0xffffffffu, a2[l].y, o);
+      a2[l].z += __shfl_xor_sync(0xffffffffu, a2[l].z, o); a2[l].w += __shfl_xor_sync(0xffffffffu, a2[l].w, o);
+    }
+  }
+  for (int w = 0; w < NWARPS; ++w) {
+    if (warp == w && lane < LPCOL) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        float4* r1 = reinterpret_cast<float4*>(&red[l * D + 4 * chunk]);
+        float4* r2 = reinterpret_cast<float4*>(&red[L * D + l * D + 4 * chunk]);
+        float4 v1 = *r1, v2 = *r2;
+        v1.x += a1[l].x; v1.y += a1[l].y; v1.z += a1[l].z; v1.w += a1[l].w;
+        v2.x += a2[l].x; v2.y += a2[l].y; v2.z += a2[l].z; v2.w += a2[l].w;
+        *r1 = v1;
+        *r2 = v2;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < 2 * L * D; i += PG_THREADS) partials[(size_t)blockIdx.x * (2 * L * D) + i] = red[i];
+}
+
 // fixed-order sum of per-CTA partials: out[i] = Σ_b partials[b][i].  One warp per output: lane k adds the partials
 // b ≡ k (mod 32) in increasing order, then a fixed shuffle tree combines the lanes (deterministic, and the nblk
 // dependent loads of a serial sum become nblk/32).
@@ -732,17 +844,34 @@ static int dispatch_vjp_main(int dir, int L, int mode, const B2BChainParams& q, 
   return B2B_EUNSUPPORTED;
 }
 
+template <int D, int L>
+static int launch_pgrad_L(const float* x, const float* yb, const float* scal, long long N, long long ldx,
+                          long long ldyb, float* partials, cudaStream_t stream) {
+  static const int force_reg = getenv("B2B_PGRAD") && atoi(getenv("B2B_PGRAD")) == 1;
+  const bool dense = ldx == D && ldyb == D && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(yb) |
+                                                 reinterpret_cast<uintptr_t>(scal)) & 15);
+  if (dense && !force_reg) {
+    auto kernel = planar_pgrad_bulk_kernel<D, L>;
+    const int smem = PGB_STAGES * (2 * PGB_CH * D * 4 + PGB_CH * 3 * L * 4);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    kernel<<<VJP_PG_GRID, PG_THREADS, smem, stream>>>(x, yb, scal, N, partials);
+  } else {
+    planar_pgrad_kernel<D, L><<<VJP_PG_GRID, PG_THREADS, 0, stream>>>(x, yb, scal, N, ldx, ldyb, partials);
+  }
+  return (int)cudaGetLastError();
+}
+
 template <int D>
 static int launch_pgrad(int L, const float* x, const float* yb, const float* scal, long long N, long long ldx,
                         long long ldyb, float* partials, cudaStream_t stream) {
   switch (L) {
-    case 1: planar_pgrad_kernel<D, 1><<<VJP_PG_GRID, PG_THREADS, 0, stream>>>(x, yb, scal, N, ldx, ldyb, partials); break;
-    case 2: planar_pgrad_kernel<D, 2><<<VJP_PG_GRID, PG_THREADS, 0, stream>>>(x, yb, scal, N, ldx, ldyb, partials); break;
-    case 4: planar_pgrad_kernel<D, 4><<<VJP_PG_GRID, PG_THREADS, 0, stream>>>(x, yb, scal, N, ldx, ldyb, partials); break;
-    case 8: planar_pgrad_kernel<D, 8><<<VJP_PG_GRID, PG_THREADS, 0, stream>>>(x, yb, scal, N, ldx, ldyb, partials); break;
+    case 1: return launch_pgrad_L<D, 1>(x, yb, scal, N, ldx, ldyb, partials, stream);
+    case 2: return launch_pgrad_L<D, 2>(x, yb, scal, N, ldx, ldyb, partials, stream);
+    case 4: return launch_pgrad_L<D, 4>(x, yb, scal, N, ldx, ldyb, partials, stream);
+    case 8: return launch_pgrad_L<D, 8>(x, yb, scal, N, ldx, ldyb, partials, stream);
     default: return B2B_EUNSUPPORTED;
   }
-  return (int)cudaGetLastError();
 }
 
 static int launch_sstat(int L, const float* scal, long long N, float* partials, cudaStream_t stream) {

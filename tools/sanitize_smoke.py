@@ -43,6 +43,24 @@ def run(D, N, variant):
 for D, N in [(128, 200), (64, 100), (32, 70), (256, 130), (10, 50)]:
     for variant in (0, 1, 10):
         run(D, N, variant)
+# constant-bank planar chains (device and host parameters, both directions, logpdf) and their reverse mode
+B.lib().b2b_set_kernel_variant(0)
+for D, L, N in [(128, 8, 333), (64, 3, 100), (32, 1, 70)]:
+    pl = [B.PlanarLayer((rng.standard_normal(D) / np.sqrt(D)).astype(f32), (rng.standard_normal(D) / np.sqrt(D)).astype(f32),
+                        rng.standard_normal(1).astype(f32)) for _ in range(L)]
+    flow = B.Composed(*pl)
+    x = B.from_numpy(rng.standard_normal((D, N)).astype(f32))
+    y, lj = B.with_logabsdet_jacobian(flow, x)
+    xi, _ = B.with_logabsdet_jacobian(B.inverse(flow), y)
+    yh, _ = B.with_logabsdet_jacobian(B.Composed(*[l.to("cpu") for l in pl]), x)
+    B.logpdf_sum(B.transformed(B.MvNormal(D), flow), y)
+    yb = B.from_numpy(rng.standard_normal((D, N)).astype(f32))
+    lb = torch.randn(N, device="cuda")
+    B.planar_chain_vjp(flow, x, yb, lb)
+    B.planar_chain_vjp(B.inverse(flow), y, yb, lb)
+    torch.cuda.synchronize()
+    assert float((xi - x).norm() / x.norm()) < 1e-3 and float((yh - y).norm() / y.norm()) < 1e-5
+    print(f"planar const / vjp D={D} L={L} ok")
 bn = B.InvertibleBatchNorm(32, training=True)
 bn.train_forward(B.from_numpy(rng.standard_normal((32, 300)).astype(f32)))
 xh = B.from_numpy(rng.standard_normal((64, 1000)).astype(f32), device="cpu", pin_memory=True)
