@@ -249,6 +249,18 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- same chain with HOST-resident parameters (the reference's own residency): b2b_planar_chain_hostparams_f32 -
+    host_flow = B.Composed(*[lay.to("cpu") for lay in B.flatten(flow)])
+    for _ in range(3):
+        B.run_chain(host_flow, x, y=y, logjac=lj)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        B.run_chain(host_flow, x, y=y, logjac=lj)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_hostparams = e0.elapsed_time(e1) / steps
+
     # ---- per-layer launches (the reference's launch structure: 8 kernels, y and logjac round-trip HBM) ---
     layers = B.flatten(flow)
 
@@ -313,6 +325,9 @@ def main():
                          "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
                          "kernel": "planar_sym_kernel: fused 8-layer chain, 1 launch/step (the timed step also holds its 1-CTA parameter-prep kernel and one 8 KB device-to-device copy into the constant bank)", "algorithmic_bytes_per_launch": bytes_fused,
                          "accounting": "chain-fused: 4*(2D+1) B/sample per launch"},
+            "host_resident_parameters": {"ms_per_step": ms_hostparams, "samples_per_s": NCOLS / (ms_hostparams * 1e-3),
+                                         "frac": NCOLS * 4 * (2 * D + 1) / (ms_hostparams * 1e-3) / 1e9 / peak,
+                                         "api": "b2b_planar_chain_hostparams_f32 (parameters as kernel arguments)"},
             "per_layer_launches": {"ms_per_step": ms_layerwise, "samples_per_s": NCOLS / (ms_layerwise * 1e-3),
                                    "achieved_gbs": bytes_layerwise / (ms_layerwise * 1e-3) / 1e9,
                                    "frac": bytes_layerwise / (ms_layerwise * 1e-3) / 1e9 / peak,

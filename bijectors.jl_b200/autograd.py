@@ -11,6 +11,9 @@ from .interface import Composed, colmajor_empty, inverse, planar_chain_vjp, run_
 from .layers import PlanarLayer
 
 
+_VJP_DIMS = (32, 64, 128)
+
+
 def _colmajor(t: torch.Tensor) -> torch.Tensor:
     """A (D, N) tensor with strides (1, D) (no copy when it already has them)."""
     if t.dim() == 2 and t.stride(0) == 1 and (t.shape[1] == 1 or t.stride(1) == t.shape[0]):
@@ -29,7 +32,7 @@ class _PlanarChainFn(torch.autograd.Function):
         t = inverse(flow) if inv else flow
         xc = _colmajor(x.detach())
         y, lj = run_chain(t, xc)
-        ctx.t, ctx.inv, ctx.L = t, inv, L
+        ctx.t, ctx.inv, ctx.L, ctx.layers = t, inv, L, layers
         ctx.save_for_backward(xc)
         return y, lj
 
@@ -39,7 +42,27 @@ class _PlanarChainFn(torch.autograd.Function):
         D, N = xc.shape
         yb = _colmajor(ybar) if ybar is not None else _colmajor(torch.zeros((D, N), device=xc.device))
         lb = ljbar.contiguous() if ljbar is not None else None
-        xbar, grads = planar_chain_vjp(ctx.t, xc, yb, lb)
+        t = ctx.t
+        Dp = next((d for d in _VJP_DIMS if d >= D), None)
+        if Dp is None:
+            raise NotImplementedError(f"planar VJP kernels cover D <= {_VJP_DIMS[-1]} (got {D})")
+        if Dp != D:
+            # The reverse-mode kernels are built for D in {32, 64, 128}.  A planar layer on zero-padded rows is the same
+            # map (w, u padded with zeros: wᵀz, wᵀu, ‖w‖² and the first D rows of û are unchanged), so smaller flows
+            # (the reference's own example is D = 2, docs/src/flows.md:40-60) run embedded in the next supported D.
+            pad = lambda v: torch.cat([v, v.new_zeros(Dp - D)])
+            layers = [PlanarLayer(pad(l.w), pad(l.u), l.b) for l in ctx.layers]
+            t = inverse(Composed(*layers)) if ctx.inv else Composed(*layers)
+            xp, ybp = colmajor_empty(Dp, N, xc.device), colmajor_empty(Dp, N, xc.device)
+            xp.zero_()
+            ybp.zero_()
+            xp[:D].copy_(xc)
+            ybp[:D].copy_(yb)
+            xc, yb = xp, ybp
+        xbar, grads = planar_chain_vjp(t, xc, yb, lb)
+        if Dp != D:
+            xbar = xbar[:D]
+            grads = [{"w": g["w"][:D], "u": g["u"][:D], "b": g["b"]} for g in grads]
         if ctx.inv:  # application order of inverse(flow) is the flow's layers reversed
             grads = grads[::-1]
         flat: List[torch.Tensor] = []

@@ -1019,3 +1019,28 @@ def test_planar_flow_trains_through_autograd(B):
     yy, ll = flow(x)
     (yy.sum() + ll.sum()).backward()
     assert x.grad is not None and torch.isfinite(x.grad).all()
+
+
+def test_autograd_small_dimension_flow_like_the_reference_example(B):
+    """docs/src/flows.md:40-110 uses PlanarLayer(2) on 1000 points: D = 2 runs embedded in the D = 32 reverse-mode
+    kernels (zero-padded rows leave a planar layer unchanged); gradients equal the oracle's."""
+    import torch
+
+    rng = np.random.default_rng(8)
+    D, N, L = 2, 1000, 2
+    flow = B.autograd.PlanarFlow(D, L, generator=torch.Generator().manual_seed(1))
+    data = B.from_numpy(rng.standard_normal((D, N)).astype(f32))
+    x, lj = flow.inverse(data)
+    loss = -((-0.5 * (x * x).sum(dim=0) - 0.5 * D * math.log(2 * math.pi)) + lj).sum()
+    loss.backward()
+    params = [(w.detach().cpu().numpy().astype(np.float64), u.detach().cpu().numpy().astype(np.float64),
+               b.detach().cpu().numpy().astype(np.float64)) for w, u, b in zip(flow.w, flow.u, flow.b)]
+    y64 = B.to_numpy(data).astype(np.float64)
+    z = y64
+    for (w, u, b) in reversed(params):
+        z, _ = O.planar_inverse(w, u, b, z)
+    _, grads_o = O.planar_inverse_chain_vjp(params, y64, z, -np.ones(N))
+    for l in range(L):
+        assert rel(flow.w[l].grad.cpu().numpy(), grads_o[l][0]) <= 1e-4
+        assert rel(flow.u[l].grad.cpu().numpy(), grads_o[l][1]) <= 1e-4
+        assert abs(float(flow.b[l].grad) - float(grads_o[l][2])) <= 1e-4 * max(1.0, abs(float(grads_o[l][2])))
