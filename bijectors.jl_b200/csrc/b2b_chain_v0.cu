@@ -79,7 +79,10 @@ __global__ void __launch_bounds__(256) chain_v0_kernel(const __grid_constant__ B
   float* sm = reinterpret_cast<float*>(smem4);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int l = warp; l < P.L; l += nwarps) stage_layer(P.layers[l], sm + P.soff[l], P.D, Dp, lane);
+  for (int l = 0; l < P.L; ++l)  // RQS tables: all threads (see stage_rqs_cta)
+    if (P.layers[l].kind == B2B_RQS) stage_rqs_cta(P.layers[l], sm + P.soff[l], P.D, Dp, threadIdx.x, blockDim.x);
+  for (int l = warp; l < P.L; l += nwarps)
+    if (P.layers[l].kind != B2B_RQS) stage_layer(P.layers[l], sm + P.soff[l], P.D, Dp, lane);
   __syncthreads();
 
   const int j = lane & (G - 1), gi = lane / G;

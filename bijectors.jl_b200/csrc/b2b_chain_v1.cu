@@ -223,7 +223,11 @@ struct InterpProg {
   using State = V1NoState;
   const B2BChainParams& P;
   __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
-    for (int l = warp; l < P.L; l += nw) stage_layer(P.layers[l], params + P.soff[l], D, D, lane);
+    // RQS tables are large: all threads of the CTA build them; every other layer is staged by one warp
+    for (int l = 0; l < P.L; ++l)
+      if (P.layers[l].kind == B2B_RQS) stage_rqs_cta(P.layers[l], params + P.soff[l], D, D, warp * 32 + lane, nw * 32);
+    for (int l = warp; l < P.L; l += nw)
+      if (P.layers[l].kind != B2B_RQS) stage_layer(P.layers[l], params + P.soff[l], D, D, lane);
   }
   __device__ __forceinline__ void apply(float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& ctx, const float* params,
                                         float (&lj)[CPT]) const {

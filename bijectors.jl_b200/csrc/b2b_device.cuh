@@ -168,6 +168,37 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// RQS tables staged by ALL threads of the CTA, one (row, knot) pair per thread: the per-warp version below walks the
+// KP knots of a row serially (KP x ~8 dependent-latency global loads and two divisions: ~15 us, a fifth of the
+// RQS kernel's run time with the other warps idle at the barrier).  Same table layout as stage_layer(B2B_RQS).
+__device__ inline void stage_rqs_cta(const b2b_layer_desc& d, float* sm, int D, int Dp, int tid, int nthreads) {
+  const int K1 = d.n0, KP = rqs_kp(K1);
+  float* Sw = sm;
+  float* Sh = sm + Dp * KP;
+  float4* cf = reinterpret_cast<float4*>(sm + 2 * Dp * KP);
+  const float inf = __int_as_float(0x7f800000);
+  for (int idx = tid; idx < Dp * KP; idx += nthreads) {
+    const int k = idx / Dp, i = idx - k * Dp;  // consecutive threads -> consecutive rows (coalesced parameter reads)
+    const bool in = i < D, kin = k < K1;
+    Sw[i * KP + k] = kin ? (in ? d.p0[(size_t)k * D + i] : 0.f) : inf;
+    Sh[i * KP + k] = kin ? (in ? d.p1[(size_t)k * D + i] : 0.f) : inf;
+    if (!kin) continue;
+    float w_k = 0.f, w = 1.f, h_k = 0.f, dy = 1.f, d_k = 1.f, d_k1 = 1.f;
+    if (in) {
+      const float Wl = d.p0[(size_t)(K1 - 1) * D + i], Hl = d.p1[(size_t)(K1 - 1) * D + i];
+      w_k = k == 0 ? -Wl : d.p0[(size_t)(k - 1) * D + i];              // rational_quadratic_spline.jl:331
+      w = d.p0[(size_t)k * D + i] - w_k;                               // :332
+      h_k = k == 0 ? -Hl : d.p1[(size_t)(k - 1) * D + i];              // :335
+      dy = d.p1[(size_t)k * D + i] - h_k;                              // :336
+      d_k = k == 0 ? 1.0f : d.p2[(size_t)(k - 1) * D + i];             // :342
+      d_k1 = k == K1 - 1 ? 1.0f : d.p2[(size_t)k * D + i];             // :343
+    }
+    const float sl = dy / w;                                           // :339
+    cf[(size_t)(i * K1 + k) * 2 + 0] = make_float4(w_k, 1.0f / w, w, h_k);
+    cf[(size_t)(i * K1 + k) * 2 + 1] = make_float4(dy, sl, d_k, d_k1 + d_k - 2.0f * sl);
+  }
+}
+
 // Executed by ONE warp per layer (different warps stage different layers concurrently).
 __device__ inline void stage_layer(const b2b_layer_desc& d, float* sm, int D, int Dp, int lane) {
   switch (d.kind) {
