@@ -67,3 +67,36 @@ def sharded_logpdf_sum(td, y_local: torch.Tensor, comm: Optional[Communicator]) 
     if comm is not None and comm.world > 1:
         comm.allreduce_sum_(total.reshape(1))
     return total
+
+
+def pack_param_grads(grads) -> torch.Tensor:
+    """[{"w", "u", "b"}, ...] -> one float64 vector (w_1 | u_1 | b_1 | w_2 | ...): the payload of the training path's
+    single exchange, the sum of the parameter cotangents over the column shards."""
+    return torch.cat([torch.cat([g["w"].reshape(-1), g["u"].reshape(-1), g["b"].reshape(-1)]) for g in grads]).to(torch.float64)
+
+
+def unpack_param_grads(buf: torch.Tensor, like) -> list:
+    """Inverse of pack_param_grads (shapes / dtypes taken from `like`)."""
+    out, off = [], 0
+    for g in like:
+        item = {}
+        for k in ("w", "u", "b"):
+            n = g[k].numel()
+            item[k] = buf[off:off + n].to(g[k].dtype).reshape(g[k].shape)
+            off += n
+        out.append(item)
+    return out
+
+
+def sharded_planar_chain_vjp(t, x_local: torch.Tensor, ybar_local: torch.Tensor, ljbar_local, comm: Optional[Communicator]):
+    """Reverse mode of a planar chain over column shards: every rank runs b2b_planar_chain_vjp_f32 on its columns
+    (x̄ stays local -- it is a per-column quantity), then ONE all-reduce sums the 2·L·D + L parameter cotangents
+    (data-parallel training's only exchange; the reference is single-process and has no counterpart)."""
+    from .interface import planar_chain_vjp
+
+    xbar, grads = planar_chain_vjp(t, x_local, ybar_local, ljbar_local)
+    if comm is not None and comm.world > 1:
+        buf = pack_param_grads(grads)
+        comm.allreduce_sum_(buf)
+        grads = unpack_param_grads(buf, grads)
+    return xbar, grads

@@ -51,6 +51,19 @@ def main():
 
     assert rel(B.to_numpy(yb), yo[:, lo:hi]) <= 1e-5 and rel(B.to_numpy(ljb), ljo[lo:hi]) <= 1e-5
     assert rel(B.to_numpy(bn.m), m1) <= 1e-5 and rel(B.to_numpy(bn.v), v1) <= 1e-5
+    # reverse mode over column shards: local VJP kernels + ONE all-reduce of the 2·L·D + L parameter cotangents
+    from bijectors_jl_b200.distributed import sharded_planar_chain_vjp
+
+    x = rng.standard_normal((D, N)).astype(f32)
+    ybar, ljbar = rng.standard_normal((D, N)).astype(f32), rng.standard_normal(N).astype(f32)
+    xbar, grads = sharded_planar_chain_vjp(flow, B.from_numpy(x[:, lo:hi]), B.from_numpy(ybar[:, lo:hi]),
+                                           torch.from_numpy(ljbar[lo:hi]).cuda(), comm)
+    p64 = [tuple(a.astype(np.float64) for a in p) for p in params]
+    xb_o, g_o = O.planar_chain_vjp(p64, x.astype(np.float64), ybar.astype(np.float64), ljbar.astype(np.float64))
+    assert rel(B.to_numpy(xbar), xb_o[:, lo:hi]) <= 1e-5
+    for l in range(len(params)):
+        assert rel(grads[l]["w"].cpu().numpy(), g_o[l][0]) <= 2e-5 and rel(grads[l]["u"].cpu().numpy(), g_o[l][1]) <= 2e-5
+        assert abs(float(grads[l]["b"]) - float(g_o[l][2])) <= 2e-5 * max(abs(float(g_o[l][2])), np.sqrt(N))
     comm.close()
     dist.barrier()
     if rank == 0:

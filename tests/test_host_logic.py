@@ -194,6 +194,22 @@ def _gloo_worker(rank, world, port, out):
         total = comm.allreduce_sum_(local.reshape(1))  # ... and ONE scalar is summed across ranks
         full = O.transformed_logpdf(layers, None, None, y).sum()
         assert abs(float(total) - full) <= 1e-9 * abs(full)
+        # the training path's exchange: parameter cotangents of column shards sum to the full-batch cotangents
+        from bijectors_jl_b200.distributed import pack_param_grads, unpack_param_grads
+
+        ybar, ljbar = rng.standard_normal((D, N)), rng.standard_normal(N)
+        ps = [(w, u, b), (u * 0.5, w * 0.7, b + 0.1)]
+        _, g_loc = O.planar_chain_vjp(ps, y[:, lo:hi], ybar[:, lo:hi], ljbar[lo:hi])
+        as_dict = [{"w": torch.tensor(gw), "u": torch.tensor(gu), "b": torch.tensor([gb])} for gw, gu, gb in g_loc]
+        buf = pack_param_grads(as_dict)
+        assert buf.dtype == torch.float64 and buf.numel() == 2 * (2 * D + 1)
+        comm.allreduce_sum_(buf)
+        g_sum = unpack_param_grads(buf, as_dict)
+        _, g_full = O.planar_chain_vjp(ps, y, ybar, ljbar)
+        for l in range(2):
+            assert np.allclose(g_sum[l]["w"].numpy(), g_full[l][0], rtol=1e-10, atol=1e-12)
+            assert np.allclose(g_sum[l]["u"].numpy(), g_full[l][1], rtol=1e-10, atol=1e-12)
+            assert np.allclose(g_sum[l]["b"].numpy(), g_full[l][2], rtol=1e-10, atol=1e-12)
         if rank == 0:
             out.put(float(total))
     finally:
