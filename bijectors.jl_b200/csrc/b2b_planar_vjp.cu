@@ -574,6 +574,8 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
   q.partials = nullptr;
   if (v1_check_io(q) != 0) return B2B_EUNSUPPORTED;
   if ((ldyb % 4) || (reinterpret_cast<uintptr_t>(ybar) & 15) || !xbar) return B2B_EUNSUPPORTED;
+  // the parameter pass re-reads ybar: it must not have been overwritten by xbar
+  if (wbar && ubar && bbar && xbar == ybar) return B2B_EINVAL;
   if (!workspace || workspace_bytes < b2b_planar_vjp_workspace(n, D, p.N)) return B2B_EWORKSPACE;
   char* wsb = static_cast<char*>(workspace);
   wsb += (256 - (reinterpret_cast<uintptr_t>(wsb) & 255)) & 255;
@@ -609,7 +611,6 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
   // ybar has been overwritten -- aliasing is therefore only allowed when the caller does not want parameter gradients.
   int nl = 2;
   if (wbar && ubar && bbar) {
-    if (xbar == ybar) return B2B_EINVAL;
     if (D == 128) rc = launch_pgrad<128>(Lp, p.x, ybar, ws.scal, p.N, p.ldx, ldyb, ws.pg_partials, stream);
     else if (D == 64) rc = launch_pgrad<64>(Lp, p.x, ybar, ws.scal, p.N, p.ldx, ldyb, ws.pg_partials, stream);
     else rc = launch_pgrad<32>(Lp, p.x, ybar, ws.scal, p.N, p.ldx, ldyb, ws.pg_partials, stream);
