@@ -135,6 +135,22 @@ end
 with_logabsdet_jacobian(b::Union{HostPlanar,ComposedFunction}, x::CuMatrix{Float32}) =
     all_host_planar(b) ? planar_hostparams(b, x) : run_chain(descs(b, false), x)
 
+# Reverse mode: a ChainRulesCore.rrule for device planar chains (what ext/BijectorsChainRulesCoreExt.jl does for the CPU
+# path, incl. the implicit find_alpha rule :42-46).  ȳ, l̄ are the cotangents of (y, logjac).
+function planar_chain_vjp(f, x::CuMatrix{Float32}, ȳ::CuMatrix{Float32}, l̄::CuVector{Float32}; inv::Bool=false)
+    ds = descs(f, inv)
+    L, (D, N) = length(ds), size(x)
+    x̄ = similar(x); w̄ = CUDA.zeros(Float32, D, L); ū = CUDA.zeros(Float32, D, L); b̄ = CUDA.zeros(Float32, L)
+    nbytes = ccall((:b2b_planar_chain_vjp_workspace_bytes, libb2b), Csize_t, (Int32, Int32, Int64), L, D, N)
+    ws = CuVector{UInt8}(undef, nbytes)
+    GC.@preserve ds ws check(ccall((:b2b_planar_chain_vjp_f32, libb2b), Cint,
+        (Ptr{LayerDesc}, Int32, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32},
+         CuPtr{Float32}, CuPtr{Float32}, Int32, Int64, Int64, Int64, Int64, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        ds, L, pointer(x), pointer(ȳ), pointer(l̄), pointer(x̄), pointer(w̄), pointer(ū), pointer(b̄),
+        D, N, stride(x, 2), stride(ȳ, 2), stride(x̄, 2), pointer(ws), nbytes, stream_handle()))
+    return x̄, w̄, ū, b̄        # column l of w̄ / ū and b̄[l] belong to the l-th applied layer
+end
+
 # logpdf(td::MvTransformed, y::Matrix) (src/transformed_distribution.jl:165-169): inverse chain + base
 # MvNormal + (optionally) the batch sum in ONE fused launch per fusable segment.
 function Distributions.logpdf(td::TransformedDistribution{<:MvNormal}, y::CuMatrix{Float32})

@@ -234,3 +234,14 @@ def test_sharded_logdensity_sum_gloo_world2():
         p.join(120)
         assert p.exitcode == 0
     assert math.isfinite(out.get(timeout=5))
+
+
+def test_autograd_module_is_importable_without_a_gpu():
+    """The torch.autograd glue builds parameters with the reference's shapes (planar_layer.jl:23-28); evaluating it
+    needs the device path (no CPU fallback)."""
+    flow = B.autograd.PlanarFlow(5, 3, device="cpu", generator=torch.Generator().manual_seed(0))
+    assert [tuple(p.shape) for p in flow.w] == [(5,)] * 3 and [tuple(p.shape) for p in flow.b] == [(1,)] * 3
+    assert len(list(flow.parameters())) == 9 and all(p.requires_grad for p in flow.parameters())
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            flow(torch.zeros(5, 4))
