@@ -25,12 +25,13 @@ def main(path):
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
         print("kernel:", d.get("Kernel Name"))
-        rd = float(d.get("dram__bytes_read.sum", 0) or 0)
-        wr = float(d.get("dram__bytes_write.sum", 0) or 0)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd = float(d.get("dram__bytes_read.sum", 0) or 0) * scale.get(u.get("dram__bytes_read.sum", "byte"), 1.0) / 1e6
+        wr = float(d.get("dram__bytes_write.sum", 0) or 0) * scale.get(u.get("dram__bytes_write.sum", "byte"), 1.0) / 1e6
         for k in KEYS:
             if k in d and d[k] != "":
                 print(f"  {k} = {d[k]} {u[k]}")
-        print(f"  dram traffic (read+write) = {rd + wr:.3f} {u.get('dram__bytes_read.sum', '')}")
+        print(f"  dram traffic (read+write) = {rd + wr:.3f} Mbyte")
         for k in hdr:
             if "issue_stalled" in k and "per_issue_active" in k:
                 try:
