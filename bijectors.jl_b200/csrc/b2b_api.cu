@@ -92,11 +92,11 @@ static thread_local int g_fused_launches = 1;
 static int launch_fused(B2BChainParams& p, cudaStream_t stream) {
   int rc = B2B_EUNSUPPORTED;
   g_fused_launches = 1;
-  // segments made of <= 8 PlanarLayers: parameters through the constant bank (variant 3 forces, 1 / 2 disable)
+  // segments made of <= 8 PlanarLayers: the unrolled planar kernel (variant 3 forces, 1 / 2 disable)
   if (g_variant == 0 || g_variant == 3) {
     rc = b2b_launch_planar_chain_const(p, stream);
     if (rc == B2B_OK) {
-      g_fused_launches = 2;  // parameter preparation kernel + main kernel (plus one 8 KB device-to-device copy)
+      g_fused_launches = 1;
       return rc;
     }
     if (g_variant == 3 || rc != B2B_EUNSUPPORTED) return rc;

@@ -1,19 +1,18 @@
-// Chains of PlanarLayers with their (derived) parameters in the CONSTANT BANK.
+// Chains of <= 8 PlanarLayers as ONE UNROLLED program on the TMA pipeline (b2b_v1_pipeline.cuh).
 //
-// Why: in the layer interpreter (b2b_chain_v1.cu) every parameter element is a warp-uniform LDS broadcast and the
-// 8-layer D = 128 headline chain is bound by LSU wavefronts (~70 % of the HBM roofline).  A constant-bank operand
-// reaches FFMA2 through a uniform register (LDCU -> UR) and costs no LSU work, but the first-level constant cache
-// only holds ~4 KB.  So: chains whose w and û fit in 4 KB read both from the constant bank (MODE 0); the 8-layer
-// D = 128 chain (8 KB) keeps w in shared memory and û in the constant bank (MODE 2), splitting the operand traffic
-// over both paths -- 86 % of the roofline instead of 72 %.
-//
-// Two parameter sources share the per-tile program:
-//   ArgSrc  parameters in HOST memory (b2b_planar_chain_hostparams_f32): derived on the host, passed BY VALUE as
-//           kernel arguments (bank 0).  No device-side preparation at all.
-//   SymSrc  parameters in DEVICE memory (b2b_chain_run_f32 segments made of PlanarLayers only): a one-CTA kernel
-//           derives û / wᵀû into a staging buffer, cudaMemcpyToSymbolAsync moves it into a __constant__ array
-//           (stream-ordered, so the constant cache is coherent), then the main kernel runs.  The symbol is per-device
-//           library state: launches that use it are serialised by an event (same stream: free).
+// Why: the layer interpreter (b2b_chain_v1.cu) runs the 8-layer D = 128 headline chain at 72 % of the HBM roofline
+// (rolled layer loop, switch on the layer kind, generic fragment mapping).  Specialising the program on (D, L,
+// direction) and unrolling the layers reaches 85-89 %.  Parameter operands:
+//   device-resident parameters (DevSrc, every b2b_chain_run_f32 segment made of PlanarLayers): each CTA derives û /
+//       wᵀû in its prologue into shared memory and all operands are warp-uniform LDS broadcasts -- one launch, no
+//       library-owned device state;
+//   host-resident parameters (ArgSrc, b2b_planar_chain_hostparams_f32): derived on the host, passed BY VALUE as kernel
+//       arguments, i.e. CONSTANT-BANK operands (LDCU -> uniform register -> FFMA2: no LSU work).  The first-level
+//       constant cache holds ~4 KB, so the 8 KB of an 8-layer D = 128 chain is split: w in shared memory, û in the
+//       constant bank (MODE 2).  This is the fastest form (88-89 %).
+// A __constant__ slot filled per call from device parameters (prep kernel + copy) was measured too: the extra
+// launch + copy-engine hop costs 13 us per call, more than constant operands gain over shared-memory ones at D >= 64.
+// (The reverse-mode kernels in b2b_planar_vjp.cu still use such a slot.)
 //
 // Reference semantics: planar_layer.jl:65-80 (get_u_hat, forward), :102-110 (logabsdetjac), :112-127 + :160-185
 // (inverse through find_alpha).
@@ -28,6 +27,7 @@ struct PlanarHP {
 
 template <int D, int L>
 struct ArgSrc {
+  static constexpr bool kDerive = false;
   const PlanarHP<D, L>& H;
   int invmask;
   __device__ __forceinline__ float w(int l, int i) const { return H.v[l * D + i]; }
@@ -43,38 +43,92 @@ struct ArgSrc {
 // DIR 0: every layer forward, 1: every layer inverse, 2: per-layer direction from the mask.  The unrolled program of
 // 8 layers is large; carrying the (unused) root-finder of the other direction in the hot path costs a quarter of the
 // forward throughput in instruction-cache misses, so the pure directions get their own kernels.
-// MVN: the chain ends in the base MvNormal log-density (P.layers[0] holds its descriptor): logpdf(td, y).
+// Device-resident parameters: the kernel derives û / wᵀû itself (get_u_hat, planar_layer.jl:65-70, one warp per layer
+// in the prologue of every CTA) into shared memory and runs the unrolled program on the shared-memory copy -- one
+// launch, no library-owned device state.  (Measured: for the unrolled program the shared-memory operands are as fast
+// as the constant-bank ones at D >= 64 -- 85 % vs 86 % of the roofline at D = 128 -- and a separate preparation
+// kernel + copy into a __constant__ slot costs 13 us per call, more than it gains.)
+template <int D, int L>
+struct DevSrc {
+  static constexpr bool kDerive = true;
+  int invmask, nreal;
+  __device__ __forceinline__ bool inv(int l) const { return (invmask >> l) & 1; }
+};
+
+// MVN: the chain ends in the base MvNormal log-density (descriptor P.layers[nreal]): logpdf(td, y).
 template <int D, int L, int MODE, int DIR, bool MVN, class Src>
 struct PlanarConstProg {
   using State = V1NoState;
   const Src src;
   const B2BChainParams& P;
-  static constexpr int MVN_OFF = MODE ? L * D : 0;
+  static constexpr bool DERIVE = Src::kDerive;
+  static constexpr int NPK = 2 * L * D + 2 * L;                    // packed w | û | c | b
+  static constexpr bool STAGED = MODE != 0 || DERIVE;
+  static constexpr int MVN_OFF = STAGED ? ((NPK + 3) & ~3) : 0;
+  static constexpr int SMEM_FLOATS = MVN_OFF + (MVN ? 2 * D + 4 : 0);
   __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
-    if (MVN && warp == nw - 1) stage_layer(P.layers[0], params + MVN_OFF, D, D, lane);
-    if constexpr (MODE != 0) {
-      for (int i = warp * 32 + lane; i < L * D; i += nw * 32) params[i] = src.raw((MODE == 1 ? L * D : 0) + i);
+    if constexpr (DERIVE) {
+      if (MVN && warp == nw - 1) stage_layer(P.layers[src.nreal], params + MVN_OFF, D, D, lane);
+      for (int l = warp; l < L; l += nw) {
+        float* w_out = params + l * D;
+        float* u_out = params + L * D + l * D;
+        if (l >= src.nreal) {  // identity padding
+          for (int i = lane; i < D; i += 32) w_out[i] = u_out[i] = 0.f;
+          if (lane == 0) params[2 * L * D + l] = params[2 * L * D + L + l] = 0.f;
+          continue;
+        }
+        const b2b_layer_desc& d = P.layers[l];
+        float s = 0.f, q = 0.f;
+        for (int i = lane; i < D; i += 32) {
+          const float w = d.p0[i], u = d.p1[i];
+          s = fmaf(w, u, s);
+          q = fmaf(w, w, q);
+        }
+        s = warp_sum(s);
+        q = warp_sum(q);
+        const float k = (softplus(-s) - 1.0f) / q;  // planar_layer.jl:67
+        for (int i = lane; i < D; i += 32) {
+          const float w = d.p0[i];
+          w_out[i] = w;
+          u_out[i] = fmaf(k, w, d.p1[i]);
+        }
+        if (lane == 0) {
+          params[2 * L * D + l] = softplus(s) - 1.0f;  // wᵀû, planar_layer.jl:68
+          params[2 * L * D + L + l] = d.p2[0];          // first(flow.b), :75
+        }
+      }
+    } else if constexpr (STAGED) {
+      for (int i = warp * 32 + lane; i < NPK; i += nw * 32) params[i] = src.raw(i);
     }
   }
-  __device__ __forceinline__ void apply(float2 (&x)[1][D / 2], const ColCtx<D, 1>& ctx, const float* params,
-                                        float (&lj)[1]) const {
+
+  template <bool WS, bool US, bool SS>
+  __device__ __forceinline__ void layers(float2 (&x)[1][D / 2], const float* params, float (&lj)[1]) const {
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      const float4* sp4 = reinterpret_cast<const float4*>(params + l * D);
+      const float4* w4 = reinterpret_cast<const float4*>(params + l * D);
+      const float4* u4 = reinterpret_cast<const float4*>(params + L * D + l * D);
       float2 acc[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < D / 4; ++i) {
         float4 w;
-        if (MODE == 2) w = sp4[i];
+        if constexpr (WS) w = w4[i];
         else w = make_float4(src.w(l, 4 * i), src.w(l, 4 * i + 1), src.w(l, 4 * i + 2), src.w(l, 4 * i + 3));
         acc[(i & 1) * 2 + 0] = __ffma2_rn(make_float2(w.x, w.y), x[0][2 * i], acc[(i & 1) * 2 + 0]);
         acc[(i & 1) * 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), x[0][2 * i + 1], acc[(i & 1) * 2 + 1]);
       }
       const float2 s = __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
       const float wz = s.x + s.y;  // aT_b(w, z), utils.jl:2
-      const float cc_ = src.c(l), bb = src.b(l);
+      float cc_, bb;
+      if constexpr (SS) {
+        cc_ = params[2 * L * D + l];
+        bb = params[2 * L * D + L + l];
+      } else {
+        cc_ = src.c(l);
+        bb = src.b(l);
+      }
       float t, s2;
       if (DIR == 0 || (DIR == 2 && !src.inv(l))) {
         tanh_sech2(wz + bb, t, s2);
@@ -88,12 +142,18 @@ struct PlanarConstProg {
 #pragma unroll
       for (int i = 0; i < D / 4; ++i) {
         float4 u;
-        if (MODE == 1) u = sp4[i];
+        if constexpr (US) u = u4[i];
         else u = make_float4(src.uh(l, 4 * i), src.uh(l, 4 * i + 1), src.uh(l, 4 * i + 2), src.uh(l, 4 * i + 3));
         x[0][2 * i] = __ffma2_rn(make_float2(u.x, u.y), t2, x[0][2 * i]);  // planar_layer.jl:78 / :124
         x[0][2 * i + 1] = __ffma2_rn(make_float2(u.z, u.w), t2, x[0][2 * i + 1]);
       }
     }
+  }
+
+  __device__ __forceinline__ void apply(float2 (&x)[1][D / 2], const ColCtx<D, 1>& ctx, const float* params,
+                                        float (&lj)[1]) const {
+    if constexpr (DERIVE) layers<true, true, true>(x, params, lj);
+    else layers<MODE == 2, MODE == 1, false>(x, params, lj);
     if (MVN) mvnormal_apply<D, 1, 1>(x, ctx, params + MVN_OFF, lj);
   }
 };
@@ -107,12 +167,12 @@ __global__ void __launch_bounds__(NW * 32, 1)
   v1_run<D, 1, 1, NW>(P, E, map_x, map_y, prog);
 }
 
-template <int D, int L, int NW, int MODE, int DIR, bool MVN>
+template <int D, int L, int NW, int DIR, bool MVN>
 __global__ void __launch_bounds__(NW * 32, 1)
-    planar_sym_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
+    planar_dev_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
                       const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
-                      const float* stage, const int invmask) {
-  const PlanarConstProg<D, L, MODE, DIR, MVN, SymSrc<D, L>> prog{{stage, invmask}, P};
+                      const int invmask, const int nreal) {
+  const PlanarConstProg<D, L, 0, DIR, MVN, DevSrc<D, L>> prog{{invmask, nreal}, P};
   v1_run<D, 1, 1, NW>(P, E, map_x, map_y, prog);
 }
 
@@ -131,68 +191,93 @@ static int launch_arg(const B2BChainParams& q, const V1Geom& g, const CUtensorMa
   return (int)cudaGetLastError();
 }
 
-template <int D, int L, int NW, int MODE, int DIR, bool MVN = false>
-static int launch_sym(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
-                      const float* stage, int invmask, cudaStream_t stream) {
-  auto kernel = planar_sym_kernel<D, L, NW, MODE, DIR, MVN>;
+template <int D, int L, int NW, int DIR, bool MVN = false>
+static int launch_dev(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
+                      int nreal, int invmask, cudaStream_t stream) {
+  auto kernel = planar_dev_kernel<D, L, NW, DIR, MVN>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
-  kernel<<<g.grid, NW * 32, g.smem, stream>>>(q, g.extra, mx, my, stage, invmask);
+  kernel<<<g.grid, NW * 32, g.smem, stream>>>(q, g.extra, mx, my, invmask, nreal);
   return (int)cudaGetLastError();
 }
 
-// dispatch over (D, L, MODE, DIR) for either source
-template <bool SYM, int D, int NW, int LL, int MM>
-static int dispatch_dir(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
-                        const float* params, int invmask, cudaStream_t stream) {
+// ---- host-resident parameters: dispatch over (D, L, MODE, DIR) -------------------------------------------------
+template <int D, int NW, int LL, int MM>
+static int dispatch_arg_dir(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
+                            const float* packed, int invmask, cudaStream_t stream) {
   const int all = (1 << LL) - 1;
   const int dir = (invmask & all) == 0 ? 0 : ((invmask & all) == all ? 1 : 2);
-  if (q.L == 1) {  // terminal MvNormal (device-resident parameters, all-inverse chains only)
-    if constexpr (SYM) {
-      if (dir == 1) return launch_sym<D, LL, NW, MM, 1, true>(q, g, mx, my, params, invmask, stream);
-    }
+  if (dir == 0) return launch_arg<D, LL, NW, MM, 0>(q, g, mx, my, packed, invmask, stream);
+  if (dir == 1) return launch_arg<D, LL, NW, MM, 1>(q, g, mx, my, packed, invmask, stream);
+  return launch_arg<D, LL, NW, MM, 2>(q, g, mx, my, packed, invmask, stream);
+}
+
+template <int D, int NW>
+static int dispatch_arg(int L, int mode, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx,
+                        const CUtensorMap& my, const float* packed, int invmask, cudaStream_t stream) {
+  if (L == 1 && mode == 0) return dispatch_arg_dir<D, NW, 1, 0>(q, g, mx, my, packed, invmask, stream);
+  if (L == 2 && mode == 0) return dispatch_arg_dir<D, NW, 2, 0>(q, g, mx, my, packed, invmask, stream);
+  if (L == 4 && mode == 0) return dispatch_arg_dir<D, NW, 4, 0>(q, g, mx, my, packed, invmask, stream);
+  if constexpr (2 * D * 8 * 4 > 4096) {
+    if (L == 8 && mode == 2) return dispatch_arg_dir<D, NW, 8, 2>(q, g, mx, my, packed, invmask, stream);
+  } else {
+    if (L == 8 && mode == 0) return dispatch_arg_dir<D, NW, 8, 0>(q, g, mx, my, packed, invmask, stream);
+  }
+  return B2B_EUNSUPPORTED;
+}
+
+// ---- device-resident parameters: dispatch over (D, L, DIR, MVN) --------------------------------------------------
+template <int D, int NW, int LL>
+static int dispatch_dev_dir(const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
+                            int nreal, int invmask, bool mvn, cudaStream_t stream) {
+  const int all = (1 << LL) - 1;
+  const int dir = (invmask & all) == 0 ? 0 : ((invmask & all) == all ? 1 : 2);
+  if (mvn) {  // terminal MvNormal: all-inverse chains only (= logpdf(td, y))
+    if (dir == 1) return launch_dev<D, LL, NW, 1, true>(q, g, mx, my, nreal, invmask, stream);
     return B2B_EUNSUPPORTED;
   }
-#define B2B_HP_DIR(DD)                                                                                   \
-  if (dir == DD)                                                                                         \
-    return SYM ? launch_sym<D, LL, NW, MM, DD>(q, g, mx, my, params, invmask, stream)                    \
-               : launch_arg<D, LL, NW, MM, DD>(q, g, mx, my, params, invmask, stream);
-  B2B_HP_DIR(0)
-  B2B_HP_DIR(1)
-  B2B_HP_DIR(2)
-#undef B2B_HP_DIR
-  return B2B_EUNSUPPORTED;
+  if (dir == 0) return launch_dev<D, LL, NW, 0>(q, g, mx, my, nreal, invmask, stream);
+  if (dir == 1) return launch_dev<D, LL, NW, 1>(q, g, mx, my, nreal, invmask, stream);
+  return launch_dev<D, LL, NW, 2>(q, g, mx, my, nreal, invmask, stream);
 }
 
-template <bool SYM, int D, int NW>
-static int dispatch_L(int L, int mode, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx,
-                      const CUtensorMap& my, const float* params, int invmask, cudaStream_t stream) {
-  if (L == 1 && mode == 0) return dispatch_dir<SYM, D, NW, 1, 0>(q, g, mx, my, params, invmask, stream);
-  if (L == 2 && mode == 0) return dispatch_dir<SYM, D, NW, 2, 0>(q, g, mx, my, params, invmask, stream);
-  if (L == 4 && mode == 0) return dispatch_dir<SYM, D, NW, 4, 0>(q, g, mx, my, params, invmask, stream);
-  if constexpr (2 * D * 8 * 4 > 4096) {
-    if (L == 8 && mode == 2) return dispatch_dir<SYM, D, NW, 8, 2>(q, g, mx, my, params, invmask, stream);
-  } else {
-    if (L == 8 && mode == 0) return dispatch_dir<SYM, D, NW, 8, 0>(q, g, mx, my, params, invmask, stream);
+template <int D, int NW>
+static int dispatch_dev(int L, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& my,
+                        int nreal, int invmask, bool mvn, cudaStream_t stream) {
+  switch (L) {
+    case 1: return dispatch_dev_dir<D, NW, 1>(q, g, mx, my, nreal, invmask, mvn, stream);
+    case 2: return dispatch_dev_dir<D, NW, 2>(q, g, mx, my, nreal, invmask, mvn, stream);
+    case 4: return dispatch_dev_dir<D, NW, 4>(q, g, mx, my, nreal, invmask, mvn, stream);
+    case 8: return dispatch_dev_dir<D, NW, 8>(q, g, mx, my, nreal, invmask, mvn, stream);
+    default: return B2B_EUNSUPPORTED;
   }
-  return B2B_EUNSUPPORTED;
 }
 
-template <bool SYM>
-static int launch_planar_const(const B2BChainParams& p, int L, const float* params, int invmask, cudaStream_t stream) {
-  B2BChainParams q = p;  // q.L: 0, or 1 when q.layers[0] is the terminal MvNormal
+// `packed` != NULL: host-resident parameters (kernel arguments); NULL: device-resident (p.layers[0..nreal), derived in
+// the kernel; p.layers[nreal] = terminal MvNormal when `mvn`).  L = padded layer count (1, 2, 4, 8).
+static int launch_planar_unrolled(const B2BChainParams& p, int L, const float* packed, int nreal, int invmask, bool mvn,
+                                  cudaStream_t stream) {
+  B2BChainParams q = p;
   q.scratch_off = -1;
   if (!(q.D == 32 || q.D == 64 || q.D == 128)) return B2B_EUNSUPPORTED;
   if (v1_check_io(q) != 0) return B2B_EUNSUPPORTED;
   const HPShape sh = hp_shape(q.D, L);
   V1Geom g;
-  const int rc = v1_geometry(q.D, q.N, sh.nw, 32, (sh.mode ? (size_t)L * q.D : 0) + (q.L ? 2 * q.D + 4 : 0), g);
+  // shared memory: the packed parameter block when it is staged (MODE != 0, or device-resident parameters)
+  const bool staged = sh.mode != 0 || !packed;
+  const size_t pf = (staged ? (size_t)((2 * L * q.D + 2 * L + 3) & ~3) : 0) + (mvn ? 2 * q.D + 4 : 0);
+  const int rc = v1_geometry(q.D, q.N, sh.nw, 32, pf, g);
   if (rc != 0) return rc;
   CUtensorMap mx, my;
   if (!make_maps(q, g.cols, &mx, &my, &g.extra.tma3d)) return B2B_EUNSUPPORTED;
-  if (q.D == 128) return dispatch_L<SYM, 128, 8>(L, sh.mode, q, g, mx, my, params, invmask, stream);
-  if (q.D == 64) return dispatch_L<SYM, 64, 12>(L, sh.mode, q, g, mx, my, params, invmask, stream);
-  return dispatch_L<SYM, 32, 16>(L, sh.mode, q, g, mx, my, params, invmask, stream);
+  if (packed) {
+    if (q.D == 128) return dispatch_arg<128, 8>(L, sh.mode, q, g, mx, my, packed, invmask, stream);
+    if (q.D == 64) return dispatch_arg<64, 12>(L, sh.mode, q, g, mx, my, packed, invmask, stream);
+    return dispatch_arg<32, 16>(L, sh.mode, q, g, mx, my, packed, invmask, stream);
+  }
+  if (q.D == 128) return dispatch_dev<128, 8>(L, q, g, mx, my, nreal, invmask, mvn, stream);
+  if (q.D == 64) return dispatch_dev<64, 12>(L, q, g, mx, my, nreal, invmask, mvn, stream);
+  return dispatch_dev<32, 16>(L, q, g, mx, my, nreal, invmask, mvn, stream);
 }
 
 }  // namespace b2b
@@ -209,12 +294,10 @@ int b2b_planar_const_grid_size(const B2BChainParams& p) {
 // `L` (1, 2, 4 or 8) planar layers, derived parameters packed for (D, L) in HOST memory -> kernel arguments
 int b2b_launch_planar_hostparams(const B2BChainParams& p, int L, const float* packed, int invmask,
                                  cudaStream_t stream) {
-  B2BChainParams q = p;
-  q.L = 0;
-  return b2b::launch_planar_const<false>(q, L, packed, invmask, stream);
+  return b2b::launch_planar_unrolled(p, L, packed, L, invmask, false, stream);
 }
 
-// Applicability of the constant-bank path to a fusable segment: 1..8 PlanarLayers, optionally followed by the
+// Applicability of the unrolled planar kernels to a fusable segment: 1..8 PlanarLayers, optionally followed by the
 // terminal MvNormal when every planar layer is inverse (= logpdf(td, y)); D in {32,64,128}; 16-byte aligned batches.
 // Returns the number of planar layers, 0 when not applicable.
 int b2b_planar_const_layers(const B2BChainParams& p) {
@@ -231,7 +314,7 @@ int b2b_planar_const_layers(const B2BChainParams& p) {
   return n;
 }
 
-// prep kernel -> staging buffer -> __constant__ symbol -> main kernel.  B2B_EUNSUPPORTED when not applicable.
+// One launch of the unrolled kernel with in-kernel parameter derivation.  B2B_EUNSUPPORTED when not applicable.
 int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream) {
   using namespace b2b;
   const int n = b2b_planar_const_layers(p);
@@ -243,24 +326,5 @@ int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream) 
   while (Lp < n) Lp <<= 1;
   // identity padding is its own inverse: an all-inverse chain stays all-inverse (the single-direction kernel)
   if (invmask == (1 << n) - 1) invmask = (1 << Lp) - 1;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return B2B_EUNSUPPORTED;
-  SlotState& st = g_slots[dev];
-  std::lock_guard<std::mutex> lock(st.mu);
-  cudaError_t e;
-  {
-    const int rcp = planar_slot_prepare(st, p, n, Lp, stream);
-    if (rcp != 0) return rcp;
-  }
-  B2BChainParams q = p;
-  q.L = 0;
-  if (p.L > n) {
-    q.L = 1;
-    q.layers[0] = p.layers[p.L - 1];
-  }
-  const int rc = launch_planar_const<true>(q, Lp, st.stage, invmask, stream);
-  if (rc != B2B_OK) return rc;
-  if ((e = cudaEventRecord(st.free_ev, stream)) != cudaSuccess) return (int)e;
-  return B2B_OK;
+  return launch_planar_unrolled(p, Lp, nullptr, n, invmask, p.L > n, stream);
 }
-
