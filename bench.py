@@ -323,7 +323,7 @@ def main():
                     "api": "with_logabsdet_jacobian(flow, pinned host D x N) -> b2b_chain_run_host_f32"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})",
-                         "kernel": "planar_sym_kernel: fused 8-layer chain, 1 launch/step (the timed step also holds its 1-CTA parameter-prep kernel and one 8 KB device-to-device copy into the constant bank)", "algorithmic_bytes_per_launch": bytes_fused,
+                         "kernel": "planar_dev_kernel: fused 8-layer chain, 1 launch/step", "algorithmic_bytes_per_launch": bytes_fused,
                          "accounting": "chain-fused: 4*(2D+1) B/sample per launch"},
             "host_resident_parameters": {"ms_per_step": ms_hostparams, "samples_per_s": NCOLS / (ms_hostparams * 1e-3),
                                          "frac": NCOLS * 4 * (2 * D + 1) / (ms_hostparams * 1e-3) / 1e9 / peak,

@@ -132,13 +132,11 @@ int b2b_last_launch_count(void);
 
 /* Select kernel implementations (testing / profiling).  Ones digit -- fused column-local kernel: 0 = auto
  * (default), 1 = lane-group direct-global kernel (v0), 2 = TMA-staged thread-per-column interpreter (v1) only,
- * 3 = constant-bank planar-chain kernel only (segments of <= 8 PlanarLayers, D in {32,64,128}; else B2B_EUNSUPPORTED).
- * Note: the constant-bank path (auto for such segments, and b2b_planar_chain_vjp_f32) orders its use of a per-device
- * __constant__ slot with a CUDA event; inside a stream capture select variant 2 (or the host-parameter entry), which
- * use no library-owned device state.
+ * 3 = unrolled planar-chain kernel only (segments of <= 8 PlanarLayers, D in {32,64,128}; else B2B_EUNSUPPORTED).
  * Tens digit -- coupling: 0 = auto (tensor cores when the mask is contiguous and workspace is given),
- * 1 = always the exact-fp32 CUDA-core kernel.  Hundreds digit -- 1 = do not fold BatchNorm layers into
- * neighbouring coupling launches. */
+ * 1 = always the exact-fp32 CUDA-core kernel.  Hundreds digit -- 1 = do not fold BatchNorm layers into neighbouring coupling launches.
+ * Note: b2b_planar_chain_vjp_f32 orders its use of a per-device __constant__ slot with a CUDA event and cannot be
+ * stream-captured; every other entry point uses no library-owned device state. */
 int b2b_set_kernel_variant(int variant);
 
 /* ---- single layers (thin wrappers over a 1-element chain) --------------------------------------- */
