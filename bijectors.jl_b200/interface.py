@@ -295,6 +295,9 @@ def run_chain(t, x: torch.Tensor, *, want_y=True, want_logjac=True, y: Optional[
     return y, lj_out
 
 
+_HOSTPARAM_CACHE: dict = {}
+
+
 def _run_planar_hostparams(descs, x, D, N, ldx, want_y, want_logjac, y, logjac, accumulate, sum_out):
     """∘-chains of PlanarLayers whose parameters are HOST tensors, on a device batch:
     b2b_planar_chain_hostparams_f32 (parameters travel as kernel arguments, include/b2b.h)."""
@@ -308,9 +311,18 @@ def _run_planar_hostparams(descs, x, D, N, ldx, want_y, want_logjac, y, logjac, 
                        "host-parameter planar chains take a device matrix, one direction, no batch sum; "
                        "move the flow to the device with .to('cuda')")
     L = len(descs)
-    w = torch.stack([d._host_planar[0] for d in descs]).contiguous()
-    u = torch.stack([d._host_planar[1] for d in descs]).contiguous()
-    b = torch.stack([d._host_planar[2].reshape(-1)[0] for d in descs]).contiguous()
+    # L x D parameter blocks in application order; cached per (tensor identity, version) -- a few KB of host memory
+    key = tuple((id(t), t._version) for d in descs for t in d._host_planar)
+    packed = _HOSTPARAM_CACHE.get(key)
+    if packed is None:
+        if len(_HOSTPARAM_CACHE) >= 16:
+            _HOSTPARAM_CACHE.clear()
+        packed = (torch.stack([d._host_planar[0] for d in descs]).contiguous(),
+                  torch.stack([d._host_planar[1] for d in descs]).contiguous(),
+                  torch.stack([d._host_planar[2].reshape(-1)[0] for d in descs]).contiguous(),
+                  [d._host_planar for d in descs])  # keeps the keyed tensors alive
+        _HOSTPARAM_CACHE[key] = packed
+    w, u, b = packed[0], packed[1], packed[2]
     if want_y:
         if y is None:
             y = colmajor_empty(D, N, x.device)
