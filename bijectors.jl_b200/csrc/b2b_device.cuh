@@ -111,21 +111,30 @@ __device__ __forceinline__ float find_alpha(float t, float c, float b) {
 //   {w_k, 1/w, w, h_k | Δy, s = Δy/w, d_k, d_{k+1} + d_k − 2s}
 // Bin k is the reference's 1-based index (searchsortedfirst − 1); bin 0 is the k == 0 branch (:331-343) that
 // only raw three-argument-constructor knots can reach.
-__host__ __device__ inline int rqs_kp(int K1) {
+__host__ __device__ constexpr inline int rqs_kp(int K1) {
   int kp = 2;
   while (kp < K1) kp <<= 1;
   return kp;
 }
 
-template <bool INV>
-__device__ __forceinline__ void rqs_element(const float* __restrict__ tab, int K1, int KP, int Dp, int row, float v,
+// K1C > 0: the knot count is a compile-time constant (the common K = 8 bins -> K1 = 9): the bin search unrolls into
+// four compare/select steps with immediate offsets and all table addresses fold into constants.
+template <bool INV, int K1C = 0>
+__device__ __forceinline__ void rqs_element(const float* __restrict__ tab, int K1rt, int KPrt, int Dp, int row, float v,
                                             float& out, float& lj) {
+  const int K1 = K1C ? K1C : K1rt;
+  const int KP = K1C ? rqs_kp(K1C) : KPrt;
   const float* S = tab + (INV ? Dp * KP : 0) + row * KP;  // heights for the inverse (:191), widths otherwise (:328)
   const float Bs = S[K1 - 1];
   const bool outside = (v <= -Bs) || (v >= Bs);  // identity outside the box, :322-324 / :186-188
   // k = number of knots < v  (searchsortedfirst − 1): branch-free binary search over the padded knots
   int k = 0;
-  for (int st = KP >> 1; st >= 1; st >>= 1) k += (S[k + st - 1] < v) ? st : 0;
+  if constexpr (K1C != 0) {
+#pragma unroll
+    for (int st = rqs_kp(K1C) >> 1; st >= 1; st >>= 1) k += (S[k + st - 1] < v) ? st : 0;
+  } else {
+    for (int st = KP >> 1; st >= 1; st >>= 1) k += (S[k + st - 1] < v) ? st : 0;
+  }
   k = min(k, K1 - 1);
   const float4* cf = reinterpret_cast<const float4*>(tab + 2 * Dp * KP) + (size_t)(row * K1 + k) * 2;
   const float4 c0 = cf[0], c1 = cf[1];

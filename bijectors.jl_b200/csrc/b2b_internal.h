@@ -50,6 +50,9 @@ int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream);
 int b2b_planar_const_grid_size(const B2BChainParams& p);
 // number of planar layers when the constant-bank path applies to the segment `p`, else 0
 int b2b_planar_const_layers(const B2BChainParams& p);
+// a single RQS layer with 9 knots as a specialised program (b2b_rqs_unrolled.cu)
+int b2b_rqs_unrolled_applicable(const B2BChainParams& p);
+int b2b_launch_rqs_unrolled(const B2BChainParams& p, cudaStream_t stream);
 // reverse mode of a forward planar chain (b2b_planar_const.cu)
 size_t b2b_planar_vjp_workspace(int L, int D, long long N);
 int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long long ldyb, const float* ljbar,
