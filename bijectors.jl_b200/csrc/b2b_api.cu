@@ -569,3 +569,42 @@ extern "C" int b2b_planar_chain_vjp_f32(const b2b_layer_desc* layers, int32_t L,
   if (rc == B2B_OK) g_last_launches = launches;
   return rc;
 }
+
+extern "C" size_t b2b_radial_chain_vjp_workspace_bytes(int32_t L, int32_t D) {
+  if (L < 1 || L > 8 || D < 1 || D > 128) return 0;
+  return b2b_radial_vjp_workspace(L, D);
+}
+
+extern "C" int b2b_radial_chain_vjp_f32(const b2b_layer_desc* layers, int32_t L, const float* x, const float* ybar,
+                                        const float* ljbar, float* xbar, float* alpha_bar, float* beta_bar,
+                                        float* z0_bar, int32_t D, int64_t N, int64_t ldx, int64_t ldybar,
+                                        int64_t ldxbar, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  g_last_launches = 0;
+  if (!layers || L < 1 || D < 1 || N < 0 || !alpha_bar || !beta_bar || !z0_bar) return B2B_EINVAL;
+  if (L > 8 || D > 128) return B2B_EUNSUPPORTED;
+  if (N == 0) {
+    cudaMemsetAsync(alpha_bar, 0, sizeof(float) * L, stream);
+    cudaMemsetAsync(beta_bar, 0, sizeof(float) * L, stream);
+    return (int)cudaMemsetAsync(z0_bar, 0, sizeof(float) * (size_t)L * D, stream);
+  }
+  if (!x || !ybar || !xbar || ldx < D || ldybar < D || ldxbar < D) return B2B_EINVAL;
+  for (int l = 0; l < L; ++l) {
+    if (layers[l].kind != B2B_RADIAL || layers[l].inverse) return B2B_EUNSUPPORTED;
+    const int rc = validate_layer(layers[l], D, false);
+    if (rc != B2B_OK) return rc;
+  }
+  B2BChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x;
+  p.N = N;
+  p.ldx = ldx;
+  p.D = D;
+  p.L = L;
+  for (int l = 0; l < L; ++l) p.layers[l] = layers[l];
+  int launches = 0;
+  const int rc = b2b_launch_radial_chain_vjp(p, ybar, ldybar, ljbar, xbar, ldxbar, alpha_bar, beta_bar, z0_bar,
+                                             workspace, workspace_bytes, &launches, stream);
+  if (rc == B2B_OK) g_last_launches = launches;
+  return rc;
+}

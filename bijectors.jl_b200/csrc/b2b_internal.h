@@ -50,6 +50,11 @@ int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream);
 int b2b_planar_const_grid_size(const B2BChainParams& p);
 // number of planar layers when the constant-bank path applies to the segment `p`, else 0
 int b2b_planar_const_layers(const B2BChainParams& p);
+// reverse mode of a forward radial chain (b2b_radial_vjp.cu)
+size_t b2b_radial_vjp_workspace(int L, int D);
+int b2b_launch_radial_chain_vjp(const B2BChainParams& p, const float* ybar, long long ldyb, const float* ljbar,
+                                float* xbar, long long ldxb, float* alpha_bar, float* beta_bar, float* z0_bar,
+                                void* workspace, size_t workspace_bytes, int* launches, cudaStream_t stream);
 // a single RQS layer with 9 knots as a specialised program (b2b_rqs_unrolled.cu)
 int b2b_rqs_unrolled_applicable(const B2BChainParams& p);
 int b2b_launch_rqs_unrolled(const B2BChainParams& p, cudaStream_t stream);

@@ -1,0 +1,221 @@
+// Reverse mode (VJP) of with_logabsdet_jacobian through a ∘-chain of RadialLayers, forward direction
+// (src/bijectors/radial_layer.jl:43-53,58-72): what the reference's AD computes when a radial flow is trained.
+//
+// Per layer, with δ = z − z0, r = ‖δ‖, h = 1/(α+r), s = β̂h, q = β̂ r h²:   y = z + sδ,
+// logjac = (D−1)·log(1+s) + log(1+s−q).  Given the cotangents ȳ (D x N) and l̄ (N):
+//   s̄ = δᵀȳ + l̄·((D−1)/(1+s) + 1/(1+s−q)),  q̄ = −l̄/(1+s−q),
+//   β̂̄ = s̄ h + q̄ r h²,  h̄ = s̄ β̂ + 2 q̄ β̂ r h,  r̄ = q̄ β̂ h² − h̄ h²,  ᾱ = −h̄ h²,  κ = r̄/r,
+//   z̄ = (1+s) ȳ + κ δ,   z̄0 = −Σ_n (s ȳ + κ δ),   then α = log1pexp(α_raw), β̂ = log1pexp(β) − α.
+//
+// Layout: a WARP owns a column (lane ↔ rows lane + 32v), CI columns in flight per warp; the two row reductions per
+// layer (‖δ‖², δᵀȳ) are warp shuffles, the per-layer δ stay in registers between the forward recompute and the
+// reverse sweep, and the parameter cotangents (z̄0: L x D, ᾱ, β̂̄: L) are lane-local accumulators over the columns a
+// warp visits -- no second pass over the batch.  Deterministic: per-CTA partials are combined in a fixed order.
+// Algorithmic traffic: read x, read ȳ, write x̄ (+ l̄).
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "b2b_device.cuh"
+
+namespace b2b {
+
+constexpr int RV_THREADS = 256;
+constexpr int RV_GRID_MAX = 592;
+
+template <int V, int L, int CI>
+__global__ void __launch_bounds__(RV_THREADS, 2)
+    radial_vjp_kernel(const __grid_constant__ B2BChainParams P, const float* __restrict__ ybar, long long ldyb,
+                      const float* __restrict__ ljbar, float* __restrict__ xbar, long long ldxb,
+                      float* __restrict__ partials) {
+  const int D = P.D, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = RV_THREADS / 32;
+  __shared__ float red[8 * 128 + 16];  // L x D + 2L (D <= 128, L <= 8)
+  float alpha[L], bhat[L], z0r[L][V];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const b2b_layer_desc& d = P.layers[l];
+    alpha[l] = softplus(d.p0[0]);             // radial_layer.jl:44
+    bhat[l] = softplus(d.p1[0]) - alpha[l];   // :45
+#pragma unroll
+    for (int v = 0; v < V; ++v) z0r[l][v] = (lane + 32 * v < D) ? d.p2[lane + 32 * v] : 0.f;
+  }
+  float acc_z0[L][V], acc_a[L], acc_b[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    acc_a[l] = acc_b[l] = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc_z0[l][v] = 0.f;
+  }
+  const float dm1 = (float)(D - 1);
+  const long long gw = (long long)blockIdx.x * nwarps + warp, stride = (long long)gridDim.x * nwarps;
+  for (long long c0 = gw * CI; c0 < P.N; c0 += stride * CI) {
+    float z[CI][V], yb[CI][V], lb[CI], dl[CI][L][V], rr[CI][L];
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) {
+      const long long c = c0 + ci;
+      const bool ok = c < P.N;
+      lb[ci] = (ok && ljbar) ? ljbar[c] : 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const bool in = ok && (lane + 32 * v < D);
+        z[ci][v] = in ? __ldcs(P.x + c * P.ldx + lane + 32 * v) : 0.f;
+        yb[ci][v] = in ? __ldcs(ybar + c * ldyb + lane + 32 * v) : 0.f;
+      }
+    }
+    // forward recompute: δ_l, r_l
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        float r2 = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          dl[ci][l][v] = z[ci][v] - z0r[l][v];
+          r2 = fmaf(dl[ci][l][v], dl[ci][l][v], r2);
+        }
+        r2 = warp_sum(r2);
+        // LinearAlgebra.norm, radial_layer.jl:47-49.  MUFU-based sqrt / reciprocals (<= 2 ulp): the IEEE division and
+        // square-root sequences (with their slow-path calls) made this kernel instruction-bound at 1750 instructions
+        // per column
+        const float r = r2 > 0.f ? r2 * rsqrtf(r2) : 0.f;
+        rr[ci][l] = r;
+        const float s = bhat[l] * __fdividef(1.0f, alpha[l] + r);
+#pragma unroll
+        for (int v = 0; v < V; ++v) z[ci][v] = fmaf(s, dl[ci][l][v], z[ci][v]);  // :51
+      }
+    }
+    // reverse sweep
+#pragma unroll
+    for (int l = L - 1; l >= 0; --l) {
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        float dot = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) dot = fmaf(dl[ci][l][v], yb[ci][v], dot);
+        dot = warp_sum(dot);
+        const float r = rr[ci][l], h = __fdividef(1.0f, alpha[l] + r), s = bhat[l] * h, q = bhat[l] * r * h * h;
+        const float i1 = __fdividef(1.0f, 1.0f + s), i2 = __fdividef(1.0f, 1.0f + s - q);
+        const float s_tot = fmaf(lb[ci], fmaf(dm1, i1, i2), dot);
+        const float q_bar = -lb[ci] * i2;
+        const float bh_bar = fmaf(s_tot, h, q_bar * r * h * h);
+        const float h_bar = fmaf(s_tot, bhat[l], 2.0f * q_bar * bhat[l] * r * h);
+        const float r_bar = (q_bar * bhat[l] - h_bar) * h * h;
+        const float kappa = r > 0.f ? r_bar * __fdividef(1.0f, r) : 0.f;
+        acc_a[l] -= h_bar * h * h;
+        acc_b[l] += bh_bar;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          acc_z0[l][v] -= fmaf(s, yb[ci][v], kappa * dl[ci][l][v]);
+          yb[ci][v] = fmaf(yb[ci][v], 1.0f + s, kappa * dl[ci][l][v]);
+        }
+      }
+    }
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) {
+      const long long c = c0 + ci;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (c < P.N && lane + 32 * v < D) xbar[c * ldxb + lane + 32 * v] = yb[ci][v];
+    }
+  }
+  // CTA partials, warps added in a fixed order.  Columns beyond N contributed zeros (their ȳ, l̄ and δ-free terms are
+  // 0 only if δ·0: out-of-range columns have z = 0, ȳ = 0, l̄ = 0 -> s̄ = 0, all cotangents 0).
+  const int nred = L * D + 2 * L;
+  for (int i = threadIdx.x; i < nred; i += RV_THREADS) red[i] = 0.f;
+  __syncthreads();
+  for (int w = 0; w < nwarps; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (lane + 32 * v < D) red[l * D + lane + 32 * v] += acc_z0[l][v];
+        if (lane == 0) {
+          red[L * D + l] += acc_a[l];
+          red[L * D + L + l] += acc_b[l];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < nred; i += RV_THREADS) partials[(size_t)blockIdx.x * nred + i] = red[i];
+}
+
+// out[i] = Σ_b partials[b][i], one warp per output (fixed order), then the chain rule through the parameter transforms:
+// α = log1pexp(α_raw), β̂ = log1pexp(β) − α  (radial_layer.jl:44-45)
+__global__ void __launch_bounds__(256)
+    radial_vjp_finalize_kernel(const __grid_constant__ B2BChainParams P, int L, const float* __restrict__ partials,
+                               int nblk, float* __restrict__ alpha_bar, float* __restrict__ beta_bar,
+                               float* __restrict__ z0_bar) {
+  const int D = P.D, n = L * D + 2 * L, lane = threadIdx.x & 31;
+  __shared__ float sums[8 * 128 + 16];
+  for (int i = threadIdx.x >> 5; i < n; i += 8) {
+    float s = 0.f;
+    for (int b = lane; b < nblk; b += 32) s += partials[(size_t)b * n + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) sums[i] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L * D; i += 256) z0_bar[i] = sums[i];
+  if (threadIdx.x < L) {
+    const int l = threadIdx.x;
+    const float a_raw = P.layers[l].p0[0], b_raw = P.layers[l].p1[0];
+    const float bh = sums[L * D + L + l], al = sums[L * D + l] - bh;
+    alpha_bar[l] = al / (1.0f + expf(-a_raw));
+    beta_bar[l] = bh / (1.0f + expf(-b_raw));
+  }
+}
+
+template <int V, int CI>
+static int launch_radial_vjp(int L, int grid, const B2BChainParams& p, const float* ybar, long long ldyb,
+                             const float* ljbar, float* xbar, long long ldxb, float* partials, cudaStream_t stream) {
+#define B2B_RV_CASE(LL)                                                                                            \
+  case LL:                                                                                                         \
+    radial_vjp_kernel<V, LL, CI><<<grid, RV_THREADS, 0, stream>>>(p, ybar, ldyb, ljbar, xbar, ldxb, partials);      \
+    break;
+  switch (L) {
+    B2B_RV_CASE(1) B2B_RV_CASE(2) B2B_RV_CASE(3) B2B_RV_CASE(4) B2B_RV_CASE(5) B2B_RV_CASE(6) B2B_RV_CASE(7) B2B_RV_CASE(8)
+    default: return B2B_EUNSUPPORTED;
+  }
+#undef B2B_RV_CASE
+  return (int)cudaGetLastError();
+}
+
+}  // namespace b2b
+
+size_t b2b_radial_vjp_workspace(int L, int D) {
+  return (size_t)b2b::RV_GRID_MAX * (size_t)(L * D + 2 * L) * sizeof(float) + 256;
+}
+
+// p: L (1..8) forward RADIAL layers, p.x, p.N, p.D (<= 128), p.ldx.  Outputs: xbar (D x N, may alias ybar),
+// alpha_bar / beta_bar (L), z0_bar (L x D).
+int b2b_launch_radial_chain_vjp(const B2BChainParams& p, const float* ybar, long long ldyb, const float* ljbar,
+                                float* xbar, long long ldxb, float* alpha_bar, float* beta_bar, float* z0_bar,
+                                void* workspace, size_t workspace_bytes, int* launches, cudaStream_t stream) {
+  using namespace b2b;
+  const int L = p.L, D = p.D;
+  if (L < 1 || L > 8 || D > 128) return B2B_EUNSUPPORTED;
+  for (int l = 0; l < L; ++l)
+    if (p.layers[l].kind != B2B_RADIAL || p.layers[l].inverse) return B2B_EUNSUPPORTED;
+  if (!workspace || workspace_bytes < b2b_radial_vjp_workspace(L, D)) return B2B_EWORKSPACE;
+  char* ws = static_cast<char*>(workspace);
+  ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;
+  float* partials = reinterpret_cast<float*>(ws);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms * 4;
+  if (grid > RV_GRID_MAX) grid = RV_GRID_MAX;
+  const long long want = (p.N + 31) / 32;
+  if (grid > want) grid = (int)want;
+  if (grid < 1) grid = 1;
+  int rc;
+  if (D <= 32) rc = launch_radial_vjp<1, 4>(L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
+  else if (D <= 64) rc = launch_radial_vjp<2, 2>(L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
+  else rc = launch_radial_vjp<4, 1>(L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
+  if (rc != B2B_OK) return rc;
+  radial_vjp_finalize_kernel<<<1, 256, 0, stream>>>(p, L, partials, grid, alpha_bar, beta_bar, z0_bar);
+  if (launches) *launches = 2;
+  return (int)cudaGetLastError();
+}

@@ -472,6 +472,36 @@ def planar_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[tor
     return xbar, grads
 
 
+def radial_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[torch.Tensor] = None):
+    """Vector-Jacobian product of ``with_logabsdet_jacobian(t, x)`` for a ∘-chain ``t`` of (≤ 8) RadialLayers (forward
+    direction, D ≤ 128).  Returns ``(xbar, grads)`` with ``grads`` = list of ``{"α_": …, "β": …, "z_0": …}`` per layer
+    (cotangents of the RAW parameters, summed over the columns)."""
+    D, N, ldx = _batch_view(x)
+    Dy, Ny, ldyb = _batch_view(ybar)
+    if (Dy, Ny) != (D, N) or not x.is_cuda or not ybar.is_cuda or x.dim() != 2:
+        raise ValueError("radial_chain_vjp: x and ybar must be device matrices of the same D×N shape")
+    descs = list(t._descs(False, D))
+    if any(d.kind != _lib.RADIAL or d.inverse for d in descs):
+        raise B2BError(_lib.B2B_EUNSUPPORTED, "radial_chain_vjp: forward RadialLayers only")
+    L = len(descs)
+    arr = _desc_array(descs)
+    if ljbar is not None and (ljbar.numel() != N or ljbar.dtype != torch.float32 or not ljbar.is_contiguous()):
+        raise ValueError("ljbar must be a contiguous float32 vector of length N")
+    xbar = colmajor_empty(D, N, x.device)
+    abar = torch.empty((L,), dtype=torch.float32, device=x.device)
+    bbar = torch.empty((L,), dtype=torch.float32, device=x.device)
+    zbar = torch.empty((L, D), dtype=torch.float32, device=x.device)
+    L_ = lib()
+    ws_bytes = L_.b2b_radial_chain_vjp_workspace_bytes(L, D)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=x.device)
+    rc = L_.b2b_radial_chain_vjp_f32(
+        arr, L, x.data_ptr(), ybar.data_ptr(), ljbar.data_ptr() if ljbar is not None else None, xbar.data_ptr(),
+        abar.data_ptr(), bbar.data_ptr(), zbar.data_ptr(), D, N, ldx, ldyb, _batch_view(xbar)[2],
+        ws.data_ptr(), ws_bytes, _stream())
+    check(rc, "b2b_radial_chain_vjp_f32")
+    return xbar, [{"α_": abar[l:l + 1], "β": bbar[l:l + 1], "z_0": zbar[l]} for l in range(L)]
+
+
 def isinvertible(t) -> bool:
     return isinstance(t, Transform)
 

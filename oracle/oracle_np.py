@@ -334,6 +334,50 @@ def radial_forward(alpha_raw, beta, z0, z):
     return y.astype(dt), np.asarray(logjac, dtype=dt)[()]
 
 
+def radial_chain_vjp(params, x, ybar, ljbar):
+    """Vector-Jacobian product of with_logabsdet_jacobian through a ∘-chain of RadialLayers, forward direction
+    (src/bijectors/radial_layer.jl:43-53,58-72) -- what reverse-mode AD of the reference computes.
+
+    params: [(alpha_raw, beta, z0)]; x, ybar (D, N); ljbar (N,).  Returns (xbar, [(alpha_raw_bar, beta_bar, z0_bar)]).
+    With δ = z − z0, r = ‖δ‖, h = 1/(α+r), s = β̂h, q = β̂ r h²:  y = z + sδ,
+    logjac = (D−1)·log(1+s) + log(1+s−q)."""
+    dt = x.dtype
+    D = x.shape[0]
+    zs, cache = [x], []
+    for (a_raw, be, z0) in params:
+        a_ = dt.type(np.asarray(a_raw).reshape(-1)[0])
+        b_ = dt.type(np.asarray(be).reshape(-1)[0])
+        z0 = z0.astype(dt)
+        alpha = dt.type(log1pexp(a_))
+        beta_hat = dt.type(-alpha + log1pexp(b_))
+        delta = zs[-1] - z0[:, None]
+        r = np.sqrt(np.sum(delta * delta, axis=0))
+        h = 1.0 / (alpha + r)
+        s = beta_hat * h
+        zs.append(zs[-1] + s[None, :] * delta)
+        cache.append((a_, b_, z0, alpha, beta_hat, delta, r, h, s))
+    yb = ybar.astype(dt).copy()
+    grads = [None] * len(params)
+    sig = lambda v: dt.type(1) / (dt.type(1) + np.exp(-v))
+    for l in range(len(params) - 1, -1, -1):
+        a_, b_, z0, alpha, beta_hat, delta, r, h, s = cache[l]
+        q = beta_hat * r * h * h
+        s_tot = np.sum(delta * yb, axis=0) + ljbar * ((D - 1) / (1 + s) + 1 / (1 + s - q))
+        q_bar = -ljbar / (1 + s - q)
+        bh_bar = s_tot * h + q_bar * r * h * h
+        h_bar = s_tot * beta_hat + q_bar * 2 * beta_hat * r * h
+        r_bar = q_bar * beta_hat * h * h - h_bar * h * h
+        alpha_bar = -h_bar * h * h
+        with np.errstate(divide="ignore", invalid="ignore"):
+            kappa = np.where(r > 0, r_bar / r, 0.0)
+        z0_bar = -(yb @ s + delta @ kappa)
+        yb = yb * (1 + s)[None, :] + delta * kappa[None, :]
+        bh = np.sum(bh_bar)
+        al = np.sum(alpha_bar) - bh          # β̂ = log1pexp(β) − α
+        grads[l] = (dt.type(al * sig(a_)), dt.type(bh * sig(b_)), z0_bar.astype(dt))
+    return yb.astype(dt), grads
+
+
 def compute_r(y_minus_z0, alpha, alpha_plus_beta_hat):
     """src/bijectors/radial_layer.jl:124-129 (vector or per-column for a matrix)."""
     dt = y_minus_z0.dtype

@@ -1049,3 +1049,35 @@ def test_autograd_small_dimension_flow_like_the_reference_example(B):
         assert rel(flow.u[l].grad.cpu().numpy(), grads_o[l][1]) <= 1e-4
         assert abs(float(flow.b[l].grad) - float(grads_o[l][2])) <= 1e-4 * max(1.0, abs(float(grads_o[l][2])))
 
+
+
+@pytest.mark.parametrize("D,L", [(64, 6), (32, 1), (128, 8), (10, 3)])
+def test_radial_chain_vjp_matches_oracle(B, D, L):
+    """b2b_radial_chain_vjp_f32 (reverse mode through radial_layer.jl:43-72) vs the float64 oracle VJP, itself pinned
+    by finite differences of the forward oracle (CPU suite).  Cotangents are w.r.t. the RAW parameters α_, β, z_0."""
+    import torch
+
+    rng = np.random.default_rng(700 * D + L)
+    N = 4001 + L
+    pairs = [make_case("radial", D, rng) for _ in range(L)]
+    flow = B.Composed(*[p[0] for p in pairs])
+    params = [(p[1].params["alpha_raw"].astype(np.float64), p[1].params["beta"].astype(np.float64),
+               p[1].params["z0"].astype(np.float64)) for p in pairs]
+    x = rng.standard_normal((D, N)).astype(f32)
+    ybar = rng.standard_normal((D, N)).astype(f32)
+    ljbar = rng.standard_normal(N).astype(f32)
+    xb_o, g_o = O.radial_chain_vjp(params, x.astype(np.float64), ybar.astype(np.float64), ljbar.astype(np.float64))
+    xbar, grads = B.radial_chain_vjp(flow, B.from_numpy(x), B.from_numpy(ybar), torch.from_numpy(ljbar).cuda())
+    assert B.lib().b2b_last_launch_count() == 2
+    assert rel(B.to_numpy(xbar), xb_o) <= 2e-5
+    for l in range(L):
+        scale = np.sqrt(N)
+        assert abs(float(grads[l]["α_"]) - float(g_o[l][0])) <= 5e-5 * max(abs(float(g_o[l][0])), scale), (l, "alpha")
+        assert abs(float(grads[l]["β"]) - float(g_o[l][1])) <= 5e-5 * max(abs(float(g_o[l][1])), scale), (l, "beta")
+        assert rel(grads[l]["z_0"].cpu().numpy(), g_o[l][2]) <= 5e-5, (l, "z0")
+    # determinism + ljbar = None
+    xbar2, grads2 = B.radial_chain_vjp(flow, B.from_numpy(x), B.from_numpy(ybar), torch.from_numpy(ljbar).cuda())
+    assert torch.equal(xbar2, xbar) and all(torch.equal(grads2[l][k], grads[l][k]) for l in range(L) for k in ("α_", "β", "z_0"))
+    xb0, _ = B.radial_chain_vjp(flow, B.from_numpy(x), B.from_numpy(ybar), None)
+    xb_o0, _ = O.radial_chain_vjp(params, x.astype(np.float64), ybar.astype(np.float64), np.zeros(N))
+    assert rel(B.to_numpy(xb0), xb_o0) <= 2e-5

@@ -230,3 +230,42 @@ def test_planar_inverse_chain_vjp_matches_finite_differences():
                 fdp[i] = (loss(ps_p, y) - loss(ps_m, y)) / (2 * eps)
             got = np.atleast_1d(np.asarray(grads[l][k], dtype=np.float64))
             assert np.allclose(got, fdp, rtol=2e-5, atol=2e-7), (l, name, got, fdp)
+
+
+def test_radial_chain_vjp_matches_finite_differences():
+    rng = np.random.default_rng(31)
+    D, N, L = 5, 4, 3
+    params = [(rng.standard_normal(1), rng.standard_normal(1), rng.standard_normal(D)) for _ in range(L)]
+    x = rng.standard_normal((D, N))
+    ybar, ljbar = rng.standard_normal((D, N)), rng.standard_normal(N)
+
+    def loss(ps, xx):
+        z, lj = xx, np.zeros(N)
+        for (a, b, z0) in ps:
+            z, l1 = O.radial_forward(a, b, z0, z)
+            lj = lj + l1
+        return float(np.sum(z * ybar) + np.sum(lj * ljbar))
+
+    xbar, grads = O.radial_chain_vjp(params, x, ybar, ljbar)
+    eps = 1e-6
+    fd = np.zeros_like(x)
+    for i in range(D):
+        for n in range(N):
+            xp, xm = x.copy(), x.copy()
+            xp[i, n] += eps
+            xm[i, n] -= eps
+            fd[i, n] = (loss(params, xp) - loss(params, xm)) / (2 * eps)
+    assert np.allclose(xbar, fd, rtol=2e-6, atol=1e-7)
+    for l in range(L):
+        for k, name in enumerate(("alpha_raw", "beta", "z0")):
+            base = np.asarray(params[l][k], dtype=np.float64)
+            fdp = np.zeros_like(base)
+            for i in range(base.size):
+                pp, pm = base.copy(), base.copy()
+                pp[i] += eps
+                pm[i] -= eps
+                ps_p = [tuple(pp if (ll == l and kk == k) else params[ll][kk] for kk in range(3)) for ll in range(L)]
+                ps_m = [tuple(pm if (ll == l and kk == k) else params[ll][kk] for kk in range(3)) for ll in range(L)]
+                fdp[i] = (loss(ps_p, x) - loss(ps_m, x)) / (2 * eps)
+            got = np.atleast_1d(np.asarray(grads[l][k], dtype=np.float64))
+            assert np.allclose(got, fdp, rtol=2e-5, atol=2e-7), (l, name, got, fdp)
