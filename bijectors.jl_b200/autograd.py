@@ -7,8 +7,8 @@ from typing import List, Sequence, Tuple
 
 import torch
 
-from .interface import Composed, colmajor_empty, inverse, planar_chain_vjp, run_chain
-from .layers import PlanarLayer
+from .interface import Composed, colmajor_empty, inverse, planar_chain_vjp, radial_chain_vjp, run_chain
+from .layers import PlanarLayer, RadialLayer
 
 
 _VJP_DIMS = (32, 64, 128)
@@ -97,3 +97,44 @@ class PlanarFlow(torch.nn.Module):
     def inverse(self, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """with_logabsdet_jacobian(inverse(flow), y), differentiable (find_alpha through its implicit rule)."""
         return _PlanarChainFn.apply(y, True, *self._wub())
+
+
+class _RadialChainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, *abz):
+        L = len(abz) // 3
+        flow = Composed(*[RadialLayer(abz[3 * l].detach(), abz[3 * l + 1].detach(), abz[3 * l + 2].detach()) for l in range(L)])
+        xc = _colmajor(x.detach())
+        y, lj = run_chain(flow, xc)
+        ctx.flow = flow
+        ctx.save_for_backward(xc)
+        return y, lj
+
+    @staticmethod
+    def backward(ctx, ybar, ljbar):
+        (xc,) = ctx.saved_tensors
+        D, N = xc.shape
+        yb = _colmajor(ybar) if ybar is not None else _colmajor(torch.zeros((D, N), device=xc.device))
+        xbar, grads = radial_chain_vjp(ctx.flow, xc, yb, ljbar.contiguous() if ljbar is not None else None)
+        flat: List[torch.Tensor] = []
+        for g in grads:
+            flat += [g["α_"], g["β"], g["z_0"]]
+        return (xbar, *flat)
+
+
+class RadialFlow(torch.nn.Module):
+    """A trainable ∘-chain of L RadialLayers (radial_layer.jl:11-27: randn-initialised α_, β, z_0), forward direction
+    (the sampling / variational path): ``with_logabsdet_jacobian`` differentiable w.r.t. x and the raw parameters."""
+
+    def __init__(self, dims: int, n_layers: int, device="cuda", generator=None):
+        super().__init__()
+        mk = lambda n: torch.nn.Parameter(torch.randn(n, generator=generator).to(device))
+        self.alpha_ = torch.nn.ParameterList([mk(1) for _ in range(n_layers)])
+        self.beta = torch.nn.ParameterList([mk(1) for _ in range(n_layers)])
+        self.z_0 = torch.nn.ParameterList([mk(dims) for _ in range(n_layers)])
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        abz = []
+        for a, b, z in zip(self.alpha_, self.beta, self.z_0):
+            abz += [a, b, z]
+        return _RadialChainFn.apply(x, *abz)

@@ -1081,3 +1081,26 @@ def test_radial_chain_vjp_matches_oracle(B, D, L):
     xb0, _ = B.radial_chain_vjp(flow, B.from_numpy(x), B.from_numpy(ybar), None)
     xb_o0, _ = O.radial_chain_vjp(params, x.astype(np.float64), ybar.astype(np.float64), np.zeros(N))
     assert rel(B.to_numpy(xb0), xb_o0) <= 2e-5
+
+
+def test_radial_flow_autograd(B):
+    """torch.autograd over b2b_radial_chain_vjp_f32: gradients of a scalar loss equal the oracle's."""
+    import torch
+
+    D, N, L = 10, 777, 2
+    flow = B.autograd.RadialFlow(D, L, generator=torch.Generator().manual_seed(2))
+    x = B.from_numpy(np.random.default_rng(9).standard_normal((D, N)).astype(f32)).requires_grad_(True)
+    y, lj = flow(x)
+    ((y * y).sum() * 0.5 + lj.sum()).backward()
+    params = [(a.detach().cpu().numpy().astype(np.float64), b.detach().cpu().numpy().astype(np.float64),
+               z.detach().cpu().numpy().astype(np.float64)) for a, b, z in zip(flow.alpha_, flow.beta, flow.z_0)]
+    x64 = B.to_numpy(x.detach()).astype(np.float64)
+    z = x64
+    for (a, b, z0) in params:
+        z, _ = O.radial_forward(a, b, z0, z)
+    xb_o, g_o = O.radial_chain_vjp(params, x64, z, np.ones(N))
+    assert rel(B.to_numpy(x.grad), xb_o) <= 5e-5
+    for l in range(L):
+        assert abs(float(flow.alpha_[l].grad) - float(g_o[l][0])) <= 1e-4 * max(1.0, abs(float(g_o[l][0])))
+        assert abs(float(flow.beta[l].grad) - float(g_o[l][1])) <= 1e-4 * max(1.0, abs(float(g_o[l][1])))
+        assert rel(flow.z_0[l].grad.cpu().numpy(), g_o[l][2]) <= 1e-4

@@ -61,6 +61,10 @@ for D, L, N in [(128, 8, 333), (64, 3, 100), (32, 1, 70)]:
     torch.cuda.synchronize()
     assert float((xi - x).norm() / x.norm()) < 1e-3 and float((yh - y).norm() / y.norm()) < 1e-5
     print(f"planar const / vjp D={D} L={L} ok")
+rf = B.Composed(*[B.RadialLayer(f32([0.2]), f32([0.3]), rng.standard_normal(64).astype(f32)) for _ in range(3)])
+B.radial_chain_vjp(rf, B.from_numpy(rng.standard_normal((64, 211)).astype(f32)), B.from_numpy(rng.standard_normal((64, 211)).astype(f32)), torch.randn(211, device="cuda"))
+torch.cuda.synchronize()
+print("radial vjp ok")
 bn = B.InvertibleBatchNorm(32, training=True)
 bn.train_forward(B.from_numpy(rng.standard_normal((32, 300)).astype(f32)))
 xh = B.from_numpy(rng.standard_normal((64, 1000)).astype(f32), device="cpu", pin_memory=True)
