@@ -151,6 +151,20 @@ function planar_chain_vjp(f, x::CuMatrix{Float32}, ȳ::CuMatrix{Float32}, l̄::C
     return x̄, w̄, ū, b̄        # column l of w̄ / ū and b̄[l] belong to the l-th applied layer
 end
 
+function radial_chain_vjp(f, x::CuMatrix{Float32}, ȳ::CuMatrix{Float32}, l̄::CuVector{Float32})
+    ds = descs(f, false)
+    L, (D, N) = length(ds), size(x)
+    x̄ = similar(x); ᾱ = CUDA.zeros(Float32, L); β̄ = CUDA.zeros(Float32, L); z̄0 = CUDA.zeros(Float32, D, L)
+    nbytes = ccall((:b2b_radial_chain_vjp_workspace_bytes, libb2b), Csize_t, (Int32, Int32), L, D)
+    ws = CuVector{UInt8}(undef, nbytes)
+    GC.@preserve ds ws check(ccall((:b2b_radial_chain_vjp_f32, libb2b), Cint,
+        (Ptr{LayerDesc}, Int32, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32},
+         CuPtr{Float32}, CuPtr{Float32}, Int32, Int64, Int64, Int64, Int64, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        ds, L, pointer(x), pointer(ȳ), pointer(l̄), pointer(x̄), pointer(ᾱ), pointer(β̄), pointer(z̄0),
+        D, N, stride(x, 2), stride(ȳ, 2), stride(x̄, 2), pointer(ws), nbytes, stream_handle()))
+    return x̄, ᾱ, β̄, z̄0        # cotangents of the raw fields α_, β, z_0 of each layer
+end
+
 # logpdf(td::MvTransformed, y::Matrix) (src/transformed_distribution.jl:165-169): inverse chain + base
 # MvNormal + (optionally) the batch sum in ONE fused launch per fusable segment.
 function Distributions.logpdf(td::TransformedDistribution{<:MvNormal}, y::CuMatrix{Float32})
