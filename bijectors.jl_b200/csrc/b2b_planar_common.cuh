@@ -1,5 +1,5 @@
-// Shared by b2b_planar_const.cu (forward / inverse evaluation) and b2b_planar_vjp.cu (reverse mode): the constant-bank
-// parameter slot, its staging buffer, the device-side get_u_hat preparation and the launch shapes.  Every translation
+// Shared by b2b_planar_const.cu (forward / inverse evaluation: launch shapes only) and b2b_planar_vjp.cu (reverse mode:
+// the constant-bank parameter slot, its staging buffer and the device-side get_u_hat preparation).  Every translation
 // unit that includes this header owns ITS OWN copy of the __constant__ slot (and of the event that serialises it).
 #pragma once
 #include <cstring>
@@ -26,21 +26,15 @@ struct SymSrc {
   __device__ __forceinline__ float b(int l) const { return c_planar[2 * L * D + L + l]; }
   __device__ __forceinline__ bool inv(int l) const { return (invmask >> l) & 1; }
   __device__ __forceinline__ float raw(int i) const { return stage[i]; }
-  __device__ __forceinline__ float cst(int i) const { return c_planar[i]; }  // dynamic index: verification only
 };
 
 // get_u_hat (planar_layer.jl:65-70) for Lp layers (the last Lp - L are identity padding), one warp per layer,
 // packed for (D, Lp) into `out`.
 static __global__ void __launch_bounds__(HP_MAX_L * 32)
-    planar_prep_kernel(const __grid_constant__ B2BChainParams P, int L, int Lp, float* __restrict__ out,
-                       float* __restrict__ out2) {
-  // `out2` (optional): a second copy, written straight into the memory behind the __constant__ slot
+    planar_prep_kernel(const __grid_constant__ B2BChainParams P, int L, int Lp, float* __restrict__ out) {
   const int lane = threadIdx.x & 31, l = threadIdx.x >> 5, D = P.D;
   if (l >= Lp) return;
-  auto put = [&](int idx, float v) {
-    out[idx] = v;
-    if (out2) out2[idx] = v;
-  };
+  auto put = [&](int idx, float v) { out[idx] = v; };
   const int wo = l * D, uo = Lp * D + l * D;
   if (l >= L) {
     for (int i = lane; i < D; i += 32) {
@@ -92,7 +86,6 @@ struct SlotState {
   std::mutex mu;
   cudaEvent_t free_ev = nullptr;
   float* stage = nullptr;
-  float* sym = nullptr;  // global address of the memory behind c_planar
 };
 static SlotState g_slots[64];
 
@@ -100,22 +93,17 @@ static SlotState g_slots[64];
 // Under the slot's mutex: wait for the previous user, derive the parameters of p.layers[0..n) (padded to Lp layers)
 // into the staging buffer and copy them into the constant bank.  The caller launches its kernels and then records
 // st.free_ev.
-static inline int planar_slot_prepare(SlotState& st, const B2BChainParams& p, int n, int Lp, cudaStream_t stream,
-                                      bool direct = false) {
+static inline int planar_slot_prepare(SlotState& st, const B2BChainParams& p, int n, int Lp, cudaStream_t stream) {
   cudaError_t e;
   if (!st.free_ev) {
     if ((e = cudaEventCreateWithFlags(&st.free_ev, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
     if ((e = cudaGetSymbolAddress(reinterpret_cast<void**>(&st.stage), g_planar_stage)) != cudaSuccess) return (int)e;
-    if ((e = cudaGetSymbolAddress(reinterpret_cast<void**>(&st.sym), c_planar)) != cudaSuccess) return (int)e;
     if ((e = cudaEventRecord(st.free_ev, stream)) != cudaSuccess) return (int)e;
   }
   // the previous user of the slot (possibly on another stream) must have finished
   if ((e = cudaStreamWaitEvent(stream, st.free_ev, 0)) != cudaSuccess) return (int)e;
-  // direct: the prep kernel also writes the constant slot's backing memory itself (no copy-engine hop); the consumer
-  // kernel then VERIFIES its view of the constant bank against the staging buffer (see PlanarConstProg::stage)
-  planar_prep_kernel<<<1, HP_MAX_L * 32, 0, stream>>>(p, n, Lp, st.stage, direct ? st.sym : nullptr);
+  planar_prep_kernel<<<1, HP_MAX_L * 32, 0, stream>>>(p, n, Lp, st.stage);
   if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
-  if (direct) return 0;
   const size_t bytes = sizeof(float) * (size_t)(2 * Lp * p.D + 2 * Lp);
   return (int)cudaMemcpyToSymbolAsync(c_planar, st.stage, bytes, 0, cudaMemcpyDeviceToDevice, stream);
 }
