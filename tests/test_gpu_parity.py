@@ -1104,3 +1104,26 @@ def test_radial_flow_autograd(B):
         assert abs(float(flow.alpha_[l].grad) - float(g_o[l][0])) <= 1e-4 * max(1.0, abs(float(g_o[l][0])))
         assert abs(float(flow.beta[l].grad) - float(g_o[l][1])) <= 1e-4 * max(1.0, abs(float(g_o[l][1])))
         assert rel(flow.z_0[l].grad.cpu().numpy(), g_o[l][2]) <= 1e-4
+
+
+def test_full_size_vjp_round_trip_property(B):
+    """Size-independent property at BASELINE config-2 size (8 layers, D = 128, N = 2^20): pulling a cotangent back
+    through inverse(flow) at y and then through flow at x returns it (J(inverse(f))(y) = J(f)(x)⁻¹), and the parameter
+    cotangents are deterministic."""
+    import torch
+
+    rng = np.random.default_rng(123)
+    D, N, L = 128, 1 << 20, 8
+    pairs = [make_case("planar", D, rng) for _ in range(L)]
+    flow = B.Composed(*[p[0] for p in pairs])
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((N, D), device="cuda", generator=gen).t()
+    v = torch.randn((N, D), device="cuda", generator=gen).t()
+    y, _ = B.with_logabsdet_jacobian(flow, x)
+    u_, _ = B.planar_chain_vjp(B.inverse(flow), y, v, None, want_param_grads=False)
+    back, grads = B.planar_chain_vjp(flow, x, u_, None)
+    err = float((back - v).norm() / v.norm())
+    assert err <= 2e-5, err
+    _, grads2 = B.planar_chain_vjp(flow, x, u_, None)
+    assert all(torch.equal(grads[l][k], grads2[l][k]) for l in range(L) for k in ("w", "u", "b"))
+    assert all(torch.isfinite(grads[l][k]).all() for l in range(L) for k in ("w", "u", "b"))

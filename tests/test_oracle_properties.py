@@ -269,3 +269,24 @@ def test_radial_chain_vjp_matches_finite_differences():
                 fdp[i] = (loss(ps_p, x) - loss(ps_m, x)) / (2 * eps)
             got = np.atleast_1d(np.asarray(grads[l][k], dtype=np.float64))
             assert np.allclose(got, fdp, rtol=2e-5, atol=2e-7), (l, name, got, fdp)
+
+
+def test_forward_and_inverse_vjp_are_mutually_inverse_maps():
+    """J(inverse(f)) at y = J(f)⁻¹ at x: pulling a cotangent back through inverse(f) and then through f returns it."""
+    rng = np.random.default_rng(41)
+    D, N, L = 7, 6, 3
+    params = [(rng.standard_normal(D) / np.sqrt(D), rng.standard_normal(D) / np.sqrt(D), rng.standard_normal(1)) for _ in range(L)]
+    x = rng.standard_normal((D, N))
+    y = x
+    for (w, u, b) in params:
+        y, _ = O.planar_forward(w, u, b, y)
+    v = rng.standard_normal((D, N))
+    u_, _ = O.planar_inverse_chain_vjp(params, y, v, np.zeros(N))     # J_inv(y)ᵀ v
+    back, _ = O.planar_chain_vjp(params, x, u_, np.zeros(N))          # J_f(x)ᵀ J_inv(y)ᵀ v = v
+    assert np.allclose(back, v, rtol=1e-9, atol=1e-10)
+    # and the two logjac cotangent paths are consistent: d/dy [logjac_inv(y)] = −J_inv(y)ᵀ d/dx [logjac_f(x)]
+    ones = np.ones(N)
+    gx, _ = O.planar_chain_vjp(params, x, np.zeros((D, N)), ones)
+    gy, _ = O.planar_inverse_chain_vjp(params, y, np.zeros((D, N)), ones)
+    pulled, _ = O.planar_inverse_chain_vjp(params, y, gx, np.zeros(N))
+    assert np.allclose(gy, -pulled, rtol=1e-8, atol=1e-9)
