@@ -12,7 +12,6 @@
 //       constant bank (MODE 2).  This is the fastest form (88-89 %).
 // A __constant__ slot filled per call from device parameters (prep kernel + copy) was measured too: the extra
 // launch + copy-engine hop costs 13 us per call, more than constant operands gain over shared-memory ones at D >= 64.
-// (The reverse-mode kernels in b2b_planar_vjp.cu still use such a slot.)
 //
 // Reference semantics: planar_layer.jl:65-80 (get_u_hat, forward), :102-110 (logabsdetjac), :112-127 + :160-185
 // (inverse through find_alpha).
@@ -69,34 +68,7 @@ struct PlanarConstProg {
   __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
     if constexpr (DERIVE) {
       if (MVN && warp == nw - 1) stage_layer(P.layers[src.nreal], params + MVN_OFF, D, D, lane);
-      for (int l = warp; l < L; l += nw) {
-        float* w_out = params + l * D;
-        float* u_out = params + L * D + l * D;
-        if (l >= src.nreal) {  // identity padding
-          for (int i = lane; i < D; i += 32) w_out[i] = u_out[i] = 0.f;
-          if (lane == 0) params[2 * L * D + l] = params[2 * L * D + L + l] = 0.f;
-          continue;
-        }
-        const b2b_layer_desc& d = P.layers[l];
-        float s = 0.f, q = 0.f;
-        for (int i = lane; i < D; i += 32) {
-          const float w = d.p0[i], u = d.p1[i];
-          s = fmaf(w, u, s);
-          q = fmaf(w, w, q);
-        }
-        s = warp_sum(s);
-        q = warp_sum(q);
-        const float k = (softplus(-s) - 1.0f) / q;  // planar_layer.jl:67
-        for (int i = lane; i < D; i += 32) {
-          const float w = d.p0[i];
-          w_out[i] = w;
-          u_out[i] = fmaf(k, w, d.p1[i]);
-        }
-        if (lane == 0) {
-          params[2 * L * D + l] = softplus(s) - 1.0f;  // wᵀû, planar_layer.jl:68
-          params[2 * L * D + L + l] = d.p2[0];          // first(flow.b), :75
-        }
-      }
+      planar_derive_smem<D, L>(P, src.nreal, params, warp, lane, nw);
     } else if constexpr (STAGED) {
       for (int i = warp * 32 + lane; i < NPK; i += nw * 32) params[i] = src.raw(i);
     }

@@ -1,5 +1,5 @@
-// Reverse mode (VJP) of planar chains through the constant-bank pipeline (see b2b_planar_const.cu for the forward
-// kernels and b2b_planar_common.cuh for the parameter slot).
+// Reverse mode (VJP) of planar chains on the TMA pipeline (see b2b_planar_const.cu for the forward kernels); parameters
+// are derived in the kernel prologue into shared memory, as in planar_dev_kernel -- no library-owned device state.
 #include "b2b_planar_common.cuh"
 
 namespace b2b {
@@ -26,45 +26,44 @@ struct VjpState {
 // differentiated with the implicit-function rule ext/BijectorsChainRulesCoreExt.jl:42-46
 // (∂α/∂(wᵀy) = X, ∂α/∂c = −tanh(α+b)·X, ∂α/∂b = X − 1, X = 1/(1 + c·sech²(α+b))):
 //   u_{k+1} = u_k − û_k th_k,  g_k = X·(−s_k·û_kᵀζ_{k+1} + 2 c th_k·l̄ s_k X),  ζ_k = ζ_{k+1} + w_k g_k.
-template <int D, int L, int MODE, int DIR>
+template <int D, int L, int DIR>
 struct PlanarVjpProg {
   using State = VjpState<L>;
-  using Src = SymSrc<D, L>;
-  const Src src;
+  const B2BChainParams& P;
+  int nreal;
   float* scal;     // [N][3][L]: g | t | l̄·s/(1+c·s)
   long long N;
   __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
-    if constexpr (MODE != 0) {
-      for (int i = warp * 32 + lane; i < L * D; i += nw * 32) params[i] = src.raw(i);  // w in shared memory
-    }
+    planar_derive_smem<D, L>(P, nreal, params, warp, lane, nw);
   }
   // forward recompute on the x fragment: t_l, s_l
   __device__ __forceinline__ void phase1(float2 (&x)[1][D / 2], const ColCtx<D, 1>&, const float* params,
                                          State& st) const {
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      const float4* sp4 = reinterpret_cast<const float4*>(params + l * D);
+      const float4* w4 = reinterpret_cast<const float4*>(params + l * D);
+      const float4* u4 = reinterpret_cast<const float4*>(params + L * D + l * D);
       float2 acc[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < D / 4; ++i) {
-        float4 w;
-        if (MODE == 2) w = sp4[i];
-        else w = make_float4(src.w(l, 4 * i), src.w(l, 4 * i + 1), src.w(l, 4 * i + 2), src.w(l, 4 * i + 3));
+        const float4 w = w4[i];
         acc[(i & 1) * 2 + 0] = __ffma2_rn(make_float2(w.x, w.y), x[0][2 * i], acc[(i & 1) * 2 + 0]);
         acc[(i & 1) * 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), x[0][2 * i + 1], acc[(i & 1) * 2 + 1]);
       }
       const float2 s = __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
-      if (DIR == 0) tanh_sech2(s.x + s.y + src.b(l), st.t[l], st.s2[l]);
-      else find_alpha_ts(s.x + s.y, src.c(l), src.b(l), st.t[l], st.s2[l]);  // planar_layer.jl:121
+      const float cc_ = params[2 * L * D + l], bb = params[2 * L * D + L + l];
+      if (DIR == 0) tanh_sech2(s.x + s.y + bb, st.t[l], st.s2[l]);
+      else find_alpha_ts(s.x + s.y, cc_, bb, st.t[l], st.s2[l]);  // planar_layer.jl:121
       if (l + 1 < L) {  // the last layer's output is not needed
         const float tt = DIR == 0 ? st.t[l] : -st.t[l];
         const float2 t2 = make_float2(tt, tt);
 #pragma unroll
         for (int i = 0; i < D / 4; ++i) {
-          x[0][2 * i] = __ffma2_rn(make_float2(src.uh(l, 4 * i), src.uh(l, 4 * i + 1)), t2, x[0][2 * i]);
-          x[0][2 * i + 1] = __ffma2_rn(make_float2(src.uh(l, 4 * i + 2), src.uh(l, 4 * i + 3)), t2, x[0][2 * i + 1]);
+          const float4 u = u4[i];
+          x[0][2 * i] = __ffma2_rn(make_float2(u.x, u.y), t2, x[0][2 * i]);
+          x[0][2 * i + 1] = __ffma2_rn(make_float2(u.z, u.w), t2, x[0][2 * i + 1]);
         }
       }
     }
@@ -75,30 +74,28 @@ struct PlanarVjpProg {
     float g[L], cb[L];
 #pragma unroll
     for (int l = L - 1; l >= 0; --l) {
+      const float4* w4 = reinterpret_cast<const float4*>(params + l * D);
+      const float4* u4 = reinterpret_cast<const float4*>(params + L * D + l * D);
       float2 acc[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < D / 4; ++i) {
-        acc[(i & 1) * 2 + 0] =
-            __ffma2_rn(make_float2(src.uh(l, 4 * i), src.uh(l, 4 * i + 1)), x[0][2 * i], acc[(i & 1) * 2 + 0]);
-        acc[(i & 1) * 2 + 1] =
-            __ffma2_rn(make_float2(src.uh(l, 4 * i + 2), src.uh(l, 4 * i + 3)), x[0][2 * i + 1], acc[(i & 1) * 2 + 1]);
+        const float4 u = u4[i];
+        acc[(i & 1) * 2 + 0] = __ffma2_rn(make_float2(u.x, u.y), x[0][2 * i], acc[(i & 1) * 2 + 0]);
+        acc[(i & 1) * 2 + 1] = __ffma2_rn(make_float2(u.z, u.w), x[0][2 * i + 1], acc[(i & 1) * 2 + 1]);
       }
       const float2 s = __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
       const float d = s.x + s.y;  // û_lᵀ ȳ_{l+1}
-      const float c = src.c(l), s2 = st.s2[l], t = st.t[l];
+      const float c = params[2 * L * D + l], s2 = st.s2[l], t = st.t[l];
       const float rden = __frcp_rn(fmaf(c, s2, 1.0f));
       cb[l] = lj[0] * s2 * rden;
       if (DIR == 0) g[l] = fmaf(s2, d, -2.0f * c * t * cb[l]);
       else g[l] = rden * fmaf(-s2, d, 2.0f * c * t * cb[l]);
       const float2 g2 = make_float2(g[l], g[l]);
-      const float4* sp4 = reinterpret_cast<const float4*>(params + l * D);
 #pragma unroll
       for (int i = 0; i < D / 4; ++i) {
-        float4 w;
-        if (MODE == 2) w = sp4[i];
-        else w = make_float4(src.w(l, 4 * i), src.w(l, 4 * i + 1), src.w(l, 4 * i + 2), src.w(l, 4 * i + 3));
+        const float4 w = w4[i];
         x[0][2 * i] = __ffma2_rn(make_float2(w.x, w.y), g2, x[0][2 * i]);
         x[0][2 * i + 1] = __ffma2_rn(make_float2(w.z, w.w), g2, x[0][2 * i + 1]);
       }
@@ -115,13 +112,13 @@ struct PlanarVjpProg {
   }
 };
 
-template <int D, int L, int NW, int MODE, int DIR>
+template <int D, int L, int NW, int DIR>
 __global__ void __launch_bounds__(NW * 32, 1)
     planar_vjp_kernel(const __grid_constant__ B2BChainParams P, const __grid_constant__ V1Extra E,
                       const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_yb,
-                      const __grid_constant__ CUtensorMap map_xb, const float* stage, float* scal) {
-  const PlanarVjpProg<D, L, MODE, DIR> prog{{stage, 0}, scal, P.N};
-  v1_run<D, 1, 1, NW, PlanarVjpProg<D, L, MODE, DIR>, 2>(P, E, map_x, map_xb, prog, &map_yb);
+                      const __grid_constant__ CUtensorMap map_xb, float* scal, const int nreal) {
+  const PlanarVjpProg<D, L, DIR> prog{P, nreal, scal, P.N};
+  v1_run<D, 1, 1, NW, PlanarVjpProg<D, L, DIR>, 2>(P, E, map_x, map_xb, prog, &map_yb);
 }
 
 // K2: A1[l][r] = Σ_n g[l,n]·x[r,n],  A2[l][r] = Σ_n t[l,n]·ȳ[r,n].  A warp handles 128/D columns at a time (lane ->
@@ -456,7 +453,7 @@ constexpr int VJP_PG_GRID = 592;   // 4 CTAs per SM
 constexpr int VJP_SS_GRID = 296;
 
 struct VjpWs {
-  float *scal, *pg_partials, *A, *ss_partials, *SS;
+  float *scal, *pg_partials, *A, *ss_partials, *SS, *packed;
   size_t bytes;
 };
 
@@ -473,33 +470,32 @@ static VjpWs vjp_carve(char* base, int Lp, int D, long long N) {
   w.A = take((size_t)2 * Lp * D);
   w.ss_partials = take((size_t)VJP_SS_GRID * (Lp * Lp + 2 * Lp));
   w.SS = take((size_t)Lp * Lp + 2 * Lp);
+  w.packed = take((size_t)2 * Lp * D + 2 * Lp);
   w.bytes = off + 256;
   return w;
 }
 
-template <int D, int L, int NW, int MODE>
+template <int D, int L, int NW>
 static int launch_vjp_main(int dir, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx, const CUtensorMap& myb,
-                           const CUtensorMap& mxb, const float* stage, float* scal, cudaStream_t stream) {
-  auto kernel = dir ? planar_vjp_kernel<D, L, NW, MODE, 1> : planar_vjp_kernel<D, L, NW, MODE, 0>;
+                           const CUtensorMap& mxb, float* scal, int nreal, cudaStream_t stream) {
+  auto kernel = dir ? planar_vjp_kernel<D, L, NW, 1> : planar_vjp_kernel<D, L, NW, 0>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return (int)e;
-  kernel<<<g.grid, NW * 32, g.smem, stream>>>(q, g.extra, mx, myb, mxb, stage, scal);
+  kernel<<<g.grid, NW * 32, g.smem, stream>>>(q, g.extra, mx, myb, mxb, scal, nreal);
   return (int)cudaGetLastError();
 }
 
 template <int D, int NW>
-static int dispatch_vjp_main(int dir, int L, int mode, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx,
-                             const CUtensorMap& myb, const CUtensorMap& mxb, const float* stage, float* scal,
+static int dispatch_vjp_main(int dir, int L, const B2BChainParams& q, const V1Geom& g, const CUtensorMap& mx,
+                             const CUtensorMap& myb, const CUtensorMap& mxb, float* scal, int nreal,
                              cudaStream_t stream) {
-  if (L == 1) return launch_vjp_main<D, 1, NW, 0>(dir, q, g, mx, myb, mxb, stage, scal, stream);
-  if (L == 2) return launch_vjp_main<D, 2, NW, 0>(dir, q, g, mx, myb, mxb, stage, scal, stream);
-  if (L == 4) return launch_vjp_main<D, 4, NW, 0>(dir, q, g, mx, myb, mxb, stage, scal, stream);
-  if constexpr (2 * D * 8 * 4 > 4096) {
-    if (L == 8 && mode == 2) return launch_vjp_main<D, 8, NW, 2>(dir, q, g, mx, myb, mxb, stage, scal, stream);
-  } else {
-    if (L == 8 && mode == 0) return launch_vjp_main<D, 8, NW, 0>(dir, q, g, mx, myb, mxb, stage, scal, stream);
+  switch (L) {
+    case 1: return launch_vjp_main<D, 1, NW>(dir, q, g, mx, myb, mxb, scal, nreal, stream);
+    case 2: return launch_vjp_main<D, 2, NW>(dir, q, g, mx, myb, mxb, scal, nreal, stream);
+    case 4: return launch_vjp_main<D, 4, NW>(dir, q, g, mx, myb, mxb, scal, nreal, stream);
+    case 8: return launch_vjp_main<D, 8, NW>(dir, q, g, mx, myb, mxb, scal, nreal, stream);
+    default: return B2B_EUNSUPPORTED;
   }
-  return B2B_EUNSUPPORTED;
 }
 
 template <int D, int L>
@@ -586,31 +582,23 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
   static const int vjp_nw = getenv("B2B_VJP_NW") ? atoi(getenv("B2B_VJP_NW")) : 0;
   // D = 128 x 8 layers: two-tensor slots are 32 KB; 7 warps leave room for 3 of them (8 warps: 2, 40 % slower)
   const int nw = (D == 128 && Lp == 8) ? ((vjp_nw == 6 || vjp_nw == 8) ? vjp_nw : 7) : sh.nw;
-  int rc = v1_geometry(D, p.N, nw, 32, sh.mode ? (size_t)Lp * D : 0, g, 2);
+  int rc = v1_geometry(D, p.N, nw, 32, (size_t)((2 * Lp * D + 2 * Lp + 3) & ~3), g, 2);
   if (rc != 0) return rc;
   CUtensorMap mx, mxb, myb;
   if (!make_maps(q, g.cols, &mx, &mxb, &g.extra.tma3d)) return B2B_EUNSUPPORTED;
   if (!make_map(&myb, ybar, D, p.N, ldyb, g.cols, g.extra.tma3d != 0)) return B2B_EUNSUPPORTED;
-
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return B2B_EUNSUPPORTED;
-  SlotState& st = g_slots[dev];
-  std::lock_guard<std::mutex> lock(st.mu);
-  cudaError_t e;
-  {
-    const int rcp = planar_slot_prepare(st, p, n, Lp, stream);
-    if (rcp != 0) return rcp;
-  }
-  if (D == 128 && Lp == 8 && g.nw == 6) rc = launch_vjp_main<128, 8, 6, 2>(dir, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
-  else if (D == 128 && Lp == 8 && g.nw == 7) rc = launch_vjp_main<128, 8, 7, 2>(dir, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
-  else if (D == 128) rc = dispatch_vjp_main<128, 8>(dir, Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
-  else if (D == 64) rc = dispatch_vjp_main<64, 12>(dir, Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
-  else rc = dispatch_vjp_main<32, 16>(dir, Lp, sh.mode, q, g, mx, myb, mxb, st.stage, ws.scal, stream);
+  if (D == 128 && Lp == 8 && g.nw == 6) rc = launch_vjp_main<128, 8, 6>(dir, q, g, mx, myb, mxb, ws.scal, n, stream);
+  else if (D == 128 && Lp == 8 && g.nw == 7) rc = launch_vjp_main<128, 8, 7>(dir, q, g, mx, myb, mxb, ws.scal, n, stream);
+  else if (D == 128) rc = dispatch_vjp_main<128, 8>(dir, Lp, q, g, mx, myb, mxb, ws.scal, n, stream);
+  else if (D == 64) rc = dispatch_vjp_main<64, 12>(dir, Lp, q, g, mx, myb, mxb, ws.scal, n, stream);
+  else rc = dispatch_vjp_main<32, 16>(dir, Lp, q, g, mx, myb, mxb, ws.scal, n, stream);
   if (rc != B2B_OK) return rc;
+  cudaError_t e;
   // parameter gradients: skinny reductions over the ORIGINAL x and ybar.  NOTE: xbar may alias ybar, in which case
   // ybar has been overwritten -- aliasing is therefore only allowed when the caller does not want parameter gradients.
-  int nl = 2;
+  int nl = 1;
   if (wbar && ubar && bbar) {
+    planar_prep_kernel<<<1, HP_MAX_L * 32, 0, stream>>>(p, n, Lp, ws.packed);  // w | û | c | b for the finalize kernel
     if (D == 128) rc = launch_pgrad<128>(Lp, p.x, ybar, ws.scal, p.N, p.ldx, ldyb, ws.pg_partials, stream);
     else if (D == 64) rc = launch_pgrad<64>(Lp, p.x, ybar, ws.scal, p.N, p.ldx, ldyb, ws.pg_partials, stream);
     else rc = launch_pgrad<32>(Lp, p.x, ybar, ws.scal, p.N, p.ldx, ldyb, ws.pg_partials, stream);
@@ -620,11 +608,10 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
     if (rc != B2B_OK) return rc;
     const int ns = Lp * Lp + 2 * Lp;
     planar_psum_kernel<<<(ns + 7) / 8, 256, 0, stream>>>(ws.ss_partials, VJP_SS_GRID, ns, ws.SS);
-    planar_vjp_finalize_kernel<<<n, 256, 0, stream>>>(p, n, Lp, dir, st.stage, ws.A, ws.SS, wbar, ubar, bbar);
+    planar_vjp_finalize_kernel<<<n, 256, 0, stream>>>(p, n, Lp, dir, ws.packed, ws.A, ws.SS, wbar, ubar, bbar);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
-    nl += 5;
+    nl += 6;
   }
-  if ((e = cudaEventRecord(st.free_ev, stream)) != cudaSuccess) return (int)e;
   if (launches) *launches = nl;
   return B2B_OK;
 }

@@ -135,8 +135,7 @@ int b2b_last_launch_count(void);
  * 3 = unrolled planar-chain kernel only (segments of <= 8 PlanarLayers, D in {32,64,128}; else B2B_EUNSUPPORTED).
  * Tens digit -- coupling: 0 = auto (tensor cores when the mask is contiguous and workspace is given),
  * 1 = always the exact-fp32 CUDA-core kernel.  Hundreds digit -- 1 = do not fold BatchNorm layers into neighbouring coupling launches.
- * Note: b2b_planar_chain_vjp_f32 orders its use of a per-device __constant__ slot with a CUDA event and cannot be
- * stream-captured; every other entry point uses no library-owned device state. */
+ * No entry point uses library-owned device state (everything is launch-only on the caller's stream). */
 int b2b_set_kernel_variant(int variant);
 
 /* ---- single layers (thin wrappers over a 1-element chain) --------------------------------------- */

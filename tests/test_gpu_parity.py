@@ -943,7 +943,7 @@ def test_planar_chain_vjp_matches_oracle(B, D, L):
     # inputs untouched; xbar-only call (no parameter cotangents), ljbar = None
     assert np.array_equal(B.to_numpy(xd), x) and np.array_equal(B.to_numpy(ybd), ybar)
     xbar2, g2 = B.planar_chain_vjp(flow, xd, ybd, None, want_param_grads=False)
-    assert g2 is None and B.lib().b2b_last_launch_count() == 2
+    assert g2 is None and B.lib().b2b_last_launch_count() == 1
     xb_o2, _ = O.planar_chain_vjp([(w.astype(np.float64), u.astype(np.float64), b.astype(np.float64)) for w, u, b in params],
                                   x.astype(np.float64), ybar.astype(np.float64), np.zeros(N))
     assert rel(B.to_numpy(xbar2), xb_o2) <= RTOL
