@@ -85,7 +85,7 @@ static __global__ void __launch_bounds__(HP_MAX_L * 32)
   }
 }
 
-// ---- host side: launch shapes, slot state ------------------------------------------------------------------
+// ---- host side: launch shapes -------------------------------------------------------------------------------
 struct HPShape {
   int nw, mode;
 };
