@@ -101,6 +101,10 @@ static int launch_fused(B2BChainParams& p, cudaStream_t stream) {
     }
     if (g_variant == 3 || rc != B2B_EUNSUPPORTED) return rc;
   }
+  if (g_variant == 0 && b2b_radial_unrolled_applicable(p)) {  // inverse radial chains: specialised program
+    rc = b2b_launch_radial_unrolled(p, stream);
+    if (rc != B2B_EUNSUPPORTED) return rc;
+  }
   if (g_variant == 0 && b2b_rqs_unrolled_applicable(p)) {  // one RQS layer, K = 8 bins: specialised program
     rc = b2b_launch_rqs_unrolled(p, stream);
     if (rc != B2B_EUNSUPPORTED) return rc;
@@ -118,7 +122,7 @@ static int fused_grid(const B2BChainParams& p) {
     const int g = b2b_planar_const_grid_size(p);
     if (g > 0 || g_variant == 3) return g;
   }
-  if (g_variant == 0 && b2b_rqs_unrolled_applicable(p)) {  // same warps-per-D table as the planar kernels
+  if (g_variant == 0 && (b2b_rqs_unrolled_applicable(p) || b2b_radial_unrolled_applicable(p))) {  // same warps-per-D table as the planar kernels
     const int g = b2b_planar_const_grid_size(p);
     if (g > 0) return g;
   }

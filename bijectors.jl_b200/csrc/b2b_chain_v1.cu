@@ -74,63 +74,6 @@ __device__ __forceinline__ void planar_apply(float2 (&x)[CPT][D / TPC / 2], cons
 }
 
 template <int D, int TPC, int CPT>
-__device__ __forceinline__ void radial_apply(float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& c, const float* sp,
-                                             bool inverse, float (&lj)[CPT]) {
-  using C = ColCtx<D, TPC>;
-  const float4* z4 = reinterpret_cast<const float4*>(sp);
-  const float alpha = sp[D], bhat = sp[D + 1], apb = sp[D + 2];
-  const float2 m1 = make_float2(-1.f, -1.f);
-  float2 acc[CPT][4];
-  B2B_FOR_COLS {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[cc][i] = make_float2(0.f, 0.f);
-  }
-  B2B_FOR_SLOTS {
-    const float4 z0 = z4[c.prm(ql, r)];
-    const int i = (ql * 8 + r) * 2;
-    B2B_FOR_COLS {
-      const float2 d0 = __ffma2_rn(make_float2(z0.x, z0.y), m1, x[cc][i]);
-      const float2 d1 = __ffma2_rn(make_float2(z0.z, z0.w), m1, x[cc][i + 1]);
-      acc[cc][(r & 1) * 2 + 0] = __ffma2_rn(d0, d0, acc[cc][(r & 1) * 2 + 0]);
-      acc[cc][(r & 1) * 2 + 1] = __ffma2_rn(d1, d1, acc[cc][(r & 1) * 2 + 1]);
-    }
-  }
-  float2 g2[CPT];
-  B2B_FOR_COLS {
-    const float2 s = __fadd2_rn(__fadd2_rn(acc[cc][0], acc[cc][1]), __fadd2_rn(acc[cc][2], acc[cc][3]));
-    const float nrm = sqrtf(part_sum<TPC>(s.x + s.y));  // radial_layer.jl:49 / :125
-    float r_ = nrm;
-    if (inverse) {
-      const float a = apb - nrm;  // radial_layer.jl:126-127
-      const float sq = sqrtf(fmaf(a, a, 4.0f * alpha * nrm));
-      r_ = a > 0.f ? (2.0f * alpha * nrm) / (sq + a) : 0.5f * (sq - a);
-    }
-    const float hh = 1.0f / (alpha + r_);
-    const float bh = bhat * hh;
-    const float ljf = (float)(D - 1) * log1pf(bh) + log1pf(bh * alpha * hh);  // radial_layer.jl:68-70
-    float g;
-    if (!inverse) {
-      g = bh;
-      lj[cc] += ljf;
-    } else {
-      g = -bhat / (apb + r_);  // (α+r)/(α+β̂+r) − 1, radial_layer.jl:96
-      lj[cc] -= ljf;
-    }
-    g2[cc] = make_float2(g, g);
-  }
-  B2B_FOR_SLOTS {
-    const float4 z0 = z4[c.prm(ql, r)];
-    const int i = (ql * 8 + r) * 2;
-    B2B_FOR_COLS {
-      const float2 d0 = __ffma2_rn(make_float2(z0.x, z0.y), m1, x[cc][i]);
-      const float2 d1 = __ffma2_rn(make_float2(z0.z, z0.w), m1, x[cc][i + 1]);
-      x[cc][i] = __ffma2_rn(g2[cc], d0, x[cc][i]);
-      x[cc][i + 1] = __ffma2_rn(g2[cc], d1, x[cc][i + 1]);
-    }
-  }
-}
-
-template <int D, int TPC, int CPT>
 __device__ __forceinline__ void batchnorm_apply(float2 (&x)[CPT][D / TPC / 2], const ColCtx<D, TPC>& c,
                                                 const float* sp, bool inverse, float (&lj)[CPT]) {
   using C = ColCtx<D, TPC>;

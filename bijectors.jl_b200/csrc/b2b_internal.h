@@ -55,6 +55,9 @@ size_t b2b_radial_vjp_workspace(int L, int D);
 int b2b_launch_radial_chain_vjp(const B2BChainParams& p, const float* ybar, long long ldyb, const float* ljbar,
                                 float* xbar, long long ldxb, float* alpha_bar, float* beta_bar, float* z0_bar,
                                 void* workspace, size_t workspace_bytes, int* launches, cudaStream_t stream);
+// 1..8 radial layers of one direction as a specialised program (b2b_radial_unrolled.cu)
+int b2b_radial_unrolled_applicable(const B2BChainParams& p);
+int b2b_launch_radial_unrolled(const B2BChainParams& p, cudaStream_t stream);
 // a single RQS layer with 9 knots as a specialised program (b2b_rqs_unrolled.cu)
 int b2b_rqs_unrolled_applicable(const B2BChainParams& p);
 int b2b_launch_rqs_unrolled(const B2BChainParams& p, cudaStream_t stream);
