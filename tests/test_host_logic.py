@@ -245,3 +245,15 @@ def test_autograd_module_is_importable_without_a_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(Exception):
             flow(torch.zeros(5, 4))
+
+
+def test_vjp_workspace_queries_are_pure_host_functions():
+    """Workspace sizes of the reverse-mode entry points can be queried without a device (b2b.h)."""
+    L_ = B.lib()
+    a = L_.b2b_planar_chain_vjp_workspace_bytes(8, 128, 1 << 20)
+    b = L_.b2b_planar_chain_vjp_workspace_bytes(8, 128, 1 << 21)
+    assert a >= (1 << 20) * 3 * 8 * 4 and b > a          # per-column scalars g | t | l̄·s/(1+c·s)
+    assert L_.b2b_planar_chain_vjp_workspace_bytes(3, 64, 1000) == L_.b2b_planar_chain_vjp_workspace_bytes(4, 64, 1000)
+    assert L_.b2b_planar_chain_vjp_workspace_bytes(9, 128, 10) == 0   # more than 8 layers: unsupported
+    r = L_.b2b_radial_chain_vjp_workspace_bytes(6, 64)
+    assert r >= 592 * (6 * 64 + 12) * 4 and L_.b2b_radial_chain_vjp_workspace_bytes(6, 200) == 0
