@@ -293,9 +293,10 @@ extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const 
       }
       rc = B2B_EUNSUPPORTED;
       if (tc_ws && g_coupling_variant != 1) {
+        int n_launch = 0;
         rc = b2b_launch_coupling_affine_tc(layers[segs[s].begin], fold, cur, cdst, logjac, D, N, cur_ld, dst_ld,
-                                           lj_started ? 1 : 0, tc_ws, tc_bytes, stream);
-        if (rc == B2B_OK) g_last_launches += 2;  // W preparation + main kernel
+                                           lj_started ? 1 : 0, tc_ws, tc_bytes, &n_launch, stream);
+        if (rc == B2B_OK) g_last_launches += n_launch;  // W preparation + main kernel (+ fp32 kernel on a ragged tail)
       }
       if (rc == B2B_EUNSUPPORTED) {
         rc = b2b_launch_coupling_affine(layers[segs[s].begin], fold, cur, cdst, logjac, D, N, cur_ld, dst_ld,

@@ -54,7 +54,6 @@ struct TcParams {
   const float* cvec;          // [2 n1] or NULL
   long long N, ldx, ldy, tiles;
   int D, n1, n2, nkb, row1, row2, accumulate, inverse;
-  int debug;  // B2B_TC_DEBUG bit mask (profiling only): 1 epilogue no global I/O, 2 producers no global I/O, 4 no MMA
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------
@@ -182,6 +181,15 @@ __global__ void __launch_bounds__(1024) coupling_prep_kernel(const float* __rest
 }
 
 // ---- main kernel -------------------------------------------------------------------------------------------
+// Template parameters: LD > 0 = compile-time leading dimension of BOTH x and y (the dense D = 256 batches of the
+// BASELINE configuration: every per-column address becomes an immediate offset), 0 = run-time strides; FOLD = a
+// neighbouring BatchNorm is folded in (per-row affine before / after); INV = inverse law.
+// Round-2 rewrite of the producer / epilogue loops: the round-1 kernel executed ~150 instructions per x₂ column and ~44
+// per x₁ element (64-bit address products, per-column bounds tests and clamps, run-time mode flags, register spills)
+// and was issue / instruction-cache bound at 46 % of the HBM roofline.  This kernel only ever sees WHOLE tiles (the
+// launcher hands the < 64 ragged columns at the end of a batch to the exact-fp32 kernel), so there is no bounds logic
+// at all, and addresses are a per-tile pointer plus immediates.
+template <int LD, bool FOLD, bool INV>
 __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* base = smem_dyn + ((1024u - (sm_u32(smem_dyn) & 1023u)) & 1023u);
@@ -194,6 +202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
   uint64_t* bars = reinterpret_cast<uint64_t*>(colscale + TC_SCALE_SLOTS * TC_T);
   // bars: [0..1] b_full, [2..3] b_empty, [4..5] acc_full, [6..7] acc_empty, [8] w_ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const long long ldx = LD ? LD : P.ldx, ldy = LD ? LD : P.ldy;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -247,8 +256,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
               const uint32_t baddr = bB + (uint32_t)((pb * nkb + kb) * TC_BBLK);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {  // 4 K-steps of 16 fp16 (32 B) inside the 128-byte swizzle atom
-                if (!(P.debug & 4))
-                  tc_mma_f16(d_tmem, umma_desc_k_sw128(aaddr + 32 * j), umma_desc_k_sw128(baddr + 32 * j), TC_IDESC, acc);
+                tc_mma_f16(d_tmem, umma_desc_k_sw128(aaddr + 32 * j), umma_desc_k_sw128(baddr + 32 * j), TC_IDESC, acc);
                 acc = 1;
               }
             }
@@ -263,51 +271,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
     // Warp p converts columns [8p, 8p+8) of every tile.  Lane l holds the float4 #l of a column (rows
     // row2+4l..+3).  The per-column maximum (operand scale) is ONE redux.sync on the float bit patterns (monotonic
     // for non-negative floats); the 8 dots with wsum (log-Jacobian) are reduced together by a transposing butterfly
-    // (7+2 shuffles), after which lane l owns column (l>>2)&7.  x₂ registers always hold the NEXT tile while the
-    // current one is being converted (refilled column by column), so DRAM latency hides behind a tile of work.
+    // (7+2 shuffles), after which lane l owns column (l>>2)&7.  The NEXT tile's eight columns are requested at the top
+    // of the loop, so a whole tile of conversion work hides their DRAM latency.
     constexpr int CW = TC_T / TC_PROD_WARPS;  // 8 columns per producer warp
     const int p = warp - TC_EPI_WARPS;
     const bool active = 4 * lane < P.n2;
-    const float4 ws = active ? *reinterpret_cast<const float4*>(P.wsum + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float inv_scale_w = P.meta[0];
-    const float csum = P.meta[1] * (P.inverse ? -1.f : 1.f) + (P.fold ? P.fold[4 * P.D] : 0.f);
-    const int kb = (4 * lane) / 64, kp = (4 * lane) % 64;
+    const int lrow = active ? 4 * lane : 0;  // inactive lanes read a valid address, result unused
     const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool fold = P.fold != nullptr;
-    const float4 preA = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + P.row2 + 4 * lane) : one4;
-    const float4 preC = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + P.D + P.row2 + 4 * lane) : zero4;
-    const float4 postA = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + 2 * P.D + P.row2 + 4 * lane) : one4;
-    const float4 postC = (fold && active) ? *reinterpret_cast<const float4*>(P.fold + 3 * P.D + P.row2 + 4 * lane) : zero4;
-    const bool write_y2 = P.y != nullptr && (P.y != P.x || fold) && !(P.debug & 2);
+    const float4 ws = active ? *reinterpret_cast<const float4*>(P.wsum + 4 * lane) : zero4;
+    const float cs_mul = 6.103515625e-05f * P.meta[0];  // 2^-14 / scaleW: undoes both operand scales
+    const float csum = P.meta[1] * (INV ? -1.f : 1.f) + (FOLD ? P.fold[4 * P.D] : 0.f);
+    float4 preA = one4, preC = zero4, postA = one4, postC = zero4;
+    if (FOLD && active) {
+      preA = *reinterpret_cast<const float4*>(P.fold + P.row2 + 4 * lane);
+      preC = *reinterpret_cast<const float4*>(P.fold + P.D + P.row2 + 4 * lane);
+      postA = *reinterpret_cast<const float4*>(P.fold + 2 * P.D + P.row2 + 4 * lane);
+      postC = *reinterpret_cast<const float4*>(P.fold + 3 * P.D + P.row2 + 4 * lane);
+    }
+    const bool write_y2 = P.y != nullptr && (P.y != P.x || FOLD);
+    const bool rest_rows = write_y2 && P.n1 + P.n2 < P.D;
     const int own = (lane >> 2) & 7;  // column owned by this lane after the transposing reduction
-    const float* xlane = P.x + P.row2 + (active ? 4 * lane : 0);  // inactive lanes read a valid address, result unused
-    float4 v[CW];
-    auto load_tile = [&](long long tile, int c) -> float4 {
-      long long col = tile * TC_T + p * CW + c;
-      col = col < P.N ? col : P.N - 1;  // clamp instead of predicating; stores are predicated
-      if (P.debug & 2) return make_float4(1.f, 2.f, 3.f, 4.f);
-      return __ldcs(reinterpret_cast<const float4*>(xlane + col * P.ldx));
-    };
+    // operand-layout offset of this lane's 8-byte group in row (8p + c): sw128_off(8p + c, kp) = st_base ^ (c<<4 | c<<7)
+    const int kb = (4 * lane) / 64, kp = (4 * lane) % 64;
+    const int st_base = p * 1024 + ((kp >> 3) << 4) + (kp & 7) * 2 + kb * TC_BBLK;
+    const int lo_off = nkb * TC_BBLK;
+    const long long tstride = (long long)gridDim.x * TC_T;  // columns between two tiles of this CTA
+    long long col0 = (long long)blockIdx.x * TC_T + p * CW;  // first column of this warp in the current tile
+    const float* xt = P.x + P.row2 + lrow + col0 * ldx;
+    float* yt = write_y2 ? P.y + P.row2 + lrow + col0 * ldy : nullptr;
+
+    float4 cur[CW];
     if (my_tiles > 0) {
 #pragma unroll
-      for (int c = 0; c < CW; ++c) v[c] = load_tile(blockIdx.x, c);
+      for (int c = 0; c < CW; ++c) cur[c] = __ldcs(reinterpret_cast<const float4*>(xt + c * ldx));
     }
     for (long long i = 0; i < my_tiles; ++i) {
       const int s = (int)(i & 1);
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
-      const long long tile = blockIdx.x + i * gridDim.x;
-      const long long col0 = tile * TC_T + p * CW;
-      const long long next_tile = (i + 1 < my_tiles) ? tile + gridDim.x : tile;
+      // x₂ registers are refilled column by column with the NEXT tile while the current one is converted (the last
+      // tile re-reads itself: harmless, keeps the loop free of branches)
+      const float* xn = (i + 1 < my_tiles) ? xt + tstride * ldx : xt;
       float dt[CW];
       unsigned emax[CW];
 #pragma unroll
       for (int c = 0; c < CW; ++c) {
-        float4 vc = v[c];
-        if (fold)
+        float4 vc = cur[c];
+        if (FOLD)
           vc = make_float4(fmaf(vc.x, preA.x, preC.x), fmaf(vc.y, preA.y, preC.y), fmaf(vc.z, preA.z, preC.z),
                            fmaf(vc.w, preA.w, preC.w));
         if (!active) vc = zero4;
-        v[c] = vc;
+        cur[c] = vc;
         const float mx = fmaxf(fmaxf(fabsf(vc.x), fabsf(vc.y)), fmaxf(fabsf(vc.z), fabsf(vc.w)));
         emax[c] = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));  // bits of max|x₂ column|
         dt[c] = fmaf(vc.x, ws.x, fmaf(vc.y, ws.y, fmaf(vc.z, ws.z, vc.w * ws.w)));
@@ -324,57 +337,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
       }
       float cdot = dt[0] + __shfl_xor_sync(0xffffffffu, dt[0], 2);
       cdot += __shfl_xor_sync(0xffffffffu, cdot, 1);
-      bar_wait(sm_u32(&bars[2 + s]), ph ^ 1);  // stage free (MMAs that read it have completed)
-      unsigned char* stage = sB + s * b_stage;
-      float* cslot = colscale + (int)(i & (TC_SCALE_SLOTS - 1)) * TC_T + p * CW;
-      if ((lane & 3) == 0) {
-        const long long col = col0 + own;
-        if (P.logjac && col < P.N) {
-          // Σ_j s_j = (Σ_j W_j)·x₂ + Σ_j c_j  (scale.jl:31); csum also carries the folded BatchNorm constants
-          const float b0 = P.accumulate ? P.logjac[col] : 0.f;
-          P.logjac[col] = b0 + (P.inverse ? -cdot : cdot) + csum;
-        }
+      if ((lane & 3) == 0 && P.logjac) {
+        // Σ_j s_j = (Σ_j W_j)·x₂ + Σ_j c_j  (scale.jl:31); csum also carries the folded BatchNorm constants
+        float* lp = P.logjac + col0 + own;
+        const float b0 = P.accumulate ? *lp : 0.f;
+        *lp = b0 + (INV ? -cdot : cdot) + csum;
       }
+      bar_wait(sm_u32(&bars[2 + s]), ph ^ 1);  // stage free (MMAs that read it have completed)
+      float* cslot = colscale + (int)(i & (TC_SCALE_SLOTS - 1)) * TC_T + p * CW;
 #pragma unroll
       for (int c = 0; c < CW; ++c) {
-        int e = (int)((emax[c] >> 23) & 0xffu) - 127;
-        e = max(-100, min(100, e));
-        const float scale = __uint_as_float((uint32_t)(127 + 14 - e) << 23);  // max|x₂ col|·scale in [2^14, 2^15)
-        if (lane == 0) cslot[c] = __uint_as_float((uint32_t)(127 - 14 + e) << 23) * inv_scale_w;  // undoes both scales
-        const float4 vc = v[c];
-        const long long col = col0 + c;
-        v[c] = load_tile(next_tile, c);  // refill with the next tile's column
+        // power of two of the column maximum, clamped to [2^-100, 2^100]; operand scale 2^14 / that (exact)
+        const float p2 = fminf(fmaxf(__uint_as_float(emax[c] & 0x7f800000u), 7.888609052210118e-31f), 1.2676506002282294e30f);
+        const float scale = __uint_as_float(0x86000000u - __float_as_uint(p2));  // 2^(14 - e): max|x₂ col|·scale in [2^14, 2^15)
+        if (lane == 0) cslot[c] = p2 * cs_mul;
+        const float4 vc = cur[c];
+        cur[c] = __ldcs(reinterpret_cast<const float4*>(xn + c * ldx));  // refill with the next tile's column
         if (active) {
-          const int n = p * CW + c;  // row of the operand tile
           const float q0 = vc.x * scale, q1 = vc.y * scale, q2 = vc.z * scale, q3 = vc.w * scale;
           const __half2 h01 = __floats2half2_rn(q0, q1), h23 = __floats2half2_rn(q2, q3);
           const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
           const __half2 l01 = __floats2half2_rn(q0 - f01.x, q1 - f01.y), l23 = __floats2half2_rn(q2 - f23.x, q3 - f23.y);
-          const int off = sw128_off(n, kp);
+          const int off = c * 128 + (c << 4);  // = (c<<4 | c<<7): XORed into the (disjoint) bits of st_base
           uint2 hi2, lo2;
           hi2.x = *reinterpret_cast<const unsigned*>(&h01);
           hi2.y = *reinterpret_cast<const unsigned*>(&h23);
           lo2.x = *reinterpret_cast<const unsigned*>(&l01);
           lo2.y = *reinterpret_cast<const unsigned*>(&l23);
-          *reinterpret_cast<uint2*>(stage + (0 * nkb + kb) * TC_BBLK + off) = hi2;
-          *reinterpret_cast<uint2*>(stage + (1 * nkb + kb) * TC_BBLK + off) = lo2;
-          if (write_y2 && col < P.N)  // x₂ passes through (plus the folded affines)
-            __stcs(reinterpret_cast<float4*>(P.y + col * P.ldy + P.row2) + lane,
-                   make_float4(fmaf(vc.x, postA.x, postC.x), fmaf(vc.y, postA.y, postC.y), fmaf(vc.z, postA.z, postC.z),
-                               fmaf(vc.w, postA.w, postC.w)));
+          unsigned char* dst = sB + s * b_stage + (st_base ^ off);
+          *reinterpret_cast<uint2*>(dst) = hi2;
+          *reinterpret_cast<uint2*>(dst + lo_off) = lo2;
+          if (write_y2) {  // x₂ passes through (plus the folded affines)
+            float4 o = vc;
+            if (FOLD)
+              o = make_float4(fmaf(vc.x, postA.x, postC.x), fmaf(vc.y, postA.y, postC.y), fmaf(vc.z, postA.z, postC.z),
+                              fmaf(vc.w, postA.w, postC.w));
+            __stcs(reinterpret_cast<float4*>(yt + c * ldy), o);
+          }
         }
       }
       // rows that belong to neither x₁ nor x₂ pass through when y != x
-      if (write_y2 && P.n1 + P.n2 < P.D) {
+      if (rest_rows) {
         for (int c = 0; c < CW; ++c) {
           const long long col = col0 + c;
-          if (col >= P.N) break;
           for (int r = lane; r < P.D; r += 32) {
             const bool in1 = r >= P.row1 && r < P.row1 + P.n1, in2 = r >= P.row2 && r < P.row2 + P.n2;
             if (!in1 && !in2) {
-              float xv = P.x[col * P.ldx + r];
-              if (fold) xv = fmaf(fmaf(xv, P.fold[r], P.fold[P.D + r]), P.fold[2 * P.D + r], P.fold[3 * P.D + r]);
-              P.y[col * P.ldy + r] = xv;
+              float xv = P.x[col * ldx + r];
+              if (FOLD) xv = fmaf(fmaf(xv, P.fold[r], P.fold[P.D + r]), P.fold[2 * P.D + r], P.fold[3 * P.D + r]);
+              P.y[col * ldy + r] = xv;
             }
           }
         }
@@ -382,52 +393,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
       fence_async_smem();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) bar_arrive(sm_u32(&bars[0 + s]));
+      col0 += tstride;
+      xt += tstride * ldx;
+      if (write_y2) yt += tstride * ldy;
     }
   } else {
     // ================================ epilogue ================================
     // Thread = TMEM lane = row j of s / t; warp w covers rows 32·(w%4)..+31 and columns 32·(w/4)..+31 of the tile
-    // as two chunks of 16 columns.  x₁ of the row is prefetched ONE chunk ahead (buffers A/B alternate).
+    // as two chunks of 16 columns.  x₁ of the row is prefetched ONE tile ahead (buffers A/B = the two chunks).
     const int j = (warp & 3) * 32 + lane;
     const int chalf = warp >> 2;  // which 32-column half of the tile
     const bool rowok = j < P.n1;
     const int jr = rowok ? j : 0;  // clamp: loads stay in bounds, stores are predicated
     const float cs_j = (rowok && P.cvec) ? P.cvec[j] : 0.f;
     const float ct_j = (rowok && P.cvec) ? P.cvec[P.n1 + j] : 0.f;
-    const bool efold = P.fold != nullptr && rowok;
-    const float preA_j = efold ? P.fold[P.row1 + j] : 1.f, preC_j = efold ? P.fold[P.D + P.row1 + j] : 0.f;
-    const float postA_j = efold ? P.fold[2 * P.D + P.row1 + j] : 1.f, postC_j = efold ? P.fold[3 * P.D + P.row1 + j] : 0.f;
-    const float* xrow = P.x + P.row1 + jr;
-    float* yrow = P.y ? P.y + P.row1 + jr : nullptr;
-    const bool do_store = P.y != nullptr && rowok && !(P.debug & 1);
-    const long long total_chunks = my_tiles * 2;  // this warp's chunks: 2 per tile
-    // first column of this warp's chunk q
-    auto chunk_col = [&](long long q) -> long long {
-      return (blockIdx.x + (q >> 1) * gridDim.x) * TC_T + chalf * 32 + (q & 1) * 16;
-    };
-    auto load_chunk = [&](long long q, float (&buf)[16]) {
-      if (q >= total_chunks || (P.debug & 1)) return;
-      const long long c0 = chunk_col(q);
+    float preA_j = 1.f, preC_j = 0.f, postA_j = 1.f, postC_j = 0.f;
+    if (FOLD && rowok) {
+      preA_j = P.fold[P.row1 + j];
+      preC_j = P.fold[P.D + P.row1 + j];
+      postA_j = P.fold[2 * P.D + P.row1 + j];
+      postC_j = P.fold[3 * P.D + P.row1 + j];
+    }
+    const bool do_store = P.y != nullptr && rowok;
+    const long long tstride = (long long)gridDim.x * TC_T;
+    long long c0 = (long long)blockIdx.x * TC_T + chalf * 32;  // first column of this warp in the current tile
+    const float* xr = P.x + P.row1 + jr + c0 * ldx;
+    float* yr = P.y ? P.y + P.row1 + jr + c0 * ldy : nullptr;
+    auto load_chunk = [&](float (&buf)[16], const float* src) {
 #pragma unroll
-      for (int n = 0; n < 16; ++n) {
-        long long col = c0 + n;
-        col = col < P.N ? col : P.N - 1;
-        buf[n] = __ldcs(xrow + col * P.ldx);
-      }
+      for (int n = 0; n < 16; ++n) buf[n] = __ldcs(src + n * ldx);
     };
     float xa[16], xb[16];
 #pragma unroll
     for (int n = 0; n < 16; ++n) xa[n] = xb[n] = 0.f;
-    load_chunk(0, xa);
-    load_chunk(1, xb);
+    if (my_tiles > 0) {
+      load_chunk(xa, xr);
+      load_chunk(xb, xr + 16 * ldx);
+    }
     for (long long i = 0; i < my_tiles; ++i) {
       const int a = (int)(i & 1);
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
       const float* cs = colscale + (int)(i & (TC_SCALE_SLOTS - 1)) * TC_T + chalf * 32;
+      const bool more = i + 1 < my_tiles;
       bar_wait(sm_u32(&bars[4 + a]), ph);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * 2 * TC_T + chalf * 32);
-      auto finish = [&](const uint32_t (&rs)[16], const uint32_t (&rt)[16], float (&xbuf)[16], long long qq, int chl) {
-        const long long c0 = chunk_col(qq);
+      auto finish = [&](const uint32_t (&rs)[16], const uint32_t (&rt)[16], float (&xbuf)[16], int chl) {
         float outv[16];
 #pragma unroll
         for (int n4 = 0; n4 < 4; ++n4) {
@@ -438,18 +449,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
             const int n = n4 * 4 + m;
             const float sv = fmaf(__uint_as_float(rs[n]), ff[m], cs_j);
             const float tv = fmaf(__uint_as_float(rt[n]), ff[m], ct_j);
-            const float xv = fmaf(xbuf[n], preA_j, preC_j);
+            const float xv = FOLD ? fmaf(xbuf[n], preA_j, preC_j) : xbuf[n];
             float out;
-            if (!P.inverse) out = fmaf(__expf(sv), xv, tv);  // exp(s)·x₁ + t  (scale.jl:13, shift.jl:14)
-            else out = (xv - tv) * __expf(-sv);               // inv.(a) .* (y₁ + (−t))  (scale.jl:16, shift.jl:12)
-            outv[n] = fmaf(out, postA_j, postC_j);
+            if (!INV) out = fmaf(__expf(sv), xv, tv);  // exp(s)·x₁ + t  (scale.jl:13, shift.jl:14)
+            else out = (xv - tv) * __expf(-sv);         // inv.(a) .* (y₁ + (−t))  (scale.jl:16, shift.jl:12)
+            outv[n] = FOLD ? fmaf(out, postA_j, postC_j) : out;
           }
         }
-        load_chunk(qq + 2, xbuf);  // refill this buffer with the same chunk of the next tile
+        // refill this buffer with the same chunk of the next tile
+        if (more) load_chunk(xbuf, xr + (tstride + chl * 16) * ldx);
         if (do_store) {
+          float* dst = yr + chl * 16 * ldy;
 #pragma unroll
-          for (int n = 0; n < 16; ++n)
-            if (c0 + n < P.N) __stcs(yrow + (c0 + n) * P.ldy, outv[n]);
+          for (int n = 0; n < 16; ++n) __stcs(dst + n * ldy, outv[n]);
         }
       };
       {
@@ -457,18 +469,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) coupling_tc_kernel(const __grid
         tc_ld16(t_lane, rs);
         tc_ld16(t_lane + TC_T, rt);
         tc_wait_ld();
-        finish(rs, rt, xa, i * 2, 0);
+        finish(rs, rt, xa, 0);
       }
       {
         uint32_t rs[16], rt[16];
         tc_ld16(t_lane + 16, rs);
         tc_ld16(t_lane + TC_T + 16, rt);
         tc_wait_ld();
-        finish(rs, rt, xb, i * 2 + 1, 1);
+        finish(rs, rt, xb, 1);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) bar_arrive(sm_u32(&bars[6 + a]));
+      c0 += tstride;
+      xr += tstride * ldx;
+      if (yr) yr += tstride * ldy;
     }
   }
 
@@ -492,7 +507,7 @@ size_t b2b_coupling_tc_workspace_bytes(int n1, int n2) {
 // SIMT kernel).  The mask must be declared contiguous through desc.n2 / desc.n3 (first rows of idx1 / idx2).
 int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* fold, const float* x, float* y,
                                   float* logjac, int D, long long N, long long ldx, long long ldy, int accumulate,
-                                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                                  void* workspace, size_t workspace_bytes, int* launches, cudaStream_t stream) {
   using namespace b2b;
   const int n1 = d.n0, n2 = d.n1;
   const size_t need = b2b_coupling_tc_workspace_bytes(n1, n2);
@@ -504,6 +519,17 @@ int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* fold, co
     return B2B_EUNSUPPORTED;
   if (y && ((ldy % 4) || (reinterpret_cast<uintptr_t>(y) & 15))) return B2B_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023)) return B2B_EUNSUPPORTED;
+  // the tensor-core kernel takes whole tiles of 64 columns; the ragged tail (< 64 columns) goes to the exact-fp32
+  // kernel -- a disjoint column range, so in-place operation and logjac accumulation are unaffected
+  const long long n_full = N / TC_T * TC_T;
+  if (n_full < N) {
+    const int rc = b2b_launch_coupling_affine(d, fold, x + n_full * ldx, y ? y + n_full * ldy : nullptr,
+                                              logjac ? logjac + n_full : nullptr, D, N - n_full, ldx, ldy, accumulate, stream);
+    if (rc != B2B_OK) return rc;
+  }
+  if (launches) *launches = (n_full < N ? 1 : 0) + (n_full > 0 ? 2 : 0);
+  if (n_full == 0) return B2B_OK;
+  N = n_full;
   const int nkb = n2 / 64;
   unsigned char* wimg = static_cast<unsigned char*>(workspace);
   float* wsum = reinterpret_cast<float*>(wimg + (size_t)4 * nkb * TC_ABLK);
@@ -523,7 +549,7 @@ int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* fold, co
   P.N = N;
   P.ldx = ldx;
   P.ldy = ldy;
-  P.tiles = (N + TC_T - 1) / TC_T;
+  P.tiles = N / TC_T;
   P.D = D;
   P.n1 = n1;
   P.n2 = n2;
@@ -532,10 +558,20 @@ int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* fold, co
   P.row2 = row2;
   P.accumulate = accumulate;
   P.inverse = d.inverse;
-  P.debug = getenv("B2B_TC_DEBUG") ? atoi(getenv("B2B_TC_DEBUG")) : 0;
   const size_t smem = (size_t)4 * nkb * TC_ABLK + (size_t)TC_STAGES * 2 * nkb * TC_BBLK +
                       TC_SCALE_SLOTS * TC_T * sizeof(float) + 16 * sizeof(uint64_t) + 1024;
-  e = cudaFuncSetAttribute(coupling_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  typedef void (*kernel_t)(const TcParams);
+  const bool dense256 = ldx == 256 && (!y || ldy == 256);
+  const bool inv = d.inverse != 0, fd = fold != nullptr;
+  kernel_t kernel;
+  if (dense256) {
+    kernel = fd ? (inv ? coupling_tc_kernel<256, true, true> : coupling_tc_kernel<256, true, false>)
+                : (inv ? coupling_tc_kernel<256, false, true> : coupling_tc_kernel<256, false, false>);
+  } else {
+    kernel = fd ? (inv ? coupling_tc_kernel<0, true, true> : coupling_tc_kernel<0, true, false>)
+                : (inv ? coupling_tc_kernel<0, false, true> : coupling_tc_kernel<0, false, false>);
+  }
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -543,6 +579,6 @@ int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* fold, co
   long long grid = sms;
   if (grid > P.tiles) grid = P.tiles;
   if (grid < 1) grid = 1;
-  coupling_tc_kernel<<<(int)grid, TC_THREADS, smem, stream>>>(P);
+  kernel<<<(int)grid, TC_THREADS, smem, stream>>>(P);
   return (int)cudaGetLastError();
 }

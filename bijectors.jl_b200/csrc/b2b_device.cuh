@@ -97,6 +97,57 @@ __device__ __forceinline__ float find_alpha_ts(float t, float c, float b, float&
   return x;
 }
 
+// Table-driven find_alpha for the unrolled planar kernels.  With u = α + b and s = t + b the equation reads
+// u + c·tanh(u) = s, so the root is a ONE-dimensional function u = G_c(s) of the column's scalar s for a fixed layer.
+// Every CTA tabulates G_c on [−R, R] (R = 9.5 + |c|; beyond it tanh is ±1 in fp32 and u = s ∓ c exactly) as PT_N cubic
+// Hermite pieces (nodes solved with find_alpha_ts, slope 1/(1 + c·sech²u)) in its prologue; a column then takes
+//   lookup (one LDS.128 + Horner) -> ONE Newton step (one tanh evaluation) -> tanh / sech² at the root by expansion,
+// about a third of the instructions and half the dependent latency of the safeguarded iteration, which the whole warp
+// falls back to (warp vote) whenever some lane's step is not tiny or its predicted error exceeds the tolerance of
+// find_alpha_ts -- e.g. for c -> −1, where G_c has an infinite slope at 0.  Results are pinned by the residual of the
+// equation exactly as before (test/normalising_flows.jl:47-71).
+constexpr int PT_N = 128;                 // Hermite pieces per layer
+constexpr int PT_FLOATS = PT_N * 4 + 4;   // coefficients + {R, PT_N/(2R), -, -}
+
+// piece `i` of layer constant c: coefficients of u(τ), τ in [0, 1], on [−R + i·h, −R + (i+1)·h]
+__device__ inline void planar_table_piece(float c, int i, float* tab) {
+  const float R = 9.5f + fabsf(c), h = 2.0f * R / PT_N;
+  const float s0 = fmaf((float)i, h, -R), s1 = fmaf((float)(i + 1), h, -R);
+  float th, q0, q1;
+  const float u0 = find_alpha_ts(s0, c, 0.0f, th, q0);
+  const float u1 = find_alpha_ts(s1, c, 0.0f, th, q1);
+  const float g0 = h / fmaf(c, q0, 1.0f), g1 = h / fmaf(c, q1, 1.0f);  // h·G'(s) = h/(1 + c·sech²u)
+  const float d = u1 - u0;
+  reinterpret_cast<float4*>(tab)[i] = make_float4(u0, g0, 3.0f * d - 2.0f * g0 - g1, g0 + g1 - 2.0f * d);
+  if (i == 0) reinterpret_cast<float4*>(tab)[PT_N] = make_float4(R, (float)PT_N / (2.0f * R), 0.f, 0.f);
+}
+
+__device__ __forceinline__ float find_alpha_tab(float t, float c, float b, const float* __restrict__ tab, float& th, float& s2) {
+  const float4 meta = reinterpret_cast<const float4*>(tab)[PT_N];
+  const float s = t + b;
+  const float pos = fminf(fmaxf(fmaf(s, meta.y, meta.x * meta.y), 0.0f), (float)PT_N - 0.0078125f);
+  const float fi = floorf(pos), tau = pos - fi;
+  const float4 q = reinterpret_cast<const float4*>(tab)[(int)fi];
+  float u0 = fmaf(fmaf(fmaf(q.w, tau, q.z), tau, q.y), tau, q.x);
+  u0 = fabsf(s) < meta.x ? u0 : s - copysignf(c, s);
+  tanh_sech2(u0, th, s2);
+  const float f = fmaf(c, th, u0) - s;
+  const float r = __frcp_rn(fmaf(c, s2, 1.0f));
+  const float n = f * r;                 // Newton step
+  const float a = c * s2 * r * th;       // −f''/(2f')
+  const float tol = 1.2e-7f * (fabsf(t) + 2.0f * fabsf(c)) + 1e-30f;
+  const bool ok = fabsf(n) <= 4e-3f && fabsf(a) * n * n <= tol;
+  if (__all_sync(0xffffffffu, ok)) {
+    const float d = -n;
+    const float ts = th * s2;
+    const float qq = s2 * fmaf(-2.0f * th, th, s2);
+    th = fmaf(d, fmaf(-d, ts, s2), th);
+    s2 = fmaf(-d, fmaf(d, qq, 2.0f * ts), s2);
+    return (u0 - n) - b;
+  }
+  return find_alpha_ts(t, c, b, th, s2);
+}
+
 __device__ __forceinline__ float find_alpha(float t, float c, float b) {
   float th, s2;
   return find_alpha_ts(t, c, b, th, s2);

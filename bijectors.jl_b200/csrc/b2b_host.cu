@@ -59,6 +59,19 @@ extern "C" int b2b_host_ctx_create(b2b_host_ctx** out, int32_t D_max, int64_t ch
   return B2B_OK;
 }
 
+// Orders the ctx's internal (non-blocking) streams after everything enqueued so far on `stream` -- e.g. an optimiser
+// step on the caller's stream that has just rewritten the layer parameters the next b2b_chain_run_host_f32 will read.
+extern "C" int b2b_host_ctx_wait_stream(b2b_host_ctx* c, void* stream) {
+  if (!c) return B2B_EINVAL;
+  cudaEvent_t ev;
+  cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaEventRecord(ev, static_cast<cudaStream_t>(stream));
+  for (size_t s = 0; s < c->streams.size() && e == cudaSuccess; ++s) e = cudaStreamWaitEvent(c->streams[s], ev, 0);
+  cudaEventDestroy(ev);
+  return (int)e;
+}
+
 extern "C" int b2b_host_ctx_destroy(b2b_host_ctx* c) {
   if (!c) return B2B_OK;
   for (size_t s = 0; s < c->streams.size(); ++s) {
@@ -71,6 +84,78 @@ extern "C" int b2b_host_ctx_destroy(b2b_host_ctx* c) {
   }
   if (c->hsum) cudaFreeHost(c->hsum);
   delete c;
+  return B2B_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NUMA placement of the calling thread next to a GPU.  On the 2-socket HGX hosts every GPU hangs off one socket's PCIe
+// root complexes; a pinned host buffer that lives on the OTHER socket makes every H2D / D2H copy cross the inter-socket
+// link, which is what capped the 8-rank host-buffer throughput in round 1 (SCALE_r01: 0.24 efficiency).  This binds the
+// calling thread (CPU affinity + preferred memory node) to the NUMA node of `device`, so that pinned buffers allocated
+// afterwards (cudaHostAlloc / torch pin_memory from this thread) and the host ctx's staging land on the local node.
+// Linux only; every step is best effort (returns B2B_OK with *node_out = -1 when the topology is not exposed).
+// ---------------------------------------------------------------------------------------------------
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#include <cctype>
+#include <cstdio>
+
+static int read_small_file(const char* path, char* buf, size_t cap) {
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  const size_t n = fread(buf, 1, cap - 1, f);
+  fclose(f);
+  buf[n] = 0;
+  return (int)n;
+}
+
+extern "C" int b2b_numa_bind_to_device(int32_t device, int32_t* node_out, int32_t* ncpus_out) {
+  if (node_out) *node_out = -1;
+  if (ncpus_out) *ncpus_out = 0;
+  char bus[64] = {0};
+  cudaError_t e = cudaDeviceGetPCIBusId(bus, sizeof(bus), device);
+  if (e != cudaSuccess) return (int)e;
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  char path[256], buf[4096];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  if (read_small_file(path, buf, sizeof(buf)) <= 0) return B2B_OK;
+  const int node = atoi(buf);
+  if (node < 0) return B2B_OK;
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  if (read_small_file(path, buf, sizeof(buf)) <= 0) return B2B_OK;
+  // cpulist: "0-31,64-95"
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int ncpu = 0;
+  for (char* p = buf; *p;) {
+    while (*p && !isdigit((unsigned char)*p)) ++p;
+    if (!*p) break;
+    long a = strtol(p, &p, 10), b = a;
+    if (*p == '-') b = strtol(p + 1, &p, 10);
+    for (long c = a; c <= b && c < CPU_SETSIZE; ++c) {
+      CPU_SET((int)c, &set);
+      ++ncpu;
+    }
+  }
+  if (ncpu == 0) return B2B_OK;
+  // intersect with what the process may use (cgroup / taskset); keep the old mask when the intersection is empty
+  cpu_set_t cur, both;
+  if (sched_getaffinity(0, sizeof(cur), &cur) == 0) {
+    CPU_AND(&both, &set, &cur);
+    if (CPU_COUNT(&both) > 0) set = both;
+  }
+  if (sched_setaffinity(0, sizeof(set), &set) != 0) return B2B_OK;
+  // set_mempolicy(MPOL_PREFERRED, {node}): allocations of this thread come from the local node when it has room
+  // (needs no privilege for the calling thread; ignored when the kernel / sandbox refuses)
+  unsigned long mask[16] = {0};
+  if (node < (int)(sizeof(mask) * 8)) {
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    (void)syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof(mask) * 8);
+  }
+  if (node_out) *node_out = node;
+  if (ncpus_out) *ncpus_out = CPU_COUNT(&set);
   return B2B_OK;
 }
 
@@ -94,6 +179,8 @@ extern "C" int b2b_chain_run_host_f32(b2b_host_ctx* c, const b2b_layer_desc* lay
     c->hsum_cap = nchunks;
   }
   int launches = 0;
+  bool has_coupling = false;
+  for (int l = 0; l < L; ++l) has_coupling |= layers[l].kind == B2B_COUPLING_AFFINE;
   for (long long k = 0; k < nchunks; ++k) {
     const int s = (int)(k % c->n_streams);
     cudaStream_t st = c->streams[s];
@@ -103,7 +190,9 @@ extern "C" int b2b_chain_run_host_f32(b2b_host_ctx* c, const b2b_layer_desc* lay
                                     cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return (int)e;
     const bool want_lj = logjac_host != nullptr || (sum_host && layers[L - 1].kind != B2B_MVNORMAL_DIAG);
-    const int rc = b2b_chain_run_f32(layers, L, c->dx[s], y_host ? c->dx[s] : nullptr,
+    // in place; a logjac-only call still needs the D x N intermediate when the chain has several segments (a
+    // coupling layer splits it), so the staging buffer doubles as that scratch
+    const int rc = b2b_chain_run_f32(layers, L, c->dx[s], (y_host || has_coupling) ? c->dx[s] : nullptr,
                                      (want_lj || layers[L - 1].kind == B2B_MVNORMAL_DIAG) ? c->dlj[s] : nullptr,
                                      sum_host ? c->dsum[s] : nullptr, D, n, D, D, 0, c->dws[s], kWsBytes, st);
     if (rc != B2B_OK) return rc;

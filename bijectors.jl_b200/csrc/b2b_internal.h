@@ -75,7 +75,7 @@ size_t b2b_coupling_tc_workspace_bytes(int n1, int n2);
 // `fold` (device, 4*D+1 floats, or NULL): folded BatchNorm neighbours, see bn_fold_prep_kernel
 int b2b_launch_coupling_affine_tc(const b2b_layer_desc& d, const float* fold, const float* x, float* y,
                                   float* logjac, int D, long long N, long long ldx, long long ldy, int accumulate,
-                                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                                  void* workspace, size_t workspace_bytes, int* launches, cudaStream_t stream);
 int b2b_launch_bn_fold_prep(const b2b_layer_desc* pre, const b2b_layer_desc* post, int D, float* out,
                             cudaStream_t stream);
 // affine coupling, exact-fp32 CUDA-core kernel (any index lists)

@@ -64,11 +64,21 @@ struct PlanarConstProg {
   static constexpr int NPK = 2 * L * D + 2 * L;                    // packed w | û | c | b
   static constexpr bool STAGED = MODE != 0 || DERIVE;
   static constexpr int MVN_OFF = STAGED ? ((NPK + 3) & ~3) : 0;
-  static constexpr int SMEM_FLOATS = MVN_OFF + (MVN ? 2 * D + 4 : 0);
+  // device-resident parameters, inverse layers: per-layer lookup tables of the root (find_alpha_tab)
+  static constexpr bool TAB = DERIVE && DIR != 0;
+  static constexpr int TAB_OFF = MVN_OFF + (MVN ? 2 * D + 4 : 0);
+  static constexpr int SMEM_FLOATS = TAB_OFF + (TAB ? L * PT_FLOATS : 0);
   __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
     if constexpr (DERIVE) {
       if (MVN && warp == nw - 1) stage_layer(P.layers[src.nreal], params + MVN_OFF, D, D, lane);
       planar_derive_smem<D, L>(P, src.nreal, params, warp, lane, nw);
+      if constexpr (TAB) {
+        __syncthreads();  // wᵀû of every layer is in shared memory
+        for (int idx = warp * 32 + lane; idx < L * PT_N; idx += nw * 32) {
+          const int l = idx / PT_N;
+          if (DIR == 1 || src.inv(l)) planar_table_piece(params[2 * L * D + l], idx - l * PT_N, params + TAB_OFF + l * PT_FLOATS);
+        }
+      }
     } else if constexpr (STAGED) {
       for (int i = warp * 32 + lane; i < NPK; i += nw * 32) params[i] = src.raw(i);
     }
@@ -106,7 +116,9 @@ struct PlanarConstProg {
         tanh_sech2(wz + bb, t, s2);
         lj[0] += log1pf(cc_ * s2);  // planar_layer.jl:107
       } else {
-        find_alpha_ts(wz, cc_, bb, t, s2);  // planar_layer.jl:121; t = tanh(α+b), s2 = sech²(α+b)
+        // planar_layer.jl:121; t = tanh(α+b), s2 = sech²(α+b)
+        if constexpr (TAB) find_alpha_tab(wz, cc_, bb, params + TAB_OFF + l * PT_FLOATS, t, s2);
+        else find_alpha_ts(wz, cc_, bb, t, s2);
         lj[0] -= log1pf(cc_ * s2);
         t = -t;
       }
@@ -237,7 +249,8 @@ static int launch_planar_unrolled(const B2BChainParams& p, int L, const float* p
   V1Geom g;
   // shared memory: the packed parameter block when it is staged (MODE != 0, or device-resident parameters)
   const bool staged = sh.mode != 0 || !packed;
-  const size_t pf = (staged ? (size_t)((2 * L * q.D + 2 * L + 3) & ~3) : 0) + (mvn ? 2 * q.D + 4 : 0);
+  const size_t pf = (staged ? (size_t)((2 * L * q.D + 2 * L + 3) & ~3) : 0) + (mvn ? 2 * q.D + 4 : 0) +
+                    ((!packed && invmask != 0) ? (size_t)L * PT_FLOATS : 0);  // root lookup tables of inverse layers
   const int rc = v1_geometry(q.D, q.N, sh.nw, 32, pf, g);
   if (rc != 0) return rc;
   CUtensorMap mx, my;

@@ -1,35 +1,162 @@
-// A single RationalQuadraticSpline layer with K = 8 bins (K1 = 9 knots, the BASELINE configuration) as a program
-// specialised on (D, K1, direction) on the TMA pipeline: the bin search is four unrolled compare/select steps with
-// immediate offsets and every table address is a compile-time constant.  The layer interpreter needs ~98 instructions
-// per element (runtime knot count, generic addressing); this program ~60: C4 forward 27 % -> 40 % of the HBM roofline
-// (the layer stays compute-bound per element).  Tables are staged by the whole CTA (stage_rqs_cta).
+// A single RationalQuadraticSpline layer with K = 4, 8, 16 or 32 bins (K1 = K + 1 knots; K = 8 is the BASELINE
+// configuration) as a program specialised on (D, K1, direction) on the TMA pipeline.
 //
-// Reference semantics: rational_quadratic_spline.jl:317-357 (forward), :183-220 (inverse), see rqs_element.
+// Reference semantics: rational_quadratic_spline.jl:317-357 (forward), :183-220 (inverse) + the forward log-Jacobian
+// at the recovered point (interface.jl:276-281).
+//
+// Per element the work is a bin search plus ~25 flops, i.e. the layer is bound by instruction issue and by
+// shared-memory wavefronts, not by HBM.  What this program does about it (round-1 kernel: ~78 instructions and 17+
+// wavefronts per element, 36 % of the HBM roofline):
+//   * ONE 48-byte record per (row, bin): {w_k, 1/w | w, h_k, Δy | s}{d_k, d_k1}{probe knot, aux} -- one LDS.128 + one
+//     LDS.64 (6 wavefronts, the minimum for six lane-divergent numbers) fetch everything the element needs; with a
+//     48-byte stride the nine bins of a row start in nine different 16-byte bank groups, so the lane-divergent fetch is
+//     conflict-free (the 32-byte stride of round 1 was 2-3-way conflicted);
+//   * the bin search walks the K - 1 INTERIOR knots only (log2(K) dependent probes instead of log2(2K)), the probes live
+//     in the records themselves so the running bin index IS the byte offset of the record (no index -> address
+//     arithmetic, no clamp), and the first knot is compared separately (only raw three-argument-constructor knots can
+//     put a point left of it, :331-343);
+//   * rcp / lg2 / sqrt through the .approx.ftz forms (one MUFU each; the default forms carry 4 extra instructions of
+//     denormal handling per call), log-Jacobian accumulated in log2 units and scaled once per column.
 #include "b2b_v1_pipeline.cuh"
 
 namespace b2b {
+
+constexpr int RQS_REC = 12;  // floats per (row, bin) record
+
+__host__ __device__ constexpr int rqs2_steps(int K1) {
+  int s = 0;
+  while ((1 << s) < K1 - 1) ++s;
+  return s;
+}
+__host__ __device__ constexpr bool rqs2_supported(int K1) { return K1 >= 5 && K1 <= 33 && (1 << rqs2_steps(K1)) == K1 - 1; }
+__host__ __device__ constexpr int rqs2_row_floats(int K1) { return (K1 + 1) * RQS_REC; }
+
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_ftz(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Records of one layer, built by the whole CTA (one (row, record) pair per thread and step).
+// Record c < K1 of row i is bin c (= the reference's k = searchsortedfirst − 1, :328 / :191; c == 0 is the k == 0 branch):
+//   [0] w_k  [1] 1/w (forward) | w (inverse)  [2] h_k  [3] Δy (forward) | s = Δy/w (inverse)  [4] d_k  [5] d_k1
+//   [8] probe: interior knot S[c+1] for c <= K1-3; record K1-2 holds {S[0], S[K1-1]} in [8], [9]
+// with S = widths (forward search on x, :328) or heights (inverse search on y, :191).  Record K1 is padding (v = +inf
+// counts every knot; the element is outside the box and its result is discarded).
+template <int K1, bool INV>
+__device__ inline void stage_rqs_records(const b2b_layer_desc& d, float* sm, int D, int tid, int nthreads) {
+  constexpr int NR = K1 + 1;
+  const float* S = INV ? d.p1 : d.p0;
+  for (int idx = tid; idx < D * NR; idx += nthreads) {
+    const int c = idx / D, i = idx - c * D;  // consecutive threads -> consecutive rows (coalesced parameter reads)
+    float* rec = sm + (size_t)(i * NR + c) * RQS_REC;
+    float w_k = 0.f, w = 1.f, h_k = 0.f, dy = 1.f, d_k = 1.f, d_k1 = 1.f;
+    if (c < K1) {
+      const float Wl = d.p0[(size_t)(K1 - 1) * D + i], Hl = d.p1[(size_t)(K1 - 1) * D + i];
+      w_k = c == 0 ? -Wl : d.p0[(size_t)(c - 1) * D + i];   // rational_quadratic_spline.jl:331
+      w = d.p0[(size_t)c * D + i] - w_k;                    // :332
+      h_k = c == 0 ? -Hl : d.p1[(size_t)(c - 1) * D + i];   // :335
+      dy = d.p1[(size_t)c * D + i] - h_k;                   // :336
+      d_k = c == 0 ? 1.0f : d.p2[(size_t)(c - 1) * D + i];  // :342
+      d_k1 = c == K1 - 1 ? 1.0f : d.p2[(size_t)c * D + i];  // :343
+    }
+    const float sl = dy / w;                                // :339
+    float4* r4 = reinterpret_cast<float4*>(rec);
+    r4[0] = INV ? make_float4(w_k, w, h_k, sl) : make_float4(w_k, 1.0f / w, h_k, dy);
+    r4[1] = make_float4(d_k, d_k1, 0.f, 0.f);
+    float p8 = 0.f, p9 = 0.f;
+    if (c <= K1 - 3) p8 = S[(size_t)(c + 1) * D + i];
+    else if (c == K1 - 2) {
+      p8 = S[i];
+      p9 = S[(size_t)(K1 - 1) * D + i];
+    }
+    r4[2] = make_float4(p8, p9, 0.f, 0.f);
+  }
+}
+
+// One element.  `row` points at the records of the element's row; `lg` receives log2 of the spline's derivative at the
+// element (0 outside the box), `out` the transformed value.
+template <int K1, bool INV>
+__device__ __forceinline__ void rqs2_element(const float* __restrict__ row, float v, float& out, float& lg) {
+  constexpr int STEPS = rqs2_steps(K1);
+  constexpr int RB = RQS_REC * 4;  // record stride in bytes
+  const char* base = reinterpret_cast<const char*>(row);
+  const float2 ends = *reinterpret_cast<const float2*>(base + (K1 - 2) * RB + 32);  // {S[0], S[K1-1]}
+  const bool outside = fabsf(v) >= ends.y;  // x <= -B or x >= B: identity, :322-324 / :186-188 (NaN goes through the spline)
+  // number of knots < v (searchsortedfirst − 1): interior knots by bisection, the first knot on its own
+  int off = 0;
+#pragma unroll
+  for (int st = 1 << (STEPS - 1); st >= 1; st >>= 1) {
+    const float probe = *reinterpret_cast<const float*>(base + off + (st - 1) * RB + 32);
+    off += (probe < v) ? st * RB : 0;
+  }
+  off += (ends.x < v) ? RB : 0;
+  const float4 c0 = *reinterpret_cast<const float4*>(base + off);
+  const float2 c1 = *reinterpret_cast<const float2*>(base + off + 16);
+  const float w_k = c0.x, h_k = c0.z;
+  const float d_k = c1.x, d_k1 = c1.y;
+  // the record holds 6 numbers (LDS.128 + LDS.64 = 6 shared-memory wavefronts; the kernel is bound by them): Δy or s
+  // is rebuilt from the other with one multiplication, d_k1 + d_k − 2s with two more instructions
+  const float sl = INV ? c0.w : c0.w * c0.y;   // s = Δy/w, :339
+  const float dy = INV ? c0.w * c0.y : c0.w;   // Δy = s·w
+  const float ds = fmaf(-2.0f, sl, d_k1 + d_k);  // :205 / :346
+  float xi, res;
+  if (INV) {
+    const float w = c0.y;
+    const float yh = v - h_k;
+    const float t = yh * ds;
+    const float a1 = fmaf(dy, sl - d_k, t);   // :208
+    const float a2 = fmaf(dy, d_k, -t);       // :210
+    const float a3n = sl * yh;                // −a3, :212
+    const float disc = fmaf(4.0f * a1, a3n, a2 * a2);               // a2² − 4·a1·a3
+    xi = (a3n + a3n) * rcp_ftz(a2 + sqrt_ftz(disc));                // :215-217
+    res = fmaf(xi, w, w_k);                                         // :219
+  } else {
+    xi = (v - w_k) * c0.y;                                          // :340
+  }
+  const float omx = 1.0f - xi, xo = xi * omx;
+  const float rden = rcp_ftz(fmaf(ds, xo, sl));                     // 1/den, :346
+  const float inner = fmaf(sl + sl, xo, fmaf(d_k1 * xi, xi, d_k * omx * omx));  // :349 without the s² factor
+  const float q = sl * rden;
+  const float arg = q * q * inner;                                  // s²·inner/den² = exp(lj), :349-350
+  if (!INV) res = fmaf(dy * fmaf(sl * xi, xi, d_k * xo), rden, h_k);  // :353-354
+  out = outside ? v : res;
+  lg = lg2_ftz(outside ? 1.0f : arg);
+}
 
 template <int D, int K1, bool INV>
 struct RqsProg {
   using State = V1NoState;
   const B2BChainParams& P;
   __device__ __forceinline__ void stage(float* params, int warp, int lane, int nw) const {
-    stage_rqs_cta(P.layers[0], params, D, D, warp * 32 + lane, nw * 32);
+    stage_rqs_records<K1, INV>(P.layers[0], params, D, warp * 32 + lane, nw * 32);
   }
   __device__ __forceinline__ void apply(float2 (&x)[1][D / 2], const ColCtx<D, 1>&, const float* params,
                                         float (&lj)[1]) const {
-    float acc = 0.f;
+    constexpr int RF = rqs2_row_floats(K1);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < D / 2; ++i) {
       float o, l1;
-      rqs_element<INV, K1>(params, K1, rqs_kp(K1), D, 2 * i, x[0][i].x, o, l1);
+      rqs2_element<K1, INV>(params + (2 * i) * RF, x[0][i].x, o, l1);
       x[0][i].x = o;
-      acc += l1;
-      rqs_element<INV, K1>(params, K1, rqs_kp(K1), D, 2 * i + 1, x[0][i].y, o, l1);
+      acc[(2 * i) & 3] += l1;
+      rqs2_element<K1, INV>(params + (2 * i + 1) * RF, x[0][i].y, o, l1);
       x[0][i].y = o;
-      acc += l1;
+      acc[(2 * i + 1) & 3] += l1;
     }
-    lj[0] += acc;  // sum over dimensions, rational_quadratic_spline.jl:304-309
+    const float s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) * 0.6931471805599453f;  // log2 -> ln
+    lj[0] += INV ? -s : s;  // sum over dimensions, rational_quadratic_spline.jl:304-309; inverse: interface.jl:278-281
   }
 };
 
@@ -41,11 +168,10 @@ __global__ void __launch_bounds__(NW * 32, 1)
   v1_run<D, 1, 1, NW>(P, E, map_x, map_y, prog);
 }
 
-template <int D, int NW>
+template <int D, int K1, int NW>
 static int launch_rqs(const B2BChainParams& q, cudaStream_t stream) {
-  constexpr int K1 = 9;
   V1Geom g;
-  const int rc = v1_geometry(D, q.N, NW, 32, (size_t)b2b_layer_smem_floats(q.layers[0], D), g);
+  const int rc = v1_geometry(D, q.N, NW, 32, (size_t)D * rqs2_row_floats(K1), g);
   if (rc != 0) return rc;
   CUtensorMap mx, my;
   if (!make_maps(q, g.cols, &mx, &my, &g.extra.tma3d)) return B2B_EUNSUPPORTED;
@@ -56,19 +182,32 @@ static int launch_rqs(const B2BChainParams& q, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
+template <int D, int NW>
+static int dispatch_rqs(const B2BChainParams& q, cudaStream_t stream) {
+  switch (q.layers[0].n0) {
+    case 5: return launch_rqs<D, 5, NW>(q, stream);
+    case 9: return launch_rqs<D, 9, NW>(q, stream);
+    case 17: return launch_rqs<D, 17, NW>(q, stream);
+    case 33: return launch_rqs<D, 33, NW>(q, stream);
+    default: return B2B_EUNSUPPORTED;
+  }
+}
+
 }  // namespace b2b
 
-// p: a segment that is exactly one RQS layer with 9 knots, D in {32, 64}; B2B_EUNSUPPORTED otherwise
+// p: a segment that is exactly one RQS layer with 5, 9, 17 or 33 knots, D in {32, 64}; B2B_EUNSUPPORTED otherwise
 int b2b_rqs_unrolled_applicable(const B2BChainParams& p) {
-  return p.L == 1 && p.layers[0].kind == B2B_RQS && p.layers[0].n0 == 9 && (p.D == 32 || p.D == 64) &&
+  return p.L == 1 && p.layers[0].kind == B2B_RQS && b2b::rqs2_supported(p.layers[0].n0) && (p.D == 32 || p.D == 64) &&
          b2b::v1_check_io(p) == 0;
 }
+
+int b2b_rqs_unrolled_warps(int D) { return D == 64 ? 12 : 16; }
 
 int b2b_launch_rqs_unrolled(const B2BChainParams& p, cudaStream_t stream) {
   using namespace b2b;
   if (!b2b_rqs_unrolled_applicable(p)) return B2B_EUNSUPPORTED;
   B2BChainParams q = p;
   q.scratch_off = -1;
-  if (q.D == 64) return launch_rqs<64, 12>(q, stream);
-  return launch_rqs<32, 16>(q, stream);
+  if (q.D == 64) return dispatch_rqs<64, 12>(q, stream);
+  return dispatch_rqs<32, 16>(q, stream);
 }

@@ -255,16 +255,13 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
       }
     }
   };
-  prog.stage(params, warp, lane, NW);
+  // tiles of this CTA: global tile id = blockIdx.x + j * gridDim.x
+  const long long my_tiles = (E.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  // The first P tile loads are issued BEFORE the parameters are staged: the DRAM latency of the first tiles (and, for
+  // the 20-60 us kernels, a visible share of the run time) overlaps the prologue arithmetic (get_u_hat, spline records).
   if (threadIdx.x == 0) {
     for (int i = 0; i < E.n_in; ++i) mbar_init(smem_u32(&bars[i]), 1);
     fence_mbar_init();
-  }
-  __syncthreads();
-
-  // tiles of this CTA: global tile id = blockIdx.x + j * gridDim.x
-  const long long my_tiles = (E.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  if (threadIdx.x == 0) {
     for (int j = 0; j < E.n_in && j < my_tiles; ++j) {
       const uint32_t bar = smem_u32(&bars[j]);
       mbar_expect_tx(bar, SLOT_BYTES);
@@ -273,6 +270,7 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
       flag_store_release(&armed[j], j);
     }
   }
+  prog.stage(params, warp, lane, NW);
   __syncthreads();
 
   C ctx;

@@ -20,6 +20,18 @@ def shard_columns(N: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def numa_bind(device: Optional[int] = None) -> Tuple[int, int]:
+    """Bind the calling thread (CPU affinity + preferred memory node) to the NUMA node of CUDA device `device`
+    (default: the current device) BEFORE allocating pinned host batches: a pinned buffer on the other socket sends every
+    H2D / D2H byte across the inter-socket link (b2b_numa_bind_to_device, include/b2b.h).  Returns (node, cpus); node is
+    -1 when the topology is not exposed.  One process per GPU calls this once."""
+    if device is None:
+        device = torch.cuda.current_device()
+    node, ncpu = ctypes.c_int32(-1), ctypes.c_int32(0)
+    check(lib().b2b_numa_bind_to_device(int(device), ctypes.byref(node), ctypes.byref(ncpu)), "b2b_numa_bind_to_device")
+    return int(node.value), int(ncpu.value)
+
+
 class Communicator:
     """b2b_comm wrapper: the NCCL unique id is created on rank 0 and broadcast through torch.distributed."""
 

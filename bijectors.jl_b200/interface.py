@@ -353,6 +353,7 @@ def _run_chain_host(arr, L, x, D, N, want_y, want_logjac, sum_out):
     if x.dim() == 2 and N > 1 and x.stride(1) != D:
         raise ValueError("host batches must be dense column-major (ld == D)")
     ctx = _host_ctx(D, HOST_CHUNK_COLS, HOST_STREAMS)
+    check(lib().b2b_host_ctx_wait_stream(ctx, _stream()), "b2b_host_ctx_wait_stream")  # parameters written on torch's stream
     pin = x.is_pinned()
     y = None
     if want_y:

@@ -253,12 +253,21 @@ int b2b_mvnormal_diag_logpdf_f32(const float* x, const float* mu, const float* s
 typedef struct b2b_host_ctx b2b_host_ctx;
 int b2b_host_ctx_create(b2b_host_ctx** ctx, int32_t D_max, int64_t chunk_cols, int32_t n_streams);
 int b2b_host_ctx_destroy(b2b_host_ctx* ctx);
+/* Orders the ctx's internal streams after the work enqueued so far on `stream` (parameters written on the caller's
+ * stream -- an optimiser step -- are then visible to the next b2b_chain_run_host_f32). */
+int b2b_host_ctx_wait_stream(b2b_host_ctx* ctx, void* stream);
 int b2b_chain_run_host_f32(b2b_host_ctx* ctx, const b2b_layer_desc* layers, int32_t L,
                            const float* x_host, float* y_host, float* logjac_host, double* sum_host,
                            int32_t D, int64_t N);
 /* cudaHostRegister / cudaHostUnregister passthroughs so a host runtime can pin its own arrays */
 int b2b_host_register(void* ptr, size_t bytes);
 int b2b_host_unregister(void* ptr);
+/* Binds the CALLING THREAD (CPU affinity + preferred memory node) to the NUMA node of CUDA device `device`, so that
+ * pinned host buffers allocated afterwards live on the socket whose PCIe root complex serves that GPU (on the 2-socket
+ * HGX hosts a remote-socket buffer sends every H2D / D2H byte across the inter-socket link).  One process per GPU calls
+ * it once before allocating its host batches.  Best effort: *node_out = -1 when the topology is not exposed
+ * (/sys/bus/pci/devices/<bus id>/numa_node); *ncpus_out = CPUs in the new affinity mask.  Linux only. */
+int b2b_numa_bind_to_device(int32_t device, int32_t* node_out, int32_t* ncpus_out);
 
 /* ---- multi-GPU: the ONE collective of the path -----------------------------------
  * Columns shard across ranks with no data-path collective; the batch log-density Σ_n logpdf[n] is

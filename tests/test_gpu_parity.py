@@ -467,7 +467,8 @@ def test_coupling_tensor_core_path(B, D, n1, row1, n2, row2):
     xd = B.from_numpy(x)
     y, lj = B.with_logabsdet_jacobian(cl, xd)
     launches = B.lib().b2b_last_launch_count()
-    assert launches == 2, "tensor-core path not taken (W preparation + main kernel expected)"
+    # W preparation + tensor-core kernel on the whole 64-column tiles + the exact-fp32 kernel on the ragged tail
+    assert launches == 3, "tensor-core path not taken (W preparation + main kernel + ragged-tail kernel expected)"
     yo, ljo = ol.forward(x.astype(np.float64))
     yo32, ljo32 = ol.forward(x)
     ok = np.isfinite(yo).all(axis=0) & np.isfinite(B.to_numpy(y)).all(axis=0)  # exp overflow in the 1e4 column is legit
@@ -653,7 +654,8 @@ def test_coupling_tc_ragged_batches(B, N):
     ol = O.Layer("coupling_affine", dict(idx1=np.asarray(idx1), idx2=np.asarray(idx2), W=W, c=c))
     x = rng.standard_normal((D, N)).astype(f32)
     y, lj = B.with_logabsdet_jacobian(cl, B.from_numpy(x))
-    assert B.lib().b2b_last_launch_count() == 2
+    # whole tiles: W preparation + tensor-core kernel; the < 64 ragged columns: exact-fp32 kernel
+    assert B.lib().b2b_last_launch_count() == (2 if N >= 64 else 0) + (1 if N % 64 else 0)
     yo, ljo = ol.forward(x.astype(np.float64))
     assert rel(B.to_numpy(y).reshape(D, N), yo) <= RTOL and rel(B.to_numpy(lj), ljo) <= RTOL
 
@@ -740,6 +742,47 @@ def test_full_size_properties_config4_rqs(B):
     assert bool(((y[:, 1:] - y[:, :-1]) * (x[:, 1:] - x[:, :-1]) >= 0).all())
 
 
+@pytest.mark.parametrize("D", [32, 64])
+@pytest.mark.parametrize("K", [4, 8, 16, 32, 6])
+def test_rqs_bin_counts_and_raw_knots(B, D, K):
+    """Specialised spline programs for K in {4, 8, 16, 32} bins (K = 6 runs in the interpreter), forward and inverse,
+    against the float64 oracle -- with B-constructed knots and with RAW three-argument-constructor knots whose first
+    knot is not -B, which reaches the k == 0 branches (rational_quadratic_spline.jl:331-343)."""
+    rng = np.random.default_rng(7000 + 10 * K + D)
+    N = 3001
+    lay = B.RationalQuadraticSpline(rng.standard_normal((D, K)).astype(f32), rng.standard_normal((D, K)).astype(f32),
+                                    rng.standard_normal((D, K - 1)).astype(f32), 3.0)
+    W, H, Dv = lay.knots()
+    cases = [(lay, W, H, Dv)]
+    W2, H2 = W.copy(), H.copy()
+    W2[:, 0] = -2.0 + 0.1 * rng.random(D).astype(f32)   # first knot right of -B = -3: points in (-3, W2[0]] hit k == 0
+    H2[:, 0] = -2.2 + 0.1 * rng.random(D).astype(f32)
+    W2[:, 1:] = np.maximum(W2[:, 1:], W2[:, :1] + 0.05 * np.arange(1, K + 1, dtype=f32))
+    H2[:, 1:] = np.maximum(H2[:, 1:], H2[:, :1] + 0.05 * np.arange(1, K + 1, dtype=f32))
+    W2[:, -1], H2[:, -1] = 3.0, 3.0
+    W2, H2 = np.sort(W2, axis=1), np.sort(H2, axis=1)
+    cases.append((B.RationalQuadraticSpline(W2, H2, Dv), W2, H2, Dv))
+    for lay_, W_, H_, D_ in cases:
+        olay = O.Layer("rqs", dict(widths=W_, heights=H_, derivs=D_))
+        x = (rng.standard_normal((D, N)) * 1.6).astype(f32)
+        x[:, 0] = W_[:, min(2, K)]          # a point exactly on a knot belongs to the bin on its left
+        x[:, 1], x[:, 2] = W_[:, -1], -W_[:, -1]  # the box edges themselves are outside (x <= -B or x >= B, :322)
+        xd = B.from_numpy(x)
+        y, lj = B.with_logabsdet_jacobian(lay_, xd)
+        yo, ljo = olay.forward(x.astype(np.float64))
+        assert rel(B.to_numpy(y), yo) <= RTOL and rel(B.to_numpy(lj), ljo) <= RTOL, (K, D, rel(B.to_numpy(y), yo), rel(B.to_numpy(lj), ljo))
+        out = np.abs(x) >= W_[:, -1:]
+        assert np.array_equal(B.to_numpy(y)[out], x[out])
+        # inverse: the exact box edges are left out (widths[end] and heights[end] may differ by an ulp, which puts
+        # y = ±widths[end] into a zero-width k == 0 bin of the HEIGHT knots -- 0/0 in the reference as well)
+        yh = B.to_numpy(y).copy()
+        yh[:, 1], yh[:, 2] = 1.01 * H_[:, -1], -1.01 * H_[:, -1]
+        xi, lji = B.with_logabsdet_jacobian(B.inverse(lay_), B.from_numpy(yh))
+        xo, ljio = olay.inverse(yh.astype(np.float64))
+        assert rel(B.to_numpy(xi), xo) <= RTOL and rel(B.to_numpy(lji), ljio) <= RTOL, (K, D, rel(B.to_numpy(xi), xo), rel(B.to_numpy(lji), ljio))
+        assert np.array_equal(B.to_numpy(xi)[:, 1:3], yh[:, 1:3])
+
+
 def test_full_size_properties_config5_realnvp_share(B):
     """BASELINE config 5, one GPU's share at 8-way sharding: 4 x (affine Coupling + InvertibleBatchNorm), D = 256,
     N = 2^19 columns."""
@@ -788,7 +831,12 @@ def test_planar_chain_with_host_resident_parameters(B, D, L):
     # inverse chain (find_alpha per layer), in place + accumulating
     xi, lji = B.with_logabsdet_jacobian(B.inverse(host_flow), y)
     xid, ljid = B.with_logabsdet_jacobian(B.inverse(dev_flow), y)
-    assert rel(B.to_numpy(xi), B.to_numpy(xid)) <= 2e-6 and rel(B.to_numpy(lji), B.to_numpy(ljid)) <= 2e-6
+    # both device paths (kernel-argument parameters + safeguarded iteration / shared-memory parameters + root table)
+    # against the float64 oracle inverse of the SAME y, and against each other
+    xo, ljio = O.chain_inverse([p[1] for p in pairs], B.to_numpy(y).astype(np.float64))
+    for xx, ll in ((xi, lji), (xid, ljid)):
+        assert rel(B.to_numpy(xx), xo) <= RTOL and rel(B.to_numpy(ll), ljio) <= RTOL, (rel(B.to_numpy(xx), xo), rel(B.to_numpy(ll), ljio))
+    assert rel(B.to_numpy(xi), B.to_numpy(xid)) <= 5e-6 and rel(B.to_numpy(lji), B.to_numpy(ljid)) <= 5e-6
     assert rel(B.to_numpy(xi), x) <= 1e-4 and rel(B.to_numpy(lji), -ljo) <= 1e-4
     buf, acc = B.from_numpy(x), torch.full((N,), 0.5, dtype=torch.float32, device="cuda")
     buf, acc = B.with_logabsdet_jacobian_(host_flow, buf, None, acc)
