@@ -217,8 +217,8 @@ def main():
                 comm.allreduce_sum_(total.reshape(1))
 
         ms = time_ms(logpdf_step, args.iters, world=world)
-        # inverse chain: BN4⁻¹ + 4 folded coupling passes + the MvNormal pass (reads D, writes 1)
-        report("C5_realnvp_logpdf_sum", Neff, ms, Neff * 4 * (5 * (2 * D + 1) + (D + 1)),
+        # inverse chain: 4 coupling passes with every BatchNorm folded in + the MvNormal pass (reads D + logjac, writes 1)
+        report("C5_realnvp_logpdf_sum", Neff, ms, Neff * 4 * (4 * (2 * D + 1) + 3 + (D + 2)),
                extra={"collective": "one ncclAllReduce(sum) of 8 bytes per step" if world > 1 else "none (1 GPU)",
                       "total_logpdf": float(total)})
 

@@ -95,6 +95,7 @@ _SIGS = {
     "b2b_host_register": (c_int, [c_void_p, c_size_t]),
     "b2b_host_unregister": (c_int, [c_void_p]),
     "b2b_numa_bind_to_device": (c_int, [c_int32, POINTER(c_int32), POINTER(c_int32)]),
+    "b2b_device_numa_node": (c_int, [c_int32, POINTER(c_int32)]),
     "b2b_comm_unique_id": (c_int, [c_void_p]),
     "b2b_comm_init_rank": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p]),
     "b2b_allreduce_sum_f64": (c_int, [c_void_p, c_void_p, c_int32, c_void_p]),

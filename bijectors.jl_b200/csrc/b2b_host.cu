@@ -111,18 +111,28 @@ static int read_small_file(const char* path, char* buf, size_t cap) {
   return (int)n;
 }
 
-extern "C" int b2b_numa_bind_to_device(int32_t device, int32_t* node_out, int32_t* ncpus_out) {
-  if (node_out) *node_out = -1;
-  if (ncpus_out) *ncpus_out = 0;
+extern "C" int b2b_device_numa_node(int32_t device, int32_t* node_out) {
+  if (!node_out) return B2B_EINVAL;
+  *node_out = -1;
   char bus[64] = {0};
   cudaError_t e = cudaDeviceGetPCIBusId(bus, sizeof(bus), device);
   if (e != cudaSuccess) return (int)e;
   for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
-  char path[256], buf[4096];
+  char path[256], buf[64];
   snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
   if (read_small_file(path, buf, sizeof(buf)) <= 0) return B2B_OK;
-  const int node = atoi(buf);
+  *node_out = atoi(buf);
+  return B2B_OK;
+}
+
+extern "C" int b2b_numa_bind_to_device(int32_t device, int32_t* node_out, int32_t* ncpus_out) {
+  if (node_out) *node_out = -1;
+  if (ncpus_out) *ncpus_out = 0;
+  int32_t node = -1;
+  const int rc = b2b_device_numa_node(device, &node);
+  if (rc != B2B_OK) return rc;
   if (node < 0) return B2B_OK;
+  char path[256], buf[4096];
   snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
   if (read_small_file(path, buf, sizeof(buf)) <= 0) return B2B_OK;
   // cpulist: "0-31,64-95"

@@ -50,7 +50,8 @@ __device__ __forceinline__ float sqrt_ftz(float x) {
 // Records of one layer, built by the whole CTA (one (row, record) pair per thread and step).
 // Record c < K1 of row i is bin c (= the reference's k = searchsortedfirst − 1, :328 / :191; c == 0 is the k == 0 branch):
 //   [0] w_k  [1] 1/w (forward) | w (inverse)  [2] h_k  [3] Δy (forward) | s = Δy/w (inverse)  [4] d_k  [5] d_k1
-//   [8] probe: interior knot S[c+1] for c <= K1-3; record K1-2 holds {S[0], S[K1-1]} in [8], [9]
+//   [8] probe: interior knot S[c+1] for c <= K1-3; the record of the FIRST probe (c = (K1-1)/2 - 1) also holds
+//       {S[0], S[K1-1]} in [9], [10]
 // with S = widths (forward search on x, :328) or heights (inverse search on y, :191).  Record K1 is padding (v = +inf
 // counts every knot; the element is outside the box and its result is discarded).
 template <int K1, bool INV>
@@ -74,35 +75,70 @@ __device__ inline void stage_rqs_records(const b2b_layer_desc& d, float* sm, int
     float4* r4 = reinterpret_cast<float4*>(rec);
     r4[0] = INV ? make_float4(w_k, w, h_k, sl) : make_float4(w_k, 1.0f / w, h_k, dy);
     r4[1] = make_float4(d_k, d_k1, 0.f, 0.f);
-    float p8 = 0.f, p9 = 0.f;
+    float p8 = 0.f, p9 = 0.f, p10 = 0.f;
     if (c <= K1 - 3) p8 = S[(size_t)(c + 1) * D + i];
-    else if (c == K1 - 2) {
-      p8 = S[i];
-      p9 = S[(size_t)(K1 - 1) * D + i];
+    if (c == (1 << (rqs2_steps(K1) - 1)) - 1) {  // the record of the first (lane-uniform) probe also carries the end knots
+      p9 = S[i];
+      p10 = S[(size_t)(K1 - 1) * D + i];
     }
-    r4[2] = make_float4(p8, p9, 0.f, 0.f);
+    r4[2] = make_float4(p8, p9, p10, 0.f);
   }
 }
 
-// One element.  `row` points at the records of the element's row; `lg` receives log2 of the spline's derivative at the
-// element (0 outside the box), `out` the transformed value.
+// Shared-memory loads by 32-bit shared-space address: the running record offset is then ONE register that the search
+// updates with predicated adds and every load uses directly (generic addressing cost an extra three-input add per
+// dependent probe and a select + add per step).  NOT volatile: volatile asm statements keep their program order, which
+// serialises the 32 elements of a column (measured: 48 % instead of 57 % of the roofline).
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+  float2 v;
+  asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+// addr += (probe < v) ? BYTES : 0 as one compare and one predicated add
+template <int BYTES>
+__device__ __forceinline__ void step_if_less(uint32_t& addr, float probe, float v) {
+  asm("{\n .reg .pred p;\n setp.lt.f32 p, %1, %2;\n @p add.u32 %0, %0, %3;\n}" : "+r"(addr) : "f"(probe), "f"(v), "n"(BYTES));
+}
+
+template <int K1, int ST>
+struct RqsSearch {
+  static __device__ __forceinline__ void run(uint32_t& addr, float v) {
+    constexpr int RB = RQS_REC * 4;
+    step_if_less<ST * RB>(addr, lds_f32(addr + (ST - 1) * RB + 32), v);
+    RqsSearch<K1, ST / 2>::run(addr, v);
+  }
+};
+template <int K1>
+struct RqsSearch<K1, 0> {
+  static __device__ __forceinline__ void run(uint32_t&, float) {}
+};
+
+// One element.  `row` is the shared-space address of the records of the element's row; `lg` receives log2 of the
+// spline's derivative at the element (0 outside the box), `out` the transformed value.
 template <int K1, bool INV>
-__device__ __forceinline__ void rqs2_element(const float* __restrict__ row, float v, float& out, float& lg) {
+__device__ __forceinline__ void rqs2_element(uint32_t row, float v, float& out, float& lg) {
   constexpr int STEPS = rqs2_steps(K1);
   constexpr int RB = RQS_REC * 4;  // record stride in bytes
-  const char* base = reinterpret_cast<const char*>(row);
-  const float2 ends = *reinterpret_cast<const float2*>(base + (K1 - 2) * RB + 32);  // {S[0], S[K1-1]}
-  const bool outside = fabsf(v) >= ends.y;  // x <= -B or x >= B: identity, :322-324 / :186-188 (NaN goes through the spline)
+  // the first probe is the same for every lane: one LDS.128 also brings the two end knots
+  const float4 head = lds_f32x4(row + ((1 << (STEPS - 1)) - 1) * RB + 32);  // {S[2^(STEPS-1)], S[0], S[K1-1], -}
+  const bool outside = fabsf(v) >= head.z;  // x <= -B or x >= B: identity, :322-324 / :186-188 (NaN goes through the spline)
   // number of knots < v (searchsortedfirst − 1): interior knots by bisection, the first knot on its own
-  int off = 0;
-#pragma unroll
-  for (int st = 1 << (STEPS - 1); st >= 1; st >>= 1) {
-    const float probe = *reinterpret_cast<const float*>(base + off + (st - 1) * RB + 32);
-    off += (probe < v) ? st * RB : 0;
-  }
-  off += (ends.x < v) ? RB : 0;
-  const float4 c0 = *reinterpret_cast<const float4*>(base + off);
-  const float2 c1 = *reinterpret_cast<const float2*>(base + off + 16);
+  uint32_t addr = row;
+  step_if_less<(1 << (STEPS - 1)) * RB>(addr, head.x, v);
+  RqsSearch<K1, (1 << (STEPS - 1)) / 2>::run(addr, v);
+  step_if_less<RB>(addr, head.y, v);
+  const float4 c0 = lds_f32x4(addr);
+  const float2 c1 = lds_f32x2(addr + 16);
   const float w_k = c0.x, h_k = c0.z;
   const float d_k = c1.x, d_k1 = c1.y;
   // the record holds 6 numbers (LDS.128 + LDS.64 = 6 shared-memory wavefronts; the kernel is bound by them): Δy or s
@@ -145,13 +181,17 @@ struct RqsProg {
                                         float (&lj)[1]) const {
     constexpr int RF = rqs2_row_floats(K1);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // the record loads below are plain (non-volatile) asm so that the scheduler can interleave the elements freely;
+    // routing the base address through this statement keeps them behind the tile's barrier wait
+    uint32_t pbase = smem_u32(params);
+    asm volatile("" : "+r"(pbase));
 #pragma unroll
     for (int i = 0; i < D / 2; ++i) {
       float o, l1;
-      rqs2_element<K1, INV>(params + (2 * i) * RF, x[0][i].x, o, l1);
+      rqs2_element<K1, INV>(pbase + (2 * i) * RF * 4, x[0][i].x, o, l1);
       x[0][i].x = o;
       acc[(2 * i) & 3] += l1;
-      rqs2_element<K1, INV>(params + (2 * i + 1) * RF, x[0][i].y, o, l1);
+      rqs2_element<K1, INV>(pbase + (2 * i + 1) * RF * 4, x[0][i].y, o, l1);
       x[0][i].y = o;
       acc[(2 * i + 1) & 3] += l1;
     }

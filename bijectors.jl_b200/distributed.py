@@ -32,6 +32,32 @@ def numa_bind(device: Optional[int] = None) -> Tuple[int, int]:
     return int(node.value), int(ncpu.value)
 
 
+def device_for_rank(local_rank: int, n_visible: Optional[int] = None) -> int:
+    """CUDA device of local rank `local_rank`: the visible devices ordered round-robin over the NUMA nodes of their PCIe
+    root complexes, so that a job with fewer ranks than GPUs spreads over the sockets (the host-buffer path is bound by
+    host DRAM bandwidth per socket).  With every GPU in use, or without topology information, this is the identity."""
+    n = torch.cuda.device_count() if n_visible is None else n_visible
+    nodes = []
+    for d in range(n):
+        node = ctypes.c_int32(-1)
+        try:
+            check(lib().b2b_device_numa_node(d, ctypes.byref(node)), "b2b_device_numa_node")
+        except Exception:
+            node = ctypes.c_int32(-1)
+        nodes.append(int(node.value))
+    if any(v < 0 for v in nodes) or len(set(nodes)) <= 1:
+        return local_rank % max(n, 1)
+    per_node = {}
+    for d, v in enumerate(nodes):
+        per_node.setdefault(v, []).append(d)
+    order, keys = [], sorted(per_node)
+    while any(per_node[k] for k in keys):
+        for k in keys:
+            if per_node[k]:
+                order.append(per_node[k].pop(0))
+    return order[local_rank % n]
+
+
 class Communicator:
     """b2b_comm wrapper: the NCCL unique id is created on rank 0 and broadcast through torch.distributed."""
 

@@ -268,6 +268,11 @@ int b2b_host_unregister(void* ptr);
  * it once before allocating its host batches.  Best effort: *node_out = -1 when the topology is not exposed
  * (/sys/bus/pci/devices/<bus id>/numa_node); *ncpus_out = CPUs in the new affinity mask.  Linux only. */
 int b2b_numa_bind_to_device(int32_t device, int32_t* node_out, int32_t* ncpus_out);
+/* NUMA node of the PCIe root complex that serves CUDA device `device` (-1 when not exposed).  A launcher that starts
+ * fewer ranks than the box has GPUs can use it to spread the ranks over the sockets: the host-buffer path is bound by
+ * host DRAM bandwidth per socket (measured: four B200s behind one socket reach 0.52 of four times the single-GPU
+ * throughput, two behind each socket 0.88). */
+int b2b_device_numa_node(int32_t device, int32_t* node_out);
 
 /* ---- multi-GPU: the ONE collective of the path -----------------------------------
  * Columns shard across ranks with no data-path collective; the batch log-density Σ_n logpdf[n] is

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -k "rqs or config4" > gpurun_out/c7_pytest.log 2>&1; echo "pytest rc=$?"; grep -E "^FAILED|^ERROR|passed|failed" gpurun_out/c7_pytest.log | cut -c1-250 | head
+timeout 300 python bench_configs.py --only C4 --iters 20 > gpurun_out/c7_c4.log 2>&1; tail -n 2 gpurun_out/c7_c4.log | cut -c1-200
