@@ -11,8 +11,8 @@ from .interface import (  # noqa: F401
     with_logabsdet_jacobian, with_logabsdet_jacobian_,
 )
 from .layers import (  # noqa: F401
-    AffineConditioner, Coupling, Elementwise, InvertibleBatchNorm, LeakyReLU, PartitionMask, Permute, PlanarLayer, RadialLayer,
-    RationalQuadraticSpline, Scale, Shift, Stacked, coupling, elementwise,
+    AffineConditioner, Coupling, Elementwise, InvertibleBatchNorm, LeakyReLU, Logit, PartitionMask, Permute, PlanarLayer, RadialLayer,
+    RationalQuadraticSpline, Scale, Shift, Stacked, TruncatedBijector, coupling, elementwise,
 )
 from .transformed_distribution import (  # noqa: F401
     MvNormal, TransformedDistribution, logpdf, logpdf_sum, rand, transformed,

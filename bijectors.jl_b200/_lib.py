@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libb2b.so")
 B2B_OK = 0
 B2B_EINVAL, B2B_EUNSUPPORTED, B2B_EWORKSPACE, B2B_ENONCCL = -1, -2, -3, -4
 PLANAR, RADIAL, RQS, COUPLING_AFFINE, BATCHNORM, PERMUTE, STACKED_EW, MVNORMAL_DIAG = 1, 2, 3, 4, 5, 6, 7, 8
-EW_IDENTITY, EW_EXP, EW_LOG, EW_SHIFT, EW_SCALE, EW_LEAKY_RELU = 0, 1, 2, 3, 4, 5
+EW_IDENTITY, EW_EXP, EW_LOG, EW_SHIFT, EW_SCALE, EW_LEAKY_RELU, EW_LOGIT, EW_TRUNCATED = 0, 1, 2, 3, 4, 5, 6, 7
 MAX_CHAIN = 24
 
 
@@ -83,7 +83,7 @@ _SIGS = {
                                             c_void_p, c_size_t, c_void_p]),
     "b2b_batchnorm_train_workspace_bytes": (c_size_t, [c_int32]),
     "b2b_permute_rows_f32": (c_int, [_F32P] * 3 + [c_void_p, c_int, c_int32, c_int64, c_int64, c_int64, c_int, c_void_p]),
-    "b2b_stacked_elementwise_f32": (c_int, [_F32P] * 3 + [c_void_p, _F32P, c_int, c_int32, c_int64, c_int64, c_int64,
+    "b2b_stacked_elementwise_f32": (c_int, [_F32P] * 3 + [c_void_p, _F32P, _F32P, c_int, c_int32, c_int64, c_int64, c_int64,
                                             c_int, c_void_p]),
     "b2b_mvnormal_diag_logpdf_f32": (c_int, [_F32P] * 5 + [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_size_t,
                                              c_void_p]),

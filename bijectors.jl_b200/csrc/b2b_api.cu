@@ -12,9 +12,10 @@ int b2b_chain_grid_size_v0(const B2BChainParams& p);
 int b2b_chain_grid_size_v1(const B2BChainParams& p);
 
 static thread_local int g_last_launches = 0;
-static int g_variant = 0;           // fused chain kernel: 0 auto, 1 v0, 2 v1 interpreter, 3 constant-bank planar
-static int g_fold_bn = 1;            // fold BatchNorm neighbours into coupling launches (hundreds digit 1 disables)
-static int g_coupling_variant = 0;  // coupling: 0 auto (tensor cores when possible), 1 force the fp32 CUDA-core kernel
+// kernel selection of b2b_set_kernel_variant: per calling thread (no mutable process-global state)
+static thread_local int g_variant = 0;           // fused chain kernel: 0 auto, 1 v0, 2 v1 interpreter, 3 unrolled planar
+static thread_local int g_fold_bn = 1;            // fold BatchNorm neighbours into coupling launches (hundreds digit 1 disables)
+static thread_local int g_coupling_variant = 0;  // coupling: 0 auto (tensor cores when possible), 1 force the fp32 CUDA-core kernel
 
 extern "C" int b2b_version(void) { return B2B_VERSION; }
 
@@ -439,11 +440,12 @@ extern "C" int b2b_permute_rows_f32(const float* x, float* y, float* logjac, con
 }
 
 extern "C" int b2b_stacked_elementwise_f32(const float* x, float* y, float* logjac, const int32_t* code,
-                                           const float* a, int inverse, int32_t D, int64_t N, int64_t ldx,
-                                           int64_t ldy, int acc, void* stream) {
+                                           const float* a, const float* b, int inverse, int32_t D, int64_t N,
+                                           int64_t ldx, int64_t ldy, int acc, void* stream) {
   b2b_layer_desc d = mk(B2B_STACKED_EW, inverse ? 1 : 0);
   d.i0 = code;
   d.p0 = a;
+  d.p1 = b;
   return run1(d, x, y, logjac, D, N, ldx, ldy, acc, stream);
 }
 

@@ -271,34 +271,12 @@ __global__ void __launch_bounds__(256) chain_v0_kernel(const __grid_constant__ B
             const int r0 = 4 * (v * G + j);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              int op = code[r0 + q];
-              const float a = av[r0 + q];
-              if (d.inverse) op = op == B2B_EW_EXP ? B2B_EW_LOG : (op == B2B_EW_LOG ? B2B_EW_EXP : op);
+              const int op = code[r0 + q];
+              const float a = av[r0 + q], b = av[Dp + r0 + q];
 #pragma unroll
               for (int c = 0; c < C; ++c) {
                 float* e = reinterpret_cast<float*>(&xr[c][v]);
-                const float xv = e[q];
-                if (op == B2B_EW_EXP) {
-                  e[q] = expf(xv);
-                  p[c] += xv;  // exp_log.jl:5-6
-                } else if (op == B2B_EW_LOG) {
-                  const float lg = logf(xv);
-                  e[q] = lg;
-                  p[c] -= lg;  // exp_log.jl:8-9
-                } else if (op == B2B_EW_SHIFT) {
-                  e[q] = d.inverse ? xv - a : a + xv;  // shift.jl:12,14
-                } else if (op == B2B_EW_SCALE) {
-                  e[q] = d.inverse ? xv / a : a * xv;  // scale.jl:13,15
-                  const float la = logf(fabsf(a));
-                  p[c] += d.inverse ? -la : la;  // scale.jl:26
-                } else if (op == B2B_EW_LEAKY_RELU) {
-                  // J = x < 0 ? α : 1 (leaky_relu.jl:18-22); inverse(b) = LeakyReLU(inv(α)) (:16)
-                  const float al = d.inverse ? 1.0f / a : a;
-                  if (xv < 0.f) {
-                    e[q] = al * xv;
-                    p[c] += logf(fabsf(al));
-                  }
-                }
+                e[q] = ew_apply(op, d.inverse != 0, a, b, e[q], p[c]);
               }
             }
           }

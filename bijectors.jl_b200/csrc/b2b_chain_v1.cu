@@ -128,32 +128,11 @@ __device__ __forceinline__ void stacked_apply(float2 (&x)[CPT][D / TPC / 2], con
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int row = c.row(ql, r, e);
-      int op = code[row];
-      const float a = av[row];
-      if (inverse) op = op == B2B_EW_EXP ? B2B_EW_LOG : (op == B2B_EW_LOG ? B2B_EW_EXP : op);
+      const int op = code[row];
+      const float a = av[row], b = av[D + row];
       B2B_FOR_COLS {
         float& xe = (e & 1) ? x[cc][(ql * 8 + r) * 2 + (e >> 1)].y : x[cc][(ql * 8 + r) * 2 + (e >> 1)].x;
-        const float xv = xe;
-        if (op == B2B_EW_EXP) {
-          xe = expf(xv);
-          acc[cc] += xv;
-        } else if (op == B2B_EW_LOG) {
-          const float lg = logf(xv);
-          xe = lg;
-          acc[cc] -= lg;
-        } else if (op == B2B_EW_SHIFT) {
-          xe = inverse ? xv - a : a + xv;
-        } else if (op == B2B_EW_SCALE) {
-          xe = inverse ? xv / a : a * xv;
-          const float la = logf(fabsf(a));
-          acc[cc] += inverse ? -la : la;
-        } else if (op == B2B_EW_LEAKY_RELU) {
-          const float al = inverse ? 1.0f / a : a;  // leaky_relu.jl:16,18-22
-          if (xv < 0.f) {
-            xe = al * xv;
-            acc[cc] += logf(fabsf(al));
-          }
-        }
+        xe = ew_apply(op, inverse, a, b, xe, acc[cc]);
       }
     }
   }

@@ -213,6 +213,90 @@ __device__ __forceinline__ void rqs_element(const float* __restrict__ tab, int K
   lj = outside ? 0.0f : (INV ? -l : l);
 }
 
+// One element of a Stacked block of elementwise laws (stacked.jl:157-166,242-252): code `op` with per-row parameters
+// (a, b); `inverse` evaluates Inverse(law) and ITS log-Jacobian.  Returns the transformed value, adds to `lj`.
+//   EXP / LOG    exp_log.jl:5-9          SHIFT shift.jl:12-24        SCALE scale.jl:13-31
+//   LEAKY_RELU   leaky_relu.jl:16-29 (inverse(b) = LeakyReLU(inv(α)))
+//   LOGIT        logit.jl:15-29: y = logit((x−a)/(b−a)), logjac = −log((x−a)(b−x)/(b−a)); the inverse has no method of
+//                its own for the log-Jacobian, so it is −logjac at the recovered x (interface.jl:276-281)
+//   TRUNCATED    truncated.jl:15-91: x is clamped to [lb, ub] first (Bijectors.jl:95-100); finite/infinite bounds pick
+//                logit / log(x−lb) / log(ub−x) / identity; the inverse has its own closed form (:62-76)
+__device__ __forceinline__ float ew_apply(int op, bool inverse, float a, float b, float xv, float& lj) {
+  switch (op) {
+    case B2B_EW_EXP:
+    case B2B_EW_LOG: {
+      const bool is_exp = (op == B2B_EW_EXP) != inverse;  // inverse(exp) = log
+      if (is_exp) {
+        lj += xv;
+        return expf(xv);
+      }
+      const float lg = logf(xv);
+      lj -= lg;
+      return lg;
+    }
+    case B2B_EW_SHIFT: return inverse ? xv - a : a + xv;
+    case B2B_EW_SCALE: {
+      const float la = logf(fabsf(a));
+      lj += inverse ? -la : la;
+      return inverse ? xv / a : a * xv;
+    }
+    case B2B_EW_LEAKY_RELU: {
+      const float al = inverse ? 1.0f / a : a;
+      if (xv < 0.f) {
+        lj += logf(fabsf(al));
+        return al * xv;
+      }
+      return xv;
+    }
+    case B2B_EW_LOGIT: {
+      if (!inverse) {
+        const float z = (xv - a) / (b - a);
+        lj -= logf((xv - a) * (b - xv) / (b - a));      // logit.jl:24
+        return logf(z / (1.0f - z));                      // LogExpFunctions.logit
+      }
+      const float sg = 1.0f / (1.0f + expf(-xv));         // LogExpFunctions.logistic
+      const float x = fmaf(b - a, sg, a);                 // logit.jl:19
+      lj += logf((x - a) * (b - x) / (b - a));
+      return x;
+    }
+    case B2B_EW_TRUNCATED: {
+      const bool lo = !isinf(a), hi = !isinf(b);
+      if (!inverse) {
+        const float x = xv < a ? a : (xv > b ? b : xv);   // _clamp, Bijectors.jl:95-100
+        if (lo && hi) {
+          lj -= logf((x - a) * (b - x) / (b - a));        // truncated.jl:55
+          return logf(((x - a) / (b - a)) / (1.0f - (x - a) / (b - a)));
+        }
+        if (lo) {
+          const float lg = logf(x - a);
+          lj -= lg;
+          return lg;
+        }
+        if (hi) {
+          const float lg = logf(b - x);
+          lj -= lg;
+          return lg;
+        }
+        return x;
+      }
+      float x = xv;
+      if (lo && hi) {
+        const float ay = fabsf(xv);
+        lj += logf(b - a) - ay - 2.0f * softplus(-ay);    // truncated.jl:70
+        x = fmaf(b - a, 1.0f / (1.0f + expf(-xv)), a);
+      } else if (lo) {
+        lj += xv;
+        x = expf(xv) + a;
+      } else if (hi) {
+        lj += xv;
+        x = b - expf(xv);
+      }
+      return x < a ? a : (x > b ? b : x);
+    }
+    default: return xv;
+  }
+}
+
 // ---- parameter staging (once per CTA) --------------------------------------------------------------
 // Layout of the staged block of one layer (floats, Dp = padded depth, rows >= D are zero):
 //   PLANAR    : w[Dp] | û[Dp] | {c = wᵀû, b, -, -}                      (get_u_hat, planar_layer.jl:65-70)
@@ -220,7 +304,7 @@ __device__ __forceinline__ void rqs_element(const float* __restrict__ tab, int K
 //   BATCHNORM : A[Dp] | C[Dp] | iA[Dp] | iC[Dp] | {Σ(logs − log(v+eps)/2)}   y = A·x + C, x = iA·y + iC
 //   RQS       : Sw[Dp][KP] | Sh[Dp][KP] | per-(row,bin) constants float4 x 2 [Dp][K1]  ((2·KP + 8·K1)·Dp floats)
 //   PERMUTE   : src_of_dst[Dp] (int)
-//   STACKED_EW: code[Dp] (int) | a[Dp]
+//   STACKED_EW: code[Dp] (int) | a[Dp] | b[Dp]
 //   MVNORMAL  : mu[Dp] | 1/sigma[Dp] | {−(D·log2π + Σ log σ²)/2}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -362,6 +446,7 @@ __device__ inline void stage_layer(const b2b_layer_desc& d, float* sm, int D, in
       for (int i = lane; i < Dp; i += 32) {
         sc[i] = i < D ? d.i0[i] : B2B_EW_IDENTITY;
         sm[Dp + i] = (i < D && d.p0) ? d.p0[i] : 0.f;
+        sm[2 * Dp + i] = (i < D && d.p1) ? d.p1[i] : 0.f;
       }
     } break;
     case B2B_MVNORMAL_DIAG: {

@@ -30,7 +30,7 @@ static inline int b2b_layer_smem_floats(const b2b_layer_desc& d, int Dp) {
       return (2 * kp + 8 * d.n0) * Dp;
     }
     case B2B_PERMUTE: return Dp;
-    case B2B_STACKED_EW: return 2 * Dp;
+    case B2B_STACKED_EW: return 3 * Dp;
     case B2B_MVNORMAL_DIAG: return 2 * Dp + 4;
     default: return 0;
   }

@@ -570,8 +570,17 @@ int b2b_launch_planar_chain_vjp(const B2BChainParams& p, const float* ybar, long
   q.partials = nullptr;
   if (v1_check_io(q) != 0) return B2B_EUNSUPPORTED;
   if ((ldyb % 4) || (reinterpret_cast<uintptr_t>(ybar) & 15) || !xbar) return B2B_EUNSUPPORTED;
-  // the parameter pass re-reads ybar: it must not have been overwritten by xbar
-  if (wbar && ubar && bbar && xbar == ybar) return B2B_EINVAL;
+  // the parameter pass re-reads x AND ybar after the main kernel has written xbar: xbar must not overlap either
+  if (wbar && ubar && bbar) {
+    auto overlaps = [&](const float* a, long long lda, const float* b, long long ldb) {
+      const char* a0 = reinterpret_cast<const char*>(a);
+      const char* a1 = a0 + ((size_t)(p.N - 1) * (size_t)lda + (size_t)D) * sizeof(float);
+      const char* b0 = reinterpret_cast<const char*>(b);
+      const char* b1 = b0 + ((size_t)(p.N - 1) * (size_t)ldb + (size_t)D) * sizeof(float);
+      return a0 < b1 && b0 < a1;
+    };
+    if (overlaps(xbar, ldxb, ybar, ldyb) || overlaps(xbar, ldxb, p.x, p.ldx)) return B2B_EINVAL;
+  }
   if (!workspace || workspace_bytes < b2b_planar_vjp_workspace(n, D, p.N)) return B2B_EWORKSPACE;
   char* wsb = static_cast<char*>(workspace);
   wsb += (256 - (reinterpret_cast<uintptr_t>(wsb) & 255)) & 255;

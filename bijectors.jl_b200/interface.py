@@ -149,8 +149,11 @@ class ComposedFunction(Transform):
         self.outer, self.inner = outer, inner
 
     def _descs(self, inverse_, D):
+        # inverse(f∘g) = inverse(g)∘inverse(f): the outer function's inverse is applied first.  Every leaf inverts by
+        # the descriptor's `inverse` flag on ITS OWN (cached) device tables -- no temporary objects whose device memory
+        # could be recycled before the launch is enqueued.
         if inverse_:
-            return inverse(self)._descs(False, D)
+            return self.outer._descs(True, D) + self.inner._descs(True, D)
         return self.inner._descs(False, D) + self.outer._descs(False, D)
 
     def _keepalive(self):
@@ -168,15 +171,17 @@ class Composed(Transform):
         self.layers = flat
 
     def _descs(self, inverse_, D):
-        if inverse_:
-            return inverse(self)._descs(False, D)
         out = []
-        for b in self.layers:
-            out.extend(b._descs(False, D))
+        for b in (reversed(self.layers) if inverse_ else self.layers):
+            out.extend(b._descs(inverse_, D))
         return out
 
     def _keepalive(self):
         return tuple(k for b in self.layers for k in b._keepalive())
+
+    def to(self, device):
+        """Functors.fmap-style movement of every layer that owns device tensors."""
+        return Composed(*[b.to(device) if hasattr(b, "to") else b for b in self.layers])
 
 
 class Columnwise(Transform):
@@ -261,6 +266,10 @@ def run_chain(t, x: torch.Tensor, *, want_y=True, want_logjac=True, y: Optional[
         return _run_planar_hostparams(descs, x, D, N, ldx, want_y, want_logjac, y, logjac, accumulate, sum_out)
     arr = _desc_array(descs)
     L = len(descs)
+    if x.is_cuda:  # raw parameter pointers are launched on x's device: they must live there
+        for kt in t._keepalive():
+            if isinstance(kt, torch.Tensor) and kt.is_cuda and kt.device != x.device:
+                raise ValueError(f"layer parameters live on {kt.device} but the batch is on {x.device}; move the flow with .to()")
     if not x.is_cuda:
         return _run_chain_host(arr, L, x, D, N, want_y, want_logjac, sum_out)
     L_ = lib()
@@ -288,7 +297,6 @@ def run_chain(t, x: torch.Tensor, *, want_y=True, want_logjac=True, y: Optional[
         D, N, ldx, ldy, 1 if accumulate else 0,
         ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
     check(rc, "b2b_chain_run_f32")
-    del keepalive
     lj_out = logjac
     if lj_out is not None and x.dim() == 1:
         lj_out = lj_out.reshape(())

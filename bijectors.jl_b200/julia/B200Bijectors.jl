@@ -1,22 +1,28 @@
 # B200Bijectors.jl -- the reference-side binding of libb2b.so (include/b2b.h).
 #
-# This is the file a Bijectors.jl maintainer adds (as a package extension on CUDA.jl, e.g.
-# ext/BijectorsB200Ext.jl) to make the batched flow path dispatch to the B200 kernels.  Bijectors.jl has no
-# FFI/plugin registry: "plugging in" = more specific methods of its own generic functions
-# (src/interface.jl:144,156,183,265).  NOT runnable in the build container (no Julia toolchain exists there);
-# the identical C ABI is exercised by the Python/ctypes harness in bijectors.jl_b200/ (tests/, bench.py).
+# This is the file a Bijectors.jl maintainer adds as a PACKAGE EXTENSION of Bijectors.jl on CUDA.jl
+# (ext/BijectorsB200Ext.jl; `[weakdeps] CUDA`, `[extensions] BijectorsB200Ext = "CUDA"`), so every method below is a
+# more specific method of Bijectors' OWN generic functions on Bijectors' OWN layer types parametrised by CuArrays --
+# no type piracy.  Bijectors.jl has no FFI/plugin registry: "plugging in" = dispatch (src/interface.jl:144,156,183,265).
+# NOT runnable in the build container (no Julia toolchain exists there); the identical C ABI is exercised by the
+# Python/ctypes harness in bijectors.jl_b200/ (tests/, bench.py), and tests/test_host_logic.py parses every `ccall` in
+# this file and checks symbol, arity and argument classes against include/b2b.h.
 #
 # Conventions (include/b2b.h): D×N Float32 CuMatrix batches (Julia is column-major, so a column is one sample);
-# every pointer is a device pointer; the stream is CUDA.jl's task-local stream; non-zero status -> error(...).
+# every pointer is a device pointer unless the C name says host; the stream is CUDA.jl's task-local stream; non-zero
+# status -> error(b2b_status_string(rc)).
 module B200Bijectors
 
 using CUDA
 using Bijectors
-using Bijectors: PlanarLayer, RadialLayer, RationalQuadraticSpline, Coupling, PartitionMask,
-                 InvertibleBatchNorm, Permute, Inverse, TransformedDistribution
+using Bijectors: PlanarLayer, RadialLayer, RationalQuadraticSpline, Coupling, PartitionMask, InvertibleBatchNorm,
+                 Permute, Stacked, Shift, Scale, LeakyReLU, Logit, TruncatedBijector, Inverse, TransformedDistribution
 import Bijectors: transform, logabsdetjac, with_logabsdet_jacobian
+import Distributions
 using Distributions: MvNormal
 using Functors: fmap
+using SparseArrays: findnz
+using Statistics: mean, var
 
 const libb2b = get(ENV, "LIBB2B", "libb2b.so")
 
@@ -30,6 +36,7 @@ struct LayerDesc
     i0::CuPtr{Int32}; i1::CuPtr{Int32}
 end
 const PLANAR, RADIAL, RQS, COUPLING_AFFINE, BATCHNORM, PERMUTE, STACKED_EW, MVNORMAL_DIAG = Int32.(1:8)
+const EW_IDENTITY, EW_EXP, EW_LOG, EW_SHIFT, EW_SCALE, EW_LEAKY_RELU, EW_LOGIT, EW_TRUNCATED = Int32.(0:7)
 const NULLF = CuPtr{Float32}(0)
 const NULLI = CuPtr{Int32}(0)
 
@@ -44,6 +51,7 @@ to_device(flow) = fmap(x -> x isa AbstractArray{<:Real} ? cu(Float32.(x)) : x, f
 
 # ---- layer -> descriptor ------------------------------------------------------------------------------
 # Parameters are passed RAW (the struct fields); û, wᵀû, softplus terms are derived on the device.
+# A descriptor only holds pointers: `owners(b)` lists the arrays that must stay rooted while a launch is in flight.
 desc(b::PlanarLayer{<:CuVector{Float32}}, inv::Bool) =
     LayerDesc(PLANAR, inv, 0, 0, 0, 0, 0f0, 0f0, pointer(b.w), pointer(b.u), pointer(b.b), NULLF, NULLI, NULLI)
 desc(b::RadialLayer{<:CuVector{Float32}}, inv::Bool) =
@@ -51,8 +59,8 @@ desc(b::RadialLayer{<:CuVector{Float32}}, inv::Bool) =
 desc(b::RationalQuadraticSpline{<:CuMatrix{Float32}}, inv::Bool) =       # fields are D×(K+1), column-major
     LayerDesc(RQS, inv, size(b.widths, 2), 0, 0, 0, 0f0, 0f0,
               pointer(b.widths), pointer(b.heights), pointer(b.derivatives), NULLF, NULLI, NULLI)
-desc(b::InvertibleBatchNorm{<:CuVector{Float32}}, inv::Bool) = begin
-    Bijectors.istraining() && error("InvertibleBatchNorm training mode is not on the device path")
+function desc(b::InvertibleBatchNorm{<:CuVector{Float32}}, inv::Bool)
+    Bijectors.istraining() && error("InvertibleBatchNorm in training mode is a separate call: batchnorm_train!")
     LayerDesc(BATCHNORM, inv, 0, 0, 0, 0, Float32(b.eps), 0f0,
               pointer(b.b), pointer(b.logs), pointer(b.m), pointer(b.v), NULLI, NULLI)
 end
@@ -64,7 +72,9 @@ struct AffineConditioner{M<:CuMatrix{Float32},V<:CuVector{Float32}}
     c::V
 end
 (θ::AffineConditioner)(x₂) = (st = θ.W * x₂ .+ θ.c; n = length(st) ÷ 2;
-                              Bijectors.Shift(st[(n + 1):end]) ∘ Bijectors.Scale(exp.(st[1:n])))
+                              Shift(st[(n + 1):end]) ∘ Scale(exp.(st[1:n])))
+# Device-side tables (index lists, elementwise codes) are built once per host object and cached, so that they outlive
+# every launch that uses them.
 struct DeviceMask            # index lists of a PartitionMask (coupling.jl:51-118), 0-based on the device
     idx1::CuVector{Int32}; idx2::CuVector{Int32}; row1::Int32; row2::Int32
 end
@@ -82,10 +92,59 @@ function desc(cl::Coupling{<:AffineConditioner}, inv::Bool)
 end
 desc(cl::Coupling, ::Bool) = error("Coupling: only AffineConditioner laws run on the device path (no CPU fallback)")
 
+# Permute(A): y[dst[i]] = x[i] with dst = the row of the single 1 in column i (permute.jl:90-100,152)
+const PERMS = IdDict{Any,CuVector{Int32}}()
+function desc(b::Permute, inv::Bool)
+    dst = get!(PERMS, b) do
+        r, c, _ = findnz(b.A)
+        d = zeros(Int32, size(b.A, 2)); d[c] .= Int32.(r .- 1)
+        cu(d)
+    end
+    LayerDesc(PERMUTE, inv, 0, 0, 0, 0, 0f0, 0f0, NULLF, NULLF, NULLF, NULLF, pointer(dst), NULLI)
+end
+
+# Stacked of elementwise laws on row ranges (stacked.jl:25-59,157-166,242-252): one law code + (a, b) per row
+ew_law(::typeof(identity)) = (EW_IDENTITY, 0f0, 0f0)
+ew_law(f::Base.Fix1{typeof(broadcast)}) = f.x === exp ? (EW_EXP, 0f0, 0f0) : f.x === log ? (EW_LOG, 0f0, 0f0) :
+    f.x === identity ? (EW_IDENTITY, 0f0, 0f0) : error("elementwise($(f.x)) is not on the device path")
+ew_law(b::Shift{<:Real}) = (EW_SHIFT, Float32(b.a), 0f0)
+ew_law(b::Scale{<:Real}) = (EW_SCALE, Float32(b.a), 0f0)
+ew_law(b::LeakyReLU{<:Real}) = (EW_LEAKY_RELU, Float32(b.α), 0f0)
+ew_law(b::Logit{<:Real,<:Real}) = (EW_LOGIT, Float32(b.a), Float32(b.b))
+ew_law(b::TruncatedBijector{<:Real,<:Real}) = (EW_TRUNCATED, Float32(b.lb), Float32(b.ub))
+ew_law(b) = error("Stacked block $(typeof(b)) is not on the device path (no CPU fallback)")
+struct DeviceStacked
+    code::CuVector{Int32}; a::CuVector{Float32}; b::CuVector{Float32}
+end
+const STACKS = IdDict{Any,DeviceStacked}()
+function DeviceStacked(sb::Stacked)
+    D = sb.length_in
+    code, a, b = zeros(Int32, D), zeros(Float32, D), zeros(Float32, D)
+    for (blk, r) in zip(sb.bs, sb.ranges_in)
+        c, pa, pb = ew_law(blk)
+        code[r] .= c; a[r] .= pa; b[r] .= pb
+    end
+    DeviceStacked(cu(code), cu(a), cu(b))
+end
+function desc(sb::Stacked, inv::Bool)
+    ds = get!(() -> DeviceStacked(sb), STACKS, sb)
+    LayerDesc(STACKED_EW, inv, 0, 0, 0, 0, 0f0, 0f0, pointer(ds.a), pointer(ds.b), NULLF, NULLF, pointer(ds.code), NULLI)
+end
+# a whole-column elementwise law is a one-block Stacked
+const ElementwiseLaw = Union{Shift{<:Real},Scale{<:Real},LeakyReLU{<:Real},Logit{<:Real,<:Real},TruncatedBijector{<:Real,<:Real}}
+
 # ---- chains: Base.ComposedFunction trees are flattened inner-most first ------------------------------
 flatten(f::ComposedFunction) = (flatten(f.inner)..., flatten(f.outer)...)
 flatten(f) = (f,)
 descs(f, inv::Bool) = inv ? [desc(b, true) for b in reverse(flatten(f))] : [desc(b, false) for b in flatten(f)]
+
+const DeviceLayer = Union{PlanarLayer{<:CuVector{Float32}},RadialLayer{<:CuVector{Float32}},
+                          RationalQuadraticSpline{<:CuMatrix{Float32}},InvertibleBatchNorm{<:CuVector{Float32}},
+                          Coupling{<:AffineConditioner},Permute,Stacked}
+const DeviceLeaf = Union{DeviceLayer,Inverse{<:DeviceLayer}}
+is_device(f::ComposedFunction) = is_device(f.inner) && is_device(f.outer)
+is_device(::DeviceLeaf) = true
+is_device(_) = false
 
 function run_chain(ds::Vector{LayerDesc}, x::CuMatrix{Float32}; y=similar(x), logjac=CUDA.zeros(Float32, size(x, 2)),
                    sum_out=nothing, accumulate=false)
@@ -106,17 +165,10 @@ function run_chain(ds::Vector{LayerDesc}, x::CuMatrix{Float32}; y=similar(x), lo
 end
 
 # ---- the methods Bijectors.jl dispatches to ------------------------------------------------------------
-const DeviceLayer = Union{PlanarLayer{<:CuVector{Float32}},RadialLayer{<:CuVector{Float32}},
-                          RationalQuadraticSpline{<:CuMatrix{Float32}},InvertibleBatchNorm{<:CuVector{Float32}},
-                          Coupling{<:AffineConditioner}}
-const DeviceTransform = Union{DeviceLayer,Inverse{<:DeviceLayer},ComposedFunction}
-
-with_logabsdet_jacobian(b::DeviceTransform, x::CuMatrix{Float32}) = run_chain(descs(b, false), x)
-transform(b::DeviceTransform, x::CuMatrix{Float32}) = first(run_chain(descs(b, false), x; logjac=nothing))
-logabsdetjac(b::DeviceTransform, x::CuMatrix{Float32}) = last(run_chain(descs(b, false), x; y=nothing))
-# in-place variants (src/interface.jl:175-176, 212-218): y aliases x, logjac accumulates
-Bijectors.with_logabsdet_jacobian!(b::DeviceTransform, x::CuMatrix{Float32}, y::CuMatrix{Float32}, logjac::CuVector{Float32}) =
-    run_chain(descs(b, false), x; y=y, logjac=logjac, accumulate=true)
+# Leaves: Bijectors' own layer types with CuArray parameters (and Inverse of them).
+with_logabsdet_jacobian(b::DeviceLeaf, x::CuMatrix{Float32}) = run_chain(descs(b, false), x)
+transform(b::DeviceLeaf, x::CuMatrix{Float32}) = first(run_chain(descs(b, false), x; logjac=nothing))
+logabsdetjac(b::DeviceLeaf, x::CuMatrix{Float32}) = last(run_chain(descs(b, false), x; y=nothing))
 
 # Host-resident PlanarLayer chains (fields are plain Arrays) on a device batch: parameters travel as kernel arguments.
 const HostPlanar = PlanarLayer{<:Vector{Float32}}
@@ -132,8 +184,46 @@ function planar_hostparams(f, x::CuMatrix{Float32}; inv::Bool=false)
         size(x, 1), size(x, 2), stride(x, 2), stride(y, 2), false, stream_handle()))
     return y, logjac
 end
-with_logabsdet_jacobian(b::Union{HostPlanar,ComposedFunction}, x::CuMatrix{Float32}) =
-    all_host_planar(b) ? planar_hostparams(b, x) : run_chain(descs(b, false), x)
+with_logabsdet_jacobian(b::HostPlanar, x::CuMatrix{Float32}) = planar_hostparams(b, x)
+
+# ∘-chains: ONE method per generic function (no ambiguity).  It takes the chain only when every leaf is a device layer
+# (or every leaf a host-resident PlanarLayer); anything else goes back to the reference's own generic method
+# (ChangesOfVariables' rule for ComposedFunction), so compositions of unrelated functions on a CuMatrix are untouched.
+function with_logabsdet_jacobian(f::ComposedFunction, x::CuMatrix{Float32})
+    is_device(f) && return run_chain(descs(f, false), x)
+    all_host_planar(f) && return planar_hostparams(f, x)
+    return invoke(with_logabsdet_jacobian, Tuple{ComposedFunction,Any}, f, x)
+end
+function transform(f::ComposedFunction, x::CuMatrix{Float32})
+    is_device(f) && return first(run_chain(descs(f, false), x; logjac=nothing))
+    return invoke(transform, Tuple{ComposedFunction,Any}, f, x)
+end
+function logabsdetjac(f::ComposedFunction, x::CuMatrix{Float32})
+    is_device(f) && return last(run_chain(descs(f, false), x; y=nothing))
+    return invoke(logabsdetjac, Tuple{ComposedFunction,Any}, f, x)
+end
+# in-place variants (src/interface.jl:175-176, 212-218): y may alias x, logjac accumulates
+function Bijectors.with_logabsdet_jacobian!(b::Union{DeviceLeaf,ComposedFunction}, x::CuMatrix{Float32},
+                                            y::CuMatrix{Float32}, logjac::CuVector{Float32})
+    is_device(b) || error("with_logabsdet_jacobian!: not a device chain")
+    run_chain(descs(b, false), x; y=y, logjac=logjac, accumulate=true)
+end
+
+# Training-mode InvertibleBatchNorm (normalise.jl:51-60): batch statistics (over all ranks when `comm` is given), moving
+# statistics updated in place.  The reference's global istraining() switch is this separate entry point.
+function batchnorm_train!(bn::InvertibleBatchNorm{<:CuVector{Float32}}, x::CuMatrix{Float32}; comm=nothing)
+    D, N = size(x)
+    y, logjac = similar(x), CUDA.zeros(Float32, N)
+    nbytes = ccall((:b2b_batchnorm_train_workspace_bytes, libb2b), Csize_t, (Int32,), D)
+    ws = CuVector{UInt8}(undef, nbytes)
+    GC.@preserve ws check(ccall((:b2b_batchnorm_train_fwd_f32, libb2b), Cint,
+        (CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32},
+         Cfloat, Cfloat, Int32, Int64, Int64, Int64, Cint, Ptr{Cvoid}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        pointer(x), pointer(y), pointer(logjac), pointer(bn.b), pointer(bn.logs), pointer(bn.m), pointer(bn.v),
+        Float32(bn.eps), Float32(bn.mtm), D, N, stride(x, 2), stride(y, 2), false,
+        comm === nothing ? C_NULL : comm.handle, pointer(ws), nbytes, stream_handle()))
+    return y, logjac
+end
 
 # Reverse mode: a ChainRulesCore.rrule for device planar chains (what ext/BijectorsChainRulesCoreExt.jl does for the CPU
 # path, incl. the implicit find_alpha rule :42-46).  ȳ, l̄ are the cotangents of (y, logjac).
@@ -168,6 +258,7 @@ end
 # logpdf(td::MvTransformed, y::Matrix) (src/transformed_distribution.jl:165-169): inverse chain + base
 # MvNormal + (optionally) the batch sum in ONE fused launch per fusable segment.
 function Distributions.logpdf(td::TransformedDistribution{<:MvNormal}, y::CuMatrix{Float32})
+    is_device(td.transform) || return invoke(Distributions.logpdf, Tuple{TransformedDistribution,AbstractMatrix}, td, y)
     ds = descs(td.transform, true)
     μ, σ = cu(Float32.(mean(td.dist))), cu(Float32.(sqrt.(var(td.dist))))
     push!(ds, LayerDesc(MVNORMAL_DIAG, 0, 0, 0, 0, 0, 0f0, 0f0, pointer(μ), pointer(σ), NULLF, NULLF, NULLI, NULLI))
@@ -176,7 +267,12 @@ end
 
 # ---- multi-GPU (one process per GPU): one NCCL sum of the batch log-density (SURVEY §8(e)) ------------
 mutable struct Comm; handle::Ptr{Cvoid}; end
-function Comm(nranks::Integer, rank::Integer, uid::Vector{UInt8})       # uid from b2b_comm_unique_id on rank 0
+function unique_id()
+    uid = Vector{UInt8}(undef, 128)
+    check(ccall((:b2b_comm_unique_id, libb2b), Cint, (Ptr{UInt8},), uid))
+    uid
+end
+function Comm(nranks::Integer, rank::Integer, uid::Vector{UInt8})       # uid from unique_id() on rank 0
     h = Ref{Ptr{Cvoid}}()
     check(ccall((:b2b_comm_init_rank, libb2b), Cint, (Ptr{Ptr{Cvoid}}, Cint, Cint, Ptr{UInt8}), h, nranks, rank, uid))
     Comm(h[])
@@ -184,5 +280,13 @@ end
 allreduce_sum!(c::Comm, v::CuVector{Float64}) =
     check(ccall((:b2b_allreduce_sum_f64, libb2b), Cint, (Ptr{Cvoid}, CuPtr{Float64}, Int32, Ptr{Cvoid}),
                 c.handle, pointer(v), length(v), stream_handle()))
+destroy!(c::Comm) = check(ccall((:b2b_comm_destroy, libb2b), Cint, (Ptr{Cvoid},), c.handle))
+
+# One process per GPU: call once, before allocating pinned host batches (CPU affinity + memory policy next to the GPU).
+function numa_bind(device::Integer=CUDA.deviceid())
+    node, ncpu = Ref{Int32}(-1), Ref{Int32}(0)
+    check(ccall((:b2b_numa_bind_to_device, libb2b), Cint, (Int32, Ptr{Int32}, Ptr{Int32}), device, node, ncpu))
+    return node[], ncpu[]
+end
 
 end # module

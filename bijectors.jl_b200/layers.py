@@ -234,6 +234,12 @@ class AffineConditioner:
             c.detach().cpu() if isinstance(c, torch.Tensor) else c, dtype=np.float32)
         self.c = _dev_f32(cn, device)
 
+    def to(self, device):
+        new = object.__new__(AffineConditioner)
+        new.n1, new.n2 = self.n1, self.n2
+        new.W, new.c = self.W.to(device), self.c.to(device)
+        return new
+
 
 class Coupling(_ParamLayer):
     """Coupling(θ, mask) (coupling.jl:178-181).  θ is an arbitrary closure in the reference; the device
@@ -261,6 +267,10 @@ class Coupling(_ParamLayer):
     @property
     def device(self):
         return self.θ.W.device
+
+    def to(self, device):
+        """fmap-style movement: the conditioner (W, c) AND the index lists follow."""
+        return Coupling(self.θ.to(device), self.mask)
 
     def _keepalive(self):
         return (self.θ.W, self.θ.c, self._idx1, self._idx2)
@@ -391,6 +401,12 @@ class Permute(_ParamLayer):
     def device(self):
         return self._dst.device
 
+    def to(self, device):
+        new = object.__new__(Permute)
+        new.dst_of_src = self.dst_of_src
+        new._dst = self._dst.to(device)
+        return new
+
     def _keepalive(self):
         return (self._dst,)
 
@@ -517,9 +533,52 @@ class LeakyReLU(Bijector):
     __hash__ = object.__hash__
 
 
+class Logit(Bijector):
+    """Logit(a, b): y = logit((x − a)/(b − a)) element-wise, logjac = −Σ log((x − a)(b − x)/(b − a))
+    (logit.jl:4-29); scalar bounds; the reference's `bounded flow` building block (docs/src/flows.md:25-36)."""
+
+    def __init__(self, a, b):
+        self.a, self.b = float(a), float(b)
+        if not self.b > self.a:
+            raise ValueError("Logit needs a < b")
+
+    code = _lib.EW_LOGIT
+
+    def _descs(self, inverse, D):
+        return _as_stacked(self, D)._descs(inverse, D)
+
+    def __eq__(self, o):
+        return isinstance(o, Logit) and (o.a, o.b) == (self.a, self.b)  # logit.jl:12
+
+    __hash__ = object.__hash__
+
+
+class TruncatedBijector(Bijector):
+    """TruncatedBijector(lb, ub) (truncated.jl:4-91): clamp to [lb, ub], then logit((x−lb)/(ub−lb)) / log(x−lb) /
+    log(ub−x) / identity depending on which bounds are finite (±inf allowed); scalar bounds."""
+
+    def __init__(self, lb, ub):
+        self.a, self.b = float(lb), float(ub)
+        if not self.b > self.a:
+            raise ValueError("TruncatedBijector needs lb < ub")
+
+    lb = property(lambda s: s.a)
+    ub = property(lambda s: s.b)
+    code = _lib.EW_TRUNCATED
+
+    def _descs(self, inverse, D):
+        return _as_stacked(self, D)._descs(inverse, D)
+
+    def __eq__(self, o):
+        return isinstance(o, TruncatedBijector) and (o.a, o.b) == (self.a, self.b)
+
+    __hash__ = object.__hash__
+
+
 class Stacked(Transform):
     """Stacked(bs, ranges): bs[i] applied to rows ranges[i] (1-based inclusive (lo, hi) like Julia
-    UnitRanges; stacked.jl:25-59).  Device scope: elementwise blocks (exp, log, identity, Shift, Scale)."""
+    UnitRanges; stacked.jl:25-59).  Device scope: elementwise blocks (exp, log, identity, Shift, Scale, LeakyReLU,
+    Logit, TruncatedBijector)."""
 
     def __init__(self, bs, ranges=None, device="cuda"):
         bs = list(bs)
@@ -529,26 +588,36 @@ class Stacked(Transform):
         if len(bs) != len(ranges):
             raise ValueError("length(bs) == length(ranges) needs to be true")
         for b in bs:
-            if not isinstance(b, (Elementwise, Shift, Scale, LeakyReLU)) and b is not None:
+            if not isinstance(b, (Elementwise, Shift, Scale, LeakyReLU, Logit, TruncatedBijector)) and b is not None:
                 raise B2BError(_lib.B2B_EUNSUPPORTED, f"Stacked block {type(b).__name__}")
         self.bs, self.ranges_in = bs, ranges
         self.length_in = sum(hi - lo + 1 for lo, hi in ranges)
         self.length_out = self.length_in
         code = np.zeros(self.length_in, np.int32)
         a = np.zeros(self.length_in, np.float32)
-        off = 0
+        b2 = np.zeros(self.length_in, np.float32)
         for b, (lo, hi) in zip(bs, ranges):
-            n = hi - lo + 1
             code[lo - 1:hi] = _lib.EW_IDENTITY if b is None else b.code
             a[lo - 1:hi] = 0.0 if b is None else b.a
-            off += n
+            b2[lo - 1:hi] = getattr(b, "b", 0.0) if b is not None else 0.0
         self._code = _dev_i32(code, device)
         self._a = _dev_f32(a, device)
+        self._b = _dev_f32(b2, device)
 
     def _keepalive(self):
-        return (self._code, self._a)
+        return (self._code, self._a, self._b)
+
+    def to(self, device):
+        new = object.__new__(Stacked)
+        new.__dict__.update(self.__dict__)
+        new._code, new._a, new._b = self._code.to(device), self._a.to(device), self._b.to(device)
+        return new
+
+    @property
+    def device(self):
+        return self._code.device
 
     def _descs(self, inverse, D):
         if self.length_in != D:
             raise RuntimeError(f"input length mismatch ({self.length_in} != {D})")  # stacked.jl:158-160,243-245
-        return [_desc(_lib.STACKED_EW, inverse, i0=self._code, p0=self._a)]
+        return [_desc(_lib.STACKED_EW, inverse, i0=self._code, p0=self._a, p1=self._b)]

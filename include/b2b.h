@@ -27,8 +27,9 @@
  *   - Index arguments are 0-based.
  *   - `stream` is a cudaStream_t (CUstream) passed as void*.  All work is enqueued on it; no entry
  *     point synchronises the host except b2b_chain_run_host_f32 and b2b_host_ctx_* .
- *   - Return value: 0 = success; negative = argument error (B2B_E*); positive = cudaError_t /
- *     ncclResult_t passed through.  Never aborts, never throws.  The Julia shim turns non-zero into
+ *   - Return value: 0 = success; negative = argument error (B2B_E*); 1 .. 99999 = the cudaError_t of the failing
+ *     runtime call passed through; 100000 + r = NCCL call failed with ncclResult_t r (the two enums overlap, hence the
+ *     offset).  Never aborts, never throws.  The Julia shim turns non-zero into
  *     `error(b2b_status_string(rc))`, matching the reference's error sites (interface.jl:160,186;
  *     normalise.jl:43; stacked.jl:158; permute.jl:109-119; rational_quadratic_spline.jl:84-85).
  *   - There is NO CPU fallback anywhere in this library.
@@ -69,6 +70,9 @@ extern "C" {
 #define B2B_EW_SHIFT 3 /* Shift(a): y = a + x                              shift.jl:14,21  */
 #define B2B_EW_SCALE 4 /* Scale(a): y = a * x, logjac += log|a|            scale.jl:13,26  */
 #define B2B_EW_LEAKY_RELU 5 /* LeakyReLU(a): y = x >= 0 ? x : a*x, logjac += x < 0 ? log|a| : 0   leaky_relu.jl:18-29 */
+#define B2B_EW_LOGIT 6      /* Logit(a, b): y = logit((x-a)/(b-a)), logjac -= log((x-a)(b-x)/(b-a))        logit.jl:15-29 */
+#define B2B_EW_TRUNCATED 7  /* TruncatedBijector(lb=a, ub=b) (either may be ±Inf): clamp, then logit / log(x-lb) /
+                               log(ub-x) / identity; closed-form inverse log-Jacobian                    truncated.jl:15-91 */
 
 /*
  * One element of a chain.  `inverse != 0` evaluates Inverse(layer) and its log-Jacobian
@@ -87,7 +91,9 @@ extern "C" {
  * BATCHNORM          b[D]        logs[D]     m[D]        v[D]     -               -             -     -    eps
  * PERMUTE            -           -           -           -        dst_of_src[D]   -             -     -    -
  *                    (y[dst_of_src[i]] = x[i], i.e. Permute(indices) of permute.jl:90-100, 0-based)
- * STACKED_EW         a[D]        -           -           -        code[D]         -             -     -    -
+ * STACKED_EW         a[D]        b[D]|NULL   -           -        code[D]         -             -     -    -
+ *                    (a = the law's parameter: Shift / Scale / LeakyReLU value, Logit / Truncated lower bound;
+ *                     b = second parameter: Logit / Truncated upper bound)
  * MVNORMAL_DIAG      mu[D]|NULL  sigma[D]|NULL -         -        -               -             -     -    -
  */
 typedef struct b2b_layer_desc {
@@ -130,12 +136,15 @@ size_t b2b_chain_workspace_bytes(const b2b_layer_desc* layers, int32_t L, int32_
 /* Number of kernel launches the previous b2b_chain_run_f32 call on this thread enqueued. */
 int b2b_last_launch_count(void);
 
-/* Select kernel implementations (testing / profiling).  Ones digit -- fused column-local kernel: 0 = auto
+/* Select kernel implementations (testing / profiling); the selection is PER CALLING THREAD (thread-local, default 0),
+ * so concurrent callers cannot disturb each other.  Ones digit -- fused column-local kernel: 0 = auto
  * (default), 1 = lane-group direct-global kernel (v0), 2 = TMA-staged thread-per-column interpreter (v1) only,
  * 3 = unrolled planar-chain kernel only (segments of <= 8 PlanarLayers, D in {32,64,128}; else B2B_EUNSUPPORTED).
  * Tens digit -- coupling: 0 = auto (tensor cores when the mask is contiguous and workspace is given),
  * 1 = always the exact-fp32 CUDA-core kernel.  Hundreds digit -- 1 = do not fold BatchNorm layers into neighbouring coupling launches.
- * No entry point uses library-owned device state (everything is launch-only on the caller's stream). */
+ * No entry point uses library-owned device state (everything is launch-only on the caller's stream), and the library
+ * keeps no mutable process-global state: the only host-side state is this thread-local selector, the thread-local
+ * launch counter and the lazily resolved driver / NCCL entry points (write-once). */
 int b2b_set_kernel_variant(int variant);
 
 /* ---- single layers (thin wrappers over a 1-element chain) --------------------------------------- */
@@ -167,8 +176,9 @@ int b2b_planar_chain_hostparams_f32(const float* w_host, const float* u_host, co
  * `layers` are B2B_PLANAR descriptors in application order, either all with inverse == 0 (the forward chain) or all
  * with inverse == 1 (the chain inverse(flow) that logpdf(td, y) evaluates, docs/src/flows.md:66-100: `x` is then the
  * observed batch y, `ybar` the cotangent of the recovered x; find_alpha is differentiated with the reference's
- * implicit-function rule, ext/BijectorsChainRulesCoreExt.jl:42-46); cotangent l of wbar/ubar/bbar belongs to layers[l].  `xbar` may alias `ybar` only when no parameter cotangents
- * are requested.  Workspace: b2b_planar_chain_vjp_workspace_bytes. */
+ * implicit-function rule, ext/BijectorsChainRulesCoreExt.jl:42-46); cotangent l of wbar/ubar/bbar belongs to layers[l].  `xbar` may alias `ybar` (or `x`) only when no parameter cotangents
+ * are requested: with them the parameter pass re-reads `x` and `ybar` after `xbar` has been written, and any overlap
+ * of the xbar range with either returns B2B_EINVAL.  Workspace: b2b_planar_chain_vjp_workspace_bytes. */
 size_t b2b_planar_chain_vjp_workspace_bytes(int32_t L, int32_t D, int64_t N);
 int b2b_planar_chain_vjp_f32(const b2b_layer_desc* layers, int32_t L, const float* x, const float* ybar,
                              const float* ljbar, float* xbar, float* wbar, float* ubar, float* bbar, int32_t D,
@@ -235,7 +245,7 @@ int b2b_permute_rows_f32(const float* x, float* y, float* logjac, const int32_t*
                          int accumulate_logjac, void* stream);
 /* Stacked of elementwise laws on rows: stacked.jl:157-166,242-252 */
 int b2b_stacked_elementwise_f32(const float* x, float* y, float* logjac, const int32_t* code,
-                                const float* a, int inverse, int32_t D, int64_t N, int64_t ldx,
+                                const float* a, const float* b, int inverse, int32_t D, int64_t N, int64_t ldx,
                                 int64_t ldy, int accumulate_logjac, void* stream);
 /* logpdf(MvNormal(mu, Diagonal(sigma.^2)), x) + logjac_in  (Distributions/PDMats);
  * logpdf_out may alias logjac_in; sum_out (device double) optional; workspace as for chains. */

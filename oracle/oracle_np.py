@@ -915,7 +915,68 @@ def elementwise_log(x):
 class EW:
     """Elementwise law codes shared with the device ABI (include/b2b.h, B2B_EW_*)."""
 
-    IDENTITY, EXP, LOG, SHIFT, SCALE, LEAKY_RELU = 0, 1, 2, 3, 4, 5
+    IDENTITY, EXP, LOG, SHIFT, SCALE, LEAKY_RELU, LOGIT, TRUNCATED = 0, 1, 2, 3, 4, 5, 6, 7
+
+
+def _logit(z):
+    """LogExpFunctions.logit: log(z / (1 - z))."""
+    return np.log(z / (1 - z))
+
+
+def _logistic(y):
+    """LogExpFunctions.logistic: 1 / (1 + exp(-y))."""
+    return 1 / (1 + np.exp(-y))
+
+
+def _clamp(x, a, b):
+    """_clamp (src/Bijectors.jl:95-100)."""
+    return np.where(x < a, a, np.where(x > b, b, x))
+
+
+def logit_forward(a, b, x):
+    """with_logabsdet_jacobian(Logit(a, b), x) per element (src/bijectors/logit.jl:15-29): returns (y, per-element logjac)."""
+    dt = x.dtype
+    a, b = dt.type(a), dt.type(b)
+    return _logit((x - a) / (b - a)), -np.log((x - a) * (b - x) / (b - a))
+
+
+def logit_inverse(a, b, y):
+    """transform(Inverse{Logit}) (logit.jl:19-21) and the default inverse log-Jacobian −logabsdetjac(Logit, x)
+    (src/interface.jl:276-281)."""
+    dt = y.dtype
+    a, b = dt.type(a), dt.type(b)
+    x = (b - a) * _logistic(y) + a
+    return x, np.log((x - a) * (b - x) / (b - a))
+
+
+def truncated_forward(lb, ub, x):
+    """TruncatedBijector(lb, ub): transform :15-31, logabsdetjac :50-66 (per element, before the sum)."""
+    dt = x.dtype
+    a, b = dt.type(lb), dt.type(ub)
+    xc = _clamp(x, a, b)
+    lo, hi = np.isfinite(a), np.isfinite(b)
+    if lo and hi:
+        return _logit((xc - a) / (b - a)), -np.log((xc - a) * (b - xc) / (b - a))
+    if lo:
+        return np.log(xc - a), -np.log(xc - a)
+    if hi:
+        return np.log(b - xc), -np.log(b - xc)
+    return xc, np.zeros_like(xc)
+
+
+def truncated_inverse(lb, ub, y):
+    """Inverse{TruncatedBijector}: transform :33-48, logabsdetjac :68-86 (per element)."""
+    dt = y.dtype
+    a, b = dt.type(lb), dt.type(ub)
+    lo, hi = np.isfinite(a), np.isfinite(b)
+    if lo and hi:
+        ay = np.abs(y)
+        return _clamp((b - a) * _logistic(y) + a, a, b), np.log(b - a) - ay - 2 * log1pexp(-ay)
+    if lo:
+        return _clamp(np.exp(y) + a, a, b), y.copy()
+    if hi:
+        return _clamp(b - np.exp(y), a, b), y.copy()
+    return _clamp(y, a, b), np.zeros_like(y)
 
 
 def stacked_forward(ops: Sequence[Tuple[int, float]], ranges: Sequence[Tuple[int, int]], x):
@@ -928,10 +989,17 @@ def stacked_forward(ops: Sequence[Tuple[int, float]], ranges: Sequence[Tuple[int
     dt = x.dtype
     y = np.empty_like(x)
     lj = np.zeros(x.shape[1:], dt)
-    for (code, a), (lo, hi) in zip(ops, ranges):
+    for op, (lo, hi) in zip(ops, ranges):
+        code, a = op[0], op[1]
         blk = x[lo - 1 : hi]
         nrow = hi - lo + 1
-        if code == EW.IDENTITY:
+        if code == EW.LOGIT:  # ops entry (code, a, b)
+            yb, le = logit_forward(a, op[2], blk)
+            l = le.sum(axis=0, dtype=dt)
+        elif code == EW.TRUNCATED:
+            yb, le = truncated_forward(a, op[2], blk)
+            l = le.sum(axis=0, dtype=dt)
+        elif code == EW.IDENTITY:
             yb, l = blk, 0
         elif code == EW.EXP:
             yb, l = np.exp(blk), blk.sum(axis=0, dtype=dt)
@@ -953,8 +1021,26 @@ def stacked_forward(ops: Sequence[Tuple[int, float]], ranges: Sequence[Tuple[int
 
 
 def stacked_inverse(ops, ranges, y):
+    if any(op[0] in (EW.LOGIT, EW.TRUNCATED) for op in ops):  # laws whose inverse is not another code of the table
+        dt = y.dtype
+        x = np.empty_like(y)
+        lj = np.zeros(y.shape[1:], dt)
+        for op, (lo, hi) in zip(ops, ranges):
+            blk = y[lo - 1 : hi]
+            if op[0] == EW.LOGIT:
+                xb, le = logit_inverse(op[1], op[2], blk)
+                l = le.sum(axis=0, dtype=dt)
+            elif op[0] == EW.TRUNCATED:
+                xb, le = truncated_inverse(op[1], op[2], blk)
+                l = le.sum(axis=0, dtype=dt)
+            else:
+                xb, l = stacked_inverse([op], [(1, hi - lo + 1)], blk)
+            x[lo - 1 : hi] = xb
+            lj = lj + l
+        return x, np.asarray(lj, dtype=dt)[()]
     inv = []
-    for code, a in ops:
+    for op in ops:
+        code, a = op[0], op[1]
         if code == EW.EXP:
             inv.append((EW.LOG, a))
         elif code == EW.LOG:

@@ -79,12 +79,21 @@ def make_case(kind, D, rng):
         ranges = [(1, r1), (r1 + 1, r2), (r2 + 1, D)]
         return (B.Stacked([B.elementwise("exp"), B.Scale(-1.7), B.Shift(0.3)], ranges),
                 O.Layer("stacked", dict(ops=[(O.EW.EXP, 0.0), (O.EW.SCALE, f32(-1.7)), (O.EW.SHIFT, f32(0.3))], ranges=ranges)))
+    if kind == "bounded":  # Logit / TruncatedBijector blocks inside Stacked: the "bounded flow" of docs/src/flows.md:25-36
+        q = max(1, D // 5)
+        ranges = [(1, q), (q + 1, 2 * q), (2 * q + 1, 3 * q), (3 * q + 1, 4 * q), (4 * q + 1, D)] if D >= 5 else [(1, 1), (2, D)]
+        inf = float("inf")
+        bs = [B.Logit(-1.0, 3.0), B.TruncatedBijector(-1.0, inf), B.TruncatedBijector(-inf, 3.0), B.TruncatedBijector(-1.0, 3.0),
+              B.TruncatedBijector(-inf, inf)][: len(ranges)]
+        ops = [(O.EW.LOGIT, -1.0, 3.0), (O.EW.TRUNCATED, -1.0, inf), (O.EW.TRUNCATED, -inf, 3.0), (O.EW.TRUNCATED, -1.0, 3.0),
+               (O.EW.TRUNCATED, -inf, inf)][: len(ranges)]
+        return B.Stacked(bs, ranges), O.Layer("stacked", dict(ops=ops, ranges=ranges))
     if kind == "leaky_relu":  # test/bijectors/leaky_relu.jl: α = 0.1
         return B.LeakyReLU(0.1), O.Layer("stacked", dict(ops=[(O.EW.LEAKY_RELU, f32(0.1))], ranges=[(1, D)]))
     raise ValueError(kind)
 
 
-KINDS = ["planar", "planar_randn", "radial", "rqs", "batchnorm", "permute", "coupling", "stacked", "leaky_relu"]
+KINDS = ["planar", "planar_randn", "radial", "rqs", "batchnorm", "permute", "coupling", "stacked", "leaky_relu", "bounded"]
 
 
 @pytest.mark.parametrize("D,N", [(128, 1000), (64, 517), (32, 2049), (256, 300), (10, 100), (3, 7), (36, 65), (200, 33)])
@@ -98,6 +107,8 @@ def test_layer_forward_inverse_parity(B, kind, D, N):
     lay, olay = make_case(kind, D, rng)
     scale = 1.5 if kind == "rqs" else 1.0  # ~5% of RQS inputs outside the box (identity branch)
     x = (rng.standard_normal((D, N)) * scale).astype(f32)
+    if kind == "bounded":
+        x = rng.uniform(-0.9, 2.9, (D, N)).astype(f32)  # inside every block's support
     xd = B.from_numpy(x)
     y, lj = B.with_logabsdet_jacobian(lay, xd)
     yo, ljo = olay.forward(x)  # float32 oracle
@@ -246,7 +257,7 @@ def test_c_abi_single_layer_entry_points(B):
     xp = np.abs(x) + f32(0.1)
     xpd = B.from_numpy(xp)
     cd, ad = dev(code), dev(av)
-    assert L.b2b_stacked_elementwise_f32(xpd.data_ptr(), yd.data_ptr(), ljd.data_ptr(), cd.data_ptr(), ad.data_ptr(), 0, D, N, D, D, 0, s) == 0
+    assert L.b2b_stacked_elementwise_f32(xpd.data_ptr(), yd.data_ptr(), ljd.data_ptr(), cd.data_ptr(), ad.data_ptr(), None, 0, D, N, D, D, 0, s) == 0
     ye = xp.copy()
     ye[:4] = np.exp(xp[:4])
     ye[4:8] = np.log(xp[4:8])

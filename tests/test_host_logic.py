@@ -257,3 +257,115 @@ def test_vjp_workspace_queries_are_pure_host_functions():
     assert L_.b2b_planar_chain_vjp_workspace_bytes(9, 128, 10) == 0   # more than 8 layers: unsupported
     r = L_.b2b_radial_chain_vjp_workspace_bytes(6, 64)
     assert r >= 592 * (6 * 64 + 12) * 4 and L_.b2b_radial_chain_vjp_workspace_bytes(6, 200) == 0
+
+
+# ---- the Julia binding is checked against the header without a Julia toolchain ----------------------------------------
+def _c_prototypes():
+    """name -> (return class, [argument classes]) of every function include/b2b.h declares."""
+    import re
+
+    hdr = open(os.path.join(ROOT, "include", "b2b.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+
+    def cls(t):
+        t = t.replace("const", " ").replace("struct", " ").strip()
+        stars = t.count("*")
+        base = t.replace("*", " ").split()
+        base = base[0] if base else ""
+        if stars == 0:
+            return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "size_t": "usize", "float": "f32", "double": "f64"}[base]
+        if stars == 2:
+            return "ptrptr"
+        return {"float": "ptr_f32", "double": "ptr_f64", "int32_t": "ptr_i32", "void": "ptr_void", "char": "ptr_u8",
+                "b2b_layer_desc": "ptr_desc", "b2b_comm": "ptr_void", "b2b_host_ctx": "ptr_void"}[base]
+
+    protos = {}
+    for m in re.finditer(r"\b(int|size_t|const char\s*\*)\s+(b2b_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
+        out = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = re.sub(r"\[\d*\]", "*", a.strip())          # char id[128] -> char* id
+                a = re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*\s*$", "", a.replace("*", " * ")).strip() if not a.strip().endswith("*") else a
+                out.append(cls(a))
+        protos[name] = ({"int": "i32", "size_t": "usize"}.get(ret, "cstring"), out)
+    return protos
+
+
+def _julia_ccalls():
+    """[(symbol, return class, [argument classes], number of actual arguments)] of every ccall in B200Bijectors.jl."""
+    import re
+
+    src = open(os.path.join(ROOT, "bijectors.jl_b200", "julia", "B200Bijectors.jl"), encoding="utf-8").read()
+    src = "\n".join(l.split("#")[0] if not l.lstrip().startswith("#") else "" for l in src.splitlines())
+
+    def balanced(s, i):  # s[i] == '(' -> index after the matching ')'
+        depth = 0
+        for j in range(i, len(s)):
+            depth += s[j] == "("
+            depth -= s[j] == ")"
+            if depth == 0:
+                return j + 1
+        raise AssertionError("unbalanced parentheses")
+
+    def split_top(s):
+        parts, depth, cur = [], 0, ""
+        for ch in s:
+            depth += ch in "({["
+            depth -= ch in ")}]"
+            if ch == "," and depth == 0:
+                parts.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            parts.append(cur.strip())
+        return parts
+
+    jl = {"Cint": "i32", "Int32": "i32", "Int64": "i64", "Csize_t": "usize", "Cfloat": "f32", "Float32": "f32", "Cstring": "cstring",
+          "CuPtr{Float32}": "ptr_f32", "Ptr{Float32}": "ptr_f32", "CuPtr{Float64}": "ptr_f64", "CuPtr{Int32}": "ptr_i32",
+          "Ptr{Int32}": "ptr_i32", "Ptr{LayerDesc}": "ptr_desc", "Ptr{Cvoid}": "ptr_void", "CuPtr{Cvoid}": "ptr_void",
+          "Ptr{UInt8}": "ptr_u8", "Ptr{Ptr{Cvoid}}": "ptrptr"}
+    calls = []
+    for m in re.finditer(r"ccall\(", src):
+        end = balanced(src, m.end() - 1)
+        parts = split_top(src[m.end():end - 1])
+        sym = re.match(r"\(\s*:([a-z0-9_]+)\s*,\s*libb2b\s*\)", parts[0]).group(1)
+        argt = split_top(parts[2].strip()[1:-1])
+        calls.append((sym, jl[parts[1]], [jl[a] for a in argt if a], len(parts) - 3))
+    return calls
+
+
+def test_julia_binding_ccalls_match_the_header():
+    """Every `ccall` of julia/B200Bijectors.jl names an exported symbol of include/b2b.h with the same arity, the same
+    return class and the same argument classes (32/64-bit integer, size_t, float, typed pointer), and passes exactly as
+    many values as it declares -- the check a Julia toolchain would do at load / first call."""
+    protos = _c_prototypes()
+    calls = _julia_ccalls()
+    assert len(calls) >= 12 and set(protos) >= {"b2b_chain_run_f32", "b2b_comm_init_rank", "b2b_numa_bind_to_device"}
+    seen = set()
+    for sym, ret, args, nvals in calls:
+        assert sym in protos, f"{sym} is not declared in include/b2b.h"
+        cret, cargs = protos[sym]
+        assert ret == cret, (sym, ret, cret)
+        assert len(args) == len(cargs) == nvals, (sym, len(args), len(cargs), nvals)
+        for k, (a, c) in enumerate(zip(args, cargs)):
+            ok = a == c or (a == "ptr_void" and c in ("ptr_void",)) or (a == "ptr_u8" and c == "ptr_u8")
+            assert ok, (sym, k, a, c)
+        seen.add(sym)
+    assert {"b2b_chain_run_f32", "b2b_chain_workspace_bytes", "b2b_planar_chain_vjp_f32", "b2b_radial_chain_vjp_f32",
+            "b2b_batchnorm_train_fwd_f32", "b2b_allreduce_sum_f64", "b2b_status_string"} <= seen
+    # the LayerDesc struct mirrors b2b_layer_desc field for field
+    import re
+
+    src = open(os.path.join(ROOT, "bijectors.jl_b200", "julia", "B200Bijectors.jl"), encoding="utf-8").read()
+    body = src[src.index("struct LayerDesc"):src.index("end", src.index("struct LayerDesc"))]
+    fields = re.findall(r"(\w+)::(\w+(?:\{\w+\})?)", body)
+    assert [f for f, _ in fields] == ["kind", "inverse", "n0", "n1", "n2", "n3", "f0", "f1", "p0", "p1", "p2", "p3", "i0", "i1"]
+    assert [t for _, t in fields] == ["Int32"] * 6 + ["Float32"] * 2 + ["CuPtr{Float32}"] * 4 + ["CuPtr{Int32}"] * 2
+    # imports the load needs (the round-1 file used Distributions.logpdf, findnz, mean, var without importing them)
+    for needed in ("import Distributions", "using SparseArrays: findnz", "using Statistics: mean, var"):
+        assert needed in src
+    # exactly one method per generic function takes a bare ComposedFunction on a CuMatrix (no dispatch ambiguity)
+    for fn in ("with_logabsdet_jacobian", "transform", "logabsdetjac"):
+        assert len(re.findall(rf"^function {fn}\(f::ComposedFunction, x::CuMatrix\{{Float32\}}\)", src, flags=re.M)) == 1

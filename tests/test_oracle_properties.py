@@ -290,3 +290,32 @@ def test_forward_and_inverse_vjp_are_mutually_inverse_maps():
     gy, _ = O.planar_inverse_chain_vjp(params, y, np.zeros((D, N)), ones)
     pulled, _ = O.planar_inverse_chain_vjp(params, y, gx, np.zeros(N))
     assert np.allclose(gy, -pulled, rtol=1e-8, atol=1e-9)
+
+
+def test_logit_and_truncated_closed_forms():
+    """Logit / TruncatedBijector restatements against closed forms and the reference's own identities:
+    Logit(0, 1)(0.5) = 0 with logjac −log(0.25) (logit.jl:15-24); a both-sided TruncatedBijector equals Logit inside its
+    support (truncated.jl:21-23 vs logit.jl:15); one-sided bounds are log links (:24-27); the inverse log-Jacobian's
+    closed form (:68-76) equals minus the forward one at the recovered point; logjac equals log|dy/dx|."""
+    y, l = O.logit_forward(0.0, 1.0, np.array([0.5]))
+    assert y[0] == 0.0 and abs(l[0] + np.log(0.25)) < 1e-15
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-0.9, 2.9, 200)
+    yl, ll = O.logit_forward(-1.0, 3.0, x)
+    yt, lt = O.truncated_forward(-1.0, 3.0, x)
+    assert np.array_equal(yl, yt) and np.array_equal(ll, lt)
+    y1, l1 = O.truncated_forward(-1.0, np.inf, x)
+    assert np.allclose(y1, np.log(x + 1.0)) and np.allclose(l1, -np.log(x + 1.0))
+    y2, l2 = O.truncated_forward(-np.inf, 3.0, x)
+    assert np.allclose(y2, np.log(3.0 - x)) and np.allclose(l2, -np.log(3.0 - x))
+    for lb, ub in ((-1.0, 3.0), (-1.0, np.inf), (-np.inf, 3.0), (-np.inf, np.inf)):
+        yy, lf = O.truncated_forward(lb, ub, x)
+        xi, li = O.truncated_inverse(lb, ub, yy)
+        assert np.allclose(xi, x, atol=1e-12) and np.allclose(li, -lf, atol=1e-12)
+        h = 1e-6
+        num = np.log(np.abs((O.truncated_forward(lb, ub, x + h)[0] - O.truncated_forward(lb, ub, x - h)[0]) / (2 * h)))
+        assert np.allclose(num, lf, atol=1e-6)
+    # out-of-support inputs are clamped to the bound first (Bijectors.jl:95-100): the link then diverges like the reference
+    with np.errstate(divide="ignore"):
+        yc, _ = O.truncated_forward(-1.0, np.inf, np.array([-2.0]))
+    assert np.isneginf(yc[0])
