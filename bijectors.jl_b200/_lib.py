@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb2b.so")
@@ -87,6 +87,9 @@ _SIGS = {
                                             c_int, c_void_p]),
     "b2b_mvnormal_diag_logpdf_f32": (c_int, [_F32P] * 5 + [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_size_t,
                                              c_void_p]),
+    "b2b_randn_f32": (c_int, [_F32P] * 3 + [c_uint64, c_uint64, c_int64, c_int32, c_int64, c_int64, c_void_p]),
+    "b2b_chain_sample_f32": (c_int, [POINTER(LayerDesc), c_int32, _F32P, _F32P, c_uint64, c_uint64, c_int64, _F32P, _F32P,
+                                     c_int32, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "b2b_host_ctx_create": (c_int, [POINTER(c_void_p), c_int32, c_int64, c_int32]),
     "b2b_host_ctx_destroy": (c_int, [c_void_p]),
     "b2b_host_ctx_wait_stream": (c_int, [c_void_p, c_void_p]),
@@ -100,6 +103,9 @@ _SIGS = {
     "b2b_comm_init_rank": (c_int, [POINTER(c_void_p), c_int, c_int, c_void_p]),
     "b2b_allreduce_sum_f64": (c_int, [c_void_p, c_void_p, c_int32, c_void_p]),
     "b2b_comm_destroy": (c_int, [c_void_p]),
+    "b2b_comm_init_all": (c_int, [POINTER(c_void_p), c_int, POINTER(c_int)]),
+    "b2b_allreduce_sum_f64_all": (c_int, [c_void_p, POINTER(c_void_p), c_int32, POINTER(c_void_p)]),
+    "b2b_workspace_bytes": (c_size_t, [POINTER(LayerDesc), c_int32, c_int64]),
 }
 
 _lib = None

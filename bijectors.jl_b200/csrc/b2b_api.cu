@@ -178,6 +178,10 @@ extern "C" size_t b2b_chain_workspace_bytes(const b2b_layer_desc* layers, int32_
   return bytes;
 }
 
+extern "C" size_t b2b_workspace_bytes(const b2b_layer_desc* op, int32_t D, int64_t N) {
+  return op ? b2b_chain_workspace_bytes(op, 1, D, N, 1, 0) : 0;
+}
+
 extern "C" int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const float* x, float* y,
                                  float* logjac, double* sum_out, int32_t D, int64_t N, int64_t ldx,
                                  int64_t ldy, int accumulate_logjac, void* workspace,

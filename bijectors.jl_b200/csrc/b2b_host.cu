@@ -247,6 +247,8 @@ typedef int (*fn_get_uid)(b2b_nccl_uid*);
 typedef int (*fn_init_rank)(b2b_nccl_comm_t*, int, b2b_nccl_uid, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, b2b_nccl_comm_t, cudaStream_t);
 typedef int (*fn_destroy)(b2b_nccl_comm_t);
+typedef int (*fn_init_all)(b2b_nccl_comm_t*, int, const int*);
+typedef int (*fn_group)(void);
 
 static struct {
   void* handle;
@@ -254,7 +256,9 @@ static struct {
   fn_init_rank init_rank;
   fn_allreduce allreduce;
   fn_destroy destroy;
-} g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  fn_init_all init_all;
+  fn_group group_start, group_end;
+} g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
 static int load_nccl() {
   if (g_nccl.handle) return B2B_OK;
@@ -265,14 +269,21 @@ static int load_nccl() {
   g_nccl.init_rank = (fn_init_rank)dlsym(h, "ncclCommInitRank");
   g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
   g_nccl.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
-  if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.destroy) return B2B_ENONCCL;
+  g_nccl.init_all = (fn_init_all)dlsym(h, "ncclCommInitAll");
+  g_nccl.group_start = (fn_group)dlsym(h, "ncclGroupStart");
+  g_nccl.group_end = (fn_group)dlsym(h, "ncclGroupEnd");
+  if (!g_nccl.get_uid || !g_nccl.init_rank || !g_nccl.allreduce || !g_nccl.destroy || !g_nccl.init_all ||
+      !g_nccl.group_start || !g_nccl.group_end)
+    return B2B_ENONCCL;
   g_nccl.handle = h;
   return B2B_OK;
 }
 
 struct b2b_comm {
-  b2b_nccl_comm_t comm;
+  b2b_nccl_comm_t comm;  // this process's rank (one process per GPU), or rank 0 of an in-process clique
   int nranks, rank;
+  std::vector<b2b_nccl_comm_t> all;  // b2b_comm_init_all: one communicator per device of the calling process
+  std::vector<int> devs;
 };
 
 extern "C" int b2b_comm_unique_id(char id_out[128]) {
@@ -311,9 +322,57 @@ extern "C" int b2b_allreduce_sum_f64(b2b_comm* c, double* dev_values, int32_t co
   return rc == 0 ? B2B_OK : 100000 + rc;
 }
 
+// ONE process driving several GPUs (a single Julia session holding all 8 devices of a box): a clique of
+// `ndev` communicators created with ncclCommInitAll, and the log-density sum issued for all of them inside one NCCL
+// group.  values[i] / streams[i] belong to device devs[i].
+extern "C" int b2b_comm_init_all(b2b_comm** out, int ndev, const int* devs) {
+  if (!out || ndev < 1 || ndev > 64) return B2B_EINVAL;
+  int rc = load_nccl();
+  if (rc != B2B_OK) return rc;
+  b2b_comm* c = new b2b_comm();
+  c->nranks = ndev;
+  c->rank = 0;
+  c->all.resize(ndev);
+  c->devs.resize(ndev);
+  for (int i = 0; i < ndev; ++i) c->devs[i] = devs ? devs[i] : i;
+  rc = g_nccl.init_all(c->all.data(), ndev, c->devs.data());
+  if (rc != 0) {
+    delete c;
+    return 100000 + rc;
+  }
+  c->comm = c->all[0];
+  *out = c;
+  return B2B_OK;
+}
+
+extern "C" int b2b_allreduce_sum_f64_all(b2b_comm* c, double* const* dev_values, int32_t count, void* const* streams) {
+  if (!c || c->all.empty() || !dev_values || !streams || count < 1) return B2B_EINVAL;
+  const int kNcclDouble = 8, kNcclSum = 0;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int rc = g_nccl.group_start();
+  for (size_t i = 0; i < c->all.size() && rc == 0; ++i) {
+    cudaSetDevice(c->devs[i]);
+    rc = g_nccl.allreduce(dev_values[i], dev_values[i], (size_t)count, kNcclDouble, kNcclSum, c->all[i],
+                          static_cast<cudaStream_t>(streams[i]));
+  }
+  const int rc2 = g_nccl.group_end();
+  cudaSetDevice(prev);
+  if (rc == 0) rc = rc2;
+  return rc == 0 ? B2B_OK : 100000 + rc;
+}
+
 extern "C" int b2b_comm_destroy(b2b_comm* c) {
   if (!c) return B2B_OK;
-  const int rc = g_nccl.destroy(c->comm);
+  int rc = 0;
+  if (!c->all.empty()) {
+    for (b2b_nccl_comm_t h : c->all) {
+      const int r = g_nccl.destroy(h);
+      if (r != 0) rc = r;
+    }
+  } else {
+    rc = g_nccl.destroy(c->comm);
+  }
   delete c;
   return rc == 0 ? B2B_OK : 100000 + rc;
 }

@@ -205,6 +205,60 @@ __device__ __forceinline__ void mvnormal_apply(const float2 (&x)[CPT][D / TPC / 
   }
 }
 
+// ---- sampling source: Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; the
+// counter-based generator of Random123 / cuRAND) + Box-Muller.  The four normals of rows 4k..4k+3 of GLOBAL column n
+// come from the counter (lo32(n), hi32(n), k, lo32(offset)) under the key (lo32(seed), hi32(seed)): a sample depends
+// only on (seed, offset, n, row), not on the launch geometry, so column shards on different ranks draw disjoint parts
+// of one stream.  Restated for the tests in oracle/oracle_np.py (philox4x32_10, philox_normals), which also checks the
+// three known-answer vectors of Random123.
+struct V1Gen {
+  unsigned long long seed, offset;
+  long long col0;       // global index of column 0 of this launch
+  const float* mu;      // base distribution MvNormal(mu, Diagonal(sigma.^2)): x = mu + sigma .* z; NULL = 0 / 1
+  const float* sigma;
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+// two standard normals from two 32-bit words: u = x·2^-32 + 2^-33 in (0, 1] (fp32), Box-Muller
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float u2 = fmaf(__uint2float_rn(b), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  z0 = r * cs;
+  z1 = r * sn;
+}
+
+// the four normals of rows 4k..4k+3 of global column n (optionally mapped through mu + sigma .* z)
+__device__ __forceinline__ float4 philox_normal4(const V1Gen& g, long long n, int k) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)n, (uint32_t)((unsigned long long)n >> 32), (uint32_t)k, (uint32_t)g.offset, (uint32_t)g.seed,
+                (uint32_t)(g.seed >> 32), o);
+  float4 z;
+  box_muller(o[0], o[1], z.x, z.y);
+  box_muller(o[2], o[3], z.z, z.w);
+  return z;
+}
+
 // The pipeline (TMA tile ring, register-resident fragments, per-warp TMA store) is independent of WHAT is applied
 // to the fragments: `prog.stage()` prepares per-CTA state, `prog.apply()` maps the fragments and accumulates logjac.
 //
@@ -214,10 +268,12 @@ __device__ __forceinline__ void mvnormal_apply(const float2 (&x)[CPT][D / TPC / 
 // program state travels in `Prog::State`; `apply` also receives the tile's first column index.
 struct V1NoState {};
 
-template <int D, int TPC, int CPT, int NW, class Prog, int NIN = 1>
+// GEN = true (sampling, rand(td, n)): there is no input batch -- every thread GENERATES the fragment of its column
+// (philox_normal4), the input ring is unused and the kernel's only HBM traffic is the D x N store: 4·(D+1) B/sample.
+template <int D, int TPC, int CPT, int NW, class Prog, int NIN = 1, bool GEN = false>
 __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E, const CUtensorMap& map_x,
                                        const CUtensorMap& map_y, const Prog& prog,
-                                       const CUtensorMap* map_x2 = nullptr) {
+                                       const CUtensorMap* map_x2 = nullptr, const V1Gen* gen = nullptr) {
   using C = ColCtx<D, TPC>;
   constexpr int NQ = D / 32;                 // boxes per tile
   constexpr int LPC = 32 / TPC;              // lane groups per warp
@@ -259,7 +315,7 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
   const long long my_tiles = (E.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   // The first P tile loads are issued BEFORE the parameters are staged: the DRAM latency of the first tiles (and, for
   // the 20-60 us kernels, a visible share of the run time) overlaps the prologue arithmetic (get_u_hat, spline records).
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && !GEN) {
     for (int i = 0; i < E.n_in; ++i) mbar_init(smem_u32(&bars[i]), 1);
     fence_mbar_init();
     for (int j = 0; j < E.n_in && j < my_tiles; ++j) {
@@ -289,8 +345,10 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
     const uint32_t parity = (uint32_t)((j / E.n_in) & 1);
     const long long tile = blockIdx.x + j * gridDim.x;
     const long long col = tile * COLS + t;
-    while (flag_load_acquire(&armed[buf]) != (int)j) __nanosleep(20);
-    mbar_wait(smem_u32(&bars[buf]), parity);
+    if constexpr (!GEN) {
+      while (flag_load_acquire(&armed[buf]) != (int)j) __nanosleep(20);
+      mbar_wait(smem_u32(&bars[buf]), parity);
+    }
 
     float2 x[CPT][C::EPT / 2];
     auto load_fragment = [&](const unsigned char* src) {
@@ -303,7 +361,27 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
         }
       }
     };
-    load_fragment(in_base + (size_t)buf * SLOT_BYTES + line);
+    if constexpr (GEN) {
+      B2B_FOR_COLS {
+        const long long n = gen->col0 + col + cc * LPC;
+        B2B_FOR_SLOTS {
+          const int row0 = ctx.row(ql, r, 0);
+          float4 z = philox_normal4(*gen, n, row0 >> 2);
+          if (gen->sigma) {
+            const float4 sg = __ldg(reinterpret_cast<const float4*>(gen->sigma + row0));
+            z = make_float4(z.x * sg.x, z.y * sg.y, z.z * sg.z, z.w * sg.w);
+          }
+          if (gen->mu) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(gen->mu + row0));
+            z = make_float4(z.x + m.x, z.y + m.y, z.z + m.z, z.w + m.w);
+          }
+          x[cc][(ql * 8 + r) * 2] = make_float2(z.x, z.y);
+          x[cc][(ql * 8 + r) * 2 + 1] = make_float2(z.z, z.w);
+        }
+      }
+    } else {
+      load_fragment(in_base + (size_t)buf * SLOT_BYTES + line);
+    }
     typename Prog::State st;
     if constexpr (NIN == 2) {
       prog.phase1(x, ctx, params, st);
@@ -313,10 +391,10 @@ __device__ __forceinline__ void v1_run(const B2BChainParams& P, const V1Extra& E
     // proxy (LDS): every lane orders its reads before later async-proxy accesses, then the warp converges.  Without
     // the proxy fence the refill can overtake reads that are still in flight (observed with the two-tensor slots:
     // torn tiles in the first refilled slot).
-    fence_proxy_async();
+    if constexpr (!GEN) fence_proxy_async();
     __syncwarp();
     // re-arm this input buffer with the tile P steps ahead
-    if (lane == 0 && j + E.n_in < my_tiles) {
+    if (!GEN && lane == 0 && j + E.n_in < my_tiles) {
       const uint32_t bar = smem_u32(&bars[buf]);
       mbar_expect_tx(bar, SLOT_BYTES);
       const long long nt = blockIdx.x + (j + E.n_in) * gridDim.x;

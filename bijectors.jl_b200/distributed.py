@@ -138,3 +138,29 @@ def sharded_planar_chain_vjp(t, x_local: torch.Tensor, ybar_local: torch.Tensor,
         comm.allreduce_sum_(buf)
         grads = unpack_param_grads(buf, grads)
     return xbar, grads
+
+
+class Clique:
+    """ONE process driving several GPUs (b2b_comm_init_all): per-device float64 scalars are summed across the devices of
+    the calling process inside one NCCL group -- what a single Julia session holding all GPUs of a box would use."""
+
+    def __init__(self, devices=None):
+        n = torch.cuda.device_count() if devices is None else len(devices)
+        self.devices = list(range(n)) if devices is None else [int(d) for d in devices]
+        arr = (ctypes.c_int * n)(*self.devices)
+        h = ctypes.c_void_p()
+        check(lib().b2b_comm_init_all(ctypes.byref(h), n, arr), "b2b_comm_init_all")
+        self.handle = h
+
+    def allreduce_sum_(self, values):
+        """values[i]: float64 CUDA tensor on devices[i] (same numel); reduced in place on every device."""
+        n = len(self.devices)
+        ptrs = (ctypes.c_void_p * n)(*[v.data_ptr() for v in values])
+        streams = (ctypes.c_void_p * n)(*[torch.cuda.current_stream(d).cuda_stream for d in self.devices])
+        check(lib().b2b_allreduce_sum_f64_all(self.handle, ptrs, values[0].numel(), streams), "b2b_allreduce_sum_f64_all")
+        return values
+
+    def close(self):
+        if self.handle is not None:
+            lib().b2b_comm_destroy(self.handle)
+            self.handle = None

@@ -41,14 +41,10 @@ class MvNormal:
         return _desc(_lib.MVNORMAL_DIAG, False, p0=self.mu if self.mu is not None else None,
                      p1=self.sigma if self.sigma is not None else None)
 
-    def rand(self, n: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        """D×n base samples (column-major); device Philox stream via torch (plumbing)."""
-        z = torch.randn((n, self.D), device=self.device, dtype=torch.float32, generator=generator)
-        if self.sigma is not None:
-            z = z * self.sigma
-        if self.mu is not None:
-            z = z + self.mu
-        return z.t()
+    def rand(self, n: int, seed: Optional[int] = None, offset: int = 0, column_offset: int = 0) -> torch.Tensor:
+        """D×n base samples mu + sigma .* z (column-major) from the library's Philox4x32-10 + Box-Muller stream
+        (b2b_randn_f32): a pure function of (seed, offset, global column, row)."""
+        return _sample(self, (), n, seed, offset, column_offset, want_logjac=False)[0]
 
 
 class _Identity(Transform):
@@ -96,8 +92,49 @@ def logpdf_sum(td, y: torch.Tensor, out: Optional[torch.Tensor] = None):
     return out, lp
 
 
-def rand(td: TransformedDistribution, n: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-    """rand(rng, td, n) (transformed_distribution.jl:212-224): the reference maps the transform over
-    columns one by one; here the whole D×n batch goes through the fused forward chain."""
-    z = td.dist.rand(n, generator)
-    return run_chain(td.transform, z, want_logjac=False)[0]
+def _seed(seed: Optional[int]) -> int:
+    """Explicit seed, or one drawn from torch's default CPU generator (so torch.manual_seed makes sampling reproducible,
+    the role `rng` plays in rand(rng, td, n))."""
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return int(seed) & 0xFFFFFFFFFFFFFFFF
+
+
+def _sample(dist: MvNormal, transform, n: int, seed, offset, column_offset, want_logjac):
+    from ._lib import check, lib
+    from .interface import _desc_array, _stream, colmajor_empty
+
+    import ctypes
+
+    D = dist.D
+    if isinstance(transform, tuple):
+        descs = list(transform)
+    else:
+        descs = list(transform._descs(False, D))
+    L = len(descs)
+    arr = _desc_array(descs) if L else None
+    dev = dist.device if not isinstance(dist.device, str) or dist.device != "cuda" else torch.device("cuda", torch.cuda.current_device())
+    y = colmajor_empty(D, n, dev)
+    lj = torch.empty((n,), dtype=torch.float32, device=y.device) if want_logjac else None
+    ws_bytes = lib().b2b_chain_workspace_bytes(arr, L, D, n, 1, 0) if L else 0
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=y.device) if ws_bytes else None
+    rc = lib().b2b_chain_sample_f32(
+        arr, L, dist.mu.data_ptr() if dist.mu is not None else None, dist.sigma.data_ptr() if dist.sigma is not None else None,
+        ctypes.c_uint64(_seed(seed)), ctypes.c_uint64(int(offset)), int(column_offset), y.data_ptr(),
+        lj.data_ptr() if lj is not None else None, D, n, D, ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+    check(rc, "b2b_chain_sample_f32")
+    return y, lj
+
+
+def rand(td, n: int, seed: Optional[int] = None, offset: int = 0, column_offset: int = 0, with_logjac: bool = False):
+    """rand(rng, td, n) (transformed_distribution.jl:212-224): base samples pushed through the forward chain.  The
+    reference draws z on the host and maps the transform over the columns one by one; here the normals are generated
+    INSIDE the chain kernel (b2b_chain_sample_f32: Philox4x32-10 + Box-Muller), so the D×n base samples never exist in
+    device memory.  `seed` plays the role of `rng` (default: drawn from torch's generator); `column_offset` lets a
+    column shard continue ONE global stream (rank r passes the index of its first column).  `with_logjac=True` also
+    returns log|det J| of the transform at the samples."""
+    if isinstance(td, MvNormal):
+        y, lj = _sample(td, (), n, seed, offset, column_offset, with_logjac)
+    else:
+        y, lj = _sample(td.dist, td.transform, n, seed, offset, column_offset, with_logjac)
+    return (y, lj) if with_logjac else y

@@ -132,6 +132,11 @@ int b2b_chain_run_f32(const b2b_layer_desc* layers, int32_t L, const float* x, f
 
 size_t b2b_chain_workspace_bytes(const b2b_layer_desc* layers, int32_t L, int32_t D, int64_t N,
                                  int want_y, int want_sum);
+/* Workspace of ONE operation (SURVEY §8(b) `b2b_workspace_bytes(op, D, N)`): what b2b_chain_workspace_bytes returns for
+ * the one-element chain {*op} with the D x N store and without the batch sum.  The specialised queries below
+ * (b2b_coupling_workspace_bytes, b2b_batchnorm_train_workspace_bytes, b2b_*_vjp_workspace_bytes) remain for entry
+ * points that are not chain elements. */
+size_t b2b_workspace_bytes(const b2b_layer_desc* op, int32_t D, int64_t N);
 
 /* Number of kernel launches the previous b2b_chain_run_f32 call on this thread enqueued. */
 int b2b_last_launch_count(void);
@@ -254,6 +259,22 @@ int b2b_mvnormal_diag_logpdf_f32(const float* x, const float* mu, const float* s
                                  int32_t D, int64_t N, int64_t ldx, void* workspace,
                                  size_t workspace_bytes, void* stream);
 
+/* ---- sampling: rand(rng, td, n) (src/transformed_distribution.jl:212-224) -----------------------------------------
+ * Base samples z ~ N(0, I) come from Philox4x32-10 (the counter-based generator of Random123 / cuRAND) + Box-Muller and
+ * are generated INSIDE the kernel: the four normals of rows 4k..4k+3 of GLOBAL column n = column_offset + local column
+ * use the counter (lo32(n), hi32(n), k, lo32(offset)) under the key (lo32(seed), hi32(seed)), so a sample depends only
+ * on (seed, offset, n, row) -- column shards on different ranks draw disjoint parts of ONE stream, and a re-run with the
+ * same arguments is bit-identical.  x = mu + sigma .* z (NULL = 0 / 1) is MvNormal(mu, Diagonal(sigma.^2)).
+ * b2b_chain_sample_f32 pushes the samples through layers[0..L) in the forward direction (L = 0: the base samples);
+ * `logjac` (optional) receives log|det J| of the chain at each sample.  Column-local chains with D in {32,64,128,256}
+ * run as ONE launch whose only HBM traffic is the D x N store; other chains take two passes (b2b_randn_f32 into y, then
+ * the chain in place; workspace as for b2b_chain_run_f32). */
+int b2b_randn_f32(float* z, const float* mu, const float* sigma, uint64_t seed, uint64_t offset, int64_t column_offset,
+                  int32_t D, int64_t N, int64_t ld, void* stream);
+int b2b_chain_sample_f32(const b2b_layer_desc* layers, int32_t L, const float* mu, const float* sigma, uint64_t seed,
+                         uint64_t offset, int64_t column_offset, float* y, float* logjac, int32_t D, int64_t N,
+                         int64_t ldy, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- host-buffer entry point (what a caller holding plain host Arrays uses; the bench's `e2e`) ----
  * Streams the batch through the device in column chunks: H2D copy, chain kernels and D2H copy of
  * successive chunks overlap on `n_streams` streams.  x_host / y_host / logjac_host are HOST pointers
@@ -293,6 +314,12 @@ typedef struct b2b_comm b2b_comm;
 int b2b_comm_unique_id(char id_out[128]);
 int b2b_comm_init_rank(b2b_comm** comm, int nranks, int rank, const char id[128]);
 int b2b_allreduce_sum_f64(b2b_comm* comm, double* dev_values, int32_t count, void* stream);
+/* ONE process driving several GPUs (e.g. a single Julia session that holds all 8 devices): a clique of `ndev`
+ * communicators over the CUDA devices devs[0..ndev) (NULL = 0..ndev-1) made with ncclCommInitAll, and the sum issued for
+ * all of them inside one NCCL group: dev_values[i] (a device pointer on devs[i], `count` doubles, reduced in place) and
+ * streams[i] belong to devs[i]. */
+int b2b_comm_init_all(b2b_comm** comm, int ndev, const int* devs);
+int b2b_allreduce_sum_f64_all(b2b_comm* comm, double* const* dev_values, int32_t count, void* const* streams);
 int b2b_comm_destroy(b2b_comm* comm);
 
 #ifdef __cplusplus

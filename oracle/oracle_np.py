@@ -1057,6 +1057,56 @@ def stacked_inverse(ops, ranges, y):
 
 
 # --------------------------------------------------------------------------------------------------
+# Sampling: Philox4x32-10 + Box-Muller (the device generator of rand(td, n), include/b2b.h)
+# --------------------------------------------------------------------------------------------------
+# The reference draws base samples with Julia's RNGs (`randn(rng, ...)`, transformed_distribution.jl:212-224), whose
+# streams cannot be reproduced here; what is restated is the generator the DEVICE path uses -- Philox4x32-10 of Salmon,
+# Moraes, Dror, Shaw, "Parallel random numbers: as easy as 1, 2, 3" (SC'11; Random123, cuRAND) -- pinned by the three
+# known-answer vectors of Random123's kat_vectors (tests/test_oracle_golden.py).
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Ten rounds of Philox-4x32 on uint32 arrays (counter words c0..c3, key words k0, k1)."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c0, c1, c2, c3 = (np.asarray(c, np.uint32) for c in (c0, c1, c2, c3))
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c0.astype(np.uint64)
+        p1 = M1 * c2.astype(np.uint64)
+        hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & mask).astype(np.uint32)
+        hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & mask).astype(np.uint32)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint32(k0), lo1, hi0 ^ c3 ^ np.uint32(k1), lo0
+        k0 = (k0 + 0x9E3779B9) & 0xFFFFFFFF
+        k1 = (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def philox_normals(seed, offset, D, N, column_offset=0, mu=None, sigma=None):
+    """The D x N base samples of b2b_randn_f32 / b2b_chain_sample_f32 in float64: rows 4k..4k+3 of global column n come
+    from the counter (lo32(n), hi32(n), k, lo32(offset)) under the key (lo32(seed), hi32(seed)); u = x·2^-32 + 2^-33
+    evaluated in float32 (as the device does), Box-Muller z0 = sqrt(-2 ln u1)·cos(2π u2), z1 = …·sin(2π u2) in float64."""
+    Dc = (D + 3) // 4
+    n = np.arange(N, dtype=np.uint64) + np.uint64(column_offset)
+    nn, kk = np.meshgrid(n, np.arange(Dc, dtype=np.uint32), indexing="xy")  # (Dc, N)
+    o = philox4x32_10((nn & np.uint64(0xFFFFFFFF)).astype(np.uint32), (nn >> np.uint64(32)).astype(np.uint32), kk,
+                      np.full(kk.shape, int(offset) & 0xFFFFFFFF, np.uint32), int(seed) & 0xFFFFFFFF, (int(seed) >> 32) & 0xFFFFFFFF)
+    f = np.float32
+    u = [(w.astype(f) * f(2.3283064365386963e-10) + f(1.1641532182693481e-10)).astype(np.float64) for w in o]
+    z = np.empty((Dc, 4, N))
+    for pair in (0, 1):
+        r = np.sqrt(-2.0 * np.log(u[2 * pair]))
+        z[:, 2 * pair, :] = r * np.cos(2.0 * np.pi * u[2 * pair + 1])
+        z[:, 2 * pair + 1, :] = r * np.sin(2.0 * np.pi * u[2 * pair + 1])
+    z = z.reshape(Dc * 4, N)[:D]
+    if sigma is not None:
+        z = z * np.asarray(sigma, np.float64)[:, None]
+    if mu is not None:
+        z = z + np.asarray(mu, np.float64)[:, None]
+    return z
+
+
+# --------------------------------------------------------------------------------------------------
 # MvNormal (Distributions/PDMats), chains, TransformedDistribution
 # --------------------------------------------------------------------------------------------------
 

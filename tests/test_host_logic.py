@@ -273,10 +273,10 @@ def _c_prototypes():
         base = t.replace("*", " ").split()
         base = base[0] if base else ""
         if stars == 0:
-            return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "size_t": "usize", "float": "f32", "double": "f64"}[base]
+            return {"int": "i32", "int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "size_t": "usize", "float": "f32", "double": "f64"}[base]
         if stars == 2:
             return "ptrptr"
-        return {"float": "ptr_f32", "double": "ptr_f64", "int32_t": "ptr_i32", "void": "ptr_void", "char": "ptr_u8",
+        return {"float": "ptr_f32", "double": "ptr_f64", "int32_t": "ptr_i32", "int": "ptr_i32", "void": "ptr_void", "char": "ptr_u8",
                 "b2b_layer_desc": "ptr_desc", "b2b_comm": "ptr_void", "b2b_host_ctx": "ptr_void"}[base]
 
     protos = {}

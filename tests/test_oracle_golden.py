@@ -218,3 +218,25 @@ def test_stacked_golden(golden):
     assert y.tolist() == g2["y"] and lj == 0
     with pytest.raises(ValueError):  # :120-121 input length mismatch
         O.stacked_forward(ops, ranges, np.ones(4))
+
+
+def test_philox4x32_10_known_answer_vectors():
+    """The device-side generator of rand(td, n) restated in the oracle: the three known-answer vectors of Random123
+    (kat_vectors, philox4x32 10 rounds)."""
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kats:
+        out = O.philox4x32_10(*[np.array([c], np.uint32) for c in ctr], key[0], key[1])
+        assert tuple(int(w[0]) for w in out) == exp
+
+
+def test_philox_normals_are_standard_normal_and_shard_consistently():
+    z = O.philox_normals(1234, 0, 10, 20000)
+    assert z.shape == (10, 20000) and abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    assert abs(np.mean(z ** 3)) < 0.03 and abs(np.mean(z ** 4) - 3) < 0.1
+    # a column shard continues the same stream
+    assert np.array_equal(O.philox_normals(1234, 0, 10, 500, column_offset=700), z[:, 700:1200])
+    assert not np.array_equal(O.philox_normals(1235, 0, 10, 500), z[:, :500])
+    zz = O.philox_normals(7, 3, 6, 100, mu=np.arange(6.0), sigma=np.full(6, 2.0))
+    assert np.allclose(zz, 2 * O.philox_normals(7, 3, 6, 100) + np.arange(6.0)[:, None])
