@@ -46,6 +46,27 @@ class LayerDesc(ctypes.Structure):
     ]
 
 
+class LayerDesc64(ctypes.Structure):
+    """b2b_layer_desc_f64 (include/b2b.h): the same fields with double parameters."""
+
+    _fields_ = [
+        ("kind", c_int32),
+        ("inverse", c_int32),
+        ("n0", c_int32),
+        ("n1", c_int32),
+        ("n2", c_int32),
+        ("n3", c_int32),
+        ("f0", c_double),
+        ("f1", c_double),
+        ("p0", c_void_p),
+        ("p1", c_void_p),
+        ("p2", c_void_p),
+        ("p3", c_void_p),
+        ("i0", c_void_p),
+        ("i1", c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/b2b.h declares
 _F32P = c_void_p
 _SIGS = {
@@ -87,6 +108,9 @@ _SIGS = {
                                             c_int, c_void_p]),
     "b2b_mvnormal_diag_logpdf_f32": (c_int, [_F32P] * 5 + [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_size_t,
                                              c_void_p]),
+    "b2b_chain_workspace_bytes_f64": (c_size_t, [c_int32, c_int]),
+    "b2b_chain_run_f64": (c_int, [POINTER(LayerDesc64), c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64,
+                                  c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "b2b_randn_f32": (c_int, [_F32P] * 3 + [c_uint64, c_uint64, c_int64, c_int32, c_int64, c_int64, c_void_p]),
     "b2b_chain_sample_f32": (c_int, [POINTER(LayerDesc), c_int32, _F32P, _F32P, c_uint64, c_uint64, c_int64, _F32P, _F32P,
                                      c_int32, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),

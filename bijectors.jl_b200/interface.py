@@ -39,9 +39,10 @@ def colmajor_empty(D: int, N: int, device="cuda", dtype=torch.float32, pin_memor
     return base.t()
 
 
-def from_numpy(a: np.ndarray, device="cuda", pin_memory=False) -> torch.Tensor:
-    """numpy (D, N) or (D,) array -> Julia-layout float32 tensor on ``device``."""
-    a = np.asarray(a, dtype=np.float32)
+def from_numpy(a: np.ndarray, device="cuda", pin_memory=False, dtype=np.float32) -> torch.Tensor:
+    """numpy (D, N) or (D,) array -> Julia-layout tensor on ``device`` (Float32 by default, dtype=np.float64 for the
+    Float64 path)."""
+    a = np.asarray(a, dtype=dtype)
     if a.ndim == 1:
         t = torch.from_numpy(np.ascontiguousarray(a))
         return t.pin_memory() if (pin_memory and device == "cpu") else t.to(device)
@@ -57,8 +58,8 @@ def to_numpy(t: torch.Tensor) -> np.ndarray:
 
 def _batch_view(x: torch.Tensor) -> Tuple[int, int, int]:
     """(D, N, ld) of a column batch; raises like a Julia MethodError for anything else."""
-    if x.dtype != torch.float32:
-        raise TypeError(f"device path is Float32 only (got {x.dtype}); Float64 is handled by the reference on the CPU")
+    if x.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"batches are Float32 (hot path) or Float64 (b2b_chain_run_f64), got {x.dtype}")
     if x.dim() == 1:
         if x.stride(0) != 1:
             raise ValueError("vector input must be contiguous")
@@ -118,8 +119,8 @@ class Inverse(Transform):
             raise TypeError(f"{orig} is not invertible")
         self.orig = orig
 
-    def _descs(self, inverse, D):
-        return self.orig._descs(not inverse, D)
+    def _descs(self, inverse, D, dtype=torch.float32):
+        return self.orig._descs(not inverse, D, dtype)
 
     def _keepalive(self):
         return self.orig._keepalive()
@@ -148,13 +149,13 @@ class ComposedFunction(Transform):
     def __init__(self, outer, inner):
         self.outer, self.inner = outer, inner
 
-    def _descs(self, inverse_, D):
+    def _descs(self, inverse_, D, dtype=torch.float32):
         # inverse(f∘g) = inverse(g)∘inverse(f): the outer function's inverse is applied first.  Every leaf inverts by
         # the descriptor's `inverse` flag on ITS OWN (cached) device tables -- no temporary objects whose device memory
         # could be recycled before the launch is enqueued.
         if inverse_:
-            return self.outer._descs(True, D) + self.inner._descs(True, D)
-        return self.inner._descs(False, D) + self.outer._descs(False, D)
+            return self.outer._descs(True, D, dtype) + self.inner._descs(True, D, dtype)
+        return self.inner._descs(False, D, dtype) + self.outer._descs(False, D, dtype)
 
     def _keepalive(self):
         return tuple(self.inner._keepalive()) + tuple(self.outer._keepalive())
@@ -170,10 +171,10 @@ class Composed(Transform):
             flat.extend(flatten(b))
         self.layers = flat
 
-    def _descs(self, inverse_, D):
+    def _descs(self, inverse_, D, dtype=torch.float32):
         out = []
         for b in (reversed(self.layers) if inverse_ else self.layers):
-            out.extend(b._descs(inverse_, D))
+            out.extend(b._descs(inverse_, D, dtype))
         return out
 
     def _keepalive(self):
@@ -193,8 +194,8 @@ class Columnwise(Transform):
     def __init__(self, f):
         self.x = f  # Fix1 field name
 
-    def _descs(self, inverse_, D):
-        return self.x._descs(inverse_, D)
+    def _descs(self, inverse_, D, dtype=torch.float32):
+        return self.x._descs(inverse_, D, dtype)
 
     def _keepalive(self):
         return self.x._keepalive()
@@ -259,9 +260,11 @@ def run_chain(t, x: torch.Tensor, *, want_y=True, want_logjac=True, y: Optional[
               extra_descs: Sequence[LayerDesc] = (), keepalive=()):
     """Evaluate transform ``t`` (any Transform / chain) on batch ``x``.  Returns (y, logjac)."""
     D, N, ldx = _batch_view(x)
-    descs = list(t._descs(False, D)) + list(extra_descs)
+    descs = list(t._descs(False, D, x.dtype)) + list(extra_descs)
     if not descs:
         raise ValueError("empty chain")
+    if x.dtype == torch.float64:
+        return _run_chain_f64(descs, x, D, N, ldx, want_y, want_logjac, y, logjac, accumulate, sum_out)
     if any(hasattr(d, "_host_planar") for d in descs):
         return _run_planar_hostparams(descs, x, D, N, ldx, want_y, want_logjac, y, logjac, accumulate, sum_out)
     arr = _desc_array(descs)
@@ -301,6 +304,47 @@ def run_chain(t, x: torch.Tensor, *, want_y=True, want_logjac=True, y: Optional[
     if lj_out is not None and x.dim() == 1:
         lj_out = lj_out.reshape(())
     return y, lj_out
+
+
+def _run_chain_f64(descs, x, D, N, ldx, want_y, want_logjac, y, logjac, accumulate, sum_out):
+    """Float64 batches: b2b_chain_run_f64 (every layer kind; a correctness path, not the hot path).  Host tensors make
+    the round trip through device memory here -- the computation itself always runs on the device."""
+    if not all(isinstance(d, _lib.LayerDesc64) for d in descs):
+        raise TypeError("Float64 batch with Float32 layer parameters: construct the layers with dtype=torch.float64")
+    if len(descs) > _lib.MAX_CHAIN:
+        raise B2BError(_lib.B2B_EUNSUPPORTED, f"chain of {len(descs)} layers (max {_lib.MAX_CHAIN})")
+    if not x.is_cuda:
+        if not torch.cuda.is_available():
+            raise B2BError(_lib.B2B_EUNSUPPORTED, "no CUDA device: bijectors.jl_b200 has no CPU fallback")
+        if sum_out is not None:
+            raise B2BError(_lib.B2B_EUNSUPPORTED, "batch sums of Float64 host tensors: move the batch to the device")
+        xd = x.cuda()
+        yd, ld_ = _run_chain_f64(descs, xd, D, N, _batch_view(xd)[2], want_y, want_logjac, None, None, False, None)
+        return (yd.cpu() if yd is not None else None), (ld_.cpu() if ld_ is not None else None)
+    arr = (_lib.LayerDesc64 * len(descs))(*descs)
+    L = len(descs)
+    if want_y:
+        if y is None:
+            y = torch.empty_like(x) if x.dim() == 1 else colmajor_empty(D, N, x.device, dtype=torch.float64)
+        ldy = _batch_view(y)[2]
+    else:
+        y, ldy = None, D
+    if want_logjac or sum_out is not None:
+        if logjac is None:
+            logjac = torch.empty((N,), dtype=torch.float64, device=x.device)
+    else:
+        logjac = None
+    L_ = lib()
+    ws_bytes = L_.b2b_chain_workspace_bytes_f64(L, 1 if sum_out is not None else 0)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device) if ws_bytes else None
+    rc = L_.b2b_chain_run_f64(arr, L, x.data_ptr(), y.data_ptr() if y is not None else None,
+                              logjac.data_ptr() if logjac is not None else None,
+                              sum_out.data_ptr() if sum_out is not None else None, D, N, ldx, ldy, 1 if accumulate else 0,
+                              ws.data_ptr() if ws is not None else None, ws_bytes, _stream())
+    check(rc, "b2b_chain_run_f64")
+    if logjac is not None and x.dim() == 1:
+        logjac = logjac.reshape(())
+    return y, logjac
 
 
 _HOSTPARAM_CACHE: dict = {}
@@ -476,7 +520,7 @@ def planar_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[tor
     Dy, Ny, ldyb = _batch_view(ybar)
     if (Dy, Ny) != (D, N) or not x.is_cuda or not ybar.is_cuda or x.dim() != 2:
         raise ValueError("planar_chain_vjp: x and ybar must be device matrices of the same D×N shape")
-    descs = list(t._descs(False, D))
+    descs = list(t._descs(False, D, x.dtype))
     if any(d.kind != _lib.PLANAR or hasattr(d, "_host_planar") for d in descs) or len({int(d.inverse) for d in descs}) != 1:
         raise B2BError(_lib.B2B_EUNSUPPORTED,
                        "planar_chain_vjp: PlanarLayers with device parameters, one direction per chain "
@@ -514,7 +558,7 @@ def radial_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[tor
     Dy, Ny, ldyb = _batch_view(ybar)
     if (Dy, Ny) != (D, N) or not x.is_cuda or not ybar.is_cuda or x.dim() != 2:
         raise ValueError("radial_chain_vjp: x and ybar must be device matrices of the same D×N shape")
-    descs = list(t._descs(False, D))
+    descs = list(t._descs(False, D, x.dtype))
     if any(d.kind != _lib.RADIAL or d.inverse for d in descs):
         raise B2BError(_lib.B2B_EUNSUPPORTED, "radial_chain_vjp: forward RadialLayers only")
     L = len(descs)

@@ -19,25 +19,37 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import B2BError, LayerDesc
+from ._lib import B2BError, LayerDesc, LayerDesc64
 from .interface import Bijector, Inverse, Transform
 
 
-def _dev_f32(v, device) -> torch.Tensor:
+def _dev_f32(v, device, dtype=torch.float32) -> torch.Tensor:
+    """Parameter tensor on `device`: Float32 (the hot path) or Float64 (the reference's own test precision; evaluated by
+    b2b_chain_run_f64)."""
+    if dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"parameters are Float32 or Float64, got {dtype}")
     if isinstance(v, torch.Tensor):
         t = v.detach()
     else:
-        t = torch.as_tensor(np.asarray(v, dtype=np.float32))
-    t = t.to(device=device, dtype=torch.float32)
+        t = torch.as_tensor(np.asarray(v, dtype=np.float64 if dtype == torch.float64 else np.float32))
+    t = t.to(device=device, dtype=dtype)
     return t.reshape(-1).contiguous() if t.dim() <= 1 else t.contiguous()
+
+
+def _check_dtype(param: torch.Tensor, dtype, what: str) -> None:
+    if param.dtype != dtype:
+        raise TypeError(f"{what} has {param.dtype} parameters but the batch is {dtype}; construct the layer with dtype={dtype} "
+                        "(Float32 is the hot path, Float64 the reference's test precision)")
 
 
 def _dev_i32(v, device) -> torch.Tensor:
     return torch.as_tensor(np.asarray(v, dtype=np.int32)).to(device).contiguous()
 
 
-def _desc(kind, inverse=False, **kw) -> LayerDesc:
-    d = LayerDesc()
+def _desc(kind, inverse=False, **kw):
+    """b2b_layer_desc, or b2b_layer_desc_f64 when the layer's parameters are Float64 tensors."""
+    f64 = any(isinstance(v, torch.Tensor) and v.dtype == torch.float64 for v in kw.values()) or kw.pop("_f64", False)
+    d = LayerDesc64() if f64 else LayerDesc()
     d.kind = kind
     d.inverse = 1 if inverse else 0
     for k, v in kw.items():
@@ -86,21 +98,22 @@ class PlanarLayer(_ParamLayer):
 
     _fields = ("w", "u", "b")
 
-    def __init__(self, w, u=None, b=None, device="cuda", generator: Optional[torch.Generator] = None):
+    def __init__(self, w, u=None, b=None, device="cuda", generator: Optional[torch.Generator] = None, dtype=torch.float32):
         if isinstance(w, int):  # PlanarLayer(dims) : randn parameters (:23-28)
             dims = w
             w = torch.randn(dims, generator=generator)
             u = torch.randn(dims, generator=generator)
             b = torch.randn(1, generator=generator)
-        self.w = _dev_f32(w, device)
-        self.u = _dev_f32(u, device)
-        self.b = _dev_f32(b, device)
+        self.w = _dev_f32(w, device, dtype)
+        self.u = _dev_f32(u, device, dtype)
+        self.b = _dev_f32(b, device, dtype)
         if self.w.numel() != self.u.numel():
             raise ValueError("w and u must have the same length")
 
-    def _descs(self, inverse, D):
+    def _descs(self, inverse, D, dtype=torch.float32):
         if D != self.w.numel():
             raise ValueError(f"DimensionMismatch: PlanarLayer has {self.w.numel()} dims, input has {D}")
+        _check_dtype(self.w, dtype, "PlanarLayer")
         d = _desc(_lib.PLANAR, inverse, p0=self.w, p1=self.u, p2=self.b)
         if not self.w.is_cuda:
             # host-resident parameters (the reference's own residency: plain Arrays, planar_layer.jl:13-18):
@@ -114,19 +127,20 @@ class RadialLayer(_ParamLayer):
 
     _fields = ("α_", "β", "z_0")
 
-    def __init__(self, α_, β=None, z_0=None, device="cuda", generator: Optional[torch.Generator] = None):
+    def __init__(self, α_, β=None, z_0=None, device="cuda", generator: Optional[torch.Generator] = None, dtype=torch.float32):
         if isinstance(α_, int) and β is None:  # RadialLayer(dims) (:22-27)
             dims = α_
             α_ = torch.randn(1, generator=generator)
             β = torch.randn(1, generator=generator)
             z_0 = torch.randn(dims, generator=generator)
-        setattr(self, "α_", _dev_f32(α_, device))
-        setattr(self, "β", _dev_f32(β, device))
-        self.z_0 = _dev_f32(z_0, device)
+        setattr(self, "α_", _dev_f32(α_, device, dtype))
+        setattr(self, "β", _dev_f32(β, device, dtype))
+        self.z_0 = _dev_f32(z_0, device, dtype)
 
-    def _descs(self, inverse, D):
+    def _descs(self, inverse, D, dtype=torch.float32):
         if D != self.z_0.numel():
             raise ValueError(f"DimensionMismatch: RadialLayer has {self.z_0.numel()} dims, input has {D}")
+        _check_dtype(self.z_0, dtype, "RadialLayer")
         return [_desc(_lib.RADIAL, inverse, p0=getattr(self, "α_"), p1=getattr(self, "β"), p2=self.z_0)]
 
 
@@ -142,38 +156,39 @@ class RationalQuadraticSpline(_ParamLayer):
 
     _fields = ("widths", "heights", "derivatives")
 
-    def __init__(self, widths, heights, derivatives, B=None, device="cuda"):
-        w = np.asarray(widths.detach().cpu() if isinstance(widths, torch.Tensor) else widths, dtype=np.float32)
-        h = np.asarray(heights.detach().cpu() if isinstance(heights, torch.Tensor) else heights, dtype=np.float32)
+    def __init__(self, widths, heights, derivatives, B=None, device="cuda", dtype=torch.float32):
+        npdt = np.float64 if dtype == torch.float64 else np.float32
+        w = np.asarray(widths.detach().cpu() if isinstance(widths, torch.Tensor) else widths, dtype=npdt)
+        h = np.asarray(heights.detach().cpu() if isinstance(heights, torch.Tensor) else heights, dtype=npdt)
         d = np.asarray(derivatives.detach().cpu() if isinstance(derivatives, torch.Tensor) else derivatives,
-                       dtype=np.float32)
+                       dtype=npdt)
         if w.ndim == 1:
             w, h, d = w[None, :], h[None, :], d[None, :]
         if B is not None:
-            w, h, d = _rqs_normalise(w, h, d, float(B))
+            w, h, d = _rqs_normalise(w, h, d, float(B), npdt)
         # struct asserts (:93-94)
         assert w.shape[1] == h.shape[1] == d.shape[1], "widths, heights and derivatives need the same number of knots"
         assert np.all(d > 0), "derivatives need to be positive"
         self.K1 = int(w.shape[1])
         self.D = int(w.shape[0])
         # device copies keep Julia's column-major (D × K1) memory order == knot-major [k][i]
-        self.widths = _dev_f32(np.ascontiguousarray(w.T), device)
-        self.heights = _dev_f32(np.ascontiguousarray(h.T), device)
-        self.derivatives = _dev_f32(np.ascontiguousarray(d.T), device)
+        self.widths = _dev_f32(np.ascontiguousarray(w.T), device, dtype)
+        self.heights = _dev_f32(np.ascontiguousarray(h.T), device, dtype)
+        self.derivatives = _dev_f32(np.ascontiguousarray(d.T), device, dtype)
 
     def knots(self):
         """(widths, heights, derivatives) as (D × K+1) numpy arrays in the reference's index order."""
         return tuple(getattr(self, k).cpu().numpy().T.copy() for k in self._fields)
 
-    def _descs(self, inverse, D):
+    def _descs(self, inverse, D, dtype=torch.float32):
         if D != self.D:
             raise ValueError(f"DimensionMismatch: RationalQuadraticSpline has {self.D} dims, input has {D}")
+        _check_dtype(self.widths, dtype, "RationalQuadraticSpline")
         return [_desc(_lib.RQS, inverse, p0=self.widths, p1=self.heights, p2=self.derivatives, n0=self.K1)]
 
 
-def _rqs_normalise(w, h, d, B):
-    """Host restatement of the normalising constructor (rational_quadratic_spline.jl:109-123), float32."""
-    f = np.float32
+def _rqs_normalise(w, h, d, B, f=np.float32):
+    """Host restatement of the normalising constructor (rational_quadratic_spline.jl:109-123) in the parameter eltype."""
 
     def softmax(v):
         e = np.exp(v - v.max(axis=1, keepdims=True))
@@ -224,15 +239,16 @@ class AffineConditioner:
     """The recognised coupling law θ(x₂) = Shift(t) ∘ Scale(exp.(s)) with [s; t] = W·x₂ + c
     (Scale scale.jl:13,31; Shift shift.jl:14,21).  W is (2·n1 × n2) in the reference's index order."""
 
-    def __init__(self, W, c=None, device="cuda"):
-        Wn = np.asarray(W.detach().cpu() if isinstance(W, torch.Tensor) else W, dtype=np.float32)
+    def __init__(self, W, c=None, device="cuda", dtype=torch.float32):
+        npdt = np.float64 if dtype == torch.float64 else np.float32
+        Wn = np.asarray(W.detach().cpu() if isinstance(W, torch.Tensor) else W, dtype=npdt)
         if Wn.ndim != 2 or Wn.shape[0] % 2:
             raise ValueError("W must be (2*n1, n2)")
         self.n1, self.n2 = Wn.shape[0] // 2, Wn.shape[1]
-        self.W = _dev_f32(np.ascontiguousarray(Wn.T), device)  # column-major (2n1 × n2)
-        cn = np.zeros(Wn.shape[0], np.float32) if c is None else np.asarray(
-            c.detach().cpu() if isinstance(c, torch.Tensor) else c, dtype=np.float32)
-        self.c = _dev_f32(cn, device)
+        self.W = _dev_f32(np.ascontiguousarray(Wn.T), device, dtype)  # column-major (2n1 × n2)
+        cn = np.zeros(Wn.shape[0], npdt) if c is None else np.asarray(
+            c.detach().cpu() if isinstance(c, torch.Tensor) else c, dtype=npdt)
+        self.c = _dev_f32(cn, device, dtype)
 
     def to(self, device):
         new = object.__new__(AffineConditioner)
@@ -275,9 +291,10 @@ class Coupling(_ParamLayer):
     def _keepalive(self):
         return (self.θ.W, self.θ.c, self._idx1, self._idx2)
 
-    def _descs(self, inverse, D):
+    def _descs(self, inverse, D, dtype=torch.float32):
         if D != self.mask.n:
             raise ValueError(f"DimensionMismatch: Coupling mask has {self.mask.n} dims, input has {D}")
+        _check_dtype(self.θ.W, dtype, "Coupling")
         return [_desc(_lib.COUPLING_AFFINE, inverse, p0=self.θ.W, p1=self.θ.c, i0=self._idx1, i1=self._idx2,
                       n0=self.θ.n1, n1=self.θ.n2, n2=self._row1, n3=self._row2)]
 
@@ -301,19 +318,20 @@ class InvertibleBatchNorm(_ParamLayer):
     _fields = ("b", "logs", "m", "v")
 
     def __init__(self, chs=None, *, b=None, logs=None, m=None, v=None, eps=1e-5, mtm=1e-1, device="cuda",
-                 training=False):
+                 training=False, dtype=torch.float32):
         if chs is not None:
             b, logs, m, v = np.zeros(chs), np.zeros(chs), np.zeros(chs), np.ones(chs)
-        self.b, self.logs, self.m, self.v = (_dev_f32(t, device) for t in (b, logs, m, v))
+        self.b, self.logs, self.m, self.v = (_dev_f32(t, device, dtype) for t in (b, logs, m, v))
         self.eps, self.mtm, self.training = float(np.float32(eps)), float(np.float32(mtm)), training
 
-    def _descs(self, inverse, D):
+    def _descs(self, inverse, D, dtype=torch.float32):
         if D != self.b.numel():
             # error text of normalise.jl:43-45
             raise RuntimeError(f"InvertibleBatchNorm expected {self.b.numel()} channels, got {D}")
         if self.training:
             raise B2BError(_lib.B2B_EUNSUPPORTED, "InvertibleBatchNorm in training mode cannot be fused into a chain "
                                                   "or inverted (normalise.jl:75); call it on its own")
+        _check_dtype(self.b, dtype, "InvertibleBatchNorm")
         return [_desc(_lib.BATCHNORM, inverse, p0=self.b, p1=self.logs, p2=self.m, p3=self.v, f0=self.eps)]
 
     def train_forward(self, x, comm=None):
@@ -410,10 +428,10 @@ class Permute(_ParamLayer):
     def _keepalive(self):
         return (self._dst,)
 
-    def _descs(self, inverse, D):
+    def _descs(self, inverse, D, dtype=torch.float32):
         if D != len(self.dst_of_src):
             raise ValueError(f"DimensionMismatch: Permute has {len(self.dst_of_src)} dims, input has {D}")
-        return [_desc(_lib.PERMUTE, inverse, i0=self._dst)]
+        return [_desc(_lib.PERMUTE, inverse, i0=self._dst, _f64=dtype == torch.float64)]
 
     def __eq__(self, o):
         return isinstance(o, Permute) and np.array_equal(self.dst_of_src, o.dst_of_src)
@@ -448,8 +466,8 @@ class Elementwise(Bijector):
             return torch.log(xt), -torch.log(xt).sum()
         return xt, xt.new_zeros(())
 
-    def _descs(self, inverse, D):
-        return _as_stacked(self, D)._descs(inverse, D)
+    def _descs(self, inverse, D, dtype=torch.float32):
+        return _as_stacked(self, D, dtype)._descs(inverse, D, dtype)
 
     def __eq__(self, o):
         return isinstance(o, Elementwise) and o.f == self.f
@@ -463,13 +481,14 @@ def elementwise(f):
     return Elementwise(name)
 
 
-def _as_stacked(b, D):
+def _as_stacked(b, D, dtype=torch.float32):
     """A whole-column elementwise law is a one-block Stacked; cached on the object so the device tables
     outlive the asynchronous launch."""
     cache = b.__dict__.setdefault("_stacked_cache", {})
-    if D not in cache:
-        cache[D] = Stacked([b], [(1, D)])
-    return cache[D]
+    key = (D, dtype)
+    if key not in cache:
+        cache[key] = Stacked([b], [(1, D)], dtype=dtype)
+    return cache[key]
 
 
 class Shift(Bijector):
@@ -483,8 +502,8 @@ class Shift(Bijector):
     def _inverse(self):
         return Shift(-self.a)  # shift.jl:12
 
-    def _descs(self, inverse, D):
-        return _as_stacked(self, D)._descs(inverse, D)
+    def _descs(self, inverse, D, dtype=torch.float32):
+        return _as_stacked(self, D, dtype)._descs(inverse, D, dtype)
 
     def __eq__(self, o):
         return isinstance(o, Shift) and o.a == self.a
@@ -500,8 +519,8 @@ class Scale(Bijector):
 
     code = _lib.EW_SCALE
 
-    def _descs(self, inverse, D):
-        return _as_stacked(self, D)._descs(inverse, D)
+    def _descs(self, inverse, D, dtype=torch.float32):
+        return _as_stacked(self, D, dtype)._descs(inverse, D, dtype)
 
     def __eq__(self, o):
         return isinstance(o, Scale) and o.a == self.a
@@ -524,8 +543,8 @@ class LeakyReLU(Bijector):
     def _inverse(self):
         return LeakyReLU(1.0 / self.a)
 
-    def _descs(self, inverse, D):
-        return _as_stacked(self, D)._descs(inverse, D)
+    def _descs(self, inverse, D, dtype=torch.float32):
+        return _as_stacked(self, D, dtype)._descs(inverse, D, dtype)
 
     def __eq__(self, o):
         return isinstance(o, LeakyReLU) and o.a == self.a
@@ -544,8 +563,8 @@ class Logit(Bijector):
 
     code = _lib.EW_LOGIT
 
-    def _descs(self, inverse, D):
-        return _as_stacked(self, D)._descs(inverse, D)
+    def _descs(self, inverse, D, dtype=torch.float32):
+        return _as_stacked(self, D, dtype)._descs(inverse, D, dtype)
 
     def __eq__(self, o):
         return isinstance(o, Logit) and (o.a, o.b) == (self.a, self.b)  # logit.jl:12
@@ -566,8 +585,8 @@ class TruncatedBijector(Bijector):
     ub = property(lambda s: s.b)
     code = _lib.EW_TRUNCATED
 
-    def _descs(self, inverse, D):
-        return _as_stacked(self, D)._descs(inverse, D)
+    def _descs(self, inverse, D, dtype=torch.float32):
+        return _as_stacked(self, D, dtype)._descs(inverse, D, dtype)
 
     def __eq__(self, o):
         return isinstance(o, TruncatedBijector) and (o.a, o.b) == (self.a, self.b)
@@ -580,7 +599,7 @@ class Stacked(Transform):
     UnitRanges; stacked.jl:25-59).  Device scope: elementwise blocks (exp, log, identity, Shift, Scale, LeakyReLU,
     Logit, TruncatedBijector)."""
 
-    def __init__(self, bs, ranges=None, device="cuda"):
+    def __init__(self, bs, ranges=None, device="cuda", dtype=torch.float32):
         bs = list(bs)
         if ranges is None:
             ranges = [(i + 1, i + 1) for i in range(len(bs))]  # Stacked(bs...) = ranges i:i (:49)
@@ -594,15 +613,16 @@ class Stacked(Transform):
         self.length_in = sum(hi - lo + 1 for lo, hi in ranges)
         self.length_out = self.length_in
         code = np.zeros(self.length_in, np.int32)
-        a = np.zeros(self.length_in, np.float32)
-        b2 = np.zeros(self.length_in, np.float32)
+        a = np.zeros(self.length_in, np.float64)
+        b2 = np.zeros(self.length_in, np.float64)
         for b, (lo, hi) in zip(bs, ranges):
             code[lo - 1:hi] = _lib.EW_IDENTITY if b is None else b.code
             a[lo - 1:hi] = 0.0 if b is None else b.a
             b2[lo - 1:hi] = getattr(b, "b", 0.0) if b is not None else 0.0
         self._code = _dev_i32(code, device)
-        self._a = _dev_f32(a, device)
-        self._b = _dev_f32(b2, device)
+        self._a = _dev_f32(a.astype(np.float64), device, dtype) if dtype == torch.float64 else _dev_f32(a, device)
+        self._b = _dev_f32(b2.astype(np.float64), device, dtype) if dtype == torch.float64 else _dev_f32(b2, device)
+        self._dtype = dtype
 
     def _keepalive(self):
         return (self._code, self._a, self._b)
@@ -617,7 +637,8 @@ class Stacked(Transform):
     def device(self):
         return self._code.device
 
-    def _descs(self, inverse, D):
+    def _descs(self, inverse, D, dtype=torch.float32):
         if self.length_in != D:
             raise RuntimeError(f"input length mismatch ({self.length_in} != {D})")  # stacked.jl:158-160,243-245
+        _check_dtype(self._a, dtype, "Stacked")
         return [_desc(_lib.STACKED_EW, inverse, i0=self._code, p0=self._a, p1=self._b)]

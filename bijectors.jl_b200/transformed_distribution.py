@@ -25,10 +25,11 @@ class MvNormal:
     """MvNormal(μ, Diagonal(σ²)) / MvNormal(zeros(D), I) (Distributions + PDMats; third-party arithmetic
     restated in the kernel: −(D·log2π + Σ log σ²)/2 − Σ((x−μ)/σ)²/2).  `sigma` is the std-dev vector."""
 
-    def __init__(self, D: int, mu=None, sigma=None, device="cuda"):
+    def __init__(self, D: int, mu=None, sigma=None, device="cuda", dtype=torch.float32):
         self.D = int(D)
-        self.mu = None if mu is None else _dev_f32(mu, device)
-        self.sigma = None if sigma is None else _dev_f32(sigma, device)
+        self.dtype = dtype
+        self.mu = None if mu is None else _dev_f32(mu, device, dtype)
+        self.sigma = None if sigma is None else _dev_f32(sigma, device, dtype)
         self.device = device
         for t in (self.mu, self.sigma):
             if t is not None and t.numel() != self.D:
@@ -39,7 +40,7 @@ class MvNormal:
 
     def _terminal_desc(self):
         return _desc(_lib.MVNORMAL_DIAG, False, p0=self.mu if self.mu is not None else None,
-                     p1=self.sigma if self.sigma is not None else None)
+                     p1=self.sigma if self.sigma is not None else None, _f64=self.dtype == torch.float64)
 
     def rand(self, n: int, seed: Optional[int] = None, offset: int = 0, column_offset: int = 0) -> torch.Tensor:
         """D×n base samples mu + sigma .* z (column-major) from the library's Philox4x32-10 + Box-Muller stream
@@ -48,7 +49,7 @@ class MvNormal:
 
 
 class _Identity(Transform):
-    def _descs(self, inverse_, D):
+    def _descs(self, inverse_, D, dtype=torch.float32):
         return []
 
 
@@ -110,7 +111,7 @@ def _sample(dist: MvNormal, transform, n: int, seed, offset, column_offset, want
     if isinstance(transform, tuple):
         descs = list(transform)
     else:
-        descs = list(transform._descs(False, D))
+        descs = list(transform._descs(False, D, torch.float32))
     L = len(descs)
     arr = _desc_array(descs) if L else None
     dev = dist.device if not isinstance(dist.device, str) or dist.device != "cuda" else torch.device("cuda", torch.cuda.current_device())

@@ -259,6 +259,29 @@ int b2b_mvnormal_diag_logpdf_f32(const float* x, const float* mu, const float* s
                                  int32_t D, int64_t N, int64_t ldx, void* workspace,
                                  size_t workspace_bytes, void* stream);
 
+/* ---- Float64 batches -------------------------------------------------------------------------------------------------
+ * The reference is generic in its element type and its own tests run in Float64 (test/normalising_flows.jl:47-71 checks
+ * find_alpha to 1e-14).  b2b_chain_run_f64 evaluates the same chains -- every layer kind, both directions, the terminal
+ * MvNormal, the deterministic batch sum -- on D x N Float64 batches with Float64 parameters (b2b_layer_desc_f64: the
+ * same fields with double pointers).  It is a straightforward double-precision restatement (one warp per column), NOT a
+ * tuned kernel: Float64 is a correctness path, Float32 the hot path.  workspace: b2b_chain_workspace_bytes_f64. */
+typedef struct b2b_layer_desc_f64 {
+  int32_t kind;
+  int32_t inverse;
+  int32_t n0, n1, n2, n3;
+  double f0, f1;
+  const double* p0;
+  const double* p1;
+  const double* p2;
+  const double* p3;
+  const int32_t* i0;
+  const int32_t* i1;
+} b2b_layer_desc_f64;
+size_t b2b_chain_workspace_bytes_f64(int32_t L, int want_sum);
+int b2b_chain_run_f64(const b2b_layer_desc_f64* layers, int32_t L, const double* x, double* y, double* logjac,
+                      double* sum_out, int32_t D, int64_t N, int64_t ldx, int64_t ldy, int accumulate_logjac,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- sampling: rand(rng, td, n) (src/transformed_distribution.jl:212-224) -----------------------------------------
  * Base samples z ~ N(0, I) come from Philox4x32-10 (the counter-based generator of Random123 / cuRAND) + Box-Muller and
  * are generated INSIDE the kernel: the four normals of rows 4k..4k+3 of GLOBAL column n = column_offset + local column

@@ -407,6 +407,139 @@ def test_find_alpha_residual_on_device(B, golden):
     assert a == pytest.approx(gi["wt_y"] + gi["wt_u_hat"], rel=1e-5)
 
 
+F64_KINDS = ["planar", "planar_randn", "radial", "rqs", "batchnorm", "permute", "coupling", "stacked", "leaky_relu", "bounded"]
+
+
+def make_case64(kind, D, rng):
+    """(Float64 device layer, oracle layer): the Float32 cases rebuilt with Float64 parameters."""
+    import torch
+
+    import bijectors_jl_b200 as B
+
+    f64 = torch.float64
+    lay, olay = make_case(kind, D, rng)
+    p = olay.params
+    if kind in ("planar", "planar_randn"):
+        w, u, b = (p[k].astype(np.float64) + 1e-9 * rng.standard_normal(p[k].shape) for k in ("w", "u", "b"))  # not fp32-representable
+        return B.PlanarLayer(w, u, b, dtype=f64), O.Layer("planar", dict(w=w, u=u, b=b))
+    if kind == "radial":
+        a, be, z0 = (p[k].astype(np.float64) + 1e-9 * rng.standard_normal(p[k].shape) for k in ("alpha_raw", "beta", "z0"))
+        return B.RadialLayer(a, be, z0, dtype=f64), O.Layer("radial", dict(alpha_raw=a, beta=be, z0=z0))
+    if kind == "rqs":
+        K = 8
+        rw, rh, rd = rng.standard_normal((D, K)), rng.standard_normal((D, K)), rng.standard_normal((D, K - 1))
+        l64 = B.RationalQuadraticSpline(rw, rh, rd, 3.0, dtype=f64)
+        W, H, Dv = l64.knots()
+        assert W.dtype == np.float64
+        return l64, O.Layer("rqs", dict(widths=W, heights=H, derivs=Dv))
+    if kind == "batchnorm":
+        bn = p["bn"]
+        b, logs, m, v = (np.asarray(t, np.float64) + 1e-9 * rng.standard_normal(D) for t in (bn.b, bn.logs, bn.m, bn.v))
+        return (B.InvertibleBatchNorm(b=b, logs=logs, m=m, v=v, dtype=f64),
+                O.Layer("batchnorm", dict(bn=O.BatchNormParams(b, logs, m, v, np.float64(np.float32(1e-5)), np.float64(0.1)))))
+    if kind == "coupling":
+        W, c = p["W"].astype(np.float64) + 1e-9 * rng.standard_normal(p["W"].shape), p["c"].astype(np.float64)
+        return (B.Coupling(B.AffineConditioner(W, c, dtype=f64), B.PartitionMask(D, list(p["idx1"]), list(p["idx2"]))),
+                O.Layer("coupling_affine", dict(idx1=p["idx1"], idx2=p["idx2"], W=W, c=c)))
+    if kind in ("stacked", "leaky_relu", "bounded"):
+        # the scalar law parameters are Python floats on the device side: give the oracle the same float64 values (the
+        # Float32 cases carry float32-rounded constants)
+        ops = [tuple([op[0]] + [{-1.7: -1.7, 0.3: 0.3, 0.1: 0.1}.get(round(float(v), 6), float(v)) for v in op[1:]]) for op in p["ops"]]
+        return (B.Stacked(lay.bs, lay.ranges_in, dtype=f64) if hasattr(lay, "bs") else lay), O.Layer("stacked", dict(ops=ops, ranges=p["ranges"]))
+    return lay, olay  # permute: no floating-point parameters
+
+
+@pytest.mark.parametrize("D,N", [(128, 300), (32, 257), (10, 100), (3, 7), (200, 33)])
+@pytest.mark.parametrize("kind", F64_KINDS)
+def test_float64_layers_match_the_float64_oracle(B, kind, D, N):
+    """Float64 batches with Float64 parameters (b2b_chain_run_f64): the reference is generic in its element type and its
+    own tests run in Float64.  Against the float64 oracle the gate is 1e-12 relative (ill-conditioned planar_randn: 1e-9),
+    bit-exact for Permute."""
+    if kind in ("coupling", "stacked", "bounded") and D < 3:
+        pytest.skip("needs D >= 3")
+    import zlib
+
+    rng = np.random.default_rng(zlib.crc32(f"f64-{kind}-{D}-{N}".encode()))
+    lay, olay = make_case64(kind, D, rng)
+    x = rng.standard_normal((D, N)) * (1.5 if kind == "rqs" else 1.0)
+    if kind == "bounded":
+        x = rng.uniform(-0.9, 2.9, (D, N))
+    xd = B.from_numpy(x, dtype=np.float64)
+    y, lj = B.with_logabsdet_jacobian(lay, xd)
+    assert y.dtype == lj.dtype and str(y.dtype) == "torch.float64"
+    yo, ljo = olay.forward(x)
+    yh, ljh = B.to_numpy(y), B.to_numpy(lj)
+    tol = 1e-9 if kind == "planar_randn" else 1e-12
+    if kind == "permute":
+        assert np.array_equal(yh.view(np.uint64), yo.view(np.uint64)) and np.all(ljh == 0)
+    else:
+        assert rel(yh, yo) <= tol, rel(yh, yo)
+        assert np.linalg.norm(ljh - ljo) <= tol * max(np.linalg.norm(ljo), math.sqrt(N) * 1e-2), rel(ljh, ljo)
+    xi, lji = B.with_logabsdet_jacobian(B.inverse(lay), y)
+    xo, ljio = olay.inverse(yh)
+    if kind == "permute":
+        assert np.array_equal(B.to_numpy(xi).view(np.uint64), x.view(np.uint64))
+    else:
+        assert rel(B.to_numpy(xi), xo) <= (1e-7 if kind == "planar_randn" else 1e-11), rel(B.to_numpy(xi), xo)
+        if kind != "planar_randn":
+            assert np.linalg.norm(B.to_numpy(lji) - ljio) <= 1e-10 * max(np.linalg.norm(ljio), math.sqrt(N) * 1e-2)
+    # the Float32 layers refuse a Float64 batch (and vice versa) instead of silently converting
+    if kind == "planar":
+        with pytest.raises(TypeError):
+            B.with_logabsdet_jacobian(make_case(kind, D, rng)[0], xd)
+
+
+def test_float64_chain_logpdf_and_find_alpha_grid(B, golden):
+    """A heterogeneous Float64 chain + TransformedDistribution logpdf + batch sum against the float64 oracle, and the
+    reference's find_alpha test in ITS precision: residual grid with atol = 1e-14 where wt_y = 0, issue 204
+    (test/normalising_flows.jl:47-71)."""
+    import torch
+
+    f64 = torch.float64
+    rng = np.random.default_rng(64)
+    D, N = 64, 501
+    kinds = ["planar", "batchnorm", "radial", "permute", "rqs", "coupling", "planar", "stacked"]
+    pairs = [make_case64(k, D, rng) for k in kinds]
+    flow = B.Composed(*[p[0] for p in pairs])
+    olayers = [p[1] for p in pairs]
+    x = rng.standard_normal((D, N))
+    y, lj = B.with_logabsdet_jacobian(flow, B.from_numpy(x, dtype=np.float64))
+    yo, ljo = O.chain_forward(olayers, x)
+    assert rel(B.to_numpy(y), yo) <= 1e-12 and rel(B.to_numpy(lj), ljo) <= 1e-12, (rel(B.to_numpy(y), yo), rel(B.to_numpy(lj), ljo))
+    mu, sigma = rng.standard_normal(D) * 0.1, rng.uniform(0.5, 2.0, D)
+    td = B.transformed(B.MvNormal(D, mu, sigma, dtype=f64), flow)
+    tot, lp = B.logpdf_sum(td, y)
+    lpo = O.transformed_logpdf(olayers, mu, sigma, B.to_numpy(y))
+    assert rel(B.to_numpy(lp), lpo) <= 1e-10, rel(B.to_numpy(lp), lpo)
+    assert abs(float(tot) - float(lpo.sum())) <= 1e-10 * abs(float(lpo.sum()))
+    # find_alpha through a D = 1 PlanarLayer with w = 1: inverse(y) = y − û·tanh(α+b) and wᵀû = softplus(u) − 1
+    g = golden["find_alpha_grid"]
+    for c in g["wt_u_hat"]:
+        if c <= -1.0:
+            continue  # c = −1 needs u = −∞
+        u = math.log(math.expm1(c + 1.0)) if c + 1.0 < 30 else c + 1.0
+        cc = math.log1p(math.exp(u)) - 1.0 if u < 30 else u - 1.0
+        for b in g["b"]:
+            lay = B.PlanarLayer(np.ones(1), np.array([u]), np.array([b]), dtype=f64)
+            ys = np.array(g["wt_y"], np.float64)[None, :]
+            # with w = 1: û = wᵀû = cc and z = y − û·tanh(α+b) = α, so the inverse's output IS the root
+            alpha = B.to_numpy(B.inverse(lay)(B.from_numpy(ys, dtype=np.float64)))[0]
+            rhs = alpha + cc * np.tanh(alpha + b)
+            # the reference's check: wt_y ≈ α + wt_u_hat·tanh(α + b) (rtol = sqrt(eps)), atol = 1e-14 when wt_y == 0;
+            # here 1e-12 relative (z is rebuilt from the root: ½ ulp of α is amplified by f′ = 1 + c·sech² <= 1 + |c|)
+            for yv, rv in zip(ys[0], rhs):
+                if yv == 0.0:
+                    assert abs(rv) <= 1e-14 * (1 + abs(cc)) ** 2, (c, b, rv)
+                else:
+                    assert abs(rv - yv) <= 1e-12 * max(abs(rv), abs(yv)) * (1 + abs(cc)), (c, b, yv, rv)
+    gi = golden["find_alpha_issue_204"]
+    u = math.log(math.expm1(gi["wt_u_hat"] + 1.0))
+    lay = B.PlanarLayer(np.ones(1), np.array([u]), np.array([gi["b"]]), dtype=f64)
+    z = float(B.to_numpy(B.inverse(lay)(B.from_numpy(np.array([[gi["wt_y"]]]), dtype=np.float64)))[0, 0])
+    # b = −1e8: tanh(α + b) = −1, so z = y + wᵀû and α = wt_y + wt_u_hat (planar_layer.jl issue 204)
+    assert z == pytest.approx(gi["wt_y"] + gi["wt_u_hat"], rel=1e-14)
+
+
 def test_host_buffer_entry_point_matches_device_path(B):
     import torch
 

@@ -82,8 +82,14 @@ def test_layout_helpers():
     assert _batch_view(torch.zeros(5)) == (5, 1, 5)
     with pytest.raises(ValueError, match="column-major"):
         _batch_view(torch.zeros(3, 4))
+    assert _batch_view(torch.zeros(3, dtype=torch.float64)) == (3, 1, 3)  # Float64 batches: b2b_chain_run_f64
     with pytest.raises(TypeError):
-        _batch_view(torch.zeros(3, dtype=torch.float64))
+        _batch_view(torch.zeros(3, dtype=torch.float16))
+    # parameter and batch element types must agree (Float32 hot path / Float64 reference-test precision)
+    lay64 = B.PlanarLayer(np.ones(3), np.zeros(3), np.ones(1), device="cpu", dtype=torch.float64)
+    assert lay64.w.dtype == torch.float64 and type(lay64._descs(False, 3, torch.float64)[0]).__name__ == "LayerDesc64"
+    with pytest.raises(TypeError, match="Float"):
+        lay64._descs(False, 3, torch.float32)
     e = B.colmajor_empty(7, 5, device="cpu")
     assert e.shape == (7, 5) and e.stride() == (1, 7)
 
@@ -277,7 +283,8 @@ def _c_prototypes():
         if stars == 2:
             return "ptrptr"
         return {"float": "ptr_f32", "double": "ptr_f64", "int32_t": "ptr_i32", "int": "ptr_i32", "void": "ptr_void", "char": "ptr_u8",
-                "b2b_layer_desc": "ptr_desc", "b2b_comm": "ptr_void", "b2b_host_ctx": "ptr_void"}[base]
+                "b2b_layer_desc": "ptr_desc", "b2b_layer_desc_f64": "ptr_desc64", "b2b_comm": "ptr_void",
+                "b2b_host_ctx": "ptr_void"}[base]
 
     protos = {}
     for m in re.finditer(r"\b(int|size_t|const char\s*\*)\s+(b2b_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
