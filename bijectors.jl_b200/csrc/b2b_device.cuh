@@ -122,6 +122,16 @@ __device__ inline void planar_table_piece(float c, int i, float* tab) {
   if (i == 0) reinterpret_cast<float4*>(tab)[PT_N] = make_float4(R, (float)PT_N / (2.0f * R), 0.f, 0.f);
 }
 
+// the safeguarded iteration as an out-of-line call: the unrolled 8-layer program would otherwise carry eight inlined
+// copies of a loop it almost never runs (ncu: 96 KB of SASS, no_instruction 0.72 warps/issue -- instruction-cache misses)
+static __device__ __noinline__ float find_alpha_ts_call(float t, float c, float b, float* th, float* s2) {
+  float th_, s2_;
+  const float x = find_alpha_ts(t, c, b, th_, s2_);
+  *th = th_;
+  *s2 = s2_;
+  return x;
+}
+
 __device__ __forceinline__ float find_alpha_tab(float t, float c, float b, const float* __restrict__ tab, float& th, float& s2) {
   const float4 meta = reinterpret_cast<const float4*>(tab)[PT_N];
   const float s = t + b;
@@ -145,7 +155,11 @@ __device__ __forceinline__ float find_alpha_tab(float t, float c, float b, const
     s2 = fmaf(-d, fmaf(d, qq, 2.0f * ts), s2);
     return (u0 - n) - b;
   }
-  return find_alpha_ts(t, c, b, th, s2);
+  float th_, s2_;
+  const float x = find_alpha_ts_call(t, c, b, &th_, &s2_);
+  th = th_;
+  s2 = s2_;
+  return x;
 }
 
 __device__ __forceinline__ float find_alpha(float t, float c, float b) {
