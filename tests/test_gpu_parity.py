@@ -613,7 +613,7 @@ def test_rand_matches_the_oracle_stream(B, D):
     base = B.MvNormal(D, mu, sigma)
     zo = O.philox_normals(seed, off, D, n, mu=mu.astype(np.float64), sigma=sigma.astype(np.float64))
     z = B.to_numpy(base.rand(n, seed=seed, offset=off))
-    assert z.shape == (D, n) and rel(z, zo) <= 1e-6, rel(z, zo)
+    assert z.shape == (D, n) and rel(z, zo) <= 3e-6, rel(z, zo)  # MUFU sin/cos/lg2: ~2^-21 absolute
     assert np.array_equal(B.to_numpy(base.rand(n, seed=seed, offset=off)), z)            # deterministic
     assert np.array_equal(B.to_numpy(base.rand(500, seed=seed, offset=off, column_offset=700)), z[:, 700:1200])
     assert not np.array_equal(B.to_numpy(base.rand(n, seed=seed + 1, offset=off)), z)
