@@ -7,8 +7,8 @@ from typing import List, Sequence, Tuple
 
 import torch
 
-from .interface import Composed, colmajor_empty, inverse, planar_chain_vjp, radial_chain_vjp, run_chain
-from .layers import PlanarLayer, RadialLayer
+from .interface import Composed, batchnorm_vjp, colmajor_empty, coupling_vjp, inverse, planar_chain_vjp, radial_chain_vjp, run_chain
+from .layers import AffineConditioner, Coupling, InvertibleBatchNorm, PartitionMask, PlanarLayer, RadialLayer
 
 
 _VJP_DIMS = (32, 64, 128)
@@ -138,3 +138,101 @@ class RadialFlow(torch.nn.Module):
         for a, b, z in zip(self.alpha_, self.beta, self.z_0):
             abz += [a, b, z]
         return _RadialChainFn.apply(x, *abz)
+
+
+# ---- RealNVP: affine Coupling + eval-mode InvertibleBatchNorm blocks (BASELINE config 5) ---------------------------------
+class _CouplingFn(torch.autograd.Function):
+    """with_logabsdet_jacobian of ONE affine coupling layer (either direction); backward = b2b_coupling_affine_vjp_f32."""
+
+    @staticmethod
+    def forward(ctx, x, W, c, mask, inv: bool):
+        cond = AffineConditioner.__new__(AffineConditioner)
+        cond.n1, cond.n2 = W.shape[0] // 2, W.shape[1]
+        cond.W, cond.c = W.detach().t().contiguous(), c.detach().contiguous()  # device layout: column-major (2n1 × n2)
+        lay = Coupling(cond, mask)
+        t = inverse(lay) if inv else lay
+        xc = _colmajor(x.detach())
+        y, lj = run_chain(t, xc)
+        ctx.t = t
+        ctx.save_for_backward(xc)
+        return y, lj
+
+    @staticmethod
+    def backward(ctx, ybar, ljbar):
+        (xc,) = ctx.saved_tensors
+        D, N = xc.shape
+        yb = _colmajor(ybar) if ybar is not None else _colmajor(torch.zeros((D, N), device=xc.device))
+        xbar, g = coupling_vjp(ctx.t, xc, yb, ljbar.contiguous() if ljbar is not None else None)
+        return xbar, g["W"], g["c"], None, None
+
+
+class _BatchNormFn(torch.autograd.Function):
+    """with_logabsdet_jacobian of ONE eval-mode InvertibleBatchNorm (either direction); backward = b2b_batchnorm_eval_vjp_f32."""
+
+    @staticmethod
+    def forward(ctx, x, b, logs, m, v, eps: float, inv: bool):
+        lay = InvertibleBatchNorm(b=b.detach(), logs=logs.detach(), m=m, v=v, eps=eps, device=x.device)
+        t = inverse(lay) if inv else lay
+        xc = _colmajor(x.detach())
+        y, lj = run_chain(t, xc)
+        ctx.t = t
+        ctx.save_for_backward(xc)
+        return y, lj
+
+    @staticmethod
+    def backward(ctx, ybar, ljbar):
+        (xc,) = ctx.saved_tensors
+        D, N = xc.shape
+        yb = _colmajor(ybar) if ybar is not None else _colmajor(torch.zeros((D, N), device=xc.device))
+        xbar, g = batchnorm_vjp(ctx.t, xc, yb, ljbar.contiguous() if ljbar is not None else None)
+        return xbar, g["b"], g["logs"], None, None, None, None
+
+
+class RealNVP(torch.nn.Module):
+    """A trainable RealNVP flow: `n_blocks` x (affine Coupling with alternating half masks + eval-mode InvertibleBatchNorm),
+    the structure of BASELINE config 5.  ``forward(x)`` / ``inverse(y)`` return (result, logjac), differentiable w.r.t.
+    the input and the parameters W, c (conditioners) and b, logs (BatchNorm; m, v are statistics); ``nll(y)`` is the
+    training objective of docs/src/flows.md:74-77 with a standard-normal base."""
+
+    def __init__(self, dims: int, n_blocks: int, device="cuda", generator=None, scale: float = 0.05):
+        super().__init__()
+        h = dims // 2
+        self.dims, self.masks = dims, []
+        Ws, cs, bs, ls = [], [], [], []
+        for l in range(n_blocks):
+            first = l % 2 == 0
+            idx1 = list(range(1, h + 1)) if first else list(range(h + 1, dims + 1))
+            idx2 = list(range(h + 1, dims + 1)) if first else list(range(1, h + 1))
+            self.masks.append(PartitionMask(dims, idx1, idx2))
+            n1, n2 = len(idx1), len(idx2)
+            Ws.append(torch.nn.Parameter((torch.randn((2 * n1, n2), generator=generator) * scale / n2 ** 0.5).to(device)))
+            cs.append(torch.nn.Parameter(torch.zeros(2 * n1, device=device)))
+            bs.append(torch.nn.Parameter(torch.zeros(dims, device=device)))
+            ls.append(torch.nn.Parameter(torch.zeros(dims, device=device)))
+        self.W, self.c = torch.nn.ParameterList(Ws), torch.nn.ParameterList(cs)
+        self.b, self.logs = torch.nn.ParameterList(bs), torch.nn.ParameterList(ls)
+        self.register_buffer("m", torch.zeros(n_blocks, dims, device=device))
+        self.register_buffer("v", torch.ones(n_blocks, dims, device=device))
+        self.eps = 1e-5
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        lj = None
+        for l in range(len(self.W)):
+            x, l1 = _CouplingFn.apply(x, self.W[l], self.c[l], self.masks[l], False)
+            x, l2 = _BatchNormFn.apply(x, self.b[l], self.logs[l], self.m[l], self.v[l], self.eps, False)
+            lj = l1 + l2 if lj is None else lj + l1 + l2
+        return x, lj
+
+    def inverse(self, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        lj = None
+        for l in reversed(range(len(self.W))):
+            y, l2 = _BatchNormFn.apply(y, self.b[l], self.logs[l], self.m[l], self.v[l], self.eps, True)
+            y, l1 = _CouplingFn.apply(y, self.W[l], self.c[l], self.masks[l], True)
+            lj = l1 + l2 if lj is None else lj + l1 + l2
+        return y, lj
+
+    def nll(self, y: torch.Tensor) -> torch.Tensor:
+        """−Σ_n logpdf(transformed(MvNormal(0, I), flow), y_n) (transformed_distribution.jl:165-169)."""
+        x, lj = self.inverse(y)
+        base = -0.5 * (x * x).sum(0) - 0.5 * self.dims * 1.8378770664093453
+        return -(base + lj).sum()

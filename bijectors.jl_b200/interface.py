@@ -580,6 +580,59 @@ def radial_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[tor
     return xbar, [{"α_": abar[l:l + 1], "β": bbar[l:l + 1], "z_0": zbar[l]} for l in range(L)]
 
 
+def _layer_vjp(t, x, ybar, ljbar, kind, which):
+    D, N, ldx = _batch_view(x)
+    Dy, Ny, ldyb = _batch_view(ybar)
+    if (Dy, Ny) != (D, N) or not x.is_cuda or not ybar.is_cuda or x.dim() != 2 or x.dtype != torch.float32:
+        raise ValueError(f"{which}: x and ybar must be Float32 device matrices of the same D×N shape")
+    descs = list(t._descs(False, D, torch.float32))
+    if len(descs) != 1 or descs[0].kind != kind:
+        raise B2BError(_lib.B2B_EUNSUPPORTED, f"{which}: one layer of the matching kind (or its Inverse)")
+    if ljbar is not None and (ljbar.numel() != N or ljbar.dtype != torch.float32 or not ljbar.is_contiguous()):
+        raise ValueError("ljbar must be a contiguous float32 vector of length N")
+    return descs[0], D, N, ldx, ldyb
+
+
+def coupling_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[torch.Tensor] = None):
+    """Vector-Jacobian product of ``with_logabsdet_jacobian(t, x)`` for ONE affine Coupling layer ``t`` (or
+    ``inverse(coupling)``, with ``x`` the observed batch): b2b_coupling_affine_vjp_f32.  Returns ``(xbar, {"W": W̄, "c": c̄})``
+    with W̄ in the reference's (2·n1 × n2) index order, summed over the columns of this batch."""
+    d, D, N, ldx, ldyb = _layer_vjp(t, x, ybar, ljbar, _lib.COUPLING_AFFINE, "coupling_vjp")
+    n1, n2 = d.n0, d.n1
+    xbar = colmajor_empty(D, N, x.device)
+    Wbar = torch.empty((n2, 2 * n1), dtype=torch.float32, device=x.device)  # column-major (2n1 × n2)
+    cbar = torch.empty((2 * n1,), dtype=torch.float32, device=x.device)
+    L_ = lib()
+    ws_bytes = L_.b2b_coupling_affine_vjp_workspace_bytes(n1, n2)
+    if ws_bytes == 0:
+        raise B2BError(_lib.B2B_EUNSUPPORTED, "coupling_vjp: n1, n2 <= 128")
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+    arr = (LayerDesc * 1)(d)
+    check(L_.b2b_coupling_affine_vjp_f32(arr, x.data_ptr(), ybar.data_ptr(), ljbar.data_ptr() if ljbar is not None else None,
+                                         xbar.data_ptr(), Wbar.data_ptr(), cbar.data_ptr(), D, N, ldx, ldyb,
+                                         _batch_view(xbar)[2], ws.data_ptr(), ws_bytes, _stream()), "b2b_coupling_affine_vjp_f32")
+    return xbar, {"W": Wbar.t(), "c": cbar}
+
+
+def batchnorm_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[torch.Tensor] = None):
+    """Vector-Jacobian product of ``with_logabsdet_jacobian(t, x)`` for ONE eval-mode InvertibleBatchNorm ``t`` (or its
+    inverse): b2b_batchnorm_eval_vjp_f32.  Returns ``(xbar, {"b": b̄, "logs": l̄ogs})`` summed over the columns."""
+    d, D, N, ldx, ldyb = _layer_vjp(t, x, ybar, ljbar, _lib.BATCHNORM, "batchnorm_vjp")
+    xbar = colmajor_empty(D, N, x.device)
+    bbar = torch.empty((D,), dtype=torch.float32, device=x.device)
+    lbar = torch.empty((D,), dtype=torch.float32, device=x.device)
+    L_ = lib()
+    ws_bytes = L_.b2b_batchnorm_eval_vjp_workspace_bytes(D)
+    if ws_bytes == 0:
+        raise B2BError(_lib.B2B_EUNSUPPORTED, "batchnorm_vjp: D <= 1024")
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+    arr = (LayerDesc * 1)(d)
+    check(L_.b2b_batchnorm_eval_vjp_f32(arr, x.data_ptr(), ybar.data_ptr(), ljbar.data_ptr() if ljbar is not None else None,
+                                        xbar.data_ptr(), bbar.data_ptr(), lbar.data_ptr(), D, N, ldx, ldyb,
+                                        _batch_view(xbar)[2], ws.data_ptr(), ws_bytes, _stream()), "b2b_batchnorm_eval_vjp_f32")
+    return xbar, {"b": bbar, "logs": lbar}
+
+
 def isinvertible(t) -> bool:
     return isinstance(t, Transform)
 

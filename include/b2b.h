@@ -199,6 +199,25 @@ int b2b_radial_chain_vjp_f32(const b2b_layer_desc* layers, int32_t L, const floa
                              const float* ljbar, float* xbar, float* alpha_bar, float* beta_bar, float* z0_bar,
                              int32_t D, int64_t N, int64_t ldx, int64_t ldybar, int64_t ldxbar, void* workspace,
                              size_t workspace_bytes, void* stream);
+/* Reverse mode of ONE affine coupling layer (either direction) -- with the eval-mode BatchNorm VJP below it makes a
+ * RealNVP flow (BASELINE config 5) trainable on the device.  What the reference's AD computes for coupling.jl:206-228
+ * with the law Shift(t)∘Scale(exp.(s)); the pullback of `combine` (ext/BijectorsChainRulesCoreExt.jl:48-62) is the row
+ * scatter of the three cotangent blocks.  `layer`: a B2B_COUPLING_AFFINE descriptor (n1, n2 <= 128, any index lists);
+ * `x`: the batch the layer was applied to (for inverse != 0 the observed y); `ybar` (D x N) / `ljbar` (N, NULL = zeros):
+ * cotangents of the layer's two outputs.  Outputs: `xbar` (D x N; may alias `ybar`), `Wbar` (2n1 x n2, column-major like
+ * W) and `cbar` (2n1), summed over the N columns (a multi-GPU caller all-reduces them).  Exact fp32 on the CUDA cores,
+ * deterministic.  Workspace: b2b_coupling_affine_vjp_workspace_bytes. */
+size_t b2b_coupling_affine_vjp_workspace_bytes(int32_t n1, int32_t n2);
+int b2b_coupling_affine_vjp_f32(const b2b_layer_desc* layer, const float* x, const float* ybar, const float* ljbar,
+                                float* xbar, float* Wbar, float* cbar, int32_t D, int64_t N, int64_t ldx, int64_t ldybar,
+                                int64_t ldxbar, void* workspace, size_t workspace_bytes, void* stream);
+/* Reverse mode of the eval-mode InvertibleBatchNorm (normalise.jl:61-67 / :74-86) w.r.t. its input and its trainable
+ * fields b, logs (Functors.@functor InvertibleBatchNorm (b, logs); m, v are statistics): `bbar`, `logsbar` (D each) are
+ * summed over the columns; arguments as above.  D <= 1024. */
+size_t b2b_batchnorm_eval_vjp_workspace_bytes(int32_t D);
+int b2b_batchnorm_eval_vjp_f32(const b2b_layer_desc* layer, const float* x, const float* ybar, const float* ljbar,
+                               float* xbar, float* bbar, float* logsbar, int32_t D, int64_t N, int64_t ldx, int64_t ldybar,
+                               int64_t ldxbar, void* workspace, size_t workspace_bytes, void* stream);
 /* RadialLayer: radial_layer.jl:58-72 (fwd), :88-102,124-129 (inverse) */
 int b2b_radial_fwd_f32(const float* x, float* y, float* logjac, const float* alpha_raw,
                        const float* beta, const float* z0, int32_t D, int64_t N, int64_t ldx,

@@ -768,6 +768,39 @@ def coupling_affine_inverse(idx1, idx2, Wm, c, y):
     return X, logjac
 
 
+def coupling_affine_vjp(idx1, idx2, Wm, c, x, ybar, ljbar, inverse=False):
+    """Vector-Jacobian product of with_logabsdet_jacobian through the affine coupling (what the reference's reverse-mode
+    AD computes for coupling.jl:206-228 with the law Shift(t)∘Scale(exp.(s)); `combine`'s pullback,
+    ext/BijectorsChainRulesCoreExt.jl:48-62, is the row scatter of the three cotangent blocks).
+    x: the layer's INPUT (D, N) (the observed y for inverse=True), ybar (D, N) / ljbar (N,): cotangents of the two outputs.
+    Returns (xbar (D, N), Wbar (2n1, n2), cbar (2n1,)), parameter cotangents summed over the columns.
+      forward : y1 = e^s x1 + t, lj = Σ s      =>  x̄1 = e^s ȳ1,  s̄ = ȳ1 e^s x1 + l̄,  t̄ = ȳ1
+      inverse : x1 = (y1 − t) e^−s, lj = −Σ s  =>  ȳ1 = e^−s x̄1, s̄ = −x1 x̄1 − l̄,   t̄ = −e^−s x̄1
+      both    : x̄2 = ȳ2 + Wᵀ[s̄; t̄],  W̄ = [s̄; t̄] x2ᵀ,  c̄ = Σ_n [s̄; t̄],  x̄3 = ȳ3."""
+    dt = x.dtype
+    i1, i2 = np.asarray(idx1) - 1, np.asarray(idx2) - 1
+    n1 = len(i1)
+    Wm, c = Wm.astype(dt), c.astype(dt)
+    st = Wm @ x[i2] + c[:, None]
+    sv, tv = st[:n1], st[n1:]
+    lb = np.zeros(x.shape[1], dt) if ljbar is None else ljbar.astype(dt)
+    xbar = ybar.astype(dt).copy()
+    if not inverse:
+        e = np.exp(sv)
+        xbar[i1] = e * ybar[i1]
+        sbar = ybar[i1] * e * x[i1] + lb[None, :]
+        tbar = ybar[i1].astype(dt)
+    else:
+        em = np.exp(-sv)
+        x1 = (x[i1] - tv) * em
+        xbar[i1] = em * ybar[i1]
+        sbar = -x1 * ybar[i1] - lb[None, :]
+        tbar = -em * ybar[i1]
+    stbar = np.concatenate([sbar, tbar], axis=0)
+    xbar[i2] = ybar[i2] + Wm.T @ stbar
+    return xbar, stbar @ x[i2].T, stbar.sum(axis=1)
+
+
 # --------------------------------------------------------------------------------------------------
 # InvertibleBatchNorm  (src/bijectors/normalise.jl)
 # --------------------------------------------------------------------------------------------------
@@ -833,6 +866,25 @@ def batchnorm_inverse(bn: BatchNormParams, y):
     x = x.astype(dt)
     _, lj = batchnorm_forward(bn, x)
     return x, -lj
+
+
+def batchnorm_eval_vjp(bn: BatchNormParams, x, ybar, ljbar, inverse=False):
+    """Vector-Jacobian product of the eval-mode InvertibleBatchNorm (normalise.jl:61-67 forward, :74-86 inverse) w.r.t. the
+    input and the trainable fields b, logs (Functors.@functor InvertibleBatchNorm (b, logs); m, v are statistics).
+      forward : y = A (x − m) + b, A = e^logs / sqrt(v+eps), lj = Σ_c (logs_c − ½ log(v_c+eps))
+                x̄ = A ȳ,  b̄ = Σ_n ȳ,  l̄ogs = Σ_n ȳ ⊙ (y − b) + Σ_n l̄
+      inverse : x = (y − b)/A + m, lj = −Σ_c(...)
+                ȳ = x̄ / A,  b̄ = −Σ_n x̄/A,  l̄ogs = −Σ_n x̄ ⊙ (x − m) − Σ_n l̄
+    Returns (input cotangent (C, N), bbar (C,), logsbar (C,))."""
+    dt = x.dtype
+    A = (np.exp(bn.logs.astype(dt)) / np.sqrt(bn.v.astype(dt) + dt.type(bn.eps)))[:, None]
+    b, m = bn.b.astype(dt)[:, None], bn.m.astype(dt)[:, None]
+    lsum = dt.type(0) if ljbar is None else ljbar.astype(dt).sum()
+    if not inverse:
+        y = A * (x - m) + b
+        return A * ybar, ybar.sum(axis=1), (ybar * (y - b)).sum(axis=1) + lsum
+    xr = (x - b) / A + m
+    return ybar / A, -(ybar / A).sum(axis=1), -(ybar * (xr - m)).sum(axis=1) - lsum
 
 
 # --------------------------------------------------------------------------------------------------

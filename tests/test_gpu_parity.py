@@ -1393,3 +1393,95 @@ def test_full_size_vjp_round_trip_property(B):
     _, grads2 = B.planar_chain_vjp(flow, x, u_, None)
     assert all(torch.equal(grads[l][k], grads2[l][k]) for l in range(L) for k in ("w", "u", "b"))
     assert all(torch.isfinite(grads[l][k]).all() for l in range(L) for k in ("w", "u", "b"))
+
+
+@pytest.mark.parametrize("inv", [False, True])
+@pytest.mark.parametrize("D,n1,idx", [(256, 128, "halves"), (256, 128, "swapped"), (64, 20, "scattered"), (10, 4, "scattered")])
+def test_coupling_and_batchnorm_vjp_match_oracle(B, D, n1, idx, inv):
+    """Reverse mode of the RealNVP layer kinds: b2b_coupling_affine_vjp_f32 (incl. the combine pullback: pass-through rows
+    and arbitrary index lists) and b2b_batchnorm_eval_vjp_f32, both directions, against the finite-difference-pinned
+    float64 oracle; deterministic; ragged N."""
+    rng = np.random.default_rng(900 + D + n1 + int(inv))
+    N = 1000 + 37
+    if idx == "halves":
+        idx1, idx2 = list(range(1, n1 + 1)), list(range(n1 + 1, D + 1))
+    elif idx == "swapped":
+        idx1, idx2 = list(range(D - n1 + 1, D + 1)), list(range(1, D - n1 + 1))
+    else:
+        perm = rng.permutation(D) + 1
+        idx1, idx2 = sorted(perm[:n1].tolist()), perm[n1:D - 2].tolist()  # two pass-through rows, x2 rows unsorted
+    n2 = len(idx2)
+    W = (rng.standard_normal((2 * n1, n2)) * 0.3 / np.sqrt(n2)).astype(f32)
+    c = (rng.standard_normal(2 * n1) * 0.1).astype(f32)
+    cl = B.Coupling(B.AffineConditioner(W, c), B.PartitionMask(D, idx1, idx2))
+    x, ybar, ljbar = (rng.standard_normal((D, N)).astype(f32), rng.standard_normal((D, N)).astype(f32), rng.standard_normal(N).astype(f32))
+    t = B.inverse(cl) if inv else cl
+    import torch
+
+    xbar, g = B.coupling_vjp(t, B.from_numpy(x), B.from_numpy(ybar), torch.as_tensor(ljbar, device="cuda"))
+    xo, Wo, co = O.coupling_affine_vjp(idx1, idx2, W.astype(np.float64), c.astype(np.float64), x.astype(np.float64),
+                                       ybar.astype(np.float64), ljbar.astype(np.float64), inverse=inv)
+    assert rel(B.to_numpy(xbar), xo) <= RTOL, rel(B.to_numpy(xbar), xo)
+    assert rel(B.to_numpy(g["W"]), Wo) <= RTOL and rel(B.to_numpy(g["c"]), co) <= RTOL, (rel(B.to_numpy(g["W"]), Wo), rel(B.to_numpy(g["c"]), co))
+    xbar2, g2 = B.coupling_vjp(t, B.from_numpy(x), B.from_numpy(ybar), torch.as_tensor(ljbar, device="cuda"))
+    assert torch.equal(xbar, xbar2) and torch.equal(g["W"], g2["W"]) and torch.equal(g["c"], g2["c"])  # deterministic
+    # eval-mode BatchNorm
+    b, logs, m = (rng.standard_normal(D) * 0.3).astype(f32), (rng.standard_normal(D) * 0.3).astype(f32), (rng.standard_normal(D) * 0.3).astype(f32)
+    v = rng.uniform(0.5, 1.5, D).astype(f32)
+    bn = B.InvertibleBatchNorm(b=b, logs=logs, m=m, v=v)
+    tb = B.inverse(bn) if inv else bn
+    xb, gb = B.batchnorm_vjp(tb, B.from_numpy(x), B.from_numpy(ybar), torch.as_tensor(ljbar, device="cuda"))
+    obn = O.BatchNormParams(b.astype(np.float64), logs.astype(np.float64), m.astype(np.float64), v.astype(np.float64), np.float64(np.float32(1e-5)), np.float64(0.1))
+    xbo, bo, lo = O.batchnorm_eval_vjp(obn, x.astype(np.float64), ybar.astype(np.float64), ljbar.astype(np.float64), inverse=inv)
+    assert rel(B.to_numpy(xb), xbo) <= RTOL and rel(B.to_numpy(gb["b"]), bo) <= RTOL and rel(B.to_numpy(gb["logs"]), lo) <= RTOL, (
+        rel(B.to_numpy(xb), xbo), rel(B.to_numpy(gb["b"]), bo), rel(B.to_numpy(gb["logs"]), lo))
+
+
+def test_realnvp_trains_through_autograd(B):
+    """BASELINE config 5's flow structure as a torch module on the device path: gradients of the NLL w.r.t. every
+    parameter equal the oracle's layer-by-layer VJP chain, and a few SGD steps lower the objective."""
+    import torch
+
+    torch.manual_seed(0)
+    D, N, nb = 64, 2048, 3
+    flow = B.autograd.RealNVP(D, nb, scale=0.1)  # (scale 0.5 makes exp(-s) overflow fp32 after three blocks)
+    with torch.no_grad():
+        for p_ in list(flow.c) + list(flow.b) + list(flow.logs):
+            p_.add_(0.05 * torch.randn_like(p_))
+    y = (torch.randn((N, D), device="cuda") * 1.3 + 0.2).t()
+    loss = flow.nll(y)
+    loss.backward()
+    # oracle: the same objective differentiated layer by layer in float64
+    yo = y.cpu().numpy().astype(np.float64)
+    acts, cur = [], yo
+    order = []
+    for l in reversed(range(nb)):
+        obn = O.BatchNormParams(*[t.detach().cpu().numpy().astype(np.float64) for t in (flow.b[l], flow.logs[l], flow.m[l], flow.v[l])],
+                                np.float64(np.float32(1e-5)), np.float64(0.1))
+        order.append(("bn", l, obn, cur))
+        cur, _ = O.batchnorm_inverse(obn, cur)
+        m_ = flow.masks[l]
+        Wl, cl_ = flow.W[l].detach().cpu().numpy().astype(np.float64), flow.c[l].detach().cpu().numpy().astype(np.float64)
+        order.append(("cpl", l, (m_.indices_1, m_.indices_2, Wl, cl_), cur))
+        cur, _ = O.coupling_affine_inverse(m_.indices_1, m_.indices_2, Wl, cl_, cur)
+    xbar = cur.copy()            # d(nll)/dx = x   (nll = −Σ(−½‖x‖² + lj) + const)
+    ljbar = -np.ones(N)
+    grads = {}
+    for kind, l, prm, inp in reversed(order):
+        if kind == "cpl":
+            xbar, Wb, cb = O.coupling_affine_vjp(prm[0], prm[1], prm[2], prm[3], inp, xbar, ljbar, inverse=True)
+            grads[("W", l)], grads[("c", l)] = Wb, cb
+        else:
+            xbar, bb, lb = O.batchnorm_eval_vjp(prm, inp, xbar, ljbar, inverse=True)
+            grads[("b", l)], grads[("logs", l)] = bb, lb
+    for l in range(nb):
+        for name, par in (("W", flow.W[l]), ("c", flow.c[l]), ("b", flow.b[l]), ("logs", flow.logs[l])):
+            assert rel(par.grad.cpu().numpy(), grads[(name, l)]) <= 5e-5, (name, l, rel(par.grad.cpu().numpy(), grads[(name, l)]))
+    opt = torch.optim.SGD(flow.parameters(), lr=1e-6)
+    l0 = float(loss)
+    for _ in range(15):
+        opt.zero_grad()
+        lo = flow.nll(y)
+        lo.backward()
+        opt.step()
+    assert float(flow.nll(y)) < l0

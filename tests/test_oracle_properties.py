@@ -319,3 +319,52 @@ def test_logit_and_truncated_closed_forms():
     with np.errstate(divide="ignore"):
         yc, _ = O.truncated_forward(-1.0, np.inf, np.array([-2.0]))
     assert np.isneginf(yc[0])
+
+
+def _fd_vjp_check(fwd, params, x, ybar, ljbar, analytic, h=1e-6, tol=2e-6):
+    """<cotangents, outputs(θ + h e)> differenced against the analytic VJP for every input / parameter entry sampled."""
+    def scalar(ps, xx):
+        y, lj = fwd(ps, xx)
+        return float((ybar * y).sum() + (ljbar * lj).sum())
+
+    rng = np.random.default_rng(0)
+    xbar, pbars = analytic
+    for _ in range(25):
+        i, n = rng.integers(x.shape[0]), rng.integers(x.shape[1])
+        xp, xm = x.copy(), x.copy()
+        xp[i, n] += h
+        xm[i, n] -= h
+        fd = (scalar(params, xp) - scalar(params, xm)) / (2 * h)
+        assert abs(fd - xbar[i, n]) <= tol * max(1.0, abs(fd)), ("x", i, n, fd, xbar[i, n])
+    for k, pbar in enumerate(pbars):
+        flat = params[k].reshape(-1)
+        for _ in range(25):
+            j = rng.integers(flat.size)
+            pp, pm = [q.copy() for q in params], [q.copy() for q in params]
+            pp[k].reshape(-1)[j] += h
+            pm[k].reshape(-1)[j] -= h
+            fd = (scalar(pp, x) - scalar(pm, x)) / (2 * h)
+            assert abs(fd - pbar.reshape(-1)[j]) <= tol * max(1.0, abs(fd)), ("param", k, j, fd, pbar.reshape(-1)[j])
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_coupling_and_batchnorm_vjp_oracles_match_finite_differences(inverse):
+    """The reverse-mode restatements that pin the device VJP kernels (coupling incl. the combine pullback,
+    ext/BijectorsChainRulesCoreExt.jl:48-62; eval-mode BatchNorm) against central finite differences of the pinned
+    forward / inverse oracles."""
+    rng = np.random.default_rng(11)
+    D, N, n1 = 10, 7, 4
+    idx1, idx2 = [2, 5, 7, 9], [1, 3, 4, 8, 10]  # row 6 passes through
+    W, c = rng.standard_normal((2 * n1, len(idx2))) * 0.3, rng.standard_normal(2 * n1) * 0.2
+    x, ybar, ljbar = rng.standard_normal((D, N)), rng.standard_normal((D, N)), rng.standard_normal(N)
+    f = (lambda ps, xx: O.coupling_affine_inverse(idx1, idx2, ps[0], ps[1], xx)) if inverse else (lambda ps, xx: O.coupling_affine_forward(idx1, idx2, ps[0], ps[1], xx))
+    xbar, Wbar, cbar = O.coupling_affine_vjp(idx1, idx2, W, c, x, ybar, ljbar, inverse=inverse)
+    _fd_vjp_check(f, [W, c], x, ybar, ljbar, (xbar, [Wbar, cbar]))
+    b, logs, m, v = rng.standard_normal(D) * 0.3, rng.standard_normal(D) * 0.3, rng.standard_normal(D) * 0.3, rng.uniform(0.5, 1.5, D)
+
+    def bn_of(ps):
+        return O.BatchNormParams(ps[0], ps[1], m, v, np.float64(1e-5), np.float64(0.1))
+
+    g = (lambda ps, xx: O.batchnorm_inverse(bn_of(ps), xx)) if inverse else (lambda ps, xx: O.batchnorm_forward(bn_of(ps), xx))
+    xb, bb, lb = O.batchnorm_eval_vjp(bn_of([b, logs]), x, ybar, ljbar, inverse=inverse)
+    _fd_vjp_check(g, [b, logs], x, ybar, ljbar, (xb, [bb, lb]))
