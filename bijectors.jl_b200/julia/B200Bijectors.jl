@@ -255,6 +255,54 @@ function radial_chain_vjp(f, x::CuMatrix{Float32}, ȳ::CuMatrix{Float32}, l̄::C
     return x̄, ᾱ, β̄, z̄0        # cotangents of the raw fields α_, β, z_0 of each layer
 end
 
+# Reverse mode of the RealNVP layer kinds: one affine Coupling (incl. the `combine` pullback,
+# ext/BijectorsChainRulesCoreExt.jl:48-62) / one eval-mode InvertibleBatchNorm, either direction.
+function coupling_vjp(cl, x::CuMatrix{Float32}, ȳ::CuMatrix{Float32}, l̄::CuVector{Float32}; inv::Bool=false)
+    d = [desc(cl, inv)]
+    n1, n2, (D, N) = Int(d[1].n0), Int(d[1].n1), size(x)
+    x̄ = similar(x); W̄ = CUDA.zeros(Float32, 2n1, n2); c̄ = CUDA.zeros(Float32, 2n1)
+    nbytes = ccall((:b2b_coupling_affine_vjp_workspace_bytes, libb2b), Csize_t, (Int32, Int32), n1, n2)
+    ws = CuVector{UInt8}(undef, nbytes)
+    GC.@preserve d ws check(ccall((:b2b_coupling_affine_vjp_f32, libb2b), Cint,
+        (Ptr{LayerDesc}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32},
+         Int32, Int64, Int64, Int64, Int64, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        d, pointer(x), pointer(ȳ), pointer(l̄), pointer(x̄), pointer(W̄), pointer(c̄),
+        D, N, stride(x, 2), stride(ȳ, 2), stride(x̄, 2), pointer(ws), nbytes, stream_handle()))
+    return x̄, W̄, c̄
+end
+function batchnorm_vjp(bn, x::CuMatrix{Float32}, ȳ::CuMatrix{Float32}, l̄::CuVector{Float32}; inv::Bool=false)
+    d = [desc(bn, inv)]
+    D, N = size(x)
+    x̄ = similar(x); b̄ = CUDA.zeros(Float32, D); l̄ogs = CUDA.zeros(Float32, D)
+    nbytes = ccall((:b2b_batchnorm_eval_vjp_workspace_bytes, libb2b), Csize_t, (Int32,), D)
+    ws = CuVector{UInt8}(undef, nbytes)
+    GC.@preserve d ws check(ccall((:b2b_batchnorm_eval_vjp_f32, libb2b), Cint,
+        (Ptr{LayerDesc}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32},
+         Int32, Int64, Int64, Int64, Int64, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        d, pointer(x), pointer(ȳ), pointer(l̄), pointer(x̄), pointer(b̄), pointer(l̄ogs),
+        D, N, stride(x, 2), stride(ȳ, 2), stride(x̄, 2), pointer(ws), nbytes, stream_handle()))
+    return x̄, b̄, l̄ogs
+end
+
+# rand(rng, td, n) (src/transformed_distribution.jl:212-224): the base samples are generated INSIDE the chain kernel
+# (Philox4x32-10 + Box-Muller); `seed` plays the role of rng, `column_offset` continues one stream across column shards.
+function device_rand(td::TransformedDistribution{<:MvNormal}, n::Integer; seed::UInt64=rand(UInt64), offset::UInt64=UInt64(0),
+                     column_offset::Integer=0)
+    ds = descs(td.transform, false)
+    D = length(td.dist)
+    μ, σ = cu(Float32.(mean(td.dist))), cu(Float32.(sqrt.(var(td.dist))))
+    y = CuMatrix{Float32}(undef, D, n)
+    ws_bytes = ccall((:b2b_chain_workspace_bytes, libb2b), Csize_t,
+                     (Ptr{LayerDesc}, Int32, Int32, Int64, Cint, Cint), ds, length(ds), D, n, true, false)
+    ws = CuVector{UInt8}(undef, ws_bytes)
+    GC.@preserve ds μ σ ws check(ccall((:b2b_chain_sample_f32, libb2b), Cint,
+        (Ptr{LayerDesc}, Int32, CuPtr{Float32}, CuPtr{Float32}, UInt64, UInt64, Int64, CuPtr{Float32}, CuPtr{Float32},
+         Int32, Int64, Int64, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        ds, length(ds), pointer(μ), pointer(σ), seed, offset, column_offset, pointer(y), NULLF,
+        D, n, stride(y, 2), pointer(ws), ws_bytes, stream_handle()))
+    return y
+end
+
 # logpdf(td::MvTransformed, y::Matrix) (src/transformed_distribution.jl:165-169): inverse chain + base
 # MvNormal + (optionally) the batch sum in ONE fused launch per fusable segment.
 function Distributions.logpdf(td::TransformedDistribution{<:MvNormal}, y::CuMatrix{Float32})

@@ -329,7 +329,7 @@ def _julia_ccalls():
             parts.append(cur.strip())
         return parts
 
-    jl = {"Cint": "i32", "Int32": "i32", "Int64": "i64", "Csize_t": "usize", "Cfloat": "f32", "Float32": "f32", "Cstring": "cstring",
+    jl = {"Cint": "i32", "Int32": "i32", "Int64": "i64", "UInt64": "u64", "Csize_t": "usize", "Cfloat": "f32", "Float32": "f32", "Cstring": "cstring",
           "CuPtr{Float32}": "ptr_f32", "Ptr{Float32}": "ptr_f32", "CuPtr{Float64}": "ptr_f64", "CuPtr{Int32}": "ptr_i32",
           "Ptr{Int32}": "ptr_i32", "Ptr{LayerDesc}": "ptr_desc", "Ptr{Cvoid}": "ptr_void", "CuPtr{Cvoid}": "ptr_void",
           "Ptr{UInt8}": "ptr_u8", "Ptr{Ptr{Cvoid}}": "ptrptr"}
@@ -361,7 +361,8 @@ def test_julia_binding_ccalls_match_the_header():
             assert ok, (sym, k, a, c)
         seen.add(sym)
     assert {"b2b_chain_run_f32", "b2b_chain_workspace_bytes", "b2b_planar_chain_vjp_f32", "b2b_radial_chain_vjp_f32",
-            "b2b_batchnorm_train_fwd_f32", "b2b_allreduce_sum_f64", "b2b_status_string"} <= seen
+            "b2b_batchnorm_train_fwd_f32", "b2b_allreduce_sum_f64", "b2b_status_string", "b2b_coupling_affine_vjp_f32",
+            "b2b_batchnorm_eval_vjp_f32", "b2b_chain_sample_f32"} <= seen
     # the LayerDesc struct mirrors b2b_layer_desc field for field
     import re
 

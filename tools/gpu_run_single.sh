@@ -1,10 +1,14 @@
 #!/bin/bash
-# one GPU box visit: tests, bench, ncu launch list + full capture of the headline kernel (numbers under ncu are never bench values)
+# one GPU box visit: the whole GPU test suite, smoke, every BASELINE config, the bench (both arms)
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print(\"smoke ok\")" > gpurun_out/smoke.log 2>&1; tail -n 1 gpurun_out/smoke.log
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench.log
-timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --profile > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:planar_dev -s 4 -c 1 -o gpurun_out/prof_planar_dev python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
-tail -n 3 gpurun_out/pytest_gpu.log; tail -n 2 gpurun_out/bench.log | cut -c1-1800; tail -n 1 gpurun_out/bench_reference.log | cut -c1-300
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; grep -E "^FAILED|^ERROR|passed|failed" gpurun_out/pytest_gpu.log | cut -c1-250 | head -20
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -n 1 gpurun_out/smoke.log
+timeout 600 python bench_configs.py --iters 20 --json gpurun_out/r02_configs_1gpu.json > gpurun_out/r02_configs_1gpu.log 2>&1; cut -c1-170 gpurun_out/r02_configs_1gpu.log | tail -n 12
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_1gpu.log 2>&1; echo "bench rc=$?"
+timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02_bench_reference.log 2>&1; tail -n 1 gpurun_out/r02_bench_reference.log | cut -c1-300
+tail -n 1 gpurun_out/r02_bench_1gpu.log | python -c "
+import sys, json
+l = json.loads(sys.stdin.readline())
+print('value', l['value'], 'frac', l['roofline']['frac'], 'e2e', l['e2e']['value'], 'cpu', l['cpu_baseline']['value'], l['cpu_baseline']['cores'])
+for k, v in l['configs'].items(): print(k, 'ms', round(v['ms'], 4), 'samples/s', '%.3e' % v['samples_per_s'], 'frac', round(v['frac'], 3))
+"
