@@ -101,12 +101,13 @@ class PlanarFlow(torch.nn.Module):
 
 class _RadialChainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, *abz):
+    def forward(ctx, x, inv: bool, *abz):
         L = len(abz) // 3
         flow = Composed(*[RadialLayer(abz[3 * l].detach(), abz[3 * l + 1].detach(), abz[3 * l + 2].detach()) for l in range(L)])
+        t = inverse(flow) if inv else flow
         xc = _colmajor(x.detach())
-        y, lj = run_chain(flow, xc)
-        ctx.flow = flow
+        y, lj = run_chain(t, xc)
+        ctx.t, ctx.inv = t, inv
         ctx.save_for_backward(xc)
         return y, lj
 
@@ -115,11 +116,13 @@ class _RadialChainFn(torch.autograd.Function):
         (xc,) = ctx.saved_tensors
         D, N = xc.shape
         yb = _colmajor(ybar) if ybar is not None else _colmajor(torch.zeros((D, N), device=xc.device))
-        xbar, grads = radial_chain_vjp(ctx.flow, xc, yb, ljbar.contiguous() if ljbar is not None else None)
+        xbar, grads = radial_chain_vjp(ctx.t, xc, yb, ljbar.contiguous() if ljbar is not None else None)
+        if ctx.inv:  # application order of inverse(flow) is the flow's layers reversed
+            grads = grads[::-1]
         flat: List[torch.Tensor] = []
         for g in grads:
             flat += [g["α_"], g["β"], g["z_0"]]
-        return (xbar, *flat)
+        return (xbar, None, *flat)
 
 
 class RadialFlow(torch.nn.Module):
@@ -134,10 +137,18 @@ class RadialFlow(torch.nn.Module):
         self.z_0 = torch.nn.ParameterList([mk(dims) for _ in range(n_layers)])
 
     def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        return _RadialChainFn.apply(x, False, *self._abz())
+
+    def _abz(self):
         abz = []
         for a, b, z in zip(self.alpha_, self.beta, self.z_0):
             abz += [a, b, z]
-        return _RadialChainFn.apply(x, *abz)
+        return abz
+
+    def inverse(self, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """with_logabsdet_jacobian(inverse(flow), y), differentiable (compute_r through its implicit rule): the
+        logpdf / NLL path of a radial flow."""
+        return _RadialChainFn.apply(y, True, *self._abz())
 
 
 # ---- RealNVP: affine Coupling + eval-mode InvertibleBatchNorm blocks (BASELINE config 5) ---------------------------------

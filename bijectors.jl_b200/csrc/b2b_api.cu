@@ -601,7 +601,7 @@ extern "C" int b2b_radial_chain_vjp_f32(const b2b_layer_desc* layers, int32_t L,
   }
   if (!x || !ybar || !xbar || ldx < D || ldybar < D || ldxbar < D) return B2B_EINVAL;
   for (int l = 0; l < L; ++l) {
-    if (layers[l].kind != B2B_RADIAL || layers[l].inverse) return B2B_EUNSUPPORTED;
+    if (layers[l].kind != B2B_RADIAL) return B2B_EUNSUPPORTED;
     const int rc = validate_layer(layers[l], D, false);
     if (rc != B2B_OK) return rc;
   }

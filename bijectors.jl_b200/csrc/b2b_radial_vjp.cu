@@ -1,5 +1,7 @@
-// Reverse mode (VJP) of with_logabsdet_jacobian through a ∘-chain of RadialLayers, forward direction
-// (src/bijectors/radial_layer.jl:43-53,58-72): what the reference's AD computes when a radial flow is trained.
+// Reverse mode (VJP) of with_logabsdet_jacobian through a ∘-chain of RadialLayers, each applied forward
+// (src/bijectors/radial_layer.jl:43-53,58-72) or as Inverse(layer) (:88-102,124-129; compute_r differentiated with the
+// implicit-function rule) -- what the reference's AD computes when a radial flow is trained, on the sampling path
+// (forward chain), the logpdf / NLL path (inverse(flow)) or any mix.
 //
 // Per layer, with δ = z − z0, r = ‖δ‖, h = 1/(α+r), s = β̂h, q = β̂ r h²:   y = z + sδ,
 // logjac = (D−1)·log(1+s) + log(1+s−q).  Given the cotangents ȳ (D x N) and l̄ (N):
@@ -31,9 +33,11 @@ __global__ void __launch_bounds__(RV_THREADS, 2)
   const int D = P.D, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = RV_THREADS / 32;
   __shared__ float red[8 * 128 + 16];  // L x D + 2L (D <= 128, L <= 8)
   float alpha[L], bhat[L], z0r[L][V];
+  bool inv[L];
 #pragma unroll
   for (int l = 0; l < L; ++l) {
     const b2b_layer_desc& d = P.layers[l];
+    inv[l] = d.inverse != 0;                  // Inverse(layer): radial_layer.jl:88-102,124-129
     alpha[l] = softplus(d.p0[0]);             // radial_layer.jl:44
     bhat[l] = softplus(d.p1[0]) - alpha[l];   // :45
 #pragma unroll
@@ -49,7 +53,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2)
   const float dm1 = (float)(D - 1);
   const long long gw = (long long)blockIdx.x * nwarps + warp, stride = (long long)gridDim.x * nwarps;
   for (long long c0 = gw * CI; c0 < P.N; c0 += stride * CI) {
-    float z[CI][V], yb[CI][V], lb[CI], dl[CI][L][V], rr[CI][L];
+    float z[CI][V], yb[CI][V], lb[CI], dl[CI][L][V], rr[CI][L], gm[CI][L];
 #pragma unroll
     for (int ci = 0; ci < CI; ++ci) {
       const long long c = c0 + ci;
@@ -77,11 +81,23 @@ __global__ void __launch_bounds__(RV_THREADS, 2)
         // LinearAlgebra.norm, radial_layer.jl:47-49.  MUFU-based sqrt / reciprocals (<= 2 ulp): the IEEE division and
         // square-root sequences (with their slow-path calls) made this kernel instruction-bound at 1750 instructions
         // per column
-        const float r = r2 > 0.f ? r2 * rsqrtf(r2) : 0.f;
-        rr[ci][l] = r;
-        const float s = bhat[l] * __fdividef(1.0f, alpha[l] + r);
+        const float nrm = r2 > 0.f ? r2 * rsqrtf(r2) : 0.f;
+        gm[ci][l] = nrm;
+        if (!inv[l]) {
+          rr[ci][l] = nrm;
+          const float s = bhat[l] * __fdividef(1.0f, alpha[l] + nrm);
 #pragma unroll
-        for (int v = 0; v < V; ++v) z[ci][v] = fmaf(s, dl[ci][l][v], z[ci][v]);  // :51
+          for (int v = 0; v < V; ++v) z[ci][v] = fmaf(s, dl[ci][l][v], z[ci][v]);  // :51
+        } else {
+          // compute_r (:124-129): the positive root of r² + (A − γ) r − αγ, without cancellation
+          const float A = alpha[l] + bhat[l], a = A - nrm;
+          const float sq = sqrtf(fmaf(a, a, 4.0f * alpha[l] * nrm));
+          const float r = a > 0.f ? __fdividef(2.0f * alpha[l] * nrm, sq + a) : 0.5f * (sq - a);
+          rr[ci][l] = r;
+          const float rho = (alpha[l] + r) * __fdividef(1.0f, A + r);  // :96
+#pragma unroll
+          for (int v = 0; v < V; ++v) z[ci][v] = fmaf(rho, dl[ci][l][v], z0r[l][v]);
+        }
       }
     }
     // reverse sweep
@@ -95,6 +111,31 @@ __global__ void __launch_bounds__(RV_THREADS, 2)
         dot = warp_sum(dot);
         const float r = rr[ci][l], h = __fdividef(1.0f, alpha[l] + r), s = bhat[l] * h, q = bhat[l] * r * h * h;
         const float i1 = __fdividef(1.0f, 1.0f + s), i2 = __fdividef(1.0f, 1.0f + s - q);
+        if (inv[l]) {
+          // Inverse(layer): z = z0 + ρ δy, lj = −F(r); r differentiated implicitly (m = 2r + A − γ):
+          // ∂r/∂γ = (α+r)/m, ∂r/∂α = γ/m, ∂r/∂A = −r/m  (oracle: radial_chain_vjp_dir)
+          const float A = alpha[l] + bhat[l], gam = gm[ci][l];
+          const float iAr = __fdividef(1.0f, A + r), rho = (alpha[l] + r) * iAr;
+          const float Fs = fmaf(dm1, i1, i2), Fq = -i2, Fb = -lb[ci];
+          const float bh2 = bhat[l] * h * h, bh3r = 2.0f * bhat[l] * r * h * h * h;
+          const float dF_dr = fmaf(Fs, -bh2, Fq * (bh2 - bh3r));
+          const float dF_da = fmaf(Fs, -bh2, Fq * -bh3r);
+          const float dF_db = fmaf(Fs, h, Fq * r * h * h);
+          const float r_bar = fmaf(dot * bhat[l], iAr * iAr, Fb * dF_dr);
+          const float im = __fdividef(1.0f, 2.0f * r + A - gam);
+          const float A_bar = fmaf(-dot * (alpha[l] + r), iAr * iAr, -r_bar * r * im);
+          acc_a[l] += fmaf(dot, iAr, fmaf(Fb, dF_da, r_bar * gam * im)) + A_bar;
+          acc_b[l] += fmaf(Fb, dF_db, A_bar);
+          const float gam_bar = r_bar * (alpha[l] + r) * im;
+          const float kap = gam > 0.f ? gam_bar * __fdividef(1.0f, gam) : 0.f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const float dyb = fmaf(yb[ci][v], rho, kap * dl[ci][l][v]);
+            acc_z0[l][v] += yb[ci][v] - dyb;
+            yb[ci][v] = dyb;
+          }
+          continue;
+        }
         const float s_tot = fmaf(lb[ci], fmaf(dm1, i1, i2), dot);
         const float q_bar = -lb[ci] * i2;
         const float bh_bar = fmaf(s_tot, h, q_bar * r * h * h);
@@ -197,7 +238,7 @@ int b2b_launch_radial_chain_vjp(const B2BChainParams& p, const float* ybar, long
   const int L = p.L, D = p.D;
   if (L < 1 || L > 8 || D > 128) return B2B_EUNSUPPORTED;
   for (int l = 0; l < L; ++l)
-    if (p.layers[l].kind != B2B_RADIAL || p.layers[l].inverse) return B2B_EUNSUPPORTED;
+    if (p.layers[l].kind != B2B_RADIAL) return B2B_EUNSUPPORTED;
   if (!workspace || workspace_bytes < b2b_radial_vjp_workspace(L, D)) return B2B_EWORKSPACE;
   char* ws = static_cast<char*>(workspace);
   ws += (256 - (reinterpret_cast<uintptr_t>(ws) & 255)) & 255;

@@ -551,16 +551,17 @@ def planar_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[tor
 
 
 def radial_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[torch.Tensor] = None):
-    """Vector-Jacobian product of ``with_logabsdet_jacobian(t, x)`` for a ∘-chain ``t`` of (≤ 8) RadialLayers (forward
-    direction, D ≤ 128).  Returns ``(xbar, grads)`` with ``grads`` = list of ``{"α_": …, "β": …, "z_0": …}`` per layer
-    (cotangents of the RAW parameters, summed over the columns)."""
+    """Vector-Jacobian product of ``with_logabsdet_jacobian(t, x)`` for a ∘-chain ``t`` of (≤ 8) RadialLayers, D ≤ 128 --
+    a flow, ``inverse(flow)`` (the logpdf / NLL path; ``x`` is then the observed batch) or a mix of directions.  Returns
+    ``(xbar, grads)`` with ``grads`` = list of ``{"α_": …, "β": …, "z_0": …}`` per layer in APPLICATION order (cotangents of
+    the RAW parameters, summed over the columns)."""
     D, N, ldx = _batch_view(x)
     Dy, Ny, ldyb = _batch_view(ybar)
     if (Dy, Ny) != (D, N) or not x.is_cuda or not ybar.is_cuda or x.dim() != 2:
         raise ValueError("radial_chain_vjp: x and ybar must be device matrices of the same D×N shape")
     descs = list(t._descs(False, D, x.dtype))
-    if any(d.kind != _lib.RADIAL or d.inverse for d in descs):
-        raise B2BError(_lib.B2B_EUNSUPPORTED, "radial_chain_vjp: forward RadialLayers only")
+    if any(d.kind != _lib.RADIAL for d in descs):
+        raise B2BError(_lib.B2B_EUNSUPPORTED, "radial_chain_vjp: RadialLayers (forward, Inverse, or mixed)")
     L = len(descs)
     arr = _desc_array(descs)
     if ljbar is not None and (ljbar.numel() != N or ljbar.dtype != torch.float32 or not ljbar.is_contiguous()):

@@ -189,8 +189,9 @@ int b2b_planar_chain_vjp_f32(const b2b_layer_desc* layers, int32_t L, const floa
                              const float* ljbar, float* xbar, float* wbar, float* ubar, float* bbar, int32_t D,
                              int64_t N, int64_t ldx, int64_t ldybar, int64_t ldxbar, void* workspace,
                              size_t workspace_bytes, void* stream);
-/* Reverse mode of with_logabsdet_jacobian through a ∘-chain of L <= 8 RadialLayers, forward direction
- * (radial_layer.jl:43-53,58-72 differentiated as the reference's AD does): inputs as for b2b_planar_chain_vjp_f32;
+/* Reverse mode of with_logabsdet_jacobian through a ∘-chain of L <= 8 RadialLayers, each layer forward or Inverse
+ * (radial_layer.jl:43-53,58-72 / :88-102,124-129 differentiated as the reference's AD does; compute_r by the
+ * implicit-function rule; directions may be mixed): inputs as for b2b_planar_chain_vjp_f32;
  * outputs `xbar` (D x N, may alias `ybar`) and the parameter cotangents summed over the columns: `alpha_bar`, `beta_bar`
  * (L each, w.r.t. the RAW parameters α_, β: the log1pexp transforms of :44-45 are differentiated through) and `z0_bar`
  * (L x D).  Any D <= 128.  Workspace: b2b_radial_chain_vjp_workspace_bytes. */

@@ -378,6 +378,81 @@ def radial_chain_vjp(params, x, ybar, ljbar):
     return yb.astype(dt), grads
 
 
+def radial_chain_vjp_dir(params, inverse_flags, x, ybar, ljbar):
+    """radial_chain_vjp for a chain whose layers are applied in EITHER direction (inverse_flags[l] true = Inverse(layer l),
+    radial_layer.jl:88-102,124-129): the VJP a reference AD computes through inverse(flow) -- the logpdf / NLL path of a
+    radial flow -- or through mixed chains.  Application order = params order.  Returns (xbar, [(α_bar, β_bar, z0_bar)]).
+
+    Inverse layer, input y: δy = y − z0, γ = ‖δy‖, r = root of r² + (A−γ)r − αγ (A = α+β̂, compute_r :124-129),
+    ρ = (α+r)/(A+r), z = z0 + ρ δy, lj = −F(r), F = (D−1)·log(1+s) + log(1+s−q), s = β̂h, q = β̂ r h², h = 1/(α+r).
+    r is differentiated implicitly: m = 2r + A − γ, ∂r/∂γ = (α+r)/m, ∂r/∂α = γ/m, ∂r/∂A = −r/m."""
+    dt = x.dtype
+    D = x.shape[0]
+    zs, cache = [x], []
+    for (a_raw, be, z0), inv in zip(params, inverse_flags):
+        a_ = dt.type(np.asarray(a_raw).reshape(-1)[0])
+        b_ = dt.type(np.asarray(be).reshape(-1)[0])
+        z0 = z0.astype(dt)
+        alpha = dt.type(log1pexp(a_))
+        A = dt.type(log1pexp(b_))
+        beta_hat = dt.type(A - alpha)
+        delta = zs[-1] - z0[:, None]
+        nrm = np.sqrt(np.sum(delta * delta, axis=0))
+        if not inv:
+            r = nrm
+            s = beta_hat / (alpha + r)
+            zs.append(zs[-1] + s[None, :] * delta)
+        else:
+            a = A - nrm
+            r = 0.5 * (np.sqrt(a * a + 4 * alpha * nrm) - a)
+            rho = (alpha + r) / (A + r)
+            zs.append(z0[:, None] + rho[None, :] * delta)
+        cache.append((a_, b_, z0, alpha, beta_hat, A, delta, nrm, r, bool(inv)))
+    yb = ybar.astype(dt).copy()
+    grads = [None] * len(params)
+    sig = lambda v: dt.type(1) / (dt.type(1) + np.exp(-v))
+    for l in range(len(params) - 1, -1, -1):
+        a_, b_, z0, alpha, beta_hat, A, delta, nrm, r, inv = cache[l]
+        h = 1.0 / (alpha + r)
+        s = beta_hat * h
+        q = beta_hat * r * h * h
+        Fs = (D - 1) / (1 + s) + 1 / (1 + s - q)
+        Fq = -1 / (1 + s - q)
+        if not inv:
+            s_tot = np.sum(delta * yb, axis=0) + ljbar * Fs
+            q_bar = ljbar * Fq
+            bh_bar = s_tot * h + q_bar * r * h * h
+            h_bar = s_tot * beta_hat + q_bar * 2 * beta_hat * r * h
+            r_bar = q_bar * beta_hat * h * h - h_bar * h * h
+            alpha_bar = -h_bar * h * h
+            with np.errstate(divide="ignore", invalid="ignore"):
+                kappa = np.where(r > 0, r_bar / r, 0.0)
+            z0_bar = -(yb @ s + delta @ kappa)
+            yb = yb * (1 + s)[None, :] + delta * kappa[None, :]
+        else:
+            rho = (alpha + r) / (A + r)
+            rho_bar = np.sum(delta * yb, axis=0)
+            F_bar = -ljbar
+            dF_dr = Fs * (-beta_hat * h * h) + Fq * (beta_hat * h * h - 2 * beta_hat * r * h ** 3)
+            dF_da = Fs * (-beta_hat * h * h) + Fq * (-2 * beta_hat * r * h ** 3)
+            dF_db = Fs * h + Fq * (r * h * h)
+            r_bar = rho_bar * beta_hat / (A + r) ** 2 + F_bar * dF_dr
+            m = 2 * r + A - nrm
+            A_bar = rho_bar * (-(alpha + r) / (A + r) ** 2) + r_bar * (-r / m)
+            alpha_bar = rho_bar / (A + r) + F_bar * dF_da + r_bar * nrm / m + A_bar      # dA/dα = 1 at fixed β̂
+            bh_bar = F_bar * dF_db + A_bar                                                  # dA/dβ̂ = 1 at fixed α
+            gam_bar = r_bar * (alpha + r) / m
+            with np.errstate(divide="ignore", invalid="ignore"):
+                kappa = np.where(nrm > 0, gam_bar / nrm, 0.0)
+            dy_bar = yb * rho[None, :] + delta * kappa[None, :]
+            z0_bar = (yb - dy_bar).sum(axis=1)
+            yb = dy_bar
+        bh = np.sum(bh_bar)
+        al = np.sum(alpha_bar) - bh          # β̂ = log1pexp(β) − α
+        grads[l] = (dt.type(al * sig(a_)), dt.type(bh * sig(b_)), z0_bar.astype(dt))
+    return yb.astype(dt), grads
+
+
 def compute_r(y_minus_z0, alpha, alpha_plus_beta_hat):
     """src/bijectors/radial_layer.jl:124-129 (vector or per-column for a matrix)."""
     dt = y_minus_z0.dtype

@@ -1485,3 +1485,45 @@ def test_realnvp_trains_through_autograd(B):
         lo.backward()
         opt.step()
     assert float(flow.nll(y)) < l0
+
+
+@pytest.mark.parametrize("D,flags", [(64, (True,) * 6), (32, (True, False, True)), (128, (False, True, True, False)), (10, (True, True))])
+def test_radial_chain_vjp_inverse_and_mixed_directions(B, D, flags):
+    """Reverse mode through Inverse(RadialLayer) (compute_r by the implicit-function rule) and through chains that mix
+    directions, against the finite-difference-pinned float64 oracle (radial_chain_vjp_dir)."""
+    import torch
+
+    rng = np.random.default_rng(300 + D + len(flags))
+    N = 1777
+    pairs = [make_case("radial", D, rng) for _ in flags]
+    chain = B.Composed(*[(B.inverse(p[0]) if f else p[0]) for p, f in zip(pairs, flags)])
+    x, ybar, ljbar = rng.standard_normal((D, N)).astype(f32), rng.standard_normal((D, N)).astype(f32), rng.standard_normal(N).astype(f32)
+    xbar, grads = B.radial_chain_vjp(chain, B.from_numpy(x), B.from_numpy(ybar), torch.as_tensor(ljbar, device="cuda"))
+    oparams = [(p[1].params["alpha_raw"].astype(np.float64), p[1].params["beta"].astype(np.float64), p[1].params["z0"].astype(np.float64)) for p in pairs]
+    xo, go = O.radial_chain_vjp_dir(oparams, flags, x.astype(np.float64), ybar.astype(np.float64), ljbar.astype(np.float64))
+    assert rel(B.to_numpy(xbar), xo) <= RTOL, rel(B.to_numpy(xbar), xo)
+    for g, (ao, bo, zo) in zip(grads, go):
+        sc = np.sqrt(N)  # sums of N O(1) terms
+        assert abs(float(g["α_"]) - float(ao)) <= 5e-5 * max(abs(float(ao)), sc), (float(g["α_"]), float(ao))
+        assert abs(float(g["β"]) - float(bo)) <= 5e-5 * max(abs(float(bo)), sc), (float(g["β"]), float(bo))
+        assert rel(B.to_numpy(g["z_0"]), zo) <= 5e-5, rel(B.to_numpy(g["z_0"]), zo)
+    # the NLL path of a radial flow through autograd: gradients flow, the loss decreases
+    if D == 64:
+        torch.manual_seed(1)
+        flow = B.autograd.RadialFlow(D, 3)
+        y = torch.randn((N, D), device="cuda").t()
+
+        def nll():
+            xx, lj = flow.inverse(y)
+            return -((-0.5 * (xx * xx).sum(0)) + lj).sum()
+
+        l0 = nll()
+        l0.backward()
+        assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in flow.parameters())
+        opt = torch.optim.SGD(flow.parameters(), lr=1e-5)
+        for _ in range(10):
+            opt.zero_grad()
+            lo = nll()
+            lo.backward()
+            opt.step()
+        assert float(nll()) < float(l0)

@@ -368,3 +368,29 @@ def test_coupling_and_batchnorm_vjp_oracles_match_finite_differences(inverse):
     g = (lambda ps, xx: O.batchnorm_inverse(bn_of(ps), xx)) if inverse else (lambda ps, xx: O.batchnorm_forward(bn_of(ps), xx))
     xb, bb, lb = O.batchnorm_eval_vjp(bn_of([b, logs]), x, ybar, ljbar, inverse=inverse)
     _fd_vjp_check(g, [b, logs], x, ybar, ljbar, (xb, [bb, lb]))
+
+
+@pytest.mark.parametrize("flags", [(False, False, False), (True, True, True), (True, False, True)])
+def test_radial_vjp_oracle_both_directions_matches_finite_differences(flags):
+    """radial_chain_vjp_dir (inverse layers differentiate compute_r implicitly) against central finite differences of the
+    pinned forward / inverse oracles; the all-forward case reproduces radial_chain_vjp."""
+    rng = np.random.default_rng(21)
+    D, N = 6, 5
+    params = [[rng.standard_normal(1), rng.standard_normal(1), rng.standard_normal(D)] for _ in flags]
+    x, ybar, ljbar = rng.standard_normal((D, N)), rng.standard_normal((D, N)), rng.standard_normal(N)
+
+    def fwd(ps, xx):
+        lj = np.zeros(N)
+        for k, inv in enumerate(flags):
+            a, b, z0 = ps[3 * k], ps[3 * k + 1], ps[3 * k + 2]
+            xx, l = (O.radial_inverse(a, b, z0, xx) if inv else O.radial_forward(a, b, z0, xx))
+            lj = lj + l
+        return xx, lj
+
+    xbar, grads = O.radial_chain_vjp_dir([tuple(p) for p in params], flags, x, ybar, ljbar)
+    flat = [q for p in params for q in p]
+    pbars = [np.asarray(g).reshape(np.asarray(q).shape) for gs in grads for g, q in zip(gs, flat[:3])]
+    _fd_vjp_check(fwd, flat, x, ybar, ljbar, (xbar, pbars), h=1e-6, tol=5e-6)
+    if not any(flags):
+        xb0, g0 = O.radial_chain_vjp([tuple(p) for p in params], x, ybar, ljbar)
+        assert np.allclose(xb0, xbar) and all(np.allclose(a, b) for ga, gb in zip(g0, grads) for a, b in zip(ga, gb))
