@@ -172,6 +172,182 @@ __global__ void __launch_bounds__(CV_THREADS, 1) coupling_vjp_kernel(const __gri
   if ((int)threadIdx.x < m2) part[(size_t)m2 * n2 + threadIdx.x] = cacc;
 }
 
+// ---- register-tiled version for n1, n2 multiples of 4 (the RealNVP shapes) -----------------------------------------------
+// Same three GEMMs, each FMA-bound instead of load-bound: tiles padded to 36 floats so that every operand is a float4,
+//   [s; t]   thread = 4 s rows + the matching 4 t rows x 4 columns: per k two float4 of W (L1) + one float4 of x₂ -> 32 FMA
+//   x̄₂       thread = 4 rows of x₂ x 4 columns: per 4 j four float4 of W + four float4 of [s̄; t̄]              -> 64 FMA
+//   W̄        warp = 32 rows of [s̄; t̄], lane = 4 rows of x₂: per 4 columns 32 broadcast float4 + 4 float4     -> 512 FMA
+constexpr int CF_LD = CV_TC + 4;
+
+__device__ __forceinline__ float4 ld4s(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4g(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float (&a)[4], float w, const float4& x) {
+  a[0] = fmaf(w, x.x, a[0]);
+  a[1] = fmaf(w, x.y, a[1]);
+  a[2] = fmaf(w, x.z, a[2]);
+  a[3] = fmaf(w, x.w, a[3]);
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(CV_THREADS, 1) coupling_vjp_fast_kernel(const __grid_constant__ CvParams P) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int D = P.D, n1 = P.n1, n2 = P.n2, m2 = 2 * n1;
+  float* X = smem_f;                       // [D][CF_LD]
+  float* YB = X + (size_t)D * CF_LD;       // [D][CF_LD]
+  float* SB = YB + (size_t)D * CF_LD;      // [2n1][CF_LD]
+  float* LB = SB + (size_t)m2 * CF_LD;     // [CV_TC]
+  int* s1 = reinterpret_cast<int*>(LB + CV_TC);
+  int* s2 = s1 + n1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rg = threadIdx.x >> 3, c4 = 4 * (threadIdx.x & 7);
+  for (int k = threadIdx.x; k < n1; k += CV_THREADS) s1[k] = P.idx1 ? P.idx1[k] : P.row1 + k;
+  for (int k = threadIdx.x; k < n2; k += CV_THREADS) s2[k] = P.idx2 ? P.idx2[k] : P.row2 + k;
+  const long long tiles = (P.N + CV_TC - 1) / CV_TC;
+  const int ldw = m2;
+  float acc[32][4];
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+  float cacc = 0.f;
+
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long col0 = tile * CV_TC;
+    __syncthreads();
+    for (int cidx = warp; cidx < CV_TC; cidx += CV_THREADS / 32) {
+      const long long col = col0 + cidx;
+      const bool ok = col < P.N;
+      for (int r = lane; r < D; r += 32) {
+        X[r * CF_LD + cidx] = ok ? __ldcs(P.x + col * P.ldx + r) : 0.f;
+        YB[r * CF_LD + cidx] = ok ? __ldcs(P.ybar + col * P.ldyb + r) : 0.f;
+      }
+      if (lane == 0) LB[cidx] = (ok && P.ljbar) ? P.ljbar[col] : 0.f;
+    }
+    __syncthreads();
+    // ---- [s; t] = W·x₂ + c and the elementwise cotangents ------------------------------------------------------------
+    if (4 * rg < n1) {
+      float sv[4][4], tv[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sv[i][q] = tv[i][q] = 0.f;
+      const float* Wp = P.W + 4 * rg;
+#pragma unroll 4
+      for (int k = 0; k < n2; ++k) {
+        const float4 xv = ld4s(X + s2[k] * CF_LD + c4);
+        const float4 ws = ld4g(Wp + (size_t)k * ldw), wt = ld4g(Wp + (size_t)k * ldw + n1);
+        fma4(sv[0], ws.x, xv);
+        fma4(sv[1], ws.y, xv);
+        fma4(sv[2], ws.z, xv);
+        fma4(sv[3], ws.w, xv);
+        fma4(tv[0], wt.x, xv);
+        fma4(tv[1], wt.y, xv);
+        fma4(tv[2], wt.z, xv);
+        fma4(tv[3], wt.w, xv);
+      }
+      const float4 lb4 = ld4s(LB + c4);
+      const float lbv[4] = {lb4.x, lb4.y, lb4.z, lb4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 4 * rg + i;
+        const float cs = P.c ? P.c[j] : 0.f, ct = P.c ? P.c[n1 + j] : 0.f;
+        const int r1 = s1[j];
+        const float4 in4 = ld4s(X + r1 * CF_LD + c4), cb4 = ld4s(YB + r1 * CF_LD + c4);
+        const float in1[4] = {in4.x, in4.y, in4.z, in4.w}, cb1[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
+        float out1[4], sbar[4], tbar[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float s_ = sv[i][q] + cs, t_ = tv[i][q] + ct;
+          if (!INV) {
+            const float e = expf(s_);
+            out1[q] = e * cb1[q];
+            sbar[q] = fmaf(cb1[q] * e, in1[q], lbv[q]);
+            tbar[q] = cb1[q];
+          } else {
+            const float em = expf(-s_);
+            const float x1 = (in1[q] - t_) * em;
+            out1[q] = em * cb1[q];
+            sbar[q] = -fmaf(x1, cb1[q], lbv[q]);
+            tbar[q] = -out1[q];
+          }
+        }
+        *reinterpret_cast<float4*>(YB + r1 * CF_LD + c4) = make_float4(out1[0], out1[1], out1[2], out1[3]);
+        *reinterpret_cast<float4*>(SB + j * CF_LD + c4) = make_float4(sbar[0], sbar[1], sbar[2], sbar[3]);
+        *reinterpret_cast<float4*>(SB + (n1 + j) * CF_LD + c4) = make_float4(tbar[0], tbar[1], tbar[2], tbar[3]);
+      }
+    }
+    __syncthreads();
+    // ---- x̄₂ = ȳ₂ + Wᵀ[s̄; t̄] -------------------------------------------------------------------------------------------
+    if (4 * rg < n2) {
+      float a[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[i][q] = 0.f;
+      const float* Wk = P.W + (size_t)(4 * rg) * ldw;
+#pragma unroll 2
+      for (int j = 0; j < m2; j += 4) {
+        const float4 sb0 = ld4s(SB + (j + 0) * CF_LD + c4), sb1 = ld4s(SB + (j + 1) * CF_LD + c4);
+        const float4 sb2 = ld4s(SB + (j + 2) * CF_LD + c4), sb3 = ld4s(SB + (j + 3) * CF_LD + c4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 w = ld4g(Wk + (size_t)i * ldw + j);
+          fma4(a[i], w.x, sb0);
+          fma4(a[i], w.y, sb1);
+          fma4(a[i], w.z, sb2);
+          fma4(a[i], w.w, sb3);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float* dst = YB + s2[4 * rg + i] * CF_LD + c4;
+        const float4 o = ld4s(dst);
+        *reinterpret_cast<float4*>(dst) = make_float4(o.x + a[i][0], o.y + a[i][1], o.z + a[i][2], o.w + a[i][3]);
+      }
+    }
+    // ---- W̄ += [s̄; t̄]·x₂ᵀ over the tile's columns (ascending); c̄ += Σ columns -----------------------------------------
+    {
+      const int rbase = 32 * warp;
+      if (rbase < m2) {
+        int xr[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xr[q] = (lane + 32 * q < n2) ? s2[lane + 32 * q] * CF_LD : -1;
+        for (int cidx = 0; cidx < CV_TC; cidx += 4) {
+          float4 b[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) b[q] = xr[q] >= 0 ? ld4s(X + xr[q] + cidx) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float4 av = (rbase + i < m2) ? ld4s(SB + (rbase + i) * CF_LD + cidx) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              acc[i][q] = fmaf(av.w, b[q].w, fmaf(av.z, b[q].z, fmaf(av.y, b[q].y, fmaf(av.x, b[q].x, acc[i][q]))));
+          }
+        }
+      }
+      if ((int)threadIdx.x < m2) {
+        float t = 0.f;
+        for (int cidx = 0; cidx < CV_TC; ++cidx) t += SB[threadIdx.x * CF_LD + cidx];
+        cacc += t;
+      }
+    }
+    __syncthreads();
+    for (int cidx = warp; cidx < CV_TC; cidx += CV_THREADS / 32) {
+      const long long col = col0 + cidx;
+      if (col < P.N)
+        for (int r = lane; r < D; r += 32) __stcs(P.xbar + col * P.ldxb + r, YB[r * CF_LD + cidx]);
+    }
+  }
+  float* part = P.part + (size_t)blockIdx.x * ((size_t)m2 * n2 + m2);
+  const int rbase = 32 * warp;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (rbase + i < m2 && lane + 32 * q < n2) part[(size_t)(lane + 32 * q) * m2 + rbase + i] = acc[i][q];
+  if ((int)threadIdx.x < m2) part[(size_t)m2 * n2 + threadIdx.x] = cacc;
+}
+
 // out[e] = Σ_cta part[cta][e], fixed order
 __global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ part, int nparts, int len, float* __restrict__ out0,
                                                           int len0, float* __restrict__ out1) {
@@ -185,7 +361,7 @@ __global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restric
 
 // ---- eval-mode InvertibleBatchNorm -------------------------------------------------------------------------------------
 // y = A(x − m) + b, A = e^logs / sqrt(v + eps) (normalise.jl:61-67).  forward: x̄ = A ȳ, b̄ = Σ ȳ, l̄ogs = Σ ȳ⊙(y − b) + Σ l̄;
-// inverse: ȳ = x̄ / A, b̄ = −Σ x̄/A, l̄ogs = −Σ x̄⊙(x − m) − Σ l̄.  Warp per column, lane r owns rows r, r+32, ...
+// inverse: ȳ = x̄ / A, b̄ = −Σ x̄/A, l̄ogs = −Σ x̄⊙(x − m) − Σ l̄.
 struct BvParams {
   const float* x;
   const float* ybar;
@@ -198,82 +374,108 @@ struct BvParams {
   int D, inverse;
 };
 
-constexpr int BV_MAXR = 32;  // rows per lane: D <= 1024
+constexpr int BV_U = 4;
 
+// Thread = one row (RPT rows 256 apart when D > 256) of a slab of columns, U columns at a time; the row's two partial sums
+// stay in registers, slabs are summed in shared memory, CTAs by the finalize kernel -- fixed order throughout.
+template <int RPT>
 __global__ void __launch_bounds__(256) bn_eval_vjp_kernel(const __grid_constant__ BvParams P) {
-  extern __shared__ float sm[];  // [8 warps][2D + 1]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, D = P.D;
-  const int nr = (D + 31) / 32;
-  float A[BV_MAXR], sh[BV_MAXR], gb[BV_MAXR], gl[BV_MAXR];
+  extern __shared__ float bsm[];  // [nslab][2D + 1]
+  const int D = P.D, Dp = RPT == 1 ? ((D + 31) & ~31) : 256, nslab = 256 / Dp;
+  const int slab = threadIdx.x / Dp, i = threadIdx.x - slab * Dp;
+  float A[RPT], sh[RPT], gb[RPT], gl[RPT];
 #pragma unroll
-  for (int i = 0; i < BV_MAXR; ++i) {
-    const int r = lane + 32 * i;
-    gb[i] = gl[i] = 0.f;
-    if (i < nr && r < D) {
-      A[i] = expf(P.logs[r]) / sqrtf(P.v[r] + P.eps);
-      sh[i] = P.inverse ? P.b[r] : P.m[r];  // the shift removed before scaling: y − b (inverse) / x − m (forward)
-    } else {
-      A[i] = 1.f;
-      sh[i] = 0.f;
+  for (int j = 0; j < RPT; ++j) {
+    const int r = i + 256 * j;
+    gb[j] = gl[j] = 0.f;
+    A[j] = 1.f;
+    sh[j] = 0.f;
+    if (r < D) {
+      A[j] = expf(P.logs[r]) / sqrtf(P.v[r] + P.eps);
+      sh[j] = P.inverse ? P.b[r] : P.m[r];  // the shift removed before scaling: y − b (inverse) / x − m (forward)
     }
   }
   float lsum = 0.f;
-  for (long long n = (long long)blockIdx.x * 8 + warp; n < P.N; n += (long long)gridDim.x * 8) {
+  const long long per = (P.N + gridDim.x - 1) / gridDim.x;
+  const long long c0 = (long long)blockIdx.x * per, c1 = (c0 + per < P.N) ? c0 + per : P.N;
+  if (slab < nslab) {
+    for (long long n0 = c0 + slab; n0 < c1; n0 += (long long)BV_U * nslab) {
+      float xv[BV_U][RPT], cb[BV_U][RPT];
 #pragma unroll
-    for (int i = 0; i < BV_MAXR; ++i) {
-      const int r = lane + 32 * i;
-      if (i < nr && r < D) {
-        const float xv = P.x[n * P.ldx + r], cb = P.ybar[n * P.ldyb + r];
-        if (!P.inverse) {
-          P.xbar[n * P.ldxb + r] = A[i] * cb;
-          gb[i] += cb;
-          gl[i] = fmaf(cb, A[i] * (xv - sh[i]), gl[i]);  // ȳ ⊙ (y − b)
-        } else {
-          const float o = cb / A[i];
-          P.xbar[n * P.ldxb + r] = o;
-          gb[i] -= o;
-          gl[i] = fmaf(-cb, (xv - sh[i]) / A[i], gl[i]);  // −x̄ ⊙ (x − m)
+      for (int u = 0; u < BV_U; ++u) {
+        const long long n = n0 + (long long)u * nslab;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const int r = i + 256 * j;
+          const bool ok = n < c1 && r < D;
+          xv[u][j] = ok ? __ldcs(P.x + n * P.ldx + r) : sh[j];
+          cb[u][j] = ok ? __ldcs(P.ybar + n * P.ldyb + r) : 0.f;
+        }
+        if (i == 0 && P.ljbar && n < c1) lsum += P.ljbar[n];
+      }
+#pragma unroll
+      for (int u = 0; u < BV_U; ++u) {
+        const long long n = n0 + (long long)u * nslab;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+          const int r = i + 256 * j;
+          if (n < c1 && r < D) {
+            if (!P.inverse) {
+              __stcs(P.xbar + n * P.ldxb + r, A[j] * cb[u][j]);
+              gb[j] += cb[u][j];
+              gl[j] = fmaf(cb[u][j], A[j] * (xv[u][j] - sh[j]), gl[j]);  // ȳ ⊙ (y − b)
+            } else {
+              const float o = cb[u][j] / A[j];
+              __stcs(P.xbar + n * P.ldxb + r, o);
+              gb[j] -= o;
+              gl[j] = fmaf(-cb[u][j], (xv[u][j] - sh[j]) / A[j], gl[j]);  // −x̄ ⊙ (x − m)
+            }
+          }
         }
       }
     }
-    if (lane == 0 && P.ljbar) lsum += P.ljbar[n];
-  }
-  float* mine = sm + (size_t)warp * (2 * D + 1);
+    float* mine = bsm + (size_t)slab * (2 * D + 1);
 #pragma unroll
-  for (int i = 0; i < BV_MAXR; ++i) {
-    const int r = lane + 32 * i;
-    if (i < nr && r < D) {
-      mine[r] = gb[i];
-      mine[D + r] = gl[i];
+    for (int j = 0; j < RPT; ++j) {
+      const int r = i + 256 * j;
+      if (r < D) {
+        mine[r] = gb[j];
+        mine[D + r] = gl[j];
+      }
     }
+    if (i == 0) mine[2 * D] = lsum;
   }
-  if (lane == 0) mine[2 * D] = lsum;
   __syncthreads();
   for (int e = threadIdx.x; e < 2 * D + 1; e += blockDim.x) {
     float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += sm[(size_t)w * (2 * D + 1) + e];
+    for (int w = 0; w < nslab; ++w) t += bsm[(size_t)w * (2 * D + 1) + e];
     P.part[(size_t)blockIdx.x * (2 * D + 1) + e] = t;
   }
 }
 
-// bbar[r] = Σ parts, logsbar[r] = Σ parts ± Σ l̄
-__global__ void bn_vjp_finalize_kernel(const float* __restrict__ part, int nparts, int D, int inverse, float* __restrict__ bbar,
-                                       float* __restrict__ logsbar) {
-  __shared__ float ls;
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int p = 0; p < nparts; ++p) t += part[(size_t)p * (2 * D + 1) + 2 * D];
-    ls = t;
-  }
+// bbar[r] = Σ parts, logsbar[r] = Σ parts ± Σ l̄; block (32, 8): 8 strided sub-sums per element, then those in order
+__global__ void __launch_bounds__(256) bn_vjp_finalize_kernel(const float* __restrict__ part, int nparts, int D, int inverse,
+                                                              float* __restrict__ bbar, float* __restrict__ logsbar) {
+  __shared__ float sub[8][32];
+  __shared__ float lsm[256];
+  const int len = 2 * D + 1, e = blockIdx.x * 32 + threadIdx.x, q = threadIdx.y * 32 + threadIdx.x;
+  float t = 0.f, l = 0.f;
+  if (e < 2 * D)
+    for (int p = threadIdx.y; p < nparts; p += 8) t += part[(size_t)p * len + e];
+  for (int p = q; p < nparts; p += 256) l += part[(size_t)p * len + 2 * D];
+  sub[threadIdx.y][threadIdx.x] = t;
+  lsm[q] = l;
   __syncthreads();
-  for (int r = threadIdx.x; r < D; r += blockDim.x) {
-    float tb = 0.f, tl = 0.f;
-    for (int p = 0; p < nparts; ++p) {
-      tb += part[(size_t)p * (2 * D + 1) + r];
-      tl += part[(size_t)p * (2 * D + 1) + D + r];
+  if (threadIdx.y == 0 && e < 2 * D) {
+    float r = 0.f, ls = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += sub[k][threadIdx.x];
+    if (e < D) {
+      bbar[e] = r;
+    } else {
+      for (int k = 0; k < 256; ++k) ls += lsm[k];
+      logsbar[e - D] = r + (inverse ? -ls : ls);
     }
-    bbar[r] = tb;
-    logsbar[r] = tl + (inverse ? -ls : ls);
   }
 }
 
@@ -333,9 +535,13 @@ extern "C" int b2b_coupling_affine_vjp_f32(const b2b_layer_desc* layer, const fl
   const long long tiles = (N + CV_TC - 1) / CV_TC;
   long long grid = sm_count();
   if (grid > tiles) grid = tiles;
-  const size_t smem = ((size_t)2 * D * CV_LD + (size_t)2 * n1 * CV_LD + CV_TC) * sizeof(float) + (size_t)(n1 + n2) * sizeof(int);
+  // float4 path: n1, n2 multiples of 4 and a 16-byte aligned W (its leading dimension 2·n1 is then a multiple of 4 too)
+  const bool fast = n1 % 4 == 0 && n2 % 4 == 0 && (reinterpret_cast<uintptr_t>(d.p0) & 15) == 0;
+  const int ld = fast ? CF_LD : CV_LD;
+  const size_t smem = ((size_t)2 * D * ld + (size_t)2 * n1 * ld + CV_TC) * sizeof(float) + (size_t)(n1 + n2) * sizeof(int);
   if (smem > 220 * 1024) return B2B_EUNSUPPORTED;
-  auto kernel = d.inverse ? coupling_vjp_kernel<true> : coupling_vjp_kernel<false>;
+  void (*kernel)(const CvParams) = fast ? (d.inverse ? coupling_vjp_fast_kernel<true> : coupling_vjp_fast_kernel<false>)
+                                        : (d.inverse ? coupling_vjp_kernel<true> : coupling_vjp_kernel<false>);
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   kernel<<<(int)grid, CV_THREADS, smem, stream>>>(P);
@@ -348,7 +554,7 @@ extern "C" int b2b_coupling_affine_vjp_f32(const b2b_layer_desc* layer, const fl
 
 extern "C" size_t b2b_batchnorm_eval_vjp_workspace_bytes(int32_t D) {
   if (D < 1 || D > 1024) return 0;
-  return (size_t)b2b::sm_count() * 2 * (size_t)(2 * D + 1) * sizeof(float) + 256;
+  return (size_t)b2b::sm_count() * 4 * (size_t)(2 * D + 1) * sizeof(float) + 256;
 }
 
 extern "C" int b2b_batchnorm_eval_vjp_f32(const b2b_layer_desc* layer, const float* x, const float* ybar, const float* ljbar,
@@ -387,15 +593,17 @@ extern "C" int b2b_batchnorm_eval_vjp_f32(const b2b_layer_desc* layer, const flo
   P.ldxb = ldxbar;
   P.D = D;
   P.inverse = d.inverse ? 1 : 0;
-  long long grid = (long long)sm_count() * 2;
-  const long long want = (N + 7) / 8;
+  const int rpt = (D + 255) / 256, Dp = rpt == 1 ? ((D + 31) & ~31) : 256, nslab = 256 / Dp;
+  long long grid = (long long)sm_count() * 4;
+  const long long want = (N + (long long)nslab * BV_U - 1) / ((long long)nslab * BV_U);
   if (grid > want) grid = want;
-  const size_t smem = (size_t)8 * (2 * D + 1) * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(bn_eval_vjp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)nslab * (2 * D + 1) * sizeof(float);
+  void (*kernel)(const BvParams) = rpt == 1   ? bn_eval_vjp_kernel<1>
+                                   : rpt == 2 ? bn_eval_vjp_kernel<2>
+                                              : bn_eval_vjp_kernel<4>;
+  kernel<<<(int)grid, 256, smem, stream>>>(P);
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  bn_eval_vjp_kernel<<<(int)grid, 256, smem, stream>>>(P);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
-  bn_vjp_finalize_kernel<<<1, 256, 0, stream>>>(P.part, (int)grid, D, P.inverse, bbar, logsbar);
+  bn_vjp_finalize_kernel<<<(2 * D + 31) / 32, dim3(32, 8), 0, stream>>>(P.part, (int)grid, D, P.inverse, bbar, logsbar);
   return (int)cudaGetLastError();
 }

@@ -634,6 +634,26 @@ def batchnorm_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[torch.
     return xbar, {"b": bbar, "logs": lbar}
 
 
+def rqs_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[torch.Tensor] = None):
+    """Vector-Jacobian product of ``with_logabsdet_jacobian(t, x)`` for ONE RationalQuadraticSpline ``t`` (or its inverse,
+    with ``x`` the observed batch): b2b_rqs_vjp_f32.  Returns ``(xbar, {"widths": W̄, "heights": H̄, "derivatives": D̄})``,
+    the cotangents of the processed (D × K+1) knot arrays, summed over the columns of this batch."""
+    d, D, N, ldx, ldyb = _layer_vjp(t, x, ybar, ljbar, _lib.RQS, "rqs_vjp")
+    K1 = d.n0
+    xbar = colmajor_empty(D, N, x.device)
+    bars = [torch.empty((K1, D), dtype=torch.float32, device=x.device) for _ in range(3)]  # column-major (D × K1)
+    L_ = lib()
+    ws_bytes = L_.b2b_rqs_vjp_workspace_bytes(K1, D)
+    if ws_bytes == 0:
+        raise B2BError(_lib.B2B_EUNSUPPORTED, "rqs_vjp: K+1 <= 64 knots, D <= 256")
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+    arr = (LayerDesc * 1)(d)
+    check(L_.b2b_rqs_vjp_f32(arr, x.data_ptr(), ybar.data_ptr(), ljbar.data_ptr() if ljbar is not None else None,
+                             xbar.data_ptr(), bars[0].data_ptr(), bars[1].data_ptr(), bars[2].data_ptr(), D, N, ldx, ldyb,
+                             _batch_view(xbar)[2], ws.data_ptr(), ws_bytes, _stream()), "b2b_rqs_vjp_f32")
+    return xbar, {"widths": bars[0].t(), "heights": bars[1].t(), "derivatives": bars[2].t()}
+
+
 def isinvertible(t) -> bool:
     return isinstance(t, Transform)
 

@@ -284,6 +284,22 @@ function batchnorm_vjp(bn, x::CuMatrix{Float32}, ȳ::CuMatrix{Float32}, l̄::CuV
     return x̄, b̄, l̄ogs
 end
 
+# Reverse mode of one RationalQuadraticSpline (either direction): cotangents of the input and of the processed fields
+# widths / heights / derivatives (D × K+1 each, like the fields themselves).
+function rqs_vjp(b, x::CuMatrix{Float32}, ȳ::CuMatrix{Float32}, l̄::CuVector{Float32}; inv::Bool=false)
+    d = [desc(b, inv)]
+    K1, (D, N) = Int(d[1].n0), size(x)
+    x̄ = similar(x); W̄ = CUDA.zeros(Float32, D, K1); H̄ = CUDA.zeros(Float32, D, K1); D̄ = CUDA.zeros(Float32, D, K1)
+    nbytes = ccall((:b2b_rqs_vjp_workspace_bytes, libb2b), Csize_t, (Int32, Int32), K1, D)
+    ws = CuVector{UInt8}(undef, nbytes)
+    GC.@preserve d ws check(ccall((:b2b_rqs_vjp_f32, libb2b), Cint,
+        (Ptr{LayerDesc}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32},
+         CuPtr{Float32}, Int32, Int64, Int64, Int64, Int64, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+        d, pointer(x), pointer(ȳ), pointer(l̄), pointer(x̄), pointer(W̄), pointer(H̄), pointer(D̄),
+        D, N, stride(x, 2), stride(ȳ, 2), stride(x̄, 2), pointer(ws), nbytes, stream_handle()))
+    return x̄, W̄, H̄, D̄
+end
+
 # rand(rng, td, n) (src/transformed_distribution.jl:212-224): the base samples are generated INSIDE the chain kernel
 # (Philox4x32-10 + Box-Muller); `seed` plays the role of rng, `column_offset` continues one stream across column shards.
 function device_rand(td::TransformedDistribution{<:MvNormal}, n::Integer; seed::UInt64=rand(UInt64), offset::UInt64=UInt64(0),

@@ -219,6 +219,18 @@ size_t b2b_batchnorm_eval_vjp_workspace_bytes(int32_t D);
 int b2b_batchnorm_eval_vjp_f32(const b2b_layer_desc* layer, const float* x, const float* ybar, const float* ljbar,
                                float* xbar, float* bbar, float* logsbar, int32_t D, int64_t N, int64_t ldx, int64_t ldybar,
                                int64_t ldxbar, void* workspace, size_t workspace_bytes, void* stream);
+/* Reverse mode of ONE RationalQuadraticSpline layer (either direction): what the reference's AD computes through
+ * rational_quadratic_spline.jl:317-357 (forward) / :183-220 (inverse, by the inverse-function theorem at the recovered
+ * point).  `layer`: a B2B_RQS descriptor (K1 = n0 <= 64 knots, D <= 256); `x`: the batch the layer was applied to (the
+ * observed y for inverse != 0).  Outputs: `xbar` (D x N; may alias `ybar`) and the cotangents of the PROCESSED knot arrays
+ * `widths_bar`, `heights_bar`, `derivs_bar` (D x K1 each, laid out like the descriptor's p0/p1/p2), summed over the N
+ * columns; elements outside the box pass `ybar` through.  The map from the raw (softmax / softplus) parameters to the
+ * processed arrays is the caller's (constructor :47-76), as in the reference.  Deterministic (no atomics).
+ * Workspace: b2b_rqs_vjp_workspace_bytes (0 = unsupported shape). */
+size_t b2b_rqs_vjp_workspace_bytes(int32_t K1, int32_t D);
+int b2b_rqs_vjp_f32(const b2b_layer_desc* layer, const float* x, const float* ybar, const float* ljbar, float* xbar,
+                    float* widths_bar, float* heights_bar, float* derivs_bar, int32_t D, int64_t N, int64_t ldx,
+                    int64_t ldybar, int64_t ldxbar, void* workspace, size_t workspace_bytes, void* stream);
 /* RadialLayer: radial_layer.jl:58-72 (fwd), :88-102,124-129 (inverse) */
 int b2b_radial_fwd_f32(const float* x, float* y, float* logjac, const float* alpha_raw,
                        const float* beta, const float* z0, int32_t D, int64_t N, int64_t ldx,

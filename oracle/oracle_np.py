@@ -670,6 +670,120 @@ def rqs_inverse(widths, heights, derivs, y):
     return x, -lj
 
 
+def rqs_vjp(widths, heights, derivs, x, ybar, ljbar, inverse=False):
+    """Vector-Jacobian product of with_logabsdet_jacobian through the RationalQuadraticSpline (mapped over columns) --
+    what the reference's reverse-mode AD computes through rational_quadratic_spline.jl:317-357 (forward) / :183-220
+    (inverse) -- w.r.t. the input and the PROCESSED knot arrays widths / heights / derivatives (D, Kn).
+    x: the layer's input (D, N) (the observed y for inverse=True); ybar (D, N) / ljbar (N,): cotangents of the outputs.
+    Returns (xbar, Wbar, Hbar, Dbar).  The reverse sweep goes through
+      w = x_{k+1} − x_k, Δ = y_{k+1} − y_k, s = Δ/w, ξ = (x − x_k)/w, o = 1 − ξ, p = ξo, ds = d_{k+1} + d_k − 2s,
+      den = s + ds·p, a = sξ² + d_k p, y = y_k + Δ·a/den, b = d_{k+1}ξ² + 2sp + d_k o², lj = 2 log s + log b − 2 log den;
+    the inverse uses the inverse-function theorem at the recovered x: with f_x = s²b/den², lj_x = (b_ξ/b − 2den_ξ/den)/w and
+    ȳ* = (x̄ − l̄·lj_x)/f_x (lj_inv = −lj_f(x)), the input cotangent is ȳ* and the knot cotangents are the forward sweep's
+    with (ȳ, l̄) replaced by (−ȳ*, −l̄).  Elements outside the box pass ȳ through; the box edge itself (a knot that also
+    selects the identity branch) is not differentiated."""
+    dt = x.dtype
+    W, Hh, Dv = widths.astype(dt), heights.astype(dt), derivs.astype(dt)
+    D, Kn = W.shape
+    N = x.shape[1]
+    rows = np.arange(D)[:, None] * np.ones((1, N), int)
+    lb = np.zeros(N, dt) if ljbar is None else ljbar.astype(dt)
+    lb = lb[None, :] * np.ones((D, 1), dt)
+    S = Hh if inverse else W
+    Bs = S[:, -1][:, None]
+    outside = (x <= -Bs) | (x >= Bs)
+    k = np.clip(_rqs_bins(S, x), 0, Kn - 1)
+    km1, kk = np.clip(k - 1, 0, Kn - 1), k
+    xk = np.where(k == 0, -W[:, -1][:, None], W[rows, km1])
+    xk1 = W[rows, kk]
+    yk = np.where(k == 0, -Hh[:, -1][:, None], Hh[rows, km1])
+    yk1 = Hh[rows, kk]
+    dk = np.where(k == 0, dt.type(1), Dv[rows, km1])
+    dk1 = np.where(k == Kn - 1, dt.type(1), Dv[rows, kk])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w = xk1 - xk
+        dyv = yk1 - yk
+        s = dyv / w
+        if inverse:
+            yh = x - yk
+            dsv = dk1 + dk - 2 * s
+            a1 = dyv * (s - dk) + yh * dsv
+            a2 = dyv * dk - yh * dsv
+            a3 = -s * yh
+            xi = -2 * a3 / (a2 + np.sqrt(a2 * a2 - 4 * a1 * a3))
+        else:
+            xi = (x - xk) / w
+        o = 1 - xi
+        p = xi * o
+        dsv = dk1 + dk - 2 * s
+        den = s + dsv * p
+        a = s * xi * xi + dk * p
+        num = dyv * a
+        b = dk1 * xi * xi + 2 * s * p + dk * o * o
+        if inverse:
+            f_x = s * s * b / (den * den)
+            b_xi = 2 * dk1 * xi + 2 * s * (1 - 2 * xi) - 2 * dk * o
+            den_xi = dsv * (1 - 2 * xi)
+            lj_x = (b_xi / b - 2 * den_xi / den) / w
+            ystar = (ybar.astype(dt) - lb * lj_x) / f_x      # cotangent of the observed y
+            yb_, lb_ = -ystar, -lb
+        else:
+            yb_, lb_ = ybar.astype(dt), lb
+        num_b = yb_ / den
+        den_b = -yb_ * num / (den * den) - 2 * lb_ / den
+        yk_b = yb_.copy()
+        b_b = lb_ / b
+        s_b = 2 * lb_ / s
+        dyv_b = num_b * a
+        a_b = num_b * dyv
+        s_b = s_b + a_b * xi * xi
+        xi_b = a_b * 2 * s * xi
+        dk_b = a_b * p
+        p_b = a_b * dk
+        dk1_b = b_b * xi * xi
+        xi_b = xi_b + b_b * 2 * dk1 * xi
+        s_b = s_b + b_b * 2 * p
+        p_b = p_b + b_b * 2 * s
+        dk_b = dk_b + b_b * o * o
+        o_b = b_b * 2 * dk * o
+        s_b = s_b + den_b
+        ds_b = den_b * p
+        p_b = p_b + den_b * dsv
+        dk1_b = dk1_b + ds_b
+        dk_b = dk_b + ds_b
+        s_b = s_b - 2 * ds_b
+        xi_b = xi_b + p_b * o
+        o_b = o_b + p_b * xi
+        xi_b = xi_b - o_b
+        x_b = xi_b / w
+        xk_b = -xi_b / w
+        w_b = -xi_b * xi / w
+        dyv_b = dyv_b + s_b / w
+        w_b = w_b - s_b * s / w
+        yk1_b = dyv_b
+        yk_b = yk_b - dyv_b
+        xk1_b = w_b
+        xk_b = xk_b - w_b
+    inside = ~outside
+    xbar = np.where(outside, ybar.astype(dt), ystar if inverse else x_b).astype(dt)
+    Wb, Hb, Db = np.zeros((D, Kn), dt), np.zeros((D, Kn), dt), np.zeros((D, Kn), dt)
+
+    def scatter(T, idx, val, mask):
+        np.add.at(T, (rows[mask], idx[mask]), val[mask])
+
+    last = np.full_like(k, Kn - 1)
+    m1, m0 = inside & (k >= 1), inside & (k == 0)
+    scatter(Wb, km1, xk_b, m1)
+    scatter(Wb, last, -xk_b, m0)            # k == 0: x_k = −widths[end]
+    scatter(Wb, kk, xk1_b, inside)
+    scatter(Hb, km1, yk_b, m1)
+    scatter(Hb, last, -yk_b, m0)
+    scatter(Hb, kk, yk1_b, inside)
+    scatter(Db, km1, dk_b, m1)              # k == 0: d_k = 1 (constant)
+    scatter(Db, kk, dk1_b, inside & (k < Kn - 1))  # k == Kn−1: d_{k+1} = 1 (constant)
+    return xbar, Wb, Hb, Db
+
+
 # --------------------------------------------------------------------------------------------------
 # PartitionMask / Coupling  (src/bijectors/coupling.jl), Shift / Scale
 # --------------------------------------------------------------------------------------------------

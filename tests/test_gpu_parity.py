@@ -1437,6 +1437,48 @@ def test_coupling_and_batchnorm_vjp_match_oracle(B, D, n1, idx, inv):
         rel(B.to_numpy(xb), xbo), rel(B.to_numpy(gb["b"]), bo), rel(B.to_numpy(gb["logs"]), lo))
 
 
+@pytest.mark.parametrize("inv", [False, True])
+@pytest.mark.parametrize("D,K", [(32, 8), (64, 8), (10, 8), (64, 32), (200, 4)])
+def test_rqs_vjp_matches_oracle(B, D, K, inv):
+    """Reverse mode of the RationalQuadraticSpline (b2b_rqs_vjp_f32), both directions, against the finite-difference-pinned
+    float64 oracle: input cotangent and the cotangents of the processed widths / heights / derivatives; raw-knot splines
+    reach the k == 0 scatter rule (x_k = −widths[end]); deterministic; ragged N; elements outside the box pass ȳ through."""
+    import torch
+
+    rng = np.random.default_rng(1200 + D + K + int(inv))
+    N = 4000 + 13
+    lay = B.RationalQuadraticSpline(rng.standard_normal((D, K)).astype(f32), rng.standard_normal((D, K)).astype(f32),
+                                    rng.standard_normal((D, K - 1)).astype(f32), 3.0)
+    W, H, Dv = lay.knots()
+    W2, H2 = W.copy(), H.copy()
+    W2[:, 0], H2[:, 0] = -2.5, -2.6  # first knot right of −B: points in (−3, W2[0]] are in the k == 0 bin
+    W2, H2 = np.sort(np.maximum(W2, W2[:, :1]), axis=1), np.sort(np.maximum(H2, H2[:, :1]), axis=1)
+    W2 += 1e-3 * np.arange(K + 1, dtype=f32)
+    H2 += 1e-3 * np.arange(K + 1, dtype=f32)
+    for lay_, W_, H_ in ((lay, W, H), (B.RationalQuadraticSpline(W2, H2, Dv), W2, H2)):
+        x = (rng.standard_normal((D, N)) * 1.7).astype(f32)
+        ybar, ljbar = rng.standard_normal((D, N)).astype(f32), rng.standard_normal(N).astype(f32)
+        t = B.inverse(lay_) if inv else lay_
+        a = (x * (H_[:, -1:] / W_[:, -1:])).astype(f32) if inv else x  # observed batch for the inverse direction
+        ad, yd, ld = B.from_numpy(a), B.from_numpy(ybar), torch.as_tensor(ljbar, device="cuda")
+        xbar, g = B.rqs_vjp(t, ad, yd, ld)
+        args64 = [v.astype(np.float64) for v in (W_, H_, Dv, a, ybar, ljbar)]
+        ref = O.rqs_vjp(*args64, inverse=inv)
+        own = O.rqs_vjp(W_, H_, Dv, a, ybar, ljbar, inverse=inv)  # the float32 oracle's own error sets the gate
+        got = (B.to_numpy(xbar), B.to_numpy(g["widths"]), B.to_numpy(g["heights"]), B.to_numpy(g["derivatives"]))
+        for name, gv, rv, ov in zip(("xbar", "widths", "heights", "derivatives"), got, ref, own):
+            assert gv.shape == rv.shape and np.isfinite(gv).all(), name
+            assert rel(gv, rv) <= gate(ov, rv), (name, D, K, inv, rel(gv, rv), rel(ov, rv))
+        S = H_ if inv else W_
+        out = np.abs(a) >= S[:, -1:]
+        assert out.any() and np.array_equal(got[0][out], ybar[out])
+        xbar2, g2 = B.rqs_vjp(t, ad, yd, ld)
+        assert torch.equal(xbar, xbar2) and all(torch.equal(g[k_], g2[k_]) for k_ in g)  # deterministic
+        xbar3, g3 = B.rqs_vjp(t, ad, yd, None)                                            # ljbar = NULL means zeros
+        r0 = O.rqs_vjp(*args64[:5], None, inverse=inv)
+        assert rel(B.to_numpy(xbar3), r0[0]) <= 1e-4 and rel(B.to_numpy(g3["derivatives"]), r0[3]) <= 1e-4
+
+
 def test_realnvp_trains_through_autograd(B):
     """BASELINE config 5's flow structure as a torch module on the device path: gradients of the NLL w.r.t. every
     parameter equal the oracle's layer-by-layer VJP chain, and a few SGD steps lower the objective."""

@@ -394,3 +394,38 @@ def test_radial_vjp_oracle_both_directions_matches_finite_differences(flags):
     if not any(flags):
         xb0, g0 = O.radial_chain_vjp([tuple(p) for p in params], x, ybar, ljbar)
         assert np.allclose(xb0, xbar) and all(np.allclose(a, b) for ga, gb in zip(g0, grads) for a, b in zip(ga, gb))
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_rqs_vjp_oracle_matches_finite_differences(inverse):
+    """rqs_vjp (input and processed-knot cotangents, both directions) against central finite differences of the pinned
+    spline oracles."""
+    rng = np.random.default_rng(5)
+    D, K, N = 4, 6, 9
+    W, H, Dv = O.rqs_params(rng.standard_normal((D, K)), rng.standard_normal((D, K)), rng.standard_normal((D, K - 1)), 3.0)
+    x = rng.standard_normal((D, N)) * 1.6
+    ybar, ljbar = rng.standard_normal((D, N)), rng.standard_normal(N)
+    xin = O.rqs_forward(W, H, Dv, x)[0] if inverse else x
+    f = (lambda ps, xx: O.rqs_inverse(ps[0], ps[1], ps[2], xx)) if inverse else (lambda ps, xx: O.rqs_forward(ps[0], ps[1], ps[2], xx))
+    xb, Wb, Hb, Db = O.rqs_vjp(W, H, Dv, xin, ybar, ljbar, inverse=inverse)
+    # the last knot also selects the identity branch (a jump): differentiate interior knots only
+    mask = np.ones_like(W, bool)
+    mask[:, -1] = False
+
+    class Interior:
+        pass
+
+    def fd_params():
+        h = 1e-6
+        for T, Tb, idx in ((W, Wb, 0), (H, Hb, 1), (Dv, Db, 2)):
+            for i in range(D):
+                for k in range(W.shape[1] - 1):
+                    ps_p, ps_m = [W.copy(), H.copy(), Dv.copy()], [W.copy(), H.copy(), Dv.copy()]
+                    ps_p[idx][i, k] += h
+                    ps_m[idx][i, k] -= h
+                    sc = lambda ps: float((ybar * f(ps, xin)[0]).sum() + (ljbar * f(ps, xin)[1]).sum())  # noqa: E731
+                    fd = (sc(ps_p) - sc(ps_m)) / (2 * h)
+                    assert abs(fd - Tb[i, k]) <= 5e-6 * max(1.0, abs(fd)), (idx, i, k, fd, Tb[i, k])
+
+    fd_params()
+    _fd_vjp_check(f, [W, H, Dv], xin, ybar, ljbar, (xb, []), h=1e-6, tol=5e-6)
