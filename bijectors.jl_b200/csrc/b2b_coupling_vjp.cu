@@ -173,179 +173,279 @@ __global__ void __launch_bounds__(CV_THREADS, 1) coupling_vjp_kernel(const __gri
 }
 
 // ---- register-tiled version for n1, n2 multiples of 4 (the RealNVP shapes) -----------------------------------------------
-// Same three GEMMs, each FMA-bound instead of load-bound: tiles padded to 36 floats so that every operand is a float4,
+// Same three GEMMs, FMA-bound instead of load-bound: every shared-memory operand is a float4,
 //   [s; t]   thread = 4 s rows + the matching 4 t rows x 4 columns: per k two float4 of W (L1) + one float4 of x₂ -> 32 FMA
 //   x̄₂       thread = 4 rows of x₂ x 4 columns: per 4 j four float4 of W + four float4 of [s̄; t̄]              -> 64 FMA
 //   W̄        warp = 32 rows of [s̄; t̄], lane = 4 rows of x₂: per 4 columns 32 broadcast float4 + 4 float4     -> 512 FMA
-constexpr int CF_LD = CV_TC + 4;
+// and every FMA is one half of a packed FFMA2 (row pairs of W / of [s̄; t̄] against a broadcast scalar, or even/odd-j
+// partial sums), which halves the issue slots the arithmetic takes.
+// The tiles are 32 floats wide with the 16-byte chunks XOR-swizzled by the row (chunk ^ (row & 7)) instead of padded:
+// conflict-free for the row-wise float4 reads, the lane-per-row reads of the W̄ product and the transposing stores alike,
+// and the CTA stays under 100 KB of shared memory -- which leaves 156 KB of L1 for W (128 KB at n1 = n2 = 128), read
+// through L1 by every tile.  (With padded 36-float tiles the carve-out was 132 KB and the cyclic sweep over W missed L1
+// on every pass.)
+constexpr int CF_LD = CV_TC;
 
 __device__ __forceinline__ float4 ld4s(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 ld4g(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// W is swept once per tile by every warp and must stay in L1: its loads ask to be evicted last, the streamed batch
+// (x, ȳ in, x̄ out) does not allocate in L1 at all.
+__device__ __forceinline__ float4 ld4g(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+  asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 __device__ __forceinline__ void fma4(float (&a)[4], float w, const float4& x) {
   a[0] = fmaf(w, x.x, a[0]);
   a[1] = fmaf(w, x.y, a[1]);
   a[2] = fmaf(w, x.z, a[2]);
   a[3] = fmaf(w, x.w, a[3]);
 }
+// float offset of chunk `ch` (4 columns) of tile row `r`, and of the single element (r, c)
+__device__ __forceinline__ int cf_chunk(int r, int ch) { return r * CF_LD + ((ch ^ (r & 7)) << 2); }
+__device__ __forceinline__ int cf_elem(int r, int c) { return r * CF_LD + ((((c >> 2) ^ (r & 7)) << 2) | (c & 3)); }
 
-template <bool INV>
+// [s̄; t̄] tile: rows stored in interleaved PAIRS -- a 16-byte chunk holds {row 2p, row 2p+1} x {col 2h, col 2h+1} -- so that
+// a float4 is two packed-FFMA2 operands (row pairs against a broadcast scalar).  Chunk h of pair p sits at h ^ (h >> 3).
+__device__ __forceinline__ int sb_chunk(int p, int h) { return p * 64 + ((h ^ (h >> 3)) << 2); }
+__device__ __forceinline__ int sb_elem(int row, int col) { return sb_chunk(row >> 1, col >> 1) + ((col & 1) << 1) + (row & 1); }
+__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
+
+// CONTIG: x₂ is a contiguous row range (row2 >= 0).
+template <bool INV, bool CONTIG>
 __global__ void __launch_bounds__(CV_THREADS, 1) coupling_vjp_fast_kernel(const __grid_constant__ CvParams P) {
   extern __shared__ __align__(16) float smem_f[];
   const int D = P.D, n1 = P.n1, n2 = P.n2, m2 = 2 * n1;
-  float* X = smem_f;                       // [D][CF_LD]
-  float* YB = X + (size_t)D * CF_LD;       // [D][CF_LD]
-  float* SB = YB + (size_t)D * CF_LD;      // [2n1][CF_LD]
-  float* LB = SB + (size_t)m2 * CF_LD;     // [CV_TC]
+  const int m2p = (m2 + 31) & ~31;
+  float* X = smem_f;                          // [D + 1][32]    row D stays zero (x₂ rows beyond n2 in the W̄ tile)
+  float* YB = X + (size_t)(D + 1) * CF_LD;    // [D][32]
+  float* SB = YB + (size_t)D * CF_LD;         // [m2p / 2][64]  row pairs; rows beyond 2n1 stay zero
+  float* LB = SB + (size_t)m2p * CF_LD;       // [CV_TC]
   int* s1 = reinterpret_cast<int*>(LB + CV_TC);
   int* s2 = s1 + n1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rg = threadIdx.x >> 3, c4 = 4 * (threadIdx.x & 7);
+  const int rg = threadIdx.x >> 3, cg = threadIdx.x & 7;  // rows 4·rg + i, columns 4·cg + q
   for (int k = threadIdx.x; k < n1; k += CV_THREADS) s1[k] = P.idx1 ? P.idx1[k] : P.row1 + k;
   for (int k = threadIdx.x; k < n2; k += CV_THREADS) s2[k] = P.idx2 ? P.idx2[k] : P.row2 + k;
+  for (int e = threadIdx.x; e < CF_LD; e += CV_THREADS) X[D * CF_LD + e] = 0.f;
+  for (int e = threadIdx.x; e < (m2p - m2) * CF_LD; e += CV_THREADS) SB[m2 * CF_LD + e] = 0.f;
   const long long tiles = (P.N + CV_TC - 1) / CV_TC;
-  const int ldw = m2;
-  float acc[32][4];
+  const int ldw = m2, nrb = (D + 7) / 8;
+  float2 acc[16][4];   // rows 32·warp + 2·ip (+1) of [s̄; t̄]  x  x₂ rows lane + 32·q
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
+  for (int i = 0; i < 16; ++i)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
-  float cacc = 0.f;
+    for (int q = 0; q < 4; ++q) acc[i][q] = make_float2(0.f, 0.f);
+  float cacc = 0.f;  // c̄ partial: thread (rg, cg) owns row 4rg + cg of s̄ (cg < 4) or of t̄ (cg >= 4)
 
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long col0 = tile * CV_TC;
     __syncthreads();
-    for (int cidx = warp; cidx < CV_TC; cidx += CV_THREADS / 32) {
+    // a warp moves 8 rows x 4 columns per step: whole 32-byte sectors in global memory, 32 distinct banks in the tiles
+    for (int cb = warp; cb < CV_TC / 4; cb += CV_THREADS / 32) {
+      const int cidx = 4 * cb + (lane >> 3);
       const long long col = col0 + cidx;
-      const bool ok = col < P.N;
-      for (int r = lane; r < D; r += 32) {
-        X[r * CF_LD + cidx] = ok ? __ldcs(P.x + col * P.ldx + r) : 0.f;
-        YB[r * CF_LD + cidx] = ok ? __ldcs(P.ybar + col * P.ldyb + r) : 0.f;
+      const bool okc = col < P.N;
+      for (int rb0 = 0; rb0 < nrb; rb0 += 8) {  // 16 loads in flight per lane
+        float xv[8], yv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = 8 * (rb0 + u) + (lane & 7);
+          const bool ok = okc && r < D;
+          xv[u] = ok ? ld_stream(P.x + col * P.ldx + r) : 0.f;
+          yv[u] = ok ? ld_stream(P.ybar + col * P.ldyb + r) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = 8 * (rb0 + u) + (lane & 7);
+          if (r < D) {
+            X[cf_elem(r, cidx)] = xv[u];
+            YB[cf_elem(r, cidx)] = yv[u];
+          }
+        }
       }
-      if (lane == 0) LB[cidx] = (ok && P.ljbar) ? P.ljbar[col] : 0.f;
     }
+    if (threadIdx.x < CV_TC) LB[threadIdx.x] = (col0 + threadIdx.x < P.N && P.ljbar) ? P.ljbar[col0 + threadIdx.x] : 0.f;
     __syncthreads();
-    // ---- [s; t] = W·x₂ + c and the elementwise cotangents ------------------------------------------------------------
+    // ---- [s; t] = W·x₂ + c ----------------------------------------------------------------------------------------------
+    float2 sv[2][4], tv[2][4];  // [row pair][column]
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sv[i][q] = tv[i][q] = make_float2(0.f, 0.f);
     if (4 * rg < n1) {
-      float sv[4][4], tv[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) sv[i][q] = tv[i][q] = 0.f;
       const float* Wp = P.W + 4 * rg;
 #pragma unroll 4
       for (int k = 0; k < n2; ++k) {
-        const float4 xv = ld4s(X + s2[k] * CF_LD + c4);
+        const int xr = CONTIG ? P.row2 + k : s2[k];
+        const float4 xv = ld4s(X + cf_chunk(xr, cg));
         const float4 ws = ld4g(Wp + (size_t)k * ldw), wt = ld4g(Wp + (size_t)k * ldw + n1);
-        fma4(sv[0], ws.x, xv);
-        fma4(sv[1], ws.y, xv);
-        fma4(sv[2], ws.z, xv);
-        fma4(sv[3], ws.w, xv);
-        fma4(tv[0], wt.x, xv);
-        fma4(tv[1], wt.y, xv);
-        fma4(tv[2], wt.z, xv);
-        fma4(tv[3], wt.w, xv);
+        const float2 ws0 = make_float2(ws.x, ws.y), ws1 = make_float2(ws.z, ws.w);
+        const float2 wt0 = make_float2(wt.x, wt.y), wt1 = make_float2(wt.z, wt.w);
+        const float xq[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          sv[0][q] = __ffma2_rn(ws0, bc2(xq[q]), sv[0][q]);
+          sv[1][q] = __ffma2_rn(ws1, bc2(xq[q]), sv[1][q]);
+          tv[0][q] = __ffma2_rn(wt0, bc2(xq[q]), tv[0][q]);
+          tv[1][q] = __ffma2_rn(wt1, bc2(xq[q]), tv[1][q]);
+        }
       }
-      const float4 lb4 = ld4s(LB + c4);
+    }
+    // ---- the elementwise cotangents ------------------------------------------------------------------------------------
+    float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // row sums of s̄ (0..3) and t̄ (4..7) over the thread's 4 columns
+    if (4 * rg < n1) {
+      const float4 lb4 = ld4s(LB + 4 * cg);
       const float lbv[4] = {lb4.x, lb4.y, lb4.z, lb4.w};
+      float sbar[4][4], tbar[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int j = 4 * rg + i;
         const float cs = P.c ? P.c[j] : 0.f, ct = P.c ? P.c[n1 + j] : 0.f;
-        const int r1 = s1[j];
-        const float4 in4 = ld4s(X + r1 * CF_LD + c4), cb4 = ld4s(YB + r1 * CF_LD + c4);
+        const int o1 = cf_chunk(s1[j], cg);
+        const float4 in4 = ld4s(X + o1), cb4 = ld4s(YB + o1);
         const float in1[4] = {in4.x, in4.y, in4.z, in4.w}, cb1[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
-        float out1[4], sbar[4], tbar[4];
+        float out1[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float s_ = sv[i][q] + cs, t_ = tv[i][q] + ct;
+          const float s_ = ((i & 1) ? sv[i >> 1][q].y : sv[i >> 1][q].x) + cs;
+          const float t_ = ((i & 1) ? tv[i >> 1][q].y : tv[i >> 1][q].x) + ct;
           if (!INV) {
             const float e = expf(s_);
             out1[q] = e * cb1[q];
-            sbar[q] = fmaf(cb1[q] * e, in1[q], lbv[q]);
-            tbar[q] = cb1[q];
+            sbar[i][q] = fmaf(cb1[q] * e, in1[q], lbv[q]);
+            tbar[i][q] = cb1[q];
           } else {
             const float em = expf(-s_);
             const float x1 = (in1[q] - t_) * em;
             out1[q] = em * cb1[q];
-            sbar[q] = -fmaf(x1, cb1[q], lbv[q]);
-            tbar[q] = -out1[q];
+            sbar[i][q] = -fmaf(x1, cb1[q], lbv[q]);
+            tbar[i][q] = -out1[q];
           }
         }
-        *reinterpret_cast<float4*>(YB + r1 * CF_LD + c4) = make_float4(out1[0], out1[1], out1[2], out1[3]);
-        *reinterpret_cast<float4*>(SB + j * CF_LD + c4) = make_float4(sbar[0], sbar[1], sbar[2], sbar[3]);
-        *reinterpret_cast<float4*>(SB + (n1 + j) * CF_LD + c4) = make_float4(tbar[0], tbar[1], tbar[2], tbar[3]);
+        *reinterpret_cast<float4*>(YB + o1) = make_float4(out1[0], out1[1], out1[2], out1[3]);
+      }
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {  // row pairs (4rg + 2pp, +1) of s̄ and of t̄, chunks 2cg, 2cg + 1
+        const int ps = 2 * rg + pp, pt = (n1 >> 1) + ps, i0 = 2 * pp, i1 = 2 * pp + 1;
+        *reinterpret_cast<float4*>(SB + sb_chunk(ps, 2 * cg)) = make_float4(sbar[i0][0], sbar[i1][0], sbar[i0][1], sbar[i1][1]);
+        *reinterpret_cast<float4*>(SB + sb_chunk(ps, 2 * cg + 1)) = make_float4(sbar[i0][2], sbar[i1][2], sbar[i0][3], sbar[i1][3]);
+        *reinterpret_cast<float4*>(SB + sb_chunk(pt, 2 * cg)) = make_float4(tbar[i0][0], tbar[i1][0], tbar[i0][1], tbar[i1][1]);
+        *reinterpret_cast<float4*>(SB + sb_chunk(pt, 2 * cg + 1)) = make_float4(tbar[i0][2], tbar[i1][2], tbar[i0][3], tbar[i1][3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rs[i] = (sbar[i][0] + sbar[i][1]) + (sbar[i][2] + sbar[i][3]);
+        rs[4 + i] = (tbar[i][0] + tbar[i][1]) + (tbar[i][2] + tbar[i][3]);
       }
     }
+    // c̄: the 8 column groups of a row group are 8 consecutive lanes (whole warps take part in the shuffles)
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (cg == i) cacc += rs[i];
     __syncthreads();
-    // ---- x̄₂ = ȳ₂ + Wᵀ[s̄; t̄] -------------------------------------------------------------------------------------------
+    // ---- x̄₂ = ȳ₂ + Wᵀ[s̄; t̄]: even-j and odd-j partial sums in the two halves of a packed accumulator -------------------
     if (4 * rg < n2) {
-      float a[4][4];
+      float2 a[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) a[i][q] = 0.f;
-      const float* Wk = P.W + (size_t)(4 * rg) * ldw;
+        for (int q = 0; q < 4; ++q) a[i][q] = make_float2(0.f, 0.f);
+      const float* wr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wr[i] = P.W + (size_t)(4 * rg + i) * ldw;
+      const int h0 = ((2 * cg) ^ (cg >> 2)) << 2, h1 = ((2 * cg + 1) ^ (cg >> 2)) << 2;
 #pragma unroll 2
       for (int j = 0; j < m2; j += 4) {
-        const float4 sb0 = ld4s(SB + (j + 0) * CF_LD + c4), sb1 = ld4s(SB + (j + 1) * CF_LD + c4);
-        const float4 sb2 = ld4s(SB + (j + 2) * CF_LD + c4), sb3 = ld4s(SB + (j + 3) * CF_LD + c4);
+        const float* sp = SB + (j >> 1) * 64;
+        const float4 p00 = ld4s(sp + h0), p01 = ld4s(sp + h1);            // rows j, j+1: columns 0,1 | 2,3
+        const float4 p10 = ld4s(sp + 64 + h0), p11 = ld4s(sp + 64 + h1);  // rows j+2, j+3
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 w = ld4g(Wk + (size_t)i * ldw + j);
-          fma4(a[i], w.x, sb0);
-          fma4(a[i], w.y, sb1);
-          fma4(a[i], w.z, sb2);
-          fma4(a[i], w.w, sb3);
+          const float4 w = ld4g(wr[i] + j);
+          const float2 w0 = make_float2(w.x, w.y), w1 = make_float2(w.z, w.w);
+          a[i][0] = __ffma2_rn(w0, make_float2(p00.x, p00.y), a[i][0]);
+          a[i][1] = __ffma2_rn(w0, make_float2(p00.z, p00.w), a[i][1]);
+          a[i][2] = __ffma2_rn(w0, make_float2(p01.x, p01.y), a[i][2]);
+          a[i][3] = __ffma2_rn(w0, make_float2(p01.z, p01.w), a[i][3]);
+          a[i][0] = __ffma2_rn(w1, make_float2(p10.x, p10.y), a[i][0]);
+          a[i][1] = __ffma2_rn(w1, make_float2(p10.z, p10.w), a[i][1]);
+          a[i][2] = __ffma2_rn(w1, make_float2(p11.x, p11.y), a[i][2]);
+          a[i][3] = __ffma2_rn(w1, make_float2(p11.z, p11.w), a[i][3]);
         }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float* dst = YB + s2[4 * rg + i] * CF_LD + c4;
+        float* dst = YB + cf_chunk(s2[4 * rg + i], cg);
         const float4 o = ld4s(dst);
-        *reinterpret_cast<float4*>(dst) = make_float4(o.x + a[i][0], o.y + a[i][1], o.z + a[i][2], o.w + a[i][3]);
+        *reinterpret_cast<float4*>(dst) = make_float4(o.x + (a[i][0].x + a[i][0].y), o.y + (a[i][1].x + a[i][1].y),
+                                                      o.z + (a[i][2].x + a[i][2].y), o.w + (a[i][3].x + a[i][3].y));
       }
     }
-    // ---- W̄ += [s̄; t̄]·x₂ᵀ over the tile's columns (ascending); c̄ += Σ columns -----------------------------------------
+    // ---- W̄ += [s̄; t̄]·x₂ᵀ over the tile's columns ----------------------------------------------------------------------
     {
       const int rbase = 32 * warp;
       if (rbase < m2) {
-        int xr[4];
+        const float* xr[4];
+        int xs[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xr[q] = (lane + 32 * q < n2) ? s2[lane + 32 * q] * CF_LD : -1;
-        for (int cidx = 0; cidx < CV_TC; cidx += 4) {
-          float4 b[4];
+        for (int q = 0; q < 4; ++q) {
+          const int r = (lane + 32 * q < n2) ? s2[lane + 32 * q] : D;
+          xr[q] = X + r * CF_LD;
+          xs[q] = r & 7;
+        }
+        const float* sbp = SB + (rbase >> 1) * 64;
+#pragma unroll 2
+        for (int ch = 0; ch < CV_TC / 4; ++ch) {
+          float4 bq[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) b[q] = xr[q] >= 0 ? ld4s(X + xr[q] + cidx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < 4; ++q) bq[q] = ld4s(xr[q] + ((ch ^ xs[q]) << 2));
+          const int g0 = ((2 * ch) ^ (ch >> 2)) << 2, g1 = ((2 * ch + 1) ^ (ch >> 2)) << 2;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float4 av = (rbase + i < m2) ? ld4s(SB + (rbase + i) * CF_LD + cidx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int ip = 0; ip < 16; ++ip) {
+            const float4 a0 = ld4s(sbp + ip * 64 + g0), a1 = ld4s(sbp + ip * 64 + g1);  // columns 4ch, +1 | +2, +3
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              acc[i][q] = fmaf(av.w, b[q].w, fmaf(av.z, b[q].z, fmaf(av.y, b[q].y, fmaf(av.x, b[q].x, acc[i][q]))));
+            for (int q = 0; q < 4; ++q) {
+              float2 t = acc[ip][q];
+              t = __ffma2_rn(make_float2(a0.x, a0.y), bc2(bq[q].x), t);
+              t = __ffma2_rn(make_float2(a0.z, a0.w), bc2(bq[q].y), t);
+              t = __ffma2_rn(make_float2(a1.x, a1.y), bc2(bq[q].z), t);
+              t = __ffma2_rn(make_float2(a1.z, a1.w), bc2(bq[q].w), t);
+              acc[ip][q] = t;
+            }
           }
         }
       }
-      if ((int)threadIdx.x < m2) {
-        float t = 0.f;
-        for (int cidx = 0; cidx < CV_TC; ++cidx) t += SB[threadIdx.x * CF_LD + cidx];
-        cacc += t;
-      }
     }
     __syncthreads();
-    for (int cidx = warp; cidx < CV_TC; cidx += CV_THREADS / 32) {
+    for (int blk = warp; blk < nrb * (CV_TC / 4); blk += CV_THREADS / 32) {
+      const int r = 8 * (blk % nrb) + (lane & 7), cidx = 4 * (blk / nrb) + (lane >> 3);
       const long long col = col0 + cidx;
-      if (col < P.N)
-        for (int r = lane; r < D; r += 32) __stcs(P.xbar + col * P.ldxb + r, YB[r * CF_LD + cidx]);
+      if (col < P.N && r < D) st_stream(P.xbar + col * P.ldxb + r, YB[cf_elem(r, cidx)]);
     }
   }
   float* part = P.part + (size_t)blockIdx.x * ((size_t)m2 * n2 + m2);
   const int rbase = 32 * warp;
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
+  for (int ip = 0; ip < 16; ++ip)
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (rbase + i < m2 && lane + 32 * q < n2) part[(size_t)(lane + 32 * q) * m2 + rbase + i] = acc[i][q];
-  if ((int)threadIdx.x < m2) part[(size_t)m2 * n2 + threadIdx.x] = cacc;
+      if (lane + 32 * q < n2) {
+        if (rbase + 2 * ip < m2) part[(size_t)(lane + 32 * q) * m2 + rbase + 2 * ip] = acc[ip][q].x;
+        if (rbase + 2 * ip + 1 < m2) part[(size_t)(lane + 32 * q) * m2 + rbase + 2 * ip + 1] = acc[ip][q].y;
+      }
+  if (4 * rg < n1) part[(size_t)m2 * n2 + (cg < 4 ? 4 * rg + cg : n1 + 4 * rg + cg - 4)] = cacc;
 }
 
 // out[e] = Σ_cta part[cta][e], fixed order
@@ -537,13 +637,17 @@ extern "C" int b2b_coupling_affine_vjp_f32(const b2b_layer_desc* layer, const fl
   if (grid > tiles) grid = tiles;
   // float4 path: n1, n2 multiples of 4 and a 16-byte aligned W (its leading dimension 2·n1 is then a multiple of 4 too)
   const bool fast = n1 % 4 == 0 && n2 % 4 == 0 && (reinterpret_cast<uintptr_t>(d.p0) & 15) == 0;
-  const int ld = fast ? CF_LD : CV_LD;
-  const size_t smem = ((size_t)2 * D * ld + (size_t)2 * n1 * ld + CV_TC) * sizeof(float) + (size_t)(n1 + n2) * sizeof(int);
+  const size_t smem = fast ? ((size_t)(2 * D + 1 + ((2 * n1 + 31) & ~31)) * CF_LD + CV_TC) * sizeof(float) + (size_t)(n1 + n2) * sizeof(int)
+                           : ((size_t)2 * D * CV_LD + (size_t)2 * n1 * CV_LD + CV_TC) * sizeof(float) + (size_t)(n1 + n2) * sizeof(int);
   if (smem > 220 * 1024) return B2B_EUNSUPPORTED;
-  void (*kernel)(const CvParams) = fast ? (d.inverse ? coupling_vjp_fast_kernel<true> : coupling_vjp_fast_kernel<false>)
-                                        : (d.inverse ? coupling_vjp_kernel<true> : coupling_vjp_kernel<false>);
+  void (*kernel)(const CvParams);
+  if (!fast) kernel = d.inverse ? coupling_vjp_kernel<true> : coupling_vjp_kernel<false>;
+  else if (d.n3 < 0) kernel = d.inverse ? coupling_vjp_fast_kernel<true, false> : coupling_vjp_fast_kernel<false, false>;
+  else kernel = d.inverse ? coupling_vjp_fast_kernel<true, true> : coupling_vjp_fast_kernel<false, true>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
+  // the smallest carve-out that holds the CTA: the rest of the 256 KB stays L1 (W is re-read through it by every tile)
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 1024) * 100 / (228 * 1024) + 1));
   kernel<<<(int)grid, CV_THREADS, smem, stream>>>(P);
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;

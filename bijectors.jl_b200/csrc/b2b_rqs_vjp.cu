@@ -45,28 +45,35 @@ struct RqvParams {
 
 struct RqvCot {
   float xk, xk1, yk, yk1, dk, dk1;
-  int k;  // −1: outside the box / no column
+  int k;
 };
 
+// The row's knots: W | H | Dv tables with this thread's row offset folded in; `stride` floats between consecutive knots.
 template <bool INV, bool STAB>
 struct RqvKnots {
   const float *W, *H, *Dv;
-  int stride, i;
-  __device__ __forceinline__ float w(int k) const { return STAB ? W[k * stride + i] : __ldg(W + (size_t)k * stride + i); }
-  __device__ __forceinline__ float h(int k) const { return STAB ? H[k * stride + i] : __ldg(H + (size_t)k * stride + i); }
-  __device__ __forceinline__ float d(int k) const { return STAB ? Dv[k * stride + i] : __ldg(Dv + (size_t)k * stride + i); }
+  int stride;
+  __device__ __forceinline__ float ld(const float* p) const { return STAB ? *p : __ldg(p); }
+  __device__ __forceinline__ float w(int k) const { return ld(W + k * stride); }
+  __device__ __forceinline__ float h(int k) const { return ld(H + k * stride); }
+  __device__ __forceinline__ float d(int k) const { return ld(Dv + k * stride); }
   __device__ __forceinline__ float s(int k) const { return INV ? h(k) : w(k); }
 };
 
-// One element: returns the input cotangent, fills the knot cotangents of its bin.
+__device__ __forceinline__ float rqv_rcp(float x) { return __fdividef(1.0f, x); }  // MUFU.RCP, <= 1 ulp
+
+// One element (v inside the box; elements outside arrive as v = 0 with zero cotangents): returns the input cotangent, fills the
+// knot cotangents of its bin.  Branch-free: the k == 0 / k == K1−1 cases are selects.
 template <bool INV, bool STAB>
 __device__ __forceinline__ float rqv_element(const RqvKnots<INV, STAB>& T, int K1, int k, float Wl, float Hl, float v, float cb,
                                               float lb, RqvCot& c) {
-  const float xk = k == 0 ? -Wl : T.w(k - 1), xk1 = T.w(k);
-  const float yk = k == 0 ? -Hl : T.h(k - 1), yk1 = T.h(k);
-  const float dk = k == 0 ? 1.0f : T.d(k - 1);
-  const float dk1 = k == K1 - 1 ? 1.0f : T.d(k);
-  const float w = xk1 - xk, dyv = yk1 - yk, iw = 1.0f / w, s = dyv / w;
+  const int km = k > 0 ? k - 1 : 0;
+  const float wa = T.w(km), ha = T.h(km), da = T.d(km), db = T.d(k);
+  const float xk = k == 0 ? -Wl : wa, xk1 = T.w(k);
+  const float yk = k == 0 ? -Hl : ha, yk1 = T.h(k);
+  const float dk = k == 0 ? 1.0f : da;
+  const float dk1 = k == K1 - 1 ? 1.0f : db;
+  const float w = xk1 - xk, dyv = yk1 - yk, iw = rqv_rcp(w), s = dyv * iw;
   const float dsv = dk1 + dk - 2.0f * s;
   float xi, o;
   if (INV) {
@@ -74,25 +81,25 @@ __device__ __forceinline__ float rqv_element(const RqvKnots<INV, STAB>& T, int K
     const bool lower = lo < hi;
     const float yh = lower ? lo : hi, dd = lower ? dk : dk1;  // solve from the nearer knot
     const float a1 = fmaf(dyv, s - dd, yh * dsv), a2 = fmaf(dyv, dd, -yh * dsv), a3 = -s * yh;
-    const float r = -2.0f * a3 / (a2 + sqrtf(fmaf(a2, a2, -4.0f * a1 * a3)));
+    const float r = -2.0f * a3 * rqv_rcp(a2 + sqrtf(fmaf(a2, a2, -4.0f * a1 * a3)));
     xi = lower ? r : 1.0f - r;
     o = lower ? 1.0f - r : r;
   } else {
-    xi = (v - xk) / w;
-    o = (xk1 - v) / w;
+    xi = (v - xk) * iw;
+    o = (xk1 - v) * iw;
   }
   const float p = xi * o;
-  const float den = fmaf(s, 1.0f - 2.0f * p, (dk1 + dk) * p), iden = 1.0f / den;
+  const float den = fmaf(s, 1.0f - 2.0f * p, (dk1 + dk) * p), iden = rqv_rcp(den);
   const float a = fmaf(s * xi, xi, dk * p), num = dyv * a;
   const float b = fmaf(dk1 * xi, xi, fmaf(2.0f * s, p, dk * o * o));
-  const float ib = 1.0f / b;
+  const float ib = rqv_rcp(b);
   float yb_ = cb, lb_ = lb, ystar = 0.f;
   if (INV) {
-    const float f_x = s * s * b * iden * iden;
+    const float if_x = den * den * rqv_rcp(s * s * b);
     const float b_xi = 2.0f * fmaf(dk1 - s, xi, (s - dk) * o);
     const float den_xi = dsv * (o - xi);
     const float lj_x = (b_xi * ib - 2.0f * den_xi * iden) * iw;
-    ystar = (cb - lb * lj_x) / f_x;
+    ystar = (cb - lb * lj_x) * if_x;
     yb_ = -ystar;
     lb_ = -lb;
   }
@@ -100,7 +107,7 @@ __device__ __forceinline__ float rqv_element(const RqvKnots<INV, STAB>& T, int K
   const float num_b = yb_ * iden;
   const float den_b = -(num_b * num + 2.0f * lb_) * iden;
   const float b_b = lb_ * ib;
-  float s_b = 2.0f * lb_ / s;
+  float s_b = 2.0f * lb_ * rqv_rcp(s);
   float dyv_b = num_b * a;
   const float a_b = num_b * dyv;
   s_b = fmaf(a_b * xi, xi, s_b);
@@ -126,12 +133,15 @@ __device__ __forceinline__ float rqv_element(const RqvKnots<INV, STAB>& T, int K
   float w_b = -x_b * xi;
   dyv_b = fmaf(s_b, iw, dyv_b);
   w_b = fmaf(-s_b * s, iw, w_b);
-  c.xk = -x_b - w_b;
+  // k == 0: x_k = −widths[end], y_k = −heights[end] (negated, scattered to the last knot), d_k = 1 (no cotangent);
+  // k == K1−1: d_{k+1} = 1
+  const float xk_b = -x_b - w_b, yk_b = yb_ - dyv_b;
+  c.xk = k == 0 ? -xk_b : xk_b;
   c.xk1 = w_b;
-  c.yk = yb_ - dyv_b;
+  c.yk = k == 0 ? -yk_b : yk_b;
   c.yk1 = dyv_b;
-  c.dk = dk_b;
-  c.dk1 = dk1_b;
+  c.dk = k == 0 ? 0.f : dk_b;
+  c.dk1 = k == K1 - 1 ? 0.f : dk1_b;
   c.k = k;
   return INV ? ystar : x_b;
 }
@@ -158,58 +168,59 @@ __global__ void __launch_bounds__(RQV_THREADS) rqs_vjp_kernel(const __grid_const
   const long long c0 = (long long)blockIdx.x * per, c1 = (c0 + per < P.N) ? c0 + per : P.N;
   if (active) {
     RqvKnots<INV, STAB> T;
-    T.W = STAB ? tab : P.W;
-    T.H = STAB ? tab + K1 * Dp : P.H;
-    T.Dv = STAB ? tab + 2 * K1 * Dp : P.Dv;
+    T.W = (STAB ? tab : P.W) + i;
+    T.H = (STAB ? tab + K1 * Dp : P.H) + i;
+    T.Dv = (STAB ? tab + 2 * K1 * Dp : P.Dv) + i;
     T.stride = STAB ? Dp : D;
-    T.i = i;
     const float Wl = T.w(K1 - 1), Hl = T.h(K1 - 1);
     const float Bs = INV ? Hl : Wl;
     float* my = acc + tid;
+    const int K1s = K1 * RQV_THREADS;
     for (long long n0 = c0 + slab; n0 < c1; n0 += (long long)RQV_U * nslab) {
-      float v[RQV_U], cb[RQV_U], lb[RQV_U];
+      float v[RQV_U], cb[RQV_U], lb[RQV_U], raw[RQV_U];
+      bool in[RQV_U];
       int kb[RQV_U];
 #pragma unroll
       for (int u = 0; u < RQV_U; ++u) {
         const long long n = n0 + (long long)u * nslab;
-        const bool ok = n < c1;
-        v[u] = ok ? P.x[n * P.ldx + i] : 0.f;
-        cb[u] = ok ? P.ybar[n * P.ldyb + i] : 0.f;
+        const bool ok = n < c1;  // columns past the range run on zeros (zero cotangents, nothing stored)
+        raw[u] = ok ? __ldcs(P.x + n * P.ldx + i) : 0.f;
+        cb[u] = ok ? __ldcs(P.ybar + n * P.ldyb + i) : 0.f;
         lb[u] = ok && P.ljbar ? P.ljbar[n] : 0.f;
-        kb[u] = ok ? 0 : -1;
+        kb[u] = 0;
+      }
+#pragma unroll
+      for (int u = 0; u < RQV_U; ++u) {
+        // identity outside the box (:322 / :188): the element is evaluated at 0 (inside every box, in a bin of positive
+        // width) with zero cotangents, so that every knot cotangent it adds is an exact 0; its own cotangent passes through
+        in[u] = raw[u] > -Bs && raw[u] < Bs;
+        v[u] = in[u] ? raw[u] : 0.f;
       }
       // bin = number of knots < v (searchsortedfirst − 1); one pass over the row's knots serves the U columns
       for (int j = 0; j < K1 - 1; ++j) {
         const float sj = T.s(j);
 #pragma unroll
-        for (int u = 0; u < RQV_U; ++u) kb[u] += (kb[u] >= 0 && sj < v[u]) ? 1 : 0;
+        for (int u = 0; u < RQV_U; ++u) kb[u] += sj < v[u] ? 1 : 0;
       }
       RqvCot c[RQV_U];
 #pragma unroll
       for (int u = 0; u < RQV_U; ++u) {
-        c[u].k = -1;
-        if (kb[u] < 0) continue;
         const long long n = n0 + (long long)u * nslab;
-        float out = cb[u];  // identity outside the box: the cotangent passes through (:322 / :188)
-        if (v[u] > -Bs && v[u] < Bs) out = rqv_element<INV, STAB>(T, K1, kb[u], Wl, Hl, v[u], cb[u], lb[u], c[u]);
-        P.xbar[n * P.ldxb + i] = out;
+        const float out = rqv_element<INV, STAB>(T, K1, kb[u], Wl, Hl, v[u], in[u] ? cb[u] : 0.f, in[u] ? lb[u] : 0.f, c[u]);
+        if (n < c1) __stcs(P.xbar + n * P.ldxb + i, in[u] ? out : cb[u]);
       }
       // scatter into this thread's own slots: W | H | Dv
 #pragma unroll
       for (int u = 0; u < RQV_U; ++u) {
         const int k = c[u].k;
-        if (k < 0) continue;
-        if (k >= 1) {
-          my[(k - 1) * RQV_THREADS] += c[u].xk;
-          my[(K1 + k - 1) * RQV_THREADS] += c[u].yk;
-          my[(2 * K1 + k - 1) * RQV_THREADS] += c[u].dk;
-        } else {  // k == 0: x_k = −widths[end], y_k = −heights[end], d_k = 1
-          my[(K1 - 1) * RQV_THREADS] -= c[u].xk;
-          my[(2 * K1 - 1) * RQV_THREADS] -= c[u].yk;
-        }
-        my[k * RQV_THREADS] += c[u].xk1;
-        my[(K1 + k) * RQV_THREADS] += c[u].yk1;
-        if (k < K1 - 1) my[(2 * K1 + k) * RQV_THREADS] += c[u].dk1;  // k == K1−1: d_{k+1} = 1
+        float* pa = my + (k > 0 ? k - 1 : K1 - 1) * RQV_THREADS;
+        float* pb = my + k * RQV_THREADS;
+        pa[0] += c[u].xk;
+        pa[K1s] += c[u].yk;
+        pa[2 * K1s] += c[u].dk;
+        pb[0] += c[u].xk1;
+        pb[K1s] += c[u].yk1;
+        pb[2 * K1s] += c[u].dk1;
       }
     }
   }
