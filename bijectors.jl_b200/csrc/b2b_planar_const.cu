@@ -231,14 +231,19 @@ static int dispatch_dev(int L, const B2BChainParams& q, const V1Geom& g, const C
   switch (L) {
     case 1: return dispatch_dev_dir<D, NW, 1>(q, g, mx, my, nreal, invmask, mvn, stream);
     case 2: return dispatch_dev_dir<D, NW, 2>(q, g, mx, my, nreal, invmask, mvn, stream);
+    case 3: return dispatch_dev_dir<D, NW, 3>(q, g, mx, my, nreal, invmask, mvn, stream);
     case 4: return dispatch_dev_dir<D, NW, 4>(q, g, mx, my, nreal, invmask, mvn, stream);
+    case 5: return dispatch_dev_dir<D, NW, 5>(q, g, mx, my, nreal, invmask, mvn, stream);
+    case 6: return dispatch_dev_dir<D, NW, 6>(q, g, mx, my, nreal, invmask, mvn, stream);
+    case 7: return dispatch_dev_dir<D, NW, 7>(q, g, mx, my, nreal, invmask, mvn, stream);
     case 8: return dispatch_dev_dir<D, NW, 8>(q, g, mx, my, nreal, invmask, mvn, stream);
     default: return B2B_EUNSUPPORTED;
   }
 }
 
 // `packed` != NULL: host-resident parameters (kernel arguments); NULL: device-resident (p.layers[0..nreal), derived in
-// the kernel; p.layers[nreal] = terminal MvNormal when `mvn`).  L = padded layer count (1, 2, 4, 8).
+// the kernel; p.layers[nreal] = terminal MvNormal when `mvn`).  L = layer count of the program (host parameters: padded
+// to 1, 2, 4, 8; device parameters: exact).
 static int launch_planar_unrolled(const B2BChainParams& p, int L, const float* packed, int nreal, int invmask, bool mvn,
                                   cudaStream_t stream) {
   B2BChainParams q = p;
@@ -307,9 +312,7 @@ int b2b_launch_planar_chain_const(const B2BChainParams& p, cudaStream_t stream) 
   int invmask = 0;
   for (int l = 0; l < n; ++l)
     if (p.layers[l].inverse) invmask |= 1 << l;
-  int Lp = 1;
-  while (Lp < n) Lp <<= 1;
-  // identity padding is its own inverse: an all-inverse chain stays all-inverse (the single-direction kernel)
-  if (invmask == (1 << n) - 1) invmask = (1 << Lp) - 1;
-  return launch_planar_unrolled(p, Lp, nullptr, n, invmask, p.L > n, stream);
+  // device-resident parameters: a program of exactly n layers (every L in 1..8 is instantiated; only the host-parameter
+  // family, whose programs are keyed by the packed argument block, pads to 1, 2, 4, 8)
+  return launch_planar_unrolled(p, n, nullptr, n, invmask, p.L > n, stream);
 }

@@ -503,32 +503,27 @@ def logabsdetjac_(t, x, logjac=None):
     return run_chain(t, x, want_y=False, logjac=logjac, accumulate=logjac is not None)[1]
 
 
-def planar_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[torch.Tensor] = None,
-                     want_param_grads: bool = True):
-    """Vector-Jacobian product of ``with_logabsdet_jacobian(t, x)`` for a ∘-chain ``t`` of (≤ 8) PlanarLayers:
-    what the reference's reverse-mode AD computes in a training step (docs/src/flows.md:93-100,
-    ext/BijectorsChainRulesCoreExt.jl).  ``ybar`` (D×N) / ``ljbar`` (N) are the cotangents of the two outputs.
+class _DescSegment(Transform):
+    """A run of already-built layer descriptors (a slice of a flattened chain)."""
 
-    ``t`` may also be ``inverse(flow)`` (the chain ``logpdf(transformed(d, flow), y)`` evaluates,
-    docs/src/flows.md:66-100): ``x`` is then the observed batch and ``find_alpha`` is differentiated with the reference's
-    implicit-function rule (ext/BijectorsChainRulesCoreExt.jl:42-46).
+    def __init__(self, descs, keep):
+        self._d, self._k = list(descs), keep
 
-    Returns ``(xbar, grads)``: ``xbar`` (D×N) and ``grads`` = list of ``{"w": …, "u": …, "b": …}``, one entry per layer
-    in APPLICATION order (``flatten(t)``; for ``inverse(flow)`` that is the flow's layers reversed), summed over the
-    columns of this batch -- or ``None`` when ``want_param_grads`` is false."""
+    def _descs(self, inverse, D, dtype=torch.float32):
+        if inverse:
+            raise B2BError(_lib.B2B_EUNSUPPORTED, "internal segment: not invertible")
+        return self._d
+
+    def _keepalive(self):
+        return self._k
+
+
+def _planar_segment_vjp(descs, x, ybar, ljbar, want_param_grads):
+    """One call of b2b_planar_chain_vjp_f32: <= 8 PlanarLayers, all forward or all Inverse."""
     D, N, ldx = _batch_view(x)
-    Dy, Ny, ldyb = _batch_view(ybar)
-    if (Dy, Ny) != (D, N) or not x.is_cuda or not ybar.is_cuda or x.dim() != 2:
-        raise ValueError("planar_chain_vjp: x and ybar must be device matrices of the same D×N shape")
-    descs = list(t._descs(False, D, x.dtype))
-    if any(d.kind != _lib.PLANAR or hasattr(d, "_host_planar") for d in descs) or len({int(d.inverse) for d in descs}) != 1:
-        raise B2BError(_lib.B2B_EUNSUPPORTED,
-                       "planar_chain_vjp: PlanarLayers with device parameters, one direction per chain "
-                       "(a flow, or inverse(flow))")
+    ldyb = _batch_view(ybar)[2]
     L = len(descs)
     arr = _desc_array(descs)
-    if ljbar is not None and (ljbar.numel() != N or ljbar.dtype != torch.float32 or not ljbar.is_contiguous()):
-        raise ValueError("ljbar must be a contiguous float32 vector of length N")
     xbar = colmajor_empty(D, N, x.device)
     wbar = ubar = bbar = None
     if want_param_grads:
@@ -548,6 +543,52 @@ def planar_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[tor
     if want_param_grads:
         grads = [{"w": wbar[l], "u": ubar[l], "b": bbar[l:l + 1]} for l in range(L)]
     return xbar, grads
+
+
+def planar_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[torch.Tensor] = None,
+                     want_param_grads: bool = True):
+    """Vector-Jacobian product of ``with_logabsdet_jacobian(t, x)`` for a ∘-chain ``t`` of PlanarLayers:
+    what the reference's reverse-mode AD computes in a training step (docs/src/flows.md:93-100,
+    ext/BijectorsChainRulesCoreExt.jl).  ``ybar`` (D×N) / ``ljbar`` (N) are the cotangents of the two outputs.
+
+    ``t`` may also be ``inverse(flow)`` (the chain ``logpdf(transformed(d, flow), y)`` evaluates,
+    docs/src/flows.md:66-100): ``x`` is then the observed batch and ``find_alpha`` is differentiated with the reference's
+    implicit-function rule (ext/BijectorsChainRulesCoreExt.jl:42-46).
+
+    The device entry point differentiates up to 8 layers of ONE direction per call.  Longer chains and chains that mix
+    PlanarLayers with Inverse(PlanarLayer)s are cut into such runs here: the run inputs are recomputed with the forward
+    kernels, then the runs are differentiated last to first (the log-Jacobians add up, so every run sees the same l̄).
+
+    Returns ``(xbar, grads)``: ``xbar`` (D×N) and ``grads`` = list of ``{"w": …, "u": …, "b": …}``, one entry per layer
+    in APPLICATION order (``flatten(t)``; for ``inverse(flow)`` that is the flow's layers reversed), summed over the
+    columns of this batch -- or ``None`` when ``want_param_grads`` is false."""
+    D, N, ldx = _batch_view(x)
+    Dy, Ny, ldyb = _batch_view(ybar)
+    if (Dy, Ny) != (D, N) or not x.is_cuda or not ybar.is_cuda or x.dim() != 2:
+        raise ValueError("planar_chain_vjp: x and ybar must be device matrices of the same D×N shape")
+    descs = list(t._descs(False, D, x.dtype))
+    if not descs or any(d.kind != _lib.PLANAR or hasattr(d, "_host_planar") for d in descs):
+        raise B2BError(_lib.B2B_EUNSUPPORTED, "planar_chain_vjp: PlanarLayers (or their Inverses) with device parameters")
+    if ljbar is not None and (ljbar.numel() != N or ljbar.dtype != torch.float32 or not ljbar.is_contiguous()):
+        raise ValueError("ljbar must be a contiguous float32 vector of length N")
+    runs = []  # maximal runs of one direction, at most 8 layers each
+    for d in descs:
+        if runs and int(runs[-1][0].inverse) == int(d.inverse) and len(runs[-1]) < 8:
+            runs[-1].append(d)
+        else:
+            runs.append([d])
+    if len(runs) == 1:
+        return _planar_segment_vjp(descs, x, ybar, ljbar, want_param_grads)
+    keep = t._keepalive()
+    inputs = [x]
+    for r in runs[:-1]:
+        inputs.append(run_chain(_DescSegment(r, keep), inputs[-1], want_logjac=False)[0])
+    cot, grads = ybar, []
+    for r, xin in zip(reversed(runs), reversed(inputs)):
+        cot, g = _planar_segment_vjp(r, xin, cot, ljbar, want_param_grads)
+        if want_param_grads:
+            grads = g + grads
+    return cot, (grads if want_param_grads else None)
 
 
 def radial_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[torch.Tensor] = None):

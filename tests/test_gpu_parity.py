@@ -1075,7 +1075,7 @@ def test_host_resident_parameters_unsupported_cases_fail_loudly(B):
 
 
 @pytest.mark.parametrize("D", [128, 64, 32])
-@pytest.mark.parametrize("L", [1, 3, 8])
+@pytest.mark.parametrize("L", [1, 3, 5, 6, 7, 8])
 def test_constant_bank_planar_chain_matches_interpreter_and_oracle(B, D, L):
     """Segments of <= 8 PlanarLayers with device-resident parameters run as one unrolled program
     (b2b_planar_const.cu): same results as the layer interpreter and the oracle, mixed directions."""
@@ -1098,21 +1098,36 @@ def test_constant_bank_planar_chain_matches_interpreter_and_oracle(B, D, L):
         lib.b2b_set_kernel_variant(0)
     y0, lj0 = B.with_logabsdet_jacobian(flow, xd)  # auto picks the unrolled planar kernel
     assert np.array_equal(B.to_numpy(y0), B.to_numpy(y3)) and np.array_equal(B.to_numpy(lj0), B.to_numpy(lj3))
-    assert rel(B.to_numpy(y3), B.to_numpy(y2)) <= 2e-6 and rel(B.to_numpy(lj3), B.to_numpy(lj2)) <= 2e-6
-    # oracle: forward layers forward, inverse layers through the float64 inverse
-    z, ljo = x.astype(np.float64), np.zeros(N)
-    for i, p in enumerate(pairs):
-        if i % 3 == 1:
-            z, l1 = O.chain_inverse([p[1]], z)
-        else:
-            z, l1 = O.chain_forward([p[1]], z)
-        ljo = ljo + l1
-    assert rel(B.to_numpy(y3), z) <= 5e-5 and rel(B.to_numpy(lj3), ljo) <= 5e-5
-    if L != 3 or True:
-        fwd = B.Composed(*[p[0] for p in pairs])
-        yf, ljf = B.with_logabsdet_jacobian(fwd, xd)
-        yo, lo = O.chain_forward([p[1] for p in pairs], x.astype(np.float64))
-        assert rel(B.to_numpy(yf), yo) <= RTOL and rel(B.to_numpy(ljf), lo) <= RTOL
+    assert rel(B.to_numpy(y3), B.to_numpy(y2)) <= 5e-6 and rel(B.to_numpy(lj3), B.to_numpy(lj2)) <= 5e-6  # two kernels, each gated against the oracle below
+    # oracle: forward layers forward, inverse layers through the oracle inverse -- in float64, and in float32 for the gate
+    def mixed(x0):
+        z, ljo = x0, np.zeros(N, x0.dtype)
+        for i, p in enumerate(pairs):
+            z, l1 = (O.chain_inverse if i % 3 == 1 else O.chain_forward)([p[1]], z)
+            ljo = ljo + l1
+        return z, ljo
+
+    z, ljo = mixed(x.astype(np.float64))
+    z32, ljo32 = mixed(x)
+    assert rel(B.to_numpy(y3), z) <= gate(z32, z) and rel(B.to_numpy(lj3), ljo) <= gate(ljo32, ljo), (
+        rel(B.to_numpy(y3), z), rel(z32, z), rel(B.to_numpy(lj3), ljo), rel(ljo32, ljo))
+    fwd = B.Composed(*[p[0] for p in pairs])
+    olayers = [p[1] for p in pairs]
+    yf, ljf = B.with_logabsdet_jacobian(fwd, xd)
+    yo, lo = O.chain_forward(olayers, x.astype(np.float64))
+    assert rel(B.to_numpy(yf), yo) <= RTOL and rel(B.to_numpy(ljf), lo) <= RTOL
+    # all-inverse program of exactly L layers, and the logpdf program (terminal MvNormal) of the same length
+    yh = B.to_numpy(yf)
+    xi, lji = B.with_logabsdet_jacobian(B.inverse(fwd), yf)
+    assert lib.b2b_last_launch_count() == 1
+    xo, ljio = O.chain_inverse(olayers, yh.astype(np.float64))
+    xo32, ljio32 = O.chain_inverse(olayers, yh)
+    assert rel(B.to_numpy(xi), xo) <= gate(xo32, xo) and rel(B.to_numpy(lji), ljio) <= gate(ljio32, ljio)
+    mu, sigma = (rng.standard_normal(D) * 0.1).astype(f32), rng.uniform(0.5, 2.0, D).astype(f32)
+    lp = B.to_numpy(B.logpdf(B.transformed(B.MvNormal(D, mu, sigma), fwd), yf))
+    assert lib.b2b_last_launch_count() == 1
+    lpo = O.transformed_logpdf(olayers, mu.astype(np.float64), sigma.astype(np.float64), yh.astype(np.float64))
+    assert rel(lp, lpo) <= gate(O.transformed_logpdf(olayers, mu, sigma, yh), lpo)
 
 
 def test_constant_bank_slot_is_safe_across_streams(B):
@@ -1240,8 +1255,51 @@ def test_planar_inverse_chain_vjp_matches_oracle(B, D, L):
         assert rel(grads[l]["w"].cpu().numpy(), grads_o[l][0]) <= 5e-5, (l, "w")
         assert rel(grads[l]["u"].cpu().numpy(), grads_o[l][1]) <= 5e-5, (l, "u")
         assert abs(float(grads[l]["b"]) - float(grads_o[l][2])) <= 5e-5 * max(abs(float(grads_o[l][2])), np.sqrt(N))
-    with pytest.raises(B.B2BError):  # mixed directions in one call are not supported
-        B.planar_chain_vjp(B.Composed(pairs[0][0], B.inverse(pairs[0][0])), B.from_numpy(y), B.from_numpy(xbar))
+
+
+@pytest.mark.parametrize("D,flags", [(64, [0, 1, 1, 0]), (32, [0] * 9 + [1, 1, 0]), (128, [1, 0, 0, 1, 1])])
+def test_planar_chain_vjp_mixed_directions_and_long_chains(B, D, flags):
+    """PlanarLayers and Inverse(PlanarLayer)s in one chain, and chains of more than 8 layers: cut into runs of one
+    direction (<= 8 layers) on the host side, each run differentiated by b2b_planar_chain_vjp_f32 -- against the float64
+    oracle composed the same way."""
+    import torch
+
+    rng = np.random.default_rng(77 + D)
+    N = 3000 + 11
+    pairs = [make_case("planar", D, rng) for _ in flags]
+    flow = B.Composed(*[B.inverse(p[0]) if f else p[0] for p, f in zip(pairs, flags)])
+    P64 = [tuple(p[1].params[k].astype(np.float64) for k in ("w", "u", "b")) for p in pairs]
+    x = rng.standard_normal((D, N)).astype(f32)
+    ybar, ljbar = rng.standard_normal((D, N)).astype(f32), rng.standard_normal(N).astype(f32)
+    # oracle: maximal runs of one direction, forward sweep for the run inputs, then the run VJPs last to first
+    runs, i = [], 0
+    while i < len(flags):
+        j = i
+        while j < len(flags) and flags[j] == flags[i]:
+            j += 1
+        runs.append((flags[i], list(range(i, j))))
+        i = j
+    ins, z = [], x.astype(np.float64)
+    for f, idx in runs:
+        ins.append(z)
+        z = O.chain_inverse([pairs[k][1] for k in idx[::-1]], z)[0] if f else O.chain_forward([pairs[k][1] for k in idx], z)[0]
+    cot, g_o = ybar.astype(np.float64), [None] * len(flags)
+    for (f, idx), zin in zip(reversed(runs), reversed(ins)):
+        if f:  # application order inv(A), inv(B) = inverse(Composed(B, A)): the oracle takes the flow's order
+            cot, gr = O.planar_inverse_chain_vjp([P64[k] for k in idx[::-1]], zin, cot, ljbar.astype(np.float64))
+            for k, g in zip(idx[::-1], gr):
+                g_o[k] = g
+        else:
+            cot, gr = O.planar_chain_vjp([P64[k] for k in idx], zin, cot, ljbar.astype(np.float64))
+            for k, g in zip(idx, gr):
+                g_o[k] = g
+    xbar, grads = B.planar_chain_vjp(flow, B.from_numpy(x), B.from_numpy(ybar), torch.from_numpy(ljbar).cuda())
+    assert len(grads) == len(flags)
+    assert rel(B.to_numpy(xbar), cot) <= 2e-5, rel(B.to_numpy(xbar), cot)
+    for l in range(len(flags)):
+        assert rel(grads[l]["w"].cpu().numpy(), g_o[l][0]) <= 5e-5, (l, "w")
+        assert rel(grads[l]["u"].cpu().numpy(), g_o[l][1]) <= 5e-5, (l, "u")
+        assert abs(float(grads[l]["b"]) - float(g_o[l][2])) <= 5e-5 * max(abs(float(g_o[l][2])), np.sqrt(N))
 
 
 def test_planar_flow_trains_through_autograd(B):
