@@ -474,13 +474,14 @@ struct BvParams {
   int D, inverse;
 };
 
-constexpr int BV_U = 4;
+constexpr int BV_U = 8;
 
 // Thread = one row (RPT rows 256 apart when D > 256) of a slab of columns, U columns at a time; the row's two partial sums
 // stay in registers, slabs are summed in shared memory, CTAs by the finalize kernel -- fixed order throughout.
 template <int RPT>
 __global__ void __launch_bounds__(256) bn_eval_vjp_kernel(const __grid_constant__ BvParams P) {
   extern __shared__ float bsm[];  // [nslab][2D + 1]
+  constexpr int U = RPT == 1 ? BV_U : BV_U / 2;  // columns in flight per thread
   const int D = P.D, Dp = RPT == 1 ? ((D + 31) & ~31) : 256, nslab = 256 / Dp;
   const int slab = threadIdx.x / Dp, i = threadIdx.x - slab * Dp;
   float A[RPT], sh[RPT], gb[RPT], gl[RPT];
@@ -499,10 +500,10 @@ __global__ void __launch_bounds__(256) bn_eval_vjp_kernel(const __grid_constant_
   const long long per = (P.N + gridDim.x - 1) / gridDim.x;
   const long long c0 = (long long)blockIdx.x * per, c1 = (c0 + per < P.N) ? c0 + per : P.N;
   if (slab < nslab) {
-    for (long long n0 = c0 + slab; n0 < c1; n0 += (long long)BV_U * nslab) {
-      float xv[BV_U][RPT], cb[BV_U][RPT];
+    for (long long n0 = c0 + slab; n0 < c1; n0 += (long long)U * nslab) {
+      float xv[U][RPT], cb[U][RPT];
 #pragma unroll
-      for (int u = 0; u < BV_U; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long n = n0 + (long long)u * nslab;
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(256) bn_eval_vjp_kernel(const __grid_constant_
         if (i == 0 && P.ljbar && n < c1) lsum += P.ljbar[n];
       }
 #pragma unroll
-      for (int u = 0; u < BV_U; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long n = n0 + (long long)u * nslab;
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
@@ -699,7 +700,8 @@ extern "C" int b2b_batchnorm_eval_vjp_f32(const b2b_layer_desc* layer, const flo
   P.inverse = d.inverse ? 1 : 0;
   const int rpt = (D + 255) / 256, Dp = rpt == 1 ? ((D + 31) & ~31) : 256, nslab = 256 / Dp;
   long long grid = (long long)sm_count() * 4;
-  const long long want = (N + (long long)nslab * BV_U - 1) / ((long long)nslab * BV_U);
+  const int bu = rpt == 1 ? BV_U : BV_U / 2;
+  const long long want = (N + (long long)nslab * bu - 1) / ((long long)nslab * bu);
   if (grid > want) grid = want;
   const size_t smem = (size_t)nslab * (2 * D + 1) * sizeof(float);
   void (*kernel)(const BvParams) = rpt == 1   ? bn_eval_vjp_kernel<1>
