@@ -7,8 +7,9 @@ from typing import List, Sequence, Tuple
 
 import torch
 
-from .interface import Composed, batchnorm_vjp, colmajor_empty, coupling_vjp, inverse, planar_chain_vjp, radial_chain_vjp, run_chain
-from .layers import AffineConditioner, Coupling, InvertibleBatchNorm, PartitionMask, PlanarLayer, RadialLayer
+from .interface import Composed, batchnorm_vjp, colmajor_empty, coupling_vjp, inverse, planar_chain_vjp, radial_chain_vjp, rqs_vjp, run_chain
+from .layers import (AffineConditioner, Coupling, InvertibleBatchNorm, PartitionMask, PlanarLayer, RadialLayer,
+                     RationalQuadraticSpline)
 
 
 _VJP_DIMS = (32, 64, 128)
@@ -247,3 +248,55 @@ class RealNVP(torch.nn.Module):
         x, lj = self.inverse(y)
         base = -0.5 * (x * x).sum(0) - 0.5 * self.dims * 1.8378770664093453
         return -(base + lj).sum()
+
+
+# ---- RationalQuadraticSpline -------------------------------------------------------------------------------------------
+class _SplineFn(torch.autograd.Function):
+    """with_logabsdet_jacobian of ONE RationalQuadraticSpline given its PROCESSED knots (D × K+1 each), either direction;
+    backward = b2b_rqs_vjp_f32 (cotangents of the input and of the three knot arrays)."""
+
+    @staticmethod
+    def forward(ctx, x, widths, heights, derivs, inv: bool):
+        lay = RationalQuadraticSpline(widths.detach(), heights.detach(), derivs.detach(), device=x.device)
+        t = inverse(lay) if inv else lay
+        xc = _colmajor(x.detach())
+        y, lj = run_chain(t, xc)
+        ctx.t = t
+        ctx.save_for_backward(xc)
+        return y, lj
+
+    @staticmethod
+    def backward(ctx, ybar, ljbar):
+        (xc,) = ctx.saved_tensors
+        D, N = xc.shape
+        yb = _colmajor(ybar) if ybar is not None else _colmajor(torch.zeros((D, N), device=xc.device))
+        xbar, g = rqs_vjp(ctx.t, xc, yb, ljbar.contiguous() if ljbar is not None else None)
+        return xbar, g["widths"], g["heights"], g["derivatives"], None
+
+
+class SplineLayer(torch.nn.Module):
+    """A trainable RationalQuadraticSpline(raw widths, raw heights, raw derivatives, B) (rational_quadratic_spline.jl:
+    99-123).  The constructor's normalisation (softmax -> cumsum -> [-B, B] knots, softplus derivatives with unit end
+    slopes) is parameter-sized torch code, differentiated by torch as the reference's AD differentiates the constructor;
+    the spline over the batch and its reverse mode run in the device kernels."""
+
+    def __init__(self, dims: int, K: int, B: float = 3.0, device="cuda", generator=None):
+        super().__init__()
+        self.B = float(B)
+        self.w = torch.nn.Parameter(torch.randn((dims, K), generator=generator).to(device))
+        self.h = torch.nn.Parameter(torch.randn((dims, K), generator=generator).to(device))
+        self.d = torch.nn.Parameter(torch.randn((dims, K - 1), generator=generator).to(device))
+
+    def knots(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        n, dev = self.w.shape[0], self.w.device
+        zero, one = torch.zeros((n, 1), device=dev), torch.ones((n, 1), device=dev)
+        W = 2 * self.B * torch.cumsum(torch.cat([zero, torch.softmax(self.w, dim=1)], dim=1), dim=1) - self.B
+        H = 2 * self.B * torch.cumsum(torch.cat([zero, torch.softmax(self.h, dim=1)], dim=1), dim=1) - self.B
+        Dv = torch.cat([one, torch.nn.functional.softplus(self.d), one], dim=1)
+        return W, H, Dv
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        return _SplineFn.apply(x, *self.knots(), False)
+
+    def inverse(self, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        return _SplineFn.apply(y, *self.knots(), True)

@@ -456,8 +456,52 @@ class GraphedCalls:
 # --------------------------------------------------------------------------------------------------
 
 
+def _batchnorm_nd(t, x, want_y=True, want_logjac=True):
+    """InvertibleBatchNorm (or its Inverse) on an array of more than two dimensions (normalise.jl:41-47,61-67,74-86): the
+    channel axis is ndims − 1, the batch axis the last one; ``x`` is Julia-layout (column-major, dense) with shape
+    (d₁, …, d_k, C, B).  The slab of one batch element is a column of S·C numbers (S = d₁⋯d_k) whose row s + S·c belongs
+    to channel c, so the elementwise map is the D×N kernel on a view of the same memory with each channel's parameters
+    repeated S times; the log-Jacobian the reference returns -- fill(sum(logs − log(v + eps)/2), B), without a factor S
+    (:66) -- is the C-channel layer's own log-Jacobian, evaluated by the library on a C×B batch."""
+    inv = isinstance(t, Inverse)
+    bn = t.orig if inv else t
+    if getattr(bn, "training", False):
+        raise B2BError(_lib.B2B_EUNSUPPORTED, "training-mode InvertibleBatchNorm takes D×N batches on the device path")
+    shape = tuple(x.shape)
+    C, Bn = shape[-2], shape[-1]
+    if C != bn.b.numel():
+        raise RuntimeError(f"InvertibleBatchNorm expected {bn.b.numel()} channels, got {C}")  # normalise.jl:43-45
+    S = 1
+    for d in shape[:-2]:
+        S *= d
+    strides, acc = [], 1
+    for d in shape:
+        strides.append(acc)
+        acc *= d
+    if tuple(x.stride()) != tuple(strides) or not x.is_cuda or x.dtype != bn.b.dtype:
+        raise ValueError("arrays of more than two dimensions must be dense Julia-layout (column-major) device tensors "
+                         "of the layer's element type")
+    y = lj = None
+    if want_y:
+        wide = bn._expanded(S)
+        y2 = run_chain(Inverse(wide) if inv else wide, x.as_strided((S * C, Bn), (1, S * C)), want_logjac=False)[0]
+        y = y2.as_strided(shape, tuple(strides))
+    if want_logjac:
+        probe = torch.zeros((Bn, C), dtype=x.dtype, device=x.device).t()
+        lj = run_chain(t, probe, want_y=False)[1]
+    return y, lj
+
+
+def _is_batchnorm_nd(t, x):
+    from .layers import InvertibleBatchNorm
+    base = t.orig if isinstance(t, Inverse) else t
+    return isinstance(x, torch.Tensor) and x.dim() > 2 and isinstance(base, InvertibleBatchNorm)
+
+
 def with_logabsdet_jacobian(t, x):
     """(transform(t, x), logabsdetjac(t, x)) in one fused pass (src/interface.jl:144)."""
+    if _is_batchnorm_nd(t, x):
+        return _batchnorm_nd(t, x)
     if hasattr(t, "_host_wladj") and not (isinstance(x, torch.Tensor) and x.is_cuda):
         return t._host_wladj(x)
     if isinstance(t, Columnwise):
@@ -471,6 +515,8 @@ def with_logabsdet_jacobian(t, x):
 
 def transform(t, x):
     """transform(b, x) (src/interface.jl:156-166)."""
+    if _is_batchnorm_nd(t, x):
+        return _batchnorm_nd(t, x, want_logjac=False)[0]
     if hasattr(t, "_host_wladj") and not (isinstance(x, torch.Tensor) and x.is_cuda):
         return t._host_wladj(x)[0]
     return run_chain(t, x, want_logjac=False)[0]
@@ -478,6 +524,8 @@ def transform(t, x):
 
 def logabsdetjac(t, x):
     """logabsdetjac(b, x) (src/interface.jl:183-192): no D×N store is issued."""
+    if _is_batchnorm_nd(t, x):
+        return _batchnorm_nd(t, x, want_y=False)[1]
     if hasattr(t, "_host_wladj") and not (isinstance(x, torch.Tensor) and x.is_cuda):
         return t._host_wladj(x)[1]
     if isinstance(t, Columnwise):  # sum over columns, interface.jl:75-77

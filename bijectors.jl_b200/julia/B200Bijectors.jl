@@ -170,6 +170,26 @@ with_logabsdet_jacobian(b::DeviceLeaf, x::CuMatrix{Float32}) = run_chain(descs(b
 transform(b::DeviceLeaf, x::CuMatrix{Float32}) = first(run_chain(descs(b, false), x; logjac=nothing))
 logabsdetjac(b::DeviceLeaf, x::CuMatrix{Float32}) = last(run_chain(descs(b, false), x; y=nothing))
 
+# InvertibleBatchNorm on arrays of more than two dimensions (normalise.jl:41-47: channel axis ndims − 1, batch axis last):
+# the slab of one batch element is a column of S·C numbers whose row s + S·c belongs to channel c, so the elementwise map
+# is the D×N kernel on a reshape of the same memory with every channel's parameters repeated S times; the log-Jacobian
+# the reference returns has no factor S (:66) -- it is the C-channel layer's own, evaluated on a C×B batch.
+const DeviceBN = InvertibleBatchNorm{<:CuVector{Float32}}
+function batchnorm_nd(b::Union{DeviceBN,Inverse{<:DeviceBN}}, x::CuArray{Float32})
+    bn = b isa Inverse ? b.orig : b
+    C, B = size(x, ndims(x) - 1), size(x, ndims(x))
+    C == length(bn.b) || error("InvertibleBatchNorm expected $(length(bn.b)) channels, got $C")
+    S = div(length(x), C * B)
+    wide = InvertibleBatchNorm(repeat(bn.b; inner=S), repeat(bn.logs; inner=S), repeat(bn.m; inner=S),
+                               repeat(bn.v; inner=S), bn.eps, bn.mtm)
+    y = first(run_chain(descs(b isa Inverse ? inverse(wide) : wide, false), reshape(x, S * C, B); logjac=nothing))
+    logjac = last(run_chain(descs(b, false), CUDA.zeros(Float32, C, B); y=nothing))
+    return reshape(y, size(x)), logjac
+end
+with_logabsdet_jacobian(b::Union{DeviceBN,Inverse{<:DeviceBN}}, x::CuArray{Float32,3}) = batchnorm_nd(b, x)
+with_logabsdet_jacobian(b::Union{DeviceBN,Inverse{<:DeviceBN}}, x::CuArray{Float32,4}) = batchnorm_nd(b, x)
+with_logabsdet_jacobian(b::Union{DeviceBN,Inverse{<:DeviceBN}}, x::CuArray{Float32,5}) = batchnorm_nd(b, x)
+
 # Host-resident PlanarLayer chains (fields are plain Arrays) on a device batch: parameters travel as kernel arguments.
 const HostPlanar = PlanarLayer{<:Vector{Float32}}
 all_host_planar(f) = all(b -> b isa HostPlanar, flatten(f))

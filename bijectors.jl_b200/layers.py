@@ -334,6 +334,15 @@ class InvertibleBatchNorm(_ParamLayer):
         _check_dtype(self.b, dtype, "InvertibleBatchNorm")
         return [_desc(_lib.BATCHNORM, inverse, p0=self.b, p1=self.logs, p2=self.m, p3=self.v, f0=self.eps)]
 
+    def _expanded(self, S: int):
+        """The same eval-mode layer with every channel's parameters repeated S times (rows s + S·c of a (d₁⋯d_k·C)×B
+        view of an array with k leading spatial axes; interface._batchnorm_nd).  Rebuilt on every call: the fields are
+        trainable and may have changed."""
+        out = InvertibleBatchNorm.__new__(InvertibleBatchNorm)
+        out.b, out.logs, out.m, out.v = (torch.repeat_interleave(p, S) for p in (self.b, self.logs, self.m, self.v))
+        out.eps, out.mtm, out.training = self.eps, self.mtm, False
+        return out
+
     def train_forward(self, x, comm=None):
         """with_logabsdet_jacobian(bn, x) with istraining() == true (normalise.jl:51-69): batch statistics (over all
         ranks of `comm`, a distributed.Communicator, when given), in-place moving-average update of self.m / self.v,

@@ -1542,6 +1542,83 @@ def test_rqs_vjp_matches_oracle(B, D, K, inv):
         assert rel(B.to_numpy(xbar3), r0[0]) <= 1e-4 and rel(B.to_numpy(g3["derivatives"]), r0[3]) <= 1e-4
 
 
+@pytest.mark.parametrize("inv", [False, True])
+def test_spline_layer_trains_through_autograd(B, inv):
+    """autograd.SplineLayer: gradients of a scalar objective w.r.t. the RAW spline parameters (through the constructor's
+    softmax / cumsum / softplus in torch and b2b_rqs_vjp_f32 on the device) equal the float64 oracle's -- oracle VJP of the
+    spline chained with a float64 torch restatement of the constructor -- and a few SGD steps lower the objective."""
+    import torch
+
+    torch.manual_seed(5)
+    D, K, N = 32, 8, 4096
+    lay = B.autograd.SplineLayer(D, K, 3.0)
+    x = (torch.randn((N, D), device="cuda") * 1.4).t()
+    x.requires_grad_(True)
+    cy, cl = torch.randn((N, D), device="cuda").t(), torch.randn(N, device="cuda")
+
+    def objective():
+        y, lj = (lay.inverse if inv else lay.forward)(x)
+        return (y * cy).sum() + (lj * cl).sum()
+
+    loss = objective()
+    loss.backward()
+    # float64 reference: oracle VJP for the knots, torch float64 autograd for the constructor
+    w64, h64, d64 = [p.detach().double().cpu().requires_grad_(True) for p in (lay.w, lay.h, lay.d)]
+    zero, one = torch.zeros((D, 1), dtype=torch.float64), torch.ones((D, 1), dtype=torch.float64)
+    W64 = 6.0 * torch.cumsum(torch.cat([zero, torch.softmax(w64, 1)], 1), 1) - 3.0
+    H64 = 6.0 * torch.cumsum(torch.cat([zero, torch.softmax(h64, 1)], 1), 1) - 3.0
+    D64 = torch.cat([one, torch.nn.functional.softplus(d64), one], 1)
+    # the spline is evaluated at the knots the device used (the float32 constructor's): next to a knot the cotangents
+    # move by 1e-4 when the knot moves by one float32 ulp, which is not the kernel's error
+    Wd, Hd, Dd = [k.detach().cpu().numpy().astype(np.float64) for k in lay.knots()]
+    assert rel(Wd, W64.detach().numpy()) <= 1e-6 and rel(Dd, D64.detach().numpy()) <= 1e-6
+    xb_o, Wb, Hb, Db = O.rqs_vjp(Wd, Hd, Dd, x.detach().cpu().numpy().astype(np.float64), cy.cpu().numpy().astype(np.float64),
+                                 cl.cpu().numpy().astype(np.float64), inverse=inv)
+    torch.autograd.backward([W64, H64, D64], [torch.from_numpy(Wb), torch.from_numpy(Hb), torch.from_numpy(Db)])
+    assert rel(x.grad.cpu().numpy(), xb_o) <= 2e-5, rel(x.grad.cpu().numpy(), xb_o)
+    for par, ref in ((lay.w, w64), (lay.h, h64), (lay.d, d64)):
+        assert rel(par.grad.cpu().numpy(), ref.grad.numpy()) <= 5e-5, rel(par.grad.cpu().numpy(), ref.grad.numpy())
+    opt = torch.optim.SGD(lay.parameters(), lr=1e-4)
+    l0 = float(loss)
+    for _ in range(5):
+        opt.zero_grad()
+        x.grad = None
+        l_ = objective()
+        l_.backward()
+        opt.step()
+    assert float(objective()) < l0
+
+
+def test_batchnorm_on_arrays_of_more_than_two_dimensions(B):
+    """InvertibleBatchNorm on (W, H, C, B) / (L, C, B) arrays: channel axis = ndims − 1 (normalise.jl:41-47), the
+    log-Jacobian is fill(sum(logs − log(v + eps)/2), B) -- no spatial factor (:66-67) -- both directions."""
+    import torch
+
+    rng = np.random.default_rng(321)
+    for shape in ((5, 3, 6, 37), (7, 4, 19), (2, 2, 2, 3, 11)):
+        C = shape[-2]
+        b, logs, m = [(rng.standard_normal(C) * 0.3).astype(f32) for _ in range(3)]
+        v = rng.uniform(0.5, 1.5, C).astype(f32)
+        bn = B.InvertibleBatchNorm(b=b, logs=logs, m=m, v=v)
+        obn = O.BatchNormParams(b, logs, m, v, f32(1e-5), f32(0.1))
+        x = rng.standard_normal(shape).astype(f32)
+        xd = torch.from_numpy(np.asfortranarray(x)).cuda()  # Julia layout: first axis fastest
+        assert xd.stride(0) == 1
+        y, lj = B.with_logabsdet_jacobian(bn, xd)
+        yo, ljo = O.batchnorm_forward(obn, x.astype(np.float64))
+        assert tuple(y.shape) == shape and tuple(y.stride()) == tuple(xd.stride()) and lj.shape == (shape[-1],)
+        assert rel(y.cpu().numpy(), yo) <= RTOL and rel(B.to_numpy(lj), ljo) <= RTOL
+        assert np.array_equal(B.transform(bn, xd).cpu().numpy(), y.cpu().numpy())
+        assert np.array_equal(B.to_numpy(B.logabsdetjac(bn, xd)), B.to_numpy(lj))
+        xi, lji = B.with_logabsdet_jacobian(B.inverse(bn), y)
+        xo, ljio = O.batchnorm_inverse(obn, y.cpu().numpy().astype(np.float64))
+        assert rel(xi.cpu().numpy(), xo) <= RTOL and rel(B.to_numpy(lji), ljio) <= RTOL
+        with pytest.raises(RuntimeError, match="expected"):
+            B.with_logabsdet_jacobian(B.InvertibleBatchNorm(C + 1), xd)
+    with pytest.raises(ValueError):  # row-major (not Julia-layout) array
+        B.with_logabsdet_jacobian(bn, torch.zeros((2, 2, 2, 3, 11), device="cuda"))
+
+
 def test_realnvp_trains_through_autograd(B):
     """BASELINE config 5's flow structure as a torch module on the device path: gradients of the NLL w.r.t. every
     parameter equal the oracle's layer-by-layer VJP chain, and a few SGD steps lower the objective."""
