@@ -1,5 +1,6 @@
-// A single RationalQuadraticSpline layer with K = 4, 8, 16 or 32 bins (K1 = K + 1 knots; K = 8 is the BASELINE
-// configuration) as a program specialised on (D, K1, direction) on the TMA pipeline.
+// A single RationalQuadraticSpline layer with K <= 32 bins (K1 = K + 1 knots; K = 8 is the BASELINE configuration) as a
+// program specialised on (D, table size, direction) on the TMA pipeline; table sizes 5 / 9 / 17 / 33 knots, a layer with
+// another knot count runs in the next larger table (padded with +inf probes: same number of search steps).
 //
 // Reference semantics: rational_quadratic_spline.jl:317-357 (forward), :183-220 (inverse) + the forward log-Jacobian
 // at the recovered point (interface.jl:276-281).
@@ -28,7 +29,7 @@ __host__ __device__ constexpr int rqs2_steps(int K1) {
   while ((1 << s) < K1 - 1) ++s;
   return s;
 }
-__host__ __device__ constexpr bool rqs2_supported(int K1) { return K1 >= 5 && K1 <= 33 && (1 << rqs2_steps(K1)) == K1 - 1; }
+__host__ __device__ constexpr bool rqs2_supported(int K1) { return K1 >= 2 && K1 <= 33; }  // padded to 5 / 9 / 17 / 33
 __host__ __device__ constexpr int rqs2_row_floats(int K1) { return (K1 + 1) * RQS_REC; }
 
 __device__ __forceinline__ float rcp_ftz(float x) {
@@ -54,32 +55,35 @@ __device__ __forceinline__ float sqrt_ftz(float x) {
 //       {S[0], S[K1-1]} in [9], [10]
 // with S = widths (forward search on x, :328) or heights (inverse search on y, :191).  Record K1 is padding (v = +inf
 // counts every knot; the element is outside the box and its result is discarded).
+// K1 is the program's (padded) knot count, 5 / 9 / 17 / 33; the layer has K1r = d.n0 <= K1 knots.  Probe slots beyond the
+// layer's interior knots hold +inf (never "< v"), so the bisection over the padded table returns the layer's own bin.
 template <int K1, bool INV>
 __device__ inline void stage_rqs_records(const b2b_layer_desc& d, float* sm, int D, int tid, int nthreads) {
   constexpr int NR = K1 + 1;
+  const int K1r = d.n0;
   const float* S = INV ? d.p1 : d.p0;
   for (int idx = tid; idx < D * NR; idx += nthreads) {
     const int c = idx / D, i = idx - c * D;  // consecutive threads -> consecutive rows (coalesced parameter reads)
     float* rec = sm + (size_t)(i * NR + c) * RQS_REC;
     float w_k = 0.f, w = 1.f, h_k = 0.f, dy = 1.f, d_k = 1.f, d_k1 = 1.f;
-    if (c < K1) {
-      const float Wl = d.p0[(size_t)(K1 - 1) * D + i], Hl = d.p1[(size_t)(K1 - 1) * D + i];
+    if (c < K1r) {
+      const float Wl = d.p0[(size_t)(K1r - 1) * D + i], Hl = d.p1[(size_t)(K1r - 1) * D + i];
       w_k = c == 0 ? -Wl : d.p0[(size_t)(c - 1) * D + i];   // rational_quadratic_spline.jl:331
       w = d.p0[(size_t)c * D + i] - w_k;                    // :332
       h_k = c == 0 ? -Hl : d.p1[(size_t)(c - 1) * D + i];   // :335
       dy = d.p1[(size_t)c * D + i] - h_k;                   // :336
       d_k = c == 0 ? 1.0f : d.p2[(size_t)(c - 1) * D + i];  // :342
-      d_k1 = c == K1 - 1 ? 1.0f : d.p2[(size_t)c * D + i];  // :343
+      d_k1 = c == K1r - 1 ? 1.0f : d.p2[(size_t)c * D + i]; // :343
     }
     const float sl = dy / w;                                // :339
     float4* r4 = reinterpret_cast<float4*>(rec);
     r4[0] = INV ? make_float4(w_k, w, h_k, sl) : make_float4(w_k, 1.0f / w, h_k, dy);
     r4[1] = make_float4(d_k, d_k1, 0.f, 0.f);
-    float p8 = 0.f, p9 = 0.f, p10 = 0.f;
-    if (c <= K1 - 3) p8 = S[(size_t)(c + 1) * D + i];
+    float p8 = __int_as_float(0x7f800000), p9 = 0.f, p10 = 0.f;  // +inf: not an interior knot of this layer
+    if (c <= K1r - 3) p8 = S[(size_t)(c + 1) * D + i];
     if (c == (1 << (rqs2_steps(K1) - 1)) - 1) {  // the record of the first (lane-uniform) probe also carries the end knots
       p9 = S[i];
-      p10 = S[(size_t)(K1 - 1) * D + i];
+      p10 = S[(size_t)(K1r - 1) * D + i];
     }
     r4[2] = make_float4(p8, p9, p10, 0.f);
   }
@@ -224,18 +228,17 @@ static int launch_rqs(const B2BChainParams& q, cudaStream_t stream) {
 
 template <int D, int NW>
 static int dispatch_rqs(const B2BChainParams& q, cudaStream_t stream) {
-  switch (q.layers[0].n0) {
-    case 5: return launch_rqs<D, 5, NW>(q, stream);
-    case 9: return launch_rqs<D, 9, NW>(q, stream);
-    case 17: return launch_rqs<D, 17, NW>(q, stream);
-    case 33: return launch_rqs<D, 33, NW>(q, stream);
-    default: return B2B_EUNSUPPORTED;
-  }
+  const int K1r = q.layers[0].n0;  // the program of the next table size 5 / 9 / 17 / 33 (same number of search steps)
+  if (K1r < 2 || K1r > 33) return B2B_EUNSUPPORTED;
+  if (K1r <= 5) return launch_rqs<D, 5, NW>(q, stream);
+  if (K1r <= 9) return launch_rqs<D, 9, NW>(q, stream);
+  if (K1r <= 17) return launch_rqs<D, 17, NW>(q, stream);
+  return launch_rqs<D, 33, NW>(q, stream);
 }
 
 }  // namespace b2b
 
-// p: a segment that is exactly one RQS layer with 5, 9, 17 or 33 knots, D in {32, 64}; B2B_EUNSUPPORTED otherwise
+// p: a segment that is exactly one RQS layer with 2..33 knots, D in {32, 64}; B2B_EUNSUPPORTED otherwise
 int b2b_rqs_unrolled_applicable(const B2BChainParams& p) {
   return p.L == 1 && p.layers[0].kind == B2B_RQS && b2b::rqs2_supported(p.layers[0].n0) && (p.D == 32 || p.D == 64) &&
          b2b::v1_check_io(p) == 0;

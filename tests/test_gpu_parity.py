@@ -964,9 +964,10 @@ def test_full_size_properties_config4_rqs(B):
 
 
 @pytest.mark.parametrize("D", [32, 64])
-@pytest.mark.parametrize("K", [4, 8, 16, 32, 6])
+@pytest.mark.parametrize("K", [4, 8, 16, 32, 6, 2, 3, 10, 20, 31])
 def test_rqs_bin_counts_and_raw_knots(B, D, K):
-    """Specialised spline programs for K in {4, 8, 16, 32} bins (K = 6 runs in the interpreter), forward and inverse,
+    """Specialised spline programs: table sizes for K in {4, 8, 16, 32} bins, any other K <= 32 in the next larger table
+    (+inf probe padding), forward and inverse,
     against the float64 oracle -- with B-constructed knots and with RAW three-argument-constructor knots whose first
     knot is not -B, which reaches the k == 0 branches (rational_quadratic_spline.jl:331-343)."""
     rng = np.random.default_rng(7000 + 10 * K + D)
