@@ -38,14 +38,16 @@ __device__ __forceinline__ float group_sum(float v) {
 // slot stride of a column group: L·D rounded up to TPC mod 32, so that the 32 / TPC groups of a warp hit disjoint banks
 __host__ __device__ inline int rv_slot_stride(int L, int D, int tpc) { return ((L * D + 31) / 32) * 32 + tpc; }
 
-template <int TPC, int L>
+// DD: 0 = D at run time, else the exact D = 8·TPC (row guards and every shared-memory offset become constants: a sixth
+// of the instructions); FWD: all layers forward (the Inverse branch and its per-layer γ are compiled out).
+template <int TPC, int L, int DD, bool FWD>
 __global__ void __launch_bounds__(RV_THREADS, 2)
     radial_vjp_kernel(const __grid_constant__ B2BChainParams P, const float* __restrict__ ybar, long long ldyb,
                       const float* __restrict__ ljbar, float* __restrict__ xbar, long long ldxb,
                       float* __restrict__ partials) {
   constexpr int V = RV_V, G = RV_THREADS / TPC;
   extern __shared__ float rsm[];
-  const int D = P.D, SL = rv_slot_stride(L, D, TPC);
+  const int D = DD ? DD : P.D, SL = rv_slot_stride(L, D, TPC);
   float* z0s = rsm;               // [L][D]
   float* slots = rsm + L * D;     // [G][SL]
   const int t = threadIdx.x % TPC, g = threadIdx.x / TPC;
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(RV_THREADS, 2)
 #pragma unroll
   for (int l = 0; l < L; ++l) {
     const b2b_layer_desc& d = P.layers[l];
-    inv[l] = d.inverse != 0;                  // Inverse(layer): radial_layer.jl:88-102,124-129
+    inv[l] = !FWD && d.inverse != 0;          // Inverse(layer): radial_layer.jl:88-102,124-129
     alpha[l] = softplus(d.p0[0]);             // radial_layer.jl:44
     bhat[l] = softplus(d.p1[0]) - alpha[l];   // :45
     for (int r = threadIdx.x; r < D; r += RV_THREADS) z0s[l * D + r] = d.p2[r];
@@ -212,13 +214,13 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <int TPC>
+template <int TPC, int DD, bool FWD>
 static int launch_radial_vjp(int L, int grid, const B2BChainParams& p, const float* ybar, long long ldyb,
                              const float* ljbar, float* xbar, long long ldxb, float* partials, cudaStream_t stream) {
   const size_t smem = ((size_t)L * p.D + (size_t)(RV_THREADS / TPC) * rv_slot_stride(L, p.D, TPC)) * sizeof(float);
 #define B2B_RV_CASE(LL)                                                                                                \
   case LL: {                                                                                                           \
-    auto kernel = radial_vjp_kernel<TPC, LL>;                                                                          \
+    auto kernel = radial_vjp_kernel<TPC, LL, DD, FWD>;                                                                 \
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
     if (e != cudaSuccess) return (int)e;                                                                               \
     kernel<<<grid, RV_THREADS, smem, stream>>>(p, ybar, ldyb, ljbar, xbar, ldxb, partials);                            \
@@ -230,6 +232,15 @@ static int launch_radial_vjp(int L, int grid, const B2BChainParams& p, const flo
   }
 #undef B2B_RV_CASE
   return (int)cudaGetLastError();
+}
+
+// exact D = 8·TPC: forward-only and any-direction programs; other D: the any-direction program with run-time D
+template <int TPC>
+static int dispatch_radial_vjp(bool exact, bool fwd, int L, int grid, const B2BChainParams& p, const float* ybar, long long ldyb,
+                               const float* ljbar, float* xbar, long long ldxb, float* partials, cudaStream_t stream) {
+  if (exact && fwd) return launch_radial_vjp<TPC, 8 * TPC, true>(L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
+  if (exact) return launch_radial_vjp<TPC, 8 * TPC, false>(L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
+  return launch_radial_vjp<TPC, 0, false>(L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
 }
 
 }  // namespace b2b
@@ -261,10 +272,13 @@ int b2b_launch_radial_chain_vjp(const B2BChainParams& p, const float* ybar, long
   const long long want = (p.N + RV_THREADS / tpc - 1) / (RV_THREADS / tpc);
   if (grid > want) grid = (int)want;
   if (grid < 1) grid = 1;
+  bool fwd = true;
+  for (int l = 0; l < L; ++l) fwd = fwd && !p.layers[l].inverse;
+  const bool exact = D == 8 * tpc;
   int rc;
-  if (tpc == 4) rc = launch_radial_vjp<4>(L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
-  else if (tpc == 8) rc = launch_radial_vjp<8>(L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
-  else rc = launch_radial_vjp<16>(L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
+  if (tpc == 4) rc = dispatch_radial_vjp<4>(exact, fwd, L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
+  else if (tpc == 8) rc = dispatch_radial_vjp<8>(exact, fwd, L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
+  else rc = dispatch_radial_vjp<16>(exact, fwd, L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
   if (rc != B2B_OK) return rc;
   radial_vjp_finalize_kernel<<<1, 256, 0, stream>>>(p, L, partials, grid, alpha_bar, beta_bar, z0_bar);
   if (launches) *launches = 2;

@@ -146,10 +146,12 @@ __device__ __forceinline__ float rqv_element(const RqvKnots<INV, STAB>& T, int K
   return INV ? ystar : x_b;
 }
 
-template <bool INV, bool STAB>
-__global__ void __launch_bounds__(RQV_THREADS) rqs_vjp_kernel(const __grid_constant__ RqvParams P) {
+// K1T / DPT: 0 = knot count / padded row count at run time, else the exact values (table offsets, accumulator slots and the
+// bin search become constants and a fully unrolled loop).
+template <bool INV, bool STAB, int K1T, int DPT>
+__global__ void __launch_bounds__(RQV_THREADS, 3) rqs_vjp_kernel(const __grid_constant__ RqvParams P) {
   extern __shared__ float rqv_sm[];
-  const int D = P.D, K1 = P.K1, Dp = (D + 31) & ~31, nslab = RQV_THREADS / Dp;
+  const int D = P.D, K1 = K1T ? K1T : P.K1, Dp = DPT ? DPT : ((D + 31) & ~31), nslab = RQV_THREADS / Dp;
   const int tid = threadIdx.x, slab = tid / Dp, i = tid - slab * Dp;
   float* acc = rqv_sm;                          // [3*K1][RQV_THREADS]
   float* tab = rqv_sm + 3 * K1 * RQV_THREADS;   // [3][K1][Dp] when STAB
@@ -197,6 +199,7 @@ __global__ void __launch_bounds__(RQV_THREADS) rqs_vjp_kernel(const __grid_const
         v[u] = in[u] ? raw[u] : 0.f;
       }
       // bin = number of knots < v (searchsortedfirst − 1); one pass over the row's knots serves the U columns
+#pragma unroll
       for (int j = 0; j < K1 - 1; ++j) {
         const float sj = T.s(j);
 #pragma unroll
@@ -326,8 +329,16 @@ extern "C" int b2b_rqs_vjp_f32(const b2b_layer_desc* layer, const float* x, cons
   int grid = sh.grid_max;
   const long long want = (N + (long long)nslab * RQV_U - 1) / ((long long)nslab * RQV_U);
   if (grid > want) grid = (int)want;
-  void (*kernel)(const RqvParams) = d.inverse ? (sh.stab ? rqs_vjp_kernel<true, true> : rqs_vjp_kernel<true, false>)
-                                              : (sh.stab ? rqs_vjp_kernel<false, true> : rqs_vjp_kernel<false, false>);
+  void (*kernel)(const RqvParams) = nullptr;
+#define B2B_RQV_EXACT(KK, DD)                                                                        \
+  if (sh.stab && K1 == KK && Dp == DD)                                                               \
+    kernel = d.inverse ? rqs_vjp_kernel<true, true, KK, DD> : rqs_vjp_kernel<false, true, KK, DD>;
+  B2B_RQV_EXACT(5, 32) B2B_RQV_EXACT(9, 32) B2B_RQV_EXACT(17, 32) B2B_RQV_EXACT(33, 32)
+  B2B_RQV_EXACT(5, 64) B2B_RQV_EXACT(9, 64) B2B_RQV_EXACT(17, 64) B2B_RQV_EXACT(33, 64)
+#undef B2B_RQV_EXACT
+  if (!kernel)
+    kernel = d.inverse ? (sh.stab ? rqs_vjp_kernel<true, true, 0, 0> : rqs_vjp_kernel<true, false, 0, 0>)
+                       : (sh.stab ? rqs_vjp_kernel<false, true, 0, 0> : rqs_vjp_kernel<false, false, 0, 0>);
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
   if (e != cudaSuccess) return (int)e;
   kernel<<<grid, RQV_THREADS, sh.smem, stream>>>(P);
