@@ -188,27 +188,39 @@ __global__ void __launch_bounds__(RV_THREADS, 2)
   }
 }
 
-// out[i] = Σ_b partials[b][i], one warp per output (fixed order), then the chain rule through the parameter transforms:
-// α = log1pexp(α_raw), β̂ = log1pexp(β) − α  (radial_layer.jl:44-45)
+// out[i] = Σ_b partials[b][i], one warp per output (lane-strided partial sums, then a shuffle tree: fixed order).  Block 0
+// owns the 2L scalar outputs and the chain rule through the parameter transforms, α = log1pexp(α_raw),
+// β̂ = log1pexp(β) − α (radial_layer.jl:44-45); blocks 1.. own 8 entries of z̄0 each.
 __global__ void __launch_bounds__(256)
     radial_vjp_finalize_kernel(const __grid_constant__ B2BChainParams P, int L, const float* __restrict__ partials,
                                int nblk, float* __restrict__ alpha_bar, float* __restrict__ beta_bar,
                                float* __restrict__ z0_bar) {
-  const int D = P.D, n = L * D + 2 * L, lane = threadIdx.x & 31;
-  __shared__ float sums[8 * 128 + 16];
-  for (int i = threadIdx.x >> 5; i < n; i += 8) {
+  const int D = P.D, n = L * D + 2 * L, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float sums[16];
+  auto total = [&](int i) {
     float s = 0.f;
     for (int b = lane; b < nblk; b += 32) s += partials[(size_t)b * n + i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sums[i] = s;
+    return s;
+  };
+  if (blockIdx.x > 0) {
+    const int i = (blockIdx.x - 1) * 8 + warp;
+    if (i < L * D) {
+      const float s = total(i);
+      if (lane == 0) z0_bar[i] = s;
+    }
+    return;
+  }
+  for (int k = warp; k < 2 * L; k += 8) {
+    const float s = total(L * D + k);
+    if (lane == 0) sums[k] = s;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < L * D; i += 256) z0_bar[i] = sums[i];
   if (threadIdx.x < L) {
     const int l = threadIdx.x;
     const float a_raw = P.layers[l].p0[0], b_raw = P.layers[l].p1[0];
-    const float bh = sums[L * D + L + l], al = sums[L * D + l] - bh;
+    const float bh = sums[L + l], al = sums[l] - bh;
     alpha_bar[l] = al / (1.0f + expf(-a_raw));
     beta_bar[l] = bh / (1.0f + expf(-b_raw));
   }
@@ -280,7 +292,7 @@ int b2b_launch_radial_chain_vjp(const B2BChainParams& p, const float* ybar, long
   else if (tpc == 8) rc = dispatch_radial_vjp<8>(exact, fwd, L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
   else rc = dispatch_radial_vjp<16>(exact, fwd, L, grid, p, ybar, ldyb, ljbar, xbar, ldxb, partials, stream);
   if (rc != B2B_OK) return rc;
-  radial_vjp_finalize_kernel<<<1, 256, 0, stream>>>(p, L, partials, grid, alpha_bar, beta_bar, z0_bar);
+  radial_vjp_finalize_kernel<<<1 + (L * D + 7) / 8, 256, 0, stream>>>(p, L, partials, grid, alpha_bar, beta_bar, z0_bar);
   if (launches) *launches = 2;
   return (int)cudaGetLastError();
 }
