@@ -478,22 +478,58 @@ constexpr int BV_U = 8;
 
 // Thread = one row (RPT rows 256 apart when D > 256) of a slab of columns, U columns at a time; the row's two partial sums
 // stay in registers, slabs are summed in shared memory, CTAs by the finalize kernel -- fixed order throughout.
-template <int RPT>
+// U columns of one slab.  FULL: every column and every row of the group exists (no guards in the body).
+template <int RPT, int U, bool INV, bool FULL>
+__device__ __forceinline__ void bn_vjp_group(const BvParams& P, long long n0, long long c1, int nslab, int i, int D,
+                                             const float (&A)[RPT], const float (&sh)[RPT], float (&gb)[RPT], float (&gl)[RPT],
+                                             float& lsum) {
+  float xv[U][RPT], cb[U][RPT];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long long n = n0 + (long long)u * nslab;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int r = i + 256 * j;
+      const bool ok = FULL || (n < c1 && r < D);
+      xv[u][j] = ok ? __ldcs(P.x + n * P.ldx + r) : sh[j];
+      cb[u][j] = ok ? __ldcs(P.ybar + n * P.ldyb + r) : 0.f;
+    }
+    if (i == 0 && P.ljbar && (FULL || n < c1)) lsum += P.ljbar[n];
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long long n = n0 + (long long)u * nslab;
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int r = i + 256 * j;
+      // forward: x̄ = A ȳ, b̄ += ȳ, l̄ogs += ȳ·A(x − m);  inverse (A holds 1/A): ȳ = x̄/A, b̄ −= ȳ, l̄ogs −= ȳ (y − b)
+      const float o = A[j] * cb[u][j];
+      if (FULL || (n < c1 && r < D)) __stcs(P.xbar + n * P.ldxb + r, o);
+      gb[j] += INV ? -o : cb[u][j];
+      gl[j] = fmaf(INV ? -o : o, xv[u][j] - sh[j], gl[j]);
+    }
+  }
+}
+
+template <int RPT, bool INV>
 __global__ void __launch_bounds__(256) bn_eval_vjp_kernel(const __grid_constant__ BvParams P) {
   extern __shared__ float bsm[];  // [nslab][2D + 1]
   constexpr int U = RPT == 1 ? BV_U : BV_U / 2;  // columns in flight per thread
   const int D = P.D, Dp = RPT == 1 ? ((D + 31) & ~31) : 256, nslab = 256 / Dp;
   const int slab = threadIdx.x / Dp, i = threadIdx.x - slab * Dp;
   float A[RPT], sh[RPT], gb[RPT], gl[RPT];
+  bool rows = true;
 #pragma unroll
   for (int j = 0; j < RPT; ++j) {
     const int r = i + 256 * j;
     gb[j] = gl[j] = 0.f;
     A[j] = 1.f;
     sh[j] = 0.f;
+    rows = rows && r < D;
     if (r < D) {
-      A[j] = expf(P.logs[r]) / sqrtf(P.v[r] + P.eps);
-      sh[j] = P.inverse ? P.b[r] : P.m[r];  // the shift removed before scaling: y − b (inverse) / x − m (forward)
+      const float a = expf(P.logs[r]) / sqrtf(P.v[r] + P.eps);
+      A[j] = INV ? 1.0f / a : a;
+      sh[j] = INV ? P.b[r] : P.m[r];  // the shift removed before scaling: y − b (inverse) / x − m (forward)
     }
   }
   float lsum = 0.f;
@@ -501,39 +537,8 @@ __global__ void __launch_bounds__(256) bn_eval_vjp_kernel(const __grid_constant_
   const long long c0 = (long long)blockIdx.x * per, c1 = (c0 + per < P.N) ? c0 + per : P.N;
   if (slab < nslab) {
     for (long long n0 = c0 + slab; n0 < c1; n0 += (long long)U * nslab) {
-      float xv[U][RPT], cb[U][RPT];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long n = n0 + (long long)u * nslab;
-#pragma unroll
-        for (int j = 0; j < RPT; ++j) {
-          const int r = i + 256 * j;
-          const bool ok = n < c1 && r < D;
-          xv[u][j] = ok ? __ldcs(P.x + n * P.ldx + r) : sh[j];
-          cb[u][j] = ok ? __ldcs(P.ybar + n * P.ldyb + r) : 0.f;
-        }
-        if (i == 0 && P.ljbar && n < c1) lsum += P.ljbar[n];
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long n = n0 + (long long)u * nslab;
-#pragma unroll
-        for (int j = 0; j < RPT; ++j) {
-          const int r = i + 256 * j;
-          if (n < c1 && r < D) {
-            if (!P.inverse) {
-              __stcs(P.xbar + n * P.ldxb + r, A[j] * cb[u][j]);
-              gb[j] += cb[u][j];
-              gl[j] = fmaf(cb[u][j], A[j] * (xv[u][j] - sh[j]), gl[j]);  // ȳ ⊙ (y − b)
-            } else {
-              const float o = cb[u][j] / A[j];
-              __stcs(P.xbar + n * P.ldxb + r, o);
-              gb[j] -= o;
-              gl[j] = fmaf(-cb[u][j], (xv[u][j] - sh[j]) / A[j], gl[j]);  // −x̄ ⊙ (x − m)
-            }
-          }
-        }
-      }
+      if (rows && n0 + (long long)(U - 1) * nslab < c1) bn_vjp_group<RPT, U, INV, true>(P, n0, c1, nslab, i, D, A, sh, gb, gl, lsum);
+      else bn_vjp_group<RPT, U, INV, false>(P, n0, c1, nslab, i, D, A, sh, gb, gl, lsum);
     }
     float* mine = bsm + (size_t)slab * (2 * D + 1);
 #pragma unroll
@@ -704,9 +709,9 @@ extern "C" int b2b_batchnorm_eval_vjp_f32(const b2b_layer_desc* layer, const flo
   const long long want = (N + (long long)nslab * bu - 1) / ((long long)nslab * bu);
   if (grid > want) grid = want;
   const size_t smem = (size_t)nslab * (2 * D + 1) * sizeof(float);
-  void (*kernel)(const BvParams) = rpt == 1   ? bn_eval_vjp_kernel<1>
-                                   : rpt == 2 ? bn_eval_vjp_kernel<2>
-                                              : bn_eval_vjp_kernel<4>;
+  void (*kernel)(const BvParams);
+  if (P.inverse) kernel = rpt == 1 ? bn_eval_vjp_kernel<1, true> : rpt == 2 ? bn_eval_vjp_kernel<2, true> : bn_eval_vjp_kernel<4, true>;
+  else kernel = rpt == 1 ? bn_eval_vjp_kernel<1, false> : rpt == 2 ? bn_eval_vjp_kernel<2, false> : bn_eval_vjp_kernel<4, false>;
   kernel<<<(int)grid, 256, smem, stream>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
