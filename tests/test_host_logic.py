@@ -299,6 +299,33 @@ def _c_prototypes():
     return protos
 
 
+def test_python_ctypes_signatures_match_the_header():
+    """bijectors.jl_b200/_lib.py declares restype / argtypes for every entry point by hand: each must agree with the
+    prototype in include/b2b.h in arity, integer widths and pointer-ness (a wrong width corrupts the call silently)."""
+    import ctypes
+
+    from bijectors_jl_b200 import _lib
+
+    protos = _c_prototypes()
+    assert set(_lib._SIGS) == set(protos), (set(_lib._SIGS) ^ set(protos))
+
+    def width(c):  # (kind, bytes) of a ctypes type
+        if isinstance(c, type) and (issubclass(c, ctypes._Pointer) or c in (ctypes.c_void_p, ctypes.c_char_p)):
+            return ("p", 8)
+        kind = {"i": "i", "l": "i", "q": "i", "I": "u", "L": "u", "Q": "u", "f": "f", "d": "f"}[c._type_]
+        return (kind, ctypes.sizeof(c))
+
+    def hclass(c):  # (kind, bytes) of a header class
+        if c.startswith("ptr") or c == "cstring":
+            return ("p", 8)
+        return {"i32": ("i", 4), "i64": ("i", 8), "u64": ("u", 8), "usize": ("u", 8), "f32": ("f", 4), "f64": ("f", 8)}[c]
+
+    for name, (ret, args) in protos.items():
+        pret, pargs = _lib._SIGS[name]
+        assert hclass(ret) == width(pret), (name, ret, pret)
+        assert [hclass(a) for a in args] == [width(a) for a in pargs], (name, args, pargs)
+
+
 def _julia_ccalls():
     """[(symbol, return class, [argument classes], number of actual arguments)] of every ccall in B200Bijectors.jl."""
     import re
