@@ -1381,7 +1381,7 @@ def test_autograd_small_dimension_flow_like_the_reference_example(B):
 
 
 
-@pytest.mark.parametrize("D,L", [(64, 6), (32, 1), (128, 8), (10, 3)])
+@pytest.mark.parametrize("D,L", [(64, 6), (32, 1), (128, 8), (10, 3), (50, 5), (100, 2)])
 def test_radial_chain_vjp_matches_oracle(B, D, L):
     """b2b_radial_chain_vjp_f32 (reverse mode through radial_layer.jl:43-72) vs the float64 oracle VJP, itself pinned
     by finite differences of the forward oracle (CPU suite).  Cotangents are w.r.t. the RAW parameters α_, β, z_0."""
@@ -1460,7 +1460,8 @@ def test_full_size_vjp_round_trip_property(B):
 
 
 @pytest.mark.parametrize("inv", [False, True])
-@pytest.mark.parametrize("D,n1,idx", [(256, 128, "halves"), (256, 128, "swapped"), (64, 20, "scattered"), (10, 4, "scattered")])
+@pytest.mark.parametrize("D,n1,idx", [(256, 128, "halves"), (256, 128, "swapped"), (64, 20, "scattered"), (10, 4, "scattered"),
+                                      (64, 24, "scattered4"), (128, 32, "scattered4")])
 def test_coupling_and_batchnorm_vjp_match_oracle(B, D, n1, idx, inv):
     """Reverse mode of the RealNVP layer kinds: b2b_coupling_affine_vjp_f32 (incl. the combine pullback: pass-through rows
     and arbitrary index lists) and b2b_batchnorm_eval_vjp_f32, both directions, against the finite-difference-pinned
@@ -1473,7 +1474,8 @@ def test_coupling_and_batchnorm_vjp_match_oracle(B, D, n1, idx, inv):
         idx1, idx2 = list(range(D - n1 + 1, D + 1)), list(range(1, D - n1 + 1))
     else:
         perm = rng.permutation(D) + 1
-        idx1, idx2 = sorted(perm[:n1].tolist()), perm[n1:D - 2].tolist()  # two pass-through rows, x2 rows unsorted
+        # two (four) pass-through rows, x2 rows unsorted; "scattered4": n1, n2 multiples of 4 = the float4 program with index lists
+        idx1, idx2 = sorted(perm[:n1].tolist()), perm[n1:D - (4 if idx == "scattered4" else 2)].tolist()
     n2 = len(idx2)
     W = (rng.standard_normal((2 * n1, n2)) * 0.3 / np.sqrt(n2)).astype(f32)
     c = (rng.standard_normal(2 * n1) * 0.1).astype(f32)
@@ -1502,7 +1504,7 @@ def test_coupling_and_batchnorm_vjp_match_oracle(B, D, n1, idx, inv):
 
 
 @pytest.mark.parametrize("inv", [False, True])
-@pytest.mark.parametrize("D,K", [(32, 8), (64, 8), (10, 8), (64, 32), (200, 4)])
+@pytest.mark.parametrize("D,K", [(32, 8), (64, 8), (10, 8), (64, 32), (200, 4), (256, 63), (64, 11)])
 def test_rqs_vjp_matches_oracle(B, D, K, inv):
     """Reverse mode of the RationalQuadraticSpline (b2b_rqs_vjp_f32), both directions, against the finite-difference-pinned
     float64 oracle: input cotangent and the cotangents of the processed widths / heights / derivatives; raw-knot splines
