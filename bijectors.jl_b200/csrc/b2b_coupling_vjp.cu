@@ -12,8 +12,9 @@
 // Three GEMMs of the forward's size per tile (recompute [s; t], the x̄₂ product, the W̄ outer-product accumulation) in
 // exact fp32 on the CUDA cores: a persistent CTA per SM, tiles of 32 columns transposed into shared memory, the CTA's
 // partial W̄ (2·n1 x n2 <= 256 x 128 floats) lives in REGISTERS for the whole launch (128 accumulators per thread) and is
-// written once; a second kernel sums the per-CTA partials in a fixed order (deterministic).  First version: the tensor-core
-// (fp16-split tcgen05) form of the forward kernel has not been carried over to the reverse mode.
+// written once; a second kernel sums the per-CTA partials in a fixed order (deterministic).  Two programs: the generic one
+// below (any n1, n2 <= 128, scalar loads) and the float4 / FFMA2 one for n1, n2 multiples of 4.  The tensor-core (fp16-split
+// tcgen05) form of the forward kernel has not been carried over to the reverse mode.
 #include <cuda_runtime.h>
 
 #include <cstring>
@@ -182,8 +183,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) coupling_vjp_kernel(const __gri
 // The tiles are 32 floats wide with the 16-byte chunks XOR-swizzled by the row (chunk ^ (row & 7)) instead of padded:
 // conflict-free for the row-wise float4 reads, the lane-per-row reads of the W̄ product and the transposing stores alike,
 // and the CTA stays under 100 KB of shared memory -- which leaves 156 KB of L1 for W (128 KB at n1 = n2 = 128), read
-// through L1 by every tile.  (With padded 36-float tiles the carve-out was 132 KB and the cyclic sweep over W missed L1
-// on every pass.)
+// through L1 by every tile.  Measured (ncu, D = 256, N = 2^19): 3.5 ms, three quarters of W's sectors hit L1, the rest
+// (L2 latency, two warps per scheduler) is what `long_scoreboard` shows; streaming W through shared memory with bulk
+// copies was tried and was slower.
 constexpr int CF_LD = CV_TC;
 
 __device__ __forceinline__ float4 ld4s(const float* p) { return *reinterpret_cast<const float4*>(p); }
