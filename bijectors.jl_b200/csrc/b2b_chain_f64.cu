@@ -3,8 +3,8 @@
 // The reference is generic in its element type and its own tests run in Float64 (e.g. the find_alpha residual grid with
 // atol = 1e-14, test/normalising_flows.jl:47-71); this kernel is the device counterpart for those element types.  It is a
 // plain, layer-by-layer restatement in double precision -- one warp per column, the column staged in shared memory,
-// lanes over rows, row reductions by warp shuffles -- NOT a tuned kernel: Float64 batches are a correctness path (B200
-// executes fp64 at 1/64 of its fp32 rate), the Float32 kernels are the hot path.  Every layer kind of the Float32 path is
+// lanes over rows, row reductions by warp shuffles -- NOT a tuned kernel: Float64 batches are a correctness path, the
+// Float32 kernels are the hot path.  Every layer kind of the Float32 path is
 // covered, including affine coupling (a per-column matrix-vector product) and the terminal MvNormal.
 //
 // Reference semantics: planar_layer.jl:65-127,160-185; radial_layer.jl:36-129; rational_quadratic_spline.jl:183-220,
