@@ -566,6 +566,17 @@ class _DescSegment(Transform):
         return self._k
 
 
+def _direction_runs(descs, max_len: int = 8):
+    """Cut a flattened chain into maximal runs of one direction (all forward / all Inverse) of at most `max_len` layers."""
+    runs = []
+    for d in descs:
+        if runs and int(runs[-1][0].inverse) == int(d.inverse) and len(runs[-1]) < max_len:
+            runs[-1].append(d)
+        else:
+            runs.append([d])
+    return runs
+
+
 def _planar_segment_vjp(descs, x, ybar, ljbar, want_param_grads):
     """One call of b2b_planar_chain_vjp_f32: <= 8 PlanarLayers, all forward or all Inverse."""
     D, N, ldx = _batch_view(x)
@@ -619,12 +630,7 @@ def planar_chain_vjp(t, x: torch.Tensor, ybar: torch.Tensor, ljbar: Optional[tor
         raise B2BError(_lib.B2B_EUNSUPPORTED, "planar_chain_vjp: PlanarLayers (or their Inverses) with device parameters")
     if ljbar is not None and (ljbar.numel() != N or ljbar.dtype != torch.float32 or not ljbar.is_contiguous()):
         raise ValueError("ljbar must be a contiguous float32 vector of length N")
-    runs = []  # maximal runs of one direction, at most 8 layers each
-    for d in descs:
-        if runs and int(runs[-1][0].inverse) == int(d.inverse) and len(runs[-1]) < 8:
-            runs[-1].append(d)
-        else:
-            runs.append([d])
+    runs = _direction_runs(descs)
     if len(runs) == 1:
         return _planar_segment_vjp(descs, x, ybar, ljbar, want_param_grads)
     keep = t._keepalive()

@@ -242,6 +242,25 @@ def test_sharded_logdensity_sum_gloo_world2():
     assert math.isfinite(out.get(timeout=5))
 
 
+def test_vjp_chains_are_cut_into_runs_of_one_direction():
+    """planar_chain_vjp differentiates <= 8 layers of one direction per device call: the host side cuts longer / mixed
+    chains into maximal such runs, in application order."""
+    from types import SimpleNamespace as NS
+
+    from bijectors_jl_b200.interface import _direction_runs
+
+    def lens(flags):
+        runs = _direction_runs([NS(inverse=f, tag=i) for i, f in enumerate(flags)])
+        assert [d.tag for r in runs for d in r] == list(range(len(flags)))          # order kept, nothing dropped
+        assert all(len({int(d.inverse) for d in r}) == 1 and 1 <= len(r) <= 8 for r in runs)
+        return [len(r) for r in runs]
+
+    assert lens([0] * 8) == [8] and lens([1] * 3) == [3]
+    assert lens([0] * 9 + [1, 1, 0]) == [8, 1, 2, 1]
+    assert lens([1, 0, 0, 1, 1]) == [1, 2, 2]
+    assert lens([0] * 20) == [8, 8, 4]
+
+
 def test_autograd_module_is_importable_without_a_gpu():
     """The torch.autograd glue builds parameters with the reference's shapes (planar_layer.jl:23-28); evaluating it
     needs the device path (no CPU fallback)."""
